@@ -1,0 +1,50 @@
+"""Pins the CPU oracle against the only golden vectors the reference holds (senskernel-1.0/TEST1)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def _model(g):
+    m = np.array(g["model"])
+    h, vp, vs, rho, Q = m.T
+    return h, vp, vs, rho, 1.0 / Q
+
+
+@pytest.mark.parametrize("wave,kind", [("R", 2), ("L", 1)])
+def test_sibling_semantics_reproduce_test1(golden_test1, wave, kind):
+    g = golden_test1
+    h, vp, vs, rho, qsinv = _model(g)
+    r = O.forward(kind, vp, vs, rho, h, qsinv, g["periods"], opts=O.sibling_opts())
+    assert r["status"] == 0
+    assert list(r["imax"]) == [10, 10]          # identical root counts, modes 0 and 1
+    for mode in (0, 1):
+        np.testing.assert_allclose(r["c"][mode], g[wave]["c"][mode], rtol=0, atol=2e-8)
+    # fundamental: group velocity and variational phase velocity pin the energy integrals
+    np.testing.assert_allclose(r["u"][0], g[wave]["u"][0], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(r["cvar"][0], g[wave]["cvar"][0], rtol=0, atol=2e-8)
+    # first overtone: T=20 s sits at an osculation (c and cvar differ by 4e-3 in the golden file itself)
+    np.testing.assert_allclose(r["u"][1], g[wave]["u"][1], rtol=0, atol=1e-5)
+
+
+def test_ellipticity_scalar(golden_test1):
+    g = golden_test1
+    h, vp, vs, rho, qsinv = _model(g)
+    r = O.forward(2, vp, vs, rho, h, qsinv, g["periods"], opts=O.sibling_opts())
+    assert abs(r["ratio"][0][0] - g["R_T10_extra"]["ellipticity"]) < 5e-7 * 10
+
+
+def test_fast_surf_semantics_close_to_golden(golden_test1):
+    """fast_surf (float32, single mode, ndiv clamp 99/(n-1)) is a different program from the TEST1
+    generator; it must still land within the float32 flattening noise of the golden c."""
+    g = golden_test1
+    h, vp, vs, rho, qsinv = _model(g)
+    ref = np.array(g["R"]["c"][0])
+    for prec, tol in ((0, 3e-4), (1, 3e-4), (2, 5e-6)):
+        r = O.forward(2, vp, vs, rho, h, qsinv, g["periods"], opts=O.make_opts(precision=prec))
+        assert r["status"] == 0 and r["imax"][0] == 10
+        assert np.abs(r["c"][0] - ref).max() < tol
+    r0 = O.forward(2, vp, vs, rho, h, qsinv, g["periods"], opts=O.make_opts(precision=0))
+    r1 = O.forward(2, vp, vs, rho, h, qsinv, g["periods"], opts=O.make_opts(precision=1))
+    # float32 solver noise on the same float32-prepared model
+    assert np.abs(r0["c"][0] - r1["c"][0]).max() < 2e-5
