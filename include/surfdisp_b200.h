@@ -1,0 +1,121 @@
+/* surfdisp_b200.h -- C ABI of the B200-native batched surface-wave dispersion forward solver.
+ *
+ * Drop-in boundary for the hot path of 001cat/pySurfInv (citations relative to the reference tree):
+ *   - fast_surf_()            replaces the gfortran symbol behind the f2py module
+ *                             (fast_surf_src/fast_surf.f:2-5, signature fast_surf_src/fast_surf.pyf:6-19,
+ *                              called from models.py:27 and senskernel.py:188)
+ *   - surfdisp_batch()        the same computation for M models at once on device buffers
+ *                             (replaces M sequential FAST_SURF calls of point.py:19 / models.py:115-121)
+ *   - surfdisp_misfit_batch() replaces Point.misfit (point.py:15-31) / PointCascadia.misfit
+ *                             (point.py:337-366) for M models
+ *   - surfdisp_host_batch()   host-buffer convenience wrapper (H2D, solve, D2H) -- what a ctypes/cffi
+ *                             caller without device memory management uses
+ *
+ * All entry points are re-entrant (no global mutable state), never print, never abort the process.
+ * Pointers documented "device" must be device-accessible; everything else is host memory.
+ * Return value: 0 on success, negative SURFDISP_E* on error.
+ */
+#ifndef SURFDISP_B200_H
+#define SURFDISP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURFDISP_KIND_LOVE 1      /* fast_surf kind0 = 1 */
+#define SURFDISP_KIND_RAYLEIGH 2  /* fast_surf kind0 = 2 */
+
+#define SURFDISP_MAX_PERIODS 200  /* fast_surf.f:9  (nper) */
+#define SURFDISP_MAX_LAYERS 1000  /* fast_surf.f:9  (nsize) */
+
+#define SURFDISP_EINVAL (-1)      /* bad argument */
+#define SURFDISP_ENOMEM (-2)      /* workspace too small / allocation failed */
+#define SURFDISP_ECUDA (-3)       /* CUDA runtime error (see surfdisp_last_cuda_error) */
+
+/* per-model status bits written to flags[] */
+#define SURFDISP_F_NO_ROOT_FIRST 1   /* no root at the first period (calcul.f:203-212): nfound = 0 */
+#define SURFDISP_F_NO_ROOT_AT_K 2    /* scan failed at a later period (calcul.f:218-219): nfound = k-1 */
+#define SURFDISP_F_ROOT_ABOVE_HS 4   /* polished root above the half-space velocity (calcul.f:191) */
+#define SURFDISP_F_SCAN_LIMIT 8      /* scan hit the iteration guard (non-finite secular function) */
+
+/* Solver options; defaults are the constants hard-coded in the reference (init.f:25,43-58). */
+typedef struct SurfdispOpts {
+  float dc;                /* scan step, km/s                 (init.f:25   dc=0.01)  */
+  float fact;              /* layer-drop depth in wavelengths (init.f:25   fact=4)   */
+  float t_base;            /* reference period of Q, s        (fast_surf.f:77  t_base=1) */
+  int ndiv;                /* sub-layers per layer for the energy integrals (init.f:25 ndiv=5);
+                              per model it is clamped to cap/(n-1) like a fresh process would
+                              (surfa.f:783-784, 414-415) */
+  int ndiv_cap_rayleigh;   /* 99  (surfa.f:783) */
+  int ndiv_cap_love;       /* 999 (surfa.f:414) */
+  int atten;               /* KEY_ATTEN (init.f:43), 1 */
+  int flatten;             /* earth flattening (calcul.f:133), 1 */
+  int stale_mmax;          /* 1: period k refreshes only the layers kept by period k-1, as the
+                              reference does (calcul.f:112-133); 0: refresh all layers */
+  int compute_group;       /* 1: also group velocity (REIGEN/LEIGEN); 0: phase velocity only */
+} SurfdispOpts;
+
+void surfdisp_default_opts(SurfdispOpts* o);
+
+/* Bytes of device scratch surfdisp_batch needs for this problem size. */
+size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods);
+
+/* Batched forward solve on device buffers.
+ *   kind          SURFDISP_KIND_LOVE / SURFDISP_KIND_RAYLEIGH
+ *   n_layers      device int[M]: layers per model incl. the half-space (2 <= n <= n_layers_max)
+ *   layers        device float[5][M][n_layers_max] in fast_surf argument order
+ *                 (a = Vp, b = Vs, rho, d = thickness km, qs = 1/Qs); layer 0 is the top, the last
+ *                 layer is the half-space (its thickness is ignored); b = 0 marks a water top layer
+ *   periods       HOST float[K], seconds, shared by all models, K <= SURFDISP_MAX_PERIODS
+ *   c_out, u_out  device float[M][K] phase / group velocity; zero beyond nfound[m]. u_out may be NULL
+ *   nfound        device int[M]   = reference imax(1), the number of periods with a root
+ *   flags         device int[M] or NULL, SURFDISP_F_* bits
+ *   workspace     device scratch of at least surfdisp_workspace_bytes()
+ *   stream        cudaStream_t (as void*), NULL = default stream.  The call is asynchronous.
+ */
+int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
+                   const int* n_layers, const float* layers, int n_periods, const float* periods,
+                   float* c_out, float* u_out, int* nfound, int* flags, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Per-model misfit of predicted phase velocities against one observed curve.
+ *   mode 0: Point.misfit (point.py:15-31); mode 1: PointCascadia.misfit (point.py:337-366)
+ *   c_pred   device float[M][K], nfound device int[M] (models with nfound < K get the failure
+ *            sentinel (88888, 88888, 0), models.py:29-32 + point.py:20-21)
+ *   obs, sigma  HOST float[K]; mask HOST unsigned char[K] or NULL (1 = observation used)
+ *   periods  HOST float[K] (only read in mode 1 for the T <= 40 s split)
+ *   out      device float[M][3] = (misfit, chiSqr, L)
+ */
+int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_pred, const int* nfound,
+                          const float* obs, const float* sigma, const unsigned char* mask,
+                          const float* periods, float* out, void* stream);
+
+/* Host-buffer wrapper: copies inputs to the device, runs surfdisp_batch, copies results back and
+ * synchronises.  All pointers are HOST memory (pinned memory makes the copies asynchronous).
+ * device = CUDA device ordinal. */
+int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_models, int n_layers_max,
+                        const int* n_layers, const float* layers, int n_periods, const float* periods,
+                        float* c_out, float* u_out, int* nfound, int* flags);
+
+/* ABI-level replacement of the gfortran symbol FAST_SURF (fast_surf.f:2-5): one model, all arguments
+ * by reference, host memory.  cvper has 200 entries of which the first *ncvper are used (init.f:62-72).
+ * Unlike the reference the four 200-long outputs are fully defined: zero beyond the
+ * found prefix and for the wave type not requested. */
+void fast_surf_(const int* n_layer0, const int* kind0, const float* a_ref0, const float* b_ref0,
+                const float* rho_ref0, const float* d_ref0, const float* qs_ref0, const float* cvper,
+                const int* ncvper, float* uR0, float* uL0, float* cR0, float* cL0);
+
+/* Device-side counters of executed work for the last surfdisp_batch on this workspace (roofline
+ * numerator): out[0] = secular layer-steps, out[1] = secular sweeps,
+ * out[2] = group-velocity sub-layer integrations, out[3] = models processed.  Host pointer. */
+int surfdisp_read_counters(const void* workspace, unsigned long long out[4], void* stream);
+
+const char* surfdisp_version(void);
+const char* surfdisp_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,234 @@
+"""Host side of the B200 dispersion solver: ctypes over the C ABI (include/surfdisp_b200.h), torch for
+device buffers and streams only.
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsurfdisp_b200.so")
+
+KIND_LOVE = 1
+KIND_RAYLEIGH = 2
+MAX_PERIODS = 200
+
+F_NO_ROOT_FIRST = 1
+F_NO_ROOT_AT_K = 2
+F_ROOT_ABOVE_HS = 4
+F_SCAN_LIMIT = 8
+
+
+class SurfdispOpts(C.Structure):
+    """Mirror of ``SurfdispOpts`` in include/surfdisp_b200.h (defaults = reference init.f:25,43-58)."""
+    _fields_ = [("dc", C.c_float), ("fact", C.c_float), ("t_base", C.c_float), ("ndiv", C.c_int),
+                ("ndiv_cap_rayleigh", C.c_int), ("ndiv_cap_love", C.c_int), ("atten", C.c_int),
+                ("flatten", C.c_int), ("stale_mmax", C.c_int), ("compute_group", C.c_int)]
+
+
+class SurfdispError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsurfdisp_b200.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SurfdispError("CUDA library %s not built: run `python -m pysurfinv_b200.build`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.surfdisp_default_opts.argtypes = [C.POINTER(SurfdispOpts)]
+    L.surfdisp_default_opts.restype = None
+    L.surfdisp_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.surfdisp_workspace_bytes.restype = C.c_size_t
+    L.surfdisp_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, fp,
+                                 vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.surfdisp_batch.restype = C.c_int
+    L.surfdisp_misfit_batch.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, fp, fp, C.POINTER(C.c_ubyte), fp, vp, vp]
+    L.surfdisp_misfit_batch.restype = C.c_int
+    L.surfdisp_host_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, C.c_int, ip, fp,
+                                      C.c_int, fp, fp, fp, ip, ip]
+    L.surfdisp_host_batch.restype = C.c_int
+    L.fast_surf_.argtypes = [ip, ip, fp, fp, fp, fp, fp, fp, ip, fp, fp, fp, fp]
+    L.fast_surf_.restype = None
+    L.surfdisp_read_counters.argtypes = [vp, C.POINTER(C.c_ulonglong), vp]
+    L.surfdisp_read_counters.restype = C.c_int
+    L.surfdisp_version.restype = C.c_char_p
+    L.surfdisp_last_cuda_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def default_opts(**kw):
+    o = SurfdispOpts()
+    load_library().surfdisp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError("unknown option %r" % k)
+        setattr(o, k, v)
+    return o
+
+
+def _check(rc, what):
+    if rc != 0:
+        names = {-1: "invalid argument", -2: "workspace too small / out of memory", -3: "CUDA error"}
+        msg = "%s failed: %s" % (what, names.get(rc, rc))
+        if rc == -3:
+            msg += " (%s)" % load_library().surfdisp_last_cuda_error().decode()
+        raise SurfdispError(msg)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class DispersionSolver:
+    """Batched Rayleigh/Love phase + group velocity on one GPU.
+
+    ``layers`` follows the argument order of ``fast_surf.fast_surf`` (reference fast_surf.pyf:6-19):
+    [5, M, Lmax] = (Vp, Vs, rho, h, 1/Qs), top layer first, last layer = half-space.
+    """
+
+    def __init__(self, device=None, opts=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise SurfdispError("no CUDA device visible: the dispersion solver has no CPU path")
+        self.torch = torch
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.lib = load_library()
+        self.opts = opts if opts is not None else default_opts()
+        self._ws = None
+        self._pinned = {}
+
+    # -- device path -------------------------------------------------------------------------------
+    def workspace(self, M, lmax, K):
+        need = int(self.lib.surfdisp_workspace_bytes(M, lmax, K))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, out=None):
+        """layers: float32 device tensor [5, M, Lmax]; nlay: int32 device tensor [M]; periods: host
+        sequence.  Returns dict of device tensors c[M,K], u[M,K], nfound[M], flags[M].  Asynchronous on
+        the current torch stream."""
+        torch = self.torch
+        if layers.dtype != torch.float32 or layers.dim() != 3 or layers.shape[0] != 5 or not layers.is_contiguous():
+            raise ValueError("layers must be a contiguous float32 tensor [5, M, Lmax]")
+        if nlay.dtype != torch.int32 or not nlay.is_contiguous() or nlay.numel() != layers.shape[1]:
+            raise ValueError("nlay must be a contiguous int32 tensor [M]")
+        if layers.device != self.device or nlay.device != self.device:
+            raise ValueError("inputs must live on %s" % self.device)
+        per = np.ascontiguousarray(periods, dtype=np.float32)
+        M, lmax, K = int(layers.shape[1]), int(layers.shape[2]), int(per.size)
+        if K < 1 or K > MAX_PERIODS:
+            raise ValueError("1 <= len(periods) <= %d" % MAX_PERIODS)
+        if out is None:
+            out = dict(c=torch.empty((M, K), dtype=torch.float32, device=self.device),
+                       u=torch.empty((M, K), dtype=torch.float32, device=self.device) if group else None,
+                       nfound=torch.empty(M, dtype=torch.int32, device=self.device),
+                       flags=torch.empty(M, dtype=torch.int32, device=self.device))
+        if M == 0:
+            return out
+        ws = self.workspace(M, lmax, K)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_batch(C.byref(self.opts), int(kind), M, lmax, nlay.data_ptr(), layers.data_ptr(),
+                                         K, _fptr(per), out["c"].data_ptr(),
+                                         out["u"].data_ptr() if (group and out.get("u") is not None) else None,
+                                         out["nfound"].data_ptr(), out["flags"].data_ptr(), ws.data_ptr(),
+                                         ws.numel(), stream)
+        _check(rc, "surfdisp_batch")
+        return out
+
+    def counters(self):
+        """(layer_steps, sweeps, u_sublayers, models) executed by the last forward()."""
+        arr = (C.c_ulonglong * 4)()
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        _check(self.lib.surfdisp_read_counters(self._ws.data_ptr(), arr, stream), "surfdisp_read_counters")
+        return tuple(int(x) for x in arr)
+
+    def misfit(self, c_pred, nfound, obs, sigma, mask=None, periods=None, mode=0):
+        """Per-model (misfit, chiSqr, L) like Point.misfit (mode 0) / PointCascadia.misfit (mode 1)."""
+        torch = self.torch
+        M, K = int(c_pred.shape[0]), int(c_pred.shape[1])
+        o = np.ascontiguousarray(obs, dtype=np.float32)
+        s = np.ascontiguousarray(sigma, dtype=np.float32)
+        if o.size != K or s.size != K:
+            raise ValueError("obs/sigma must have one entry per period")
+        mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        pr = None if periods is None else np.ascontiguousarray(periods, dtype=np.float32)
+        out = torch.empty((M, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_misfit_batch(int(mode), M, K, c_pred.data_ptr(), nfound.data_ptr(), _fptr(o),
+                                                _fptr(s), None if mk is None else mk.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                                None if pr is None else _fptr(pr), out.data_ptr(), stream)
+        _check(rc, "surfdisp_misfit_batch")
+        return out
+
+    # -- host path (what a reference-side caller uses): pinned staging, H2D, solve, D2H --------------
+    def _pin(self, key, shape, dtype):
+        t = self._pinned.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self.torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[key] = t
+        return t
+
+    def forward_host(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True):
+        """numpy in, numpy out.  Inputs are staged through pinned memory, copied to the GPU, solved and
+        copied back; returns dict(c, u, nfound, flags) of numpy arrays."""
+        torch = self.torch
+        lay = np.ascontiguousarray(layers, dtype=np.float32)
+        nl = np.ascontiguousarray(nlay, dtype=np.int32)
+        hl = self._pin("lay", lay.shape, torch.float32)
+        hn = self._pin("nl", nl.shape, torch.int32)
+        hl.numpy()[...] = lay
+        hn.numpy()[...] = nl
+        return self.forward_pinned(hl, hn, periods, kind, group)
+
+    def forward_pinned(self, hl, hn, periods, kind=KIND_RAYLEIGH, group=True):
+        """Same as forward_host but the caller already holds pinned host tensors."""
+        torch = self.torch
+        dl = hl.to(self.device, non_blocking=True)
+        dn = hn.to(self.device, non_blocking=True)
+        out = self.forward(dl, dn, periods, kind, group)
+        M, K = out["c"].shape
+        hc = self._pin("c", (M, K), torch.float32)
+        hf = self._pin("nf", (M,), torch.int32)
+        hg = self._pin("fl", (M,), torch.int32)
+        hc.copy_(out["c"], non_blocking=True)
+        hf.copy_(out["nfound"], non_blocking=True)
+        hg.copy_(out["flags"], non_blocking=True)
+        hu = None
+        if group:
+            hu = self._pin("u", (M, K), torch.float32)
+            hu.copy_(out["u"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+
+
+def host_batch(layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, opts=None, device=0):
+    """Pure C-ABI host call (surfdisp_host_batch): no torch involved.  numpy in, numpy out."""
+    L = load_library()
+    lay = np.ascontiguousarray(layers, dtype=np.float32)
+    nl = np.ascontiguousarray(nlay, dtype=np.int32)
+    per = np.ascontiguousarray(periods, dtype=np.float32)
+    M, lmax, K = lay.shape[1], lay.shape[2], per.size
+    c = np.zeros((M, K), np.float32)
+    u = np.zeros((M, K), np.float32) if group else None
+    nf = np.zeros(M, np.int32)
+    fl = np.zeros(M, np.int32)
+    ip = C.POINTER(C.c_int)
+    o = opts if opts is not None else default_opts()
+    rc = L.surfdisp_host_batch(C.byref(o), int(device), int(kind), M, lmax, nl.ctypes.data_as(ip), _fptr(lay), K,
+                               _fptr(per), _fptr(c), None if u is None else _fptr(u), nf.ctypes.data_as(ip),
+                               fl.ctypes.data_as(ip))
+    _check(rc, "surfdisp_host_batch")
+    return dict(c=c, u=u, nfound=nf, flags=fl)

@@ -1,0 +1,625 @@
+// surfdisp_core.cuh -- per-lane arithmetic of the batched dispersion solver.
+//
+// Everything here is written from the physics/algorithm of the reference hot path
+// (fast_surf_src/{flat1,calcul,surfa}.f of 001cat/pySurfInv; line numbers cited per function), laid
+// out for one GPU lane evaluating one trial phase velocity (or one period) against a layer stack
+// staged in shared memory.  The functions are __host__ __device__ so that tests/hostmirror can compile
+// the same source with g++ and check the math against the CPU oracle without a GPU; the product only
+// ever runs the __device__ instantiation (see surfdisp_kernels.cu).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SD_HD __host__ __device__ __forceinline__
+#else
+#define SD_HD inline
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+#endif
+
+// Exactly-rounded float32 basic ops without FMA contraction.  The model-preparation stage (attenuation
+// + earth flattening) suffers catastrophic cancellation in float32 (relative 1e-4 per layer), so the
+// reference's results are only reproducible if these roundings happen in the reference's order.
+#if defined(__CUDA_ARCH__)
+#define SD_ADD(a, b) __fadd_rn((a), (b))
+#define SD_SUB(a, b) __fsub_rn((a), (b))
+#define SD_MUL(a, b) __fmul_rn((a), (b))
+#define SD_DIV(a, b) __fdiv_rn((a), (b))
+#else
+static inline float sd_add(float a, float b) { volatile float r = a + b; return r; }
+static inline float sd_sub(float a, float b) { volatile float r = a - b; return r; }
+static inline float sd_mul(float a, float b) { volatile float r = a * b; return r; }
+static inline float sd_div(float a, float b) { volatile float r = a / b; return r; }
+#define SD_ADD(a, b) sd_add((a), (b))
+#define SD_SUB(a, b) sd_sub((a), (b))
+#define SD_MUL(a, b) sd_mul((a), (b))
+#define SD_DIV(a, b) sd_div((a), (b))
+#endif
+
+namespace sd {
+
+// float32 literals of the reference
+#define SD_PI_ATT 3.1415927f      /* calcul.f:32 */
+#define SD_TWOPI 6.2831855f       /* 6.28318531 / 6.2831853 / 6.2831853072 all round to this float */
+#define SD_R0 6371.0f             /* flat1.f:21 */
+
+// Per-model, per-layer constants written once by the prep kernel (period independent part of
+// calcul.f:112-133 + flat1.f).  One row of NCONST arrays per model.
+enum { C_AREF = 0, C_BREF = 1, C_QS = 2, C_DIF = 3, C_RHOFL = 4, C_DFL = 5, C_HSF = 6, C_RHOHS = 7, NCONST = 8 };
+
+// Working layer record in shared memory (what one secular-function layer step reads).
+//   q0 = (1/a^2, 1/b^2, 2 b^2, rho)      b == 0 (liquid) is flagged by q0.y == 0
+//   q1 = (d, b, 1/rho, a)
+struct LayerRec { float4 q0, q1; };
+
+// ----------------------------------------------------------------------------------------------
+// Model preparation.  flat1.f:33-69 evaluated once per model: radii by sequential float32 prefix sum,
+// velocity factor dif(i), density factor, flattened thickness, plus the factors layer i would get if it
+// were the (effective) half-space.  logs and powers go through double to be as close to a correctly
+// rounded float result as possible (the reference uses glibc logf/powf).
+// Arrays are indexed [0..n-1]; out rows have stride ld.
+SD_HD float sd_logf_cr(float x) { return (float)log((double)x); }
+SD_HD float sd_powf_cr(float x, float p) { return (float)pow((double)x, (double)p); }
+
+SD_HD void prep_model(int n, int kind, int flatten, const float* a, const float* b, const float* rho,
+                      const float* d, const float* qs, float* out, int ld) {
+  const float A = SD_R0;
+  const float pwr = (kind == 1) ? 5.0f : 2.2750f;
+  const float apw = sd_powf_cr(A, pwr);
+  float hs = 0.f, z0 = 0.f;
+  float r_i = A;  // radius of the top of layer i
+  for (int i = 0; i < n; ++i) {
+    float ht = hs;
+    hs = SD_ADD(hs, d[i]);
+    r_i = SD_SUB(A, ht);
+    float r_n = SD_SUB(A, hs);  // radius of the top of layer i+1
+    out[C_AREF * ld + i] = a[i];
+    out[C_BREF * ld + i] = b[i];
+    out[C_QS * ld + i] = qs[i];
+    if (!flatten) {
+      out[C_DIF * ld + i] = 1.f; out[C_RHOFL * ld + i] = rho[i]; out[C_DFL * ld + i] = d[i];
+      out[C_HSF * ld + i] = 1.f; out[C_RHOHS * ld + i] = rho[i];
+      continue;
+    }
+    // as a regular layer (flat1.f:41-56), needs the next boundary
+    float fltd = sd_logf_cr(SD_DIV(r_i, r_n));
+    float dif = SD_DIV(SD_MUL(SD_SUB(SD_DIV(1.0f, r_n), SD_DIV(1.0f, r_i)), A), fltd);
+    float difr = SD_SUB(sd_powf_cr(r_i, pwr), sd_powf_cr(r_n, pwr));
+    float qqq = SD_DIV(difr, SD_MUL(SD_MUL(fltd, apw), pwr));
+    out[C_DIF * ld + i] = dif;
+    out[C_RHOFL * ld + i] = SD_MUL(rho[i], qqq);
+    // flattened thickness of layer i: z(i+1) - z(i)  (flat1.f:65-68)
+    float z1 = SD_MUL(A, sd_logf_cr(SD_DIV(A, r_n)));
+    out[C_DFL * ld + i] = SD_SUB(z1, z0);
+    z0 = z1;
+    // as the half-space (flat1.f:58-62)
+    float fct = SD_DIV(A, r_i);
+    out[C_HSF * ld + i] = fct;
+    out[C_RHOHS * ld + i] = SD_MUL(rho[i], sd_powf_cr(SD_DIV(1.0f, fct), pwr));
+  }
+}
+
+// Attenuation-corrected, flattened (a, b) of layer i for the period whose log term is lt = ln(t_base/T)
+// (calcul.f:121-127 then flat1 scaling).  as_half selects the half-space flattening factor.
+SD_HD void layer_ab(const float* cst, int ld, int i, float lt, int atten, bool as_half, float& a, float& b) {
+  float ar = cst[C_AREF * ld + i], br = cst[C_BREF * ld + i];
+  a = ar; b = br;
+  if (atten) {
+    float qsq = SD_DIV(SD_MUL(cst[C_QS * ld + i], lt), SD_PI_ATT);
+    float qpq = SD_DIV(SD_MUL(SD_MUL(qsq, 1.33333333f), SD_MUL(br, br)), SD_MUL(ar, ar));
+    b = SD_MUL(br, SD_ADD(1.0f, qsq));
+    a = SD_MUL(ar, SD_ADD(1.0f, qpq));
+  }
+  float f = as_half ? cst[C_HSF * ld + i] : cst[C_DIF * ld + i];
+  a = SD_MUL(a, f);
+  b = SD_MUL(b, f);
+}
+
+SD_HD LayerRec make_rec(float a, float b, float rho, float d) {
+  LayerRec r;
+  r.q0 = make_float4(1.0f / (a * a), (b > 0.f) ? 1.0f / (b * b) : 0.f, 2.0f * b * b, rho);
+  r.q1 = make_float4(d, b, 1.0f / rho, a);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Layer dropping, surfa.f:92-106.  Returns mmax (1-based count of layers kept, >= 2).
+SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* q1) {
+  const float dmax = SD_MUL(SD_MUL(fact, c), T);
+  float sum = 0.f;
+  int mmax = nmax;
+  for (int ii = 0; ii < nmax; ++ii) {
+    float4 e = q1[ii];
+    if (c < e.y) {
+      sum = SD_ADD(sum, e.x);
+      if (sum > dmax) { mmax = ii + 1; break; }
+    }
+  }
+  return mmax < 2 ? 2 : mmax;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Rayleigh secular function: Dunkin compound-matrix vector propagated top-down through layers
+// 1..mmax-1 and contracted with the half-space row (surfa.f:193-357).
+//   start = 1: dispersion function (returns -bb1)
+//   start = 2 / 3: the two ellipticity sweeps (returns bb1); liquid layers are skipped there
+//   (surfa.f:220).
+SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const float4* q1, int start) {
+  const float wvno = SD_TWOPI / (c * T);
+  const float csq = c * c;
+  const float icsq = 1.0f / csq;
+  float b1 = (start == 1) ? 1.f : 0.f, b2 = (start == 2) ? 1.f : 0.f, b3 = (start == 3) ? 1.f : 0.f;
+  float b4 = 0.f, b5 = 0.f;
+  const int last = mmax - 1;
+  for (int m = 0; m < last; ++m) {
+    const float4 L = q0[m];
+    const float4 E = q1[m];
+    const float kd = wvno * E.x;
+    const float arga = 1.0f - csq * L.x;
+    const float ta = fabsf(arga);
+    float rsinp, sinpr, cosp;
+    if (arga > 0.f) {            // c < a : evanescent P (surfa.f:267-269 / 228-230)
+      float s = sqrtf(ta);
+      float ex = expf(kd * s);
+      float em = 1.0f / ex;
+      float sh = 0.5f * (ex - em);
+      cosp = 0.5f * (ex + em);
+      rsinp = -s * sh;
+      sinpr = sh / s;
+    } else if (arga < 0.f) {     // c > a : oscillatory P (surfa.f:271-273 / 232-234)
+      float s = sqrtf(ta);
+      float sn, cs;
+      sincosf(kd * s, &sn, &cs);
+      cosp = cs;
+      rsinp = s * sn;
+      sinpr = sn / s;
+    } else {                     // surfa.f:263-265
+      rsinp = 0.f; sinpr = kd; cosp = 1.f;
+    }
+    if (L.y == 0.f) {
+      // liquid layer (surfa.f:219-251): only a11 = cosp, a21 = rho c^2 sinpr are non-zero
+      if (start != 1) continue;
+      if (ta < 1.e-8f * 1.e-8f) { sinpr = kd; cosp = 1.f; }
+      const float a21 = L.w * csq * sinpr;
+      const float n1 = cosp * b1;
+      const float n2 = a21 * b1;
+      const float n5 = cosp * b5;
+      const float n4 = -a21 * b4;
+      // bb3 = 0.5*a13*b5 = 0 ; bb4 = a22*b4 - a12*b5 = 0 ; full form of surfa.f:326-330 with zeros
+      b1 = n1; b2 = n2; b3 = 0.f; b4 = 0.f; b5 = n4 + n5;
+      continue;
+    }
+    const float argb = 1.0f - csq * L.y;
+    const float tb = fabsf(argb);
+    float rsinq, sinqr, cosq;
+    if (tb < 1.e-16f) {          // |rb| < 1e-8 (surfa.f:275,285-287)
+      rsinq = 0.f; sinqr = kd; cosq = 1.f;
+    } else if (argb > 0.f) {     // c < b : evanescent S (surfa.f:277-279)
+      float s = sqrtf(tb);
+      float ex = expf(kd * s);
+      float em = 1.0f / ex;
+      float sh = 0.5f * (ex - em);
+      cosq = 0.5f * (ex + em);
+      rsinq = -s * sh;
+      sinqr = sh / s;
+    } else {                     // c > b (surfa.f:281-283)
+      float s = sqrtf(tb);
+      float sn, cs;
+      sincosf(kd * s, &sn, &cs);
+      cosq = cs;
+      rsinq = s * sn;
+      sinqr = sn / s;
+    }
+    const float g = L.z * icsq;
+    const float g1 = g - 1.0f;
+    const float rhoc = L.w * csq;
+    const float irhoc = E.z * icsq;
+    // surfa.f:289-320
+    const float rr = rsinp * rsinq, ss = sinpr * sinqr, cc = cosp * cosq;
+    const float rs1 = rsinp * cosq, rs2 = sinqr * cosp, rs3 = sinpr * cosq, rs4 = rsinq * cosp;
+    const float gm = 2.f * g - 1.f, gs = g * g, g1s = g1 * g1, ccm = 1.f - cc, gg1 = g * g1;
+    const float suu = gs * rr + g1s * ss;
+    const float a11 = (2.f * gs - gm) * cc - suu - 2.f * gg1;
+    const float a12 = -(rs1 + rs2) * irhoc;
+    const float a13 = -2.f * (gm * ccm + g1 * ss + g * rr) * irhoc;
+    const float a14 = (rs3 + rs4) * irhoc;
+    const float a15 = (2.f * ccm + rr + ss) * irhoc * irhoc;
+    const float a21 = rhoc * (g1s * rs3 + gs * rs4);
+    const float a22 = cc;
+    const float a23 = 2.f * (g * rs4 + g1 * rs3);
+    const float a24 = sinpr * rsinq;
+    const float a31 = rhoc * (gg1 * gm * ccm + g1s * g1 * ss + gs * g * rr);
+    const float a32 = g1 * rs2 + g * rs1;
+    const float a33 = 1.f + 2.f * (2.f * gg1 * ccm + suu);
+    const float a41 = -rhoc * (g1s * rs2 + gs * rs1);
+    const float a42 = rsinp * sinqr;
+    const float a51 = rhoc * rhoc * (2.f * gs * g1s * ccm + gs * gs * rr + g1s * g1s * ss);
+    // surfa.f:326-330
+    const float n1 = a11 * b1 + a12 * b2 + a13 * b3 + a14 * b4 + a15 * b5;
+    const float n2 = a21 * b1 + a22 * b2 + a23 * b3 + a24 * b4 - a14 * b5;
+    const float n3 = a31 * b1 + a32 * b2 + a33 * b3 - 0.5f * a23 * b4 + 0.5f * a13 * b5;
+    const float n4 = a41 * b1 + a42 * b2 - 2.f * a32 * b3 + a22 * b4 - a12 * b5;
+    const float n5 = a51 * b1 - a41 * b2 + 2.f * a31 * b3 - a21 * b4 + a11 * b5;
+    b1 = n1; b2 = n2; b3 = n3; b4 = n4; b5 = n5;
+  }
+  // half-space row (surfa.f:341-354)
+  {
+    const float4 L = q0[last];
+    const float4 E = q1[last];
+    const float arga = 1.0f - csq * L.x;
+    const float argb = 1.0f - csq * L.y;
+    float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
+    float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
+    const float g = L.z * icsq;
+    const float g1 = g - 1.0f;
+    const float pp = E.w;
+    const float sss = 0.5f * L.z;
+    const float ppp = pp * pp;
+    const float rhp = L.w * pp;
+    const float gra = g * ra;
+    const float g1s = g1 * g1;
+    const float rba = rb - 1.0f / ra;
+    const float h11 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
+    float h12 = rhp * pp;
+    const float h13 = -rb / h12 + g1 / h12 / gra;
+    const float h14 = rb / h12 / gra;
+    const float h15 = rba / rhp / rhp / csq / g;
+    h12 = -1.0f / g / h12;
+    const float bb1 = h11 * b1 + h12 * b2 + 2.f * h13 * b3 + h14 * b4 + h15 * b5;
+    return (start == 1) ? -bb1 : bb1;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Love secular function: (displacement, stress) propagated from the half-space up (surfa.f:143-182).
+SD_HD float love_sweep(float c, float T, int mmax, const float4* q0, const float4* q1) {
+  const float wvno = SD_TWOPI / (c * T);
+  const float csq = c * c;
+  const int last = mmax - 1;
+  float ut, tt;
+  {
+    const float4 L = q0[last];
+    const float h = L.w * 0.5f * L.z;
+    const float rb = sqrtf(fabsf(csq * L.y - 1.0f));
+    ut = 1.f;
+    tt = h * rb;
+  }
+  for (int m = last - 1; m >= 0; --m) {
+    const float4 L = q0[m];
+    if (L.y == 0.f) continue;  // liquid layer skipped (surfa.f:152)
+    const float4 E = q1[m];
+    const float x = csq * L.y - 1.0f;
+    const float rb = sqrtf(fabsf(x));
+    const float h = L.w * 0.5f * L.z;
+    const float kd = wvno * E.x;
+    float y, z, cosq;
+    if (rb < 0.1e-20f || x == 0.f) {      // surfa.f:164-166
+      y = -kd; z = 0.f; cosq = 1.f;
+    } else if (x > 0.f) {                 // c > b (surfa.f:159-162), q = -k d rb
+      float sn, cs;
+      sincosf(-kd * rb, &sn, &cs);
+      y = sn / rb; z = rb * sn; cosq = cs;
+    } else {                              // c < b (surfa.f:168-172)
+      float exqp = expf(-kd * rb);
+      float exqm = 1.0f / exqp;
+      y = (exqp - exqm) / (2.f * rb);
+      z = -rb * rb * y;
+      cosq = 0.5f * (exqp + exqm);
+    }
+    const float eut = cosq * ut - y * tt / h;
+    const float ett = h * z * ut + cosq * tt;
+    ut = eut;
+    tt = ett;
+  }
+  return -tt;
+}
+
+// ==============================================================================================
+// Group velocity (phase 2 of calcul.f:224-404)
+// On-the-fly view of the period-T model of calcul.f:325-337 (all n layers refreshed, flat1 with n).
+struct ModelView {
+  const float* cst;
+  int ld, n, atten, ndiv, jj0;
+  float lt;
+  SD_HD void ab(int j, float& a, float& b) const { layer_ab(cst, ld, j, lt, atten, j == n - 1, a, b); }
+  SD_HD float rho(int j) const { return (j == n - 1) ? cst[C_RHOHS * ld + j] : cst[C_RHOFL * ld + j]; }
+  SD_HD int nsub(int j) const { return (ndiv > 1 && j >= jj0 && j < n - 1) ? ndiv : 1; }
+  SD_HD float dsub(int j) const {
+    if (j == n - 1) return 0.f;
+    const float d = cst[C_DFL * ld + j];
+    return (ndiv > 1 && j >= jj0) ? SD_DIV(d, (float)ndiv) : d;
+  }
+};
+
+// REIGEN / LEIGEN layer dropping on the subdivided stack (surfa.f:854-866, 475-487).  Returns the layer
+// whose properties serve as half-space (jh) and how many sub-layers of layer jl = jh or jh-1 are
+// integrated (the walk can end on the last sub-layer of a layer).
+struct DropResult { int jh; int jlast; int nlast; };
+
+SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, bool use_a) {
+  const float dmax = SD_MUL(SD_MUL(fact, T), c);
+  float sum = 0.f;
+  const int n = mv.n;
+  DropResult r; r.jh = n - 1; r.jlast = n - 2; r.nlast = mv.nsub(n - 2 < 0 ? 0 : n - 2);
+  for (int j = 0; j < n; ++j) {
+    float a, b;
+    mv.ab(j, a, b);
+    if (!(c - b < 0.f)) continue;
+    const int ns = mv.nsub(j);
+    const float ds = mv.dsub(j);
+    for (int s = 0; s < ns; ++s) sum = SD_ADD(sum, ds);  // interior sub-layers never trigger (equal neighbours)
+    if (j == n - 1) break;  // ii == mmax
+    if (sum <= dmax) continue;
+    // sum may have crossed dmax on an interior sub-layer: the reference then keeps walking because the
+    // next sub-layer has identical a,b (surfa.f:862-863 fall to 900), so the decision is taken here
+    float a2, b2;
+    mv.ab(j + 1, a2, b2);
+    int dec;  // -1: half-space = this sub-layer, +1: next one, 0: keep going
+    if (use_a) {
+      const float da = a2 - a;
+      if (da < 0.f) dec = -1; else if (da > 0.f) dec = 1;
+      else { const float db = b2 - b; dec = (db < 0.f) ? -1 : ((db > 0.f) ? 1 : 0); }
+    } else {
+      const float db = b2 - b; dec = (db < 0.f) ? -1 : ((db > 0.f) ? 1 : 0);
+    }
+    if (dec == 0) continue;
+    if (dec < 0) {
+      r.jh = j; r.jlast = j; r.nlast = ns - 1;
+      if (r.nlast == 0) { r.jlast = j - 1; r.nlast = (j > 0) ? mv.nsub(j - 1) : 0; }
+    } else {
+      r.jh = j + 1; r.jlast = j; r.nlast = ns;
+    }
+    return r;
+  }
+  return r;
+}
+
+struct RkCoef { double a12, a13, a21, a24, a31, a34, a42, a43; double w2, w4, v1, v2; };
+
+// one classical RK4 step of the 4x4 stress-displacement system (surfa.f:955-972), state FP64,
+// coefficients float32-valued like the reference
+SD_HD void rk4_step(const RkCoef& k, double& ur, double& uz, double& tz, double& tr) {
+  double eur = ur, euz = uz, etz = tz, etr = tr;
+  // stage 1 (wwt = 0)
+  double dur = k.a31 * uz + k.a34 * tr;
+  double duz = k.a12 * tz + k.a13 * ur;
+  double dtz = k.a21 * uz + k.a24 * tr;
+  double dtr = k.a42 * tz + k.a43 * ur;
+  eur += k.v1 * dur; euz += k.v1 * duz; etz += k.v1 * dtz; etr += k.v1 * dtr;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {  // stages 2,3 (wwt = 0.5)
+    const double sur = ur + k.w2 * dur, suz = uz + k.w2 * duz, stz = tz + k.w2 * dtz, str = tr + k.w2 * dtr;
+    dur = k.a31 * suz + k.a34 * str;
+    duz = k.a12 * stz + k.a13 * sur;
+    dtz = k.a21 * suz + k.a24 * str;
+    dtr = k.a42 * stz + k.a43 * sur;
+    eur += k.v2 * dur; euz += k.v2 * duz; etz += k.v2 * dtz; etr += k.v2 * dtr;
+  }
+  {  // stage 4 (wwt = 1)
+    const double sur = ur + k.w4 * dur, suz = uz + k.w4 * duz, stz = tz + k.w4 * dtz, str = tr + k.w4 * dtr;
+    dur = k.a31 * suz + k.a34 * str;
+    duz = k.a12 * stz + k.a13 * sur;
+    dtz = k.a21 * suz + k.a24 * str;
+    dtr = k.a42 * stz + k.a43 * sur;
+    eur += k.v1 * dur; euz += k.v1 * duz; etz += k.v1 * dtz; etr += k.v1 * dtr;
+  }
+  ur = eur; uz = euz; tz = etz; tr = etr;
+}
+
+struct Quad9 { double i0yy, i0yz, i0zz, i1yy, i1yz, i1zz, i2yy, i2yz, i2zz; };
+
+// Rayleigh group velocity by energy integrals (REIGEN, surfa.f:714-1190), streaming form: both
+// half-space solutions are integrated together and the Boole-rule integrals are accumulated as
+// quadratic forms in (y, z), combined with xnorm at the end -- no per-knot storage.
+SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, float fact,
+                               unsigned long long& nsubsteps) {
+  const int n = mv.n;
+  const DropResult dr = eigen_drop(mv, c, T, fact, true);
+  const float wvno = SD_DIV(SD_TWOPI, SD_MUL(c, T));
+  const float wvnosq = SD_MUL(wvno, wvno);
+  const float omega = SD_DIV(SD_TWOPI, T);
+  const float omegsq = SD_MUL(omega, omega);
+  const bool water = !(mv.cst[C_BREF * mv.ld + 0] > 0.f);
+  // water layer integrals (surfa.f:879-910)
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if (water) {
+    float a1, b1;
+    mv.ab(0, a1, b1);
+    const float rho1 = mv.rho(0), d1 = mv.dsub(0);
+    const float xl1 = rho1 * (a1 * a1 - 2.f * b1 * b1);
+    const float ra = c / a1;
+    const float x = ra * ra - 1.f;
+    const float mag = wvno * sqrtf(fabsf(x));
+    if (mag <= 1.0e-35f) { w0 = rho1 * d1; }
+    else {
+      float sin2ra, cosra, rab1;
+      if (x >= 0.f) {
+        sin2ra = sinf(2.f * mag * d1) / (4.f * mag); cosra = cosf(mag * d1); rab1 = mag * mag;
+      } else {
+        const float e2 = expf(2.f * mag * d1);
+        sin2ra = (0.5f * (e2 - 1.f / e2)) / (4.f * mag);
+        const float e1 = expf(mag * d1);
+        cosra = 0.5f * (e1 + 1.f / e1); rab1 = -(mag * mag);
+      }
+      const float cos2rm = 1.f / (cosra * cosra);
+      const float fac1 = (0.5f * d1 + sin2ra) * cos2rm;
+      const float fac3 = wvno * (0.5f * d1 - sin2ra) * cos2rm;
+      const float fac2 = wvno * fac3 / rab1;
+      w0 = rho1 * (fac1 + fac2); w1 = xl1 * fac2; w2 = xl1 * fac3;
+    }
+  }
+  // half-space (surfa.f:913-926), float32 like the reference
+  float ah, bh;
+  mv.ab(dr.jh, ah, bh);
+  const float rhoh = mv.rho(dr.jh);
+  const float cova = SD_DIV(c, ah), covb = SD_DIV(c, bh);
+  const float gam = SD_DIV(2.f, SD_MUL(covb, covb));
+  const float gamm1 = SD_SUB(gam, 1.f);
+  const float ra = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(cova, cova), 1.f))));
+  const float rb = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(covb, covb), 1.f))));
+  const float det = SD_SUB(wvnosq, SD_MUL(ra, rb));
+  const float h = SD_MUL(rhoh, omegsq);
+  const float brkt = SD_ADD(SD_MUL(-gamm1, wvno), SD_DIV(SD_MUL(SD_MUL(gam, ra), rb), wvno));
+  const double y0tz = (double)SD_DIV(SD_MUL(-h, brkt), det), y0tr = (double)SD_DIV(SD_MUL(-h, ra), det);
+  const double z0tz = (double)SD_DIV(SD_MUL(-h, rb), det), z0tr = y0tz;
+  if (rb == 0.f) return bh;  // surfa.f:1165
+
+  double xnorm = 0.0, bb = 1.0;
+  double zs_ur = 0.0, zs_uz = 1.0, zs_tz = z0tz, zs_tr = z0tr;  // start vector of solution 2
+  Quad9 Q;
+  const int jfirst = water ? 1 : 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    double yur = 1.0, yuz = 0.0, ytz = y0tz, ytr = y0tr;
+    double zur = zs_ur, zuz = zs_uz, ztz = zs_tz, ztr = zs_tr;
+    Q.i0yy = Q.i0yz = Q.i0zz = Q.i1yy = Q.i1yz = Q.i1zz = Q.i2yy = Q.i2yz = Q.i2zz = 0.0;
+    const bool acc = (pass == 1);
+    for (int j = dr.jlast; j >= jfirst; --j) {
+      float a, b;
+      mv.ab(j, a, b);
+      if (!(b > 0.f)) continue;
+      const float rho = mv.rho(j);
+      const float xmu = SD_MUL(SD_MUL(rho, b), b);
+      const float xlamb = SD_MUL(rho, SD_SUB(SD_MUL(a, a), SD_MUL(SD_MUL(2.f, b), b)));
+      const float ds = mv.dsub(j);
+      const float ddz = SD_DIV(-ds, 4.f);
+      const float f12 = SD_DIV(1.f, SD_ADD(xlamb, SD_MUL(2.f, xmu)));
+      const float f13 = SD_MUL(SD_MUL(wvno, xlamb), f12);
+      const float f21 = SD_MUL(-omegsq, rho);
+      const float f34 = SD_DIV(1.f, xmu);
+      const float f43 = SD_ADD(f21, SD_MUL(SD_MUL(SD_MUL(SD_MUL(4.f, wvnosq), xmu), SD_ADD(xlamb, xmu)), f12));
+      RkCoef kc;
+      kc.a12 = f12; kc.a13 = f13; kc.a21 = f21; kc.a24 = wvno; kc.a31 = -wvno; kc.a34 = f34; kc.a42 = -f13; kc.a43 = f43;
+      kc.w2 = (double)SD_MUL(0.5f, ddz); kc.w4 = (double)ddz;
+      kc.v1 = (double)SD_MUL(SD_DIV(1.f, 6.f), ddz); kc.v2 = (double)SD_MUL(SD_DIV(1.f, 3.f), ddz);
+      const int ns = (j == dr.jlast) ? dr.nlast : mv.nsub(j);
+      const double qw = (double)SD_DIV(SD_DIV(ds, 4.f), 22.5f);
+      const double dk = (double)wvno, dlam = (double)xlamb, dmu = (double)xmu, drho = (double)rho;
+      const double l2m = (double)SD_ADD(xlamb, SD_MUL(2.f, xmu));
+      for (int s = 0; s < ns; ++s) {
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) {
+          if (acc) {
+            const double wq = qw * ((kk == 0 || kk == 4) ? 7.0 : ((kk == 2) ? 12.0 : 32.0));
+            const double ydur = ytr * kc.a34 - dk * yuz, yduz = (ytz + dk * dlam * yur) * kc.a12;
+            const double zdur = ztr * kc.a34 - dk * zuz, zduz = (ztz + dk * dlam * zur) * kc.a12;
+            const double rr_yy = yur * yur, rr_yz = 2.0 * yur * zur, rr_zz = zur * zur;
+            const double zz_yy = yuz * yuz, zz_yz = 2.0 * yuz * zuz, zz_zz = zuz * zuz;
+            Q.i0yy += wq * drho * (rr_yy + zz_yy); Q.i0yz += wq * drho * (rr_yz + zz_yz); Q.i0zz += wq * drho * (rr_zz + zz_zz);
+            Q.i1yy += wq * (l2m * rr_yy + dmu * zz_yy); Q.i1yz += wq * (l2m * rr_yz + dmu * zz_yz); Q.i1zz += wq * (l2m * rr_zz + dmu * zz_zz);
+            Q.i2yy += wq * (dmu * yuz * ydur - dlam * yur * yduz);
+            Q.i2yz += wq * (dmu * (yuz * zdur + zuz * ydur) - dlam * (yur * zduz + zur * yduz));
+            Q.i2zz += wq * (dmu * zuz * zdur - dlam * zur * zduz);
+          }
+          if (kk < 4) { rk4_step(kc, yur, yuz, ytz, ytr); rk4_step(kc, zur, zuz, ztz, ztr); }
+        }
+      }
+      nsubsteps += (unsigned)ns;
+    }
+    // combine with the surface ellipticity (surfa.f:1056-1065)
+    const double aa = zur - (double)ratio * zuz;
+    double b_ = (double)ratio * yuz - yur;
+    if (fabs(b_) < 1.e-10) b_ = copysign(1.e-10, b_);
+    xnorm = aa / b_;
+    bb = xnorm * yuz + zuz;
+    if (fabs(bb) < 1.e-10) bb = copysign(1.e-10, bb);
+    if (pass == 0) {
+      const float ampur = (float)((xnorm * yur + zur) / bb);
+      const float xtest = fabsf(ampur / ratio - 1.f);
+      if (xtest >= 0.00001f) {  // second iteration of the reference (surfa.f:1066-1069, 986-998)
+        zs_ur = 0.0 + xnorm * 1.0; zs_uz = 1.0 + xnorm * 0.0; zs_tz = z0tz + xnorm * y0tz; zs_tr = z0tr + xnorm * y0tr;
+      }
+    }
+  }
+  const double ib2 = 1.0 / (bb * bb);
+  double s0 = (double)w0 + (xnorm * xnorm * Q.i0yy + xnorm * Q.i0yz + Q.i0zz) * ib2;
+  double s1 = (double)w1 + (xnorm * xnorm * Q.i1yy + xnorm * Q.i1yz + Q.i1zz) * ib2;
+  double s2 = (double)w2 + (xnorm * xnorm * Q.i2yy + xnorm * Q.i2yz + Q.i2zz) * ib2;
+  // half-space tail (surfa.f:1151-1178)
+  {
+    double aur = (xnorm * 1.0 + zs_ur) / bb, auz = (xnorm * 0.0 + zs_uz) / bb;
+    if (water && dr.jh == 1) { aur = ratio; auz = 1.0; }
+    const double dra = ra, drb = rb, ddet = det, dk = wvno, drho = rhoh;
+    const double xmu = (double)SD_MUL(SD_MUL(rhoh, bh), bh);
+    const double xlamb = (double)SD_MUL(rhoh, SD_SUB(SD_MUL(ah, ah), SD_MUL(SD_MUL(2.f, bh), bh)));
+    const double ap = -drho * (dk * aur + drb * auz) / ddet;
+    const double bp = -drho * (-dra * aur / dk - auz) / ddet;
+    const double a1 = -dk * ap / drho, a2 = -dk * drb * bp / drho, a3 = dra * ap / drho, a4 = (double)wvnosq * bp / drho;
+    const double dmmr = a1 * a1 / (2. * dra) + 2. * a1 * a2 / (dra + drb) + a2 * a2 / (2. * drb);
+    const double dmmz = a3 * a3 / (2. * dra) + 2. * a3 * a4 / (dra + drb) + a4 * a4 / (2. * drb);
+    const double drsz = -a1 * a3 / 2. - (a1 * a4 * drb + a2 * a3 * dra) / (dra + drb) - a2 * a4 / 2.;
+    const double dzsr = -a1 * a3 / 2. - (a1 * a4 * dra + a2 * a3 * drb) / (dra + drb) - a2 * a4 / 2.;
+    s0 += drho * (dmmr + dmmz);
+    s1 += (xlamb + 2. * xmu) * dmmr + xmu * dmmz;
+    s2 += xmu * dzsr - xlamb * drsz;
+  }
+  (void)n;
+  return (float)(((double)wvno * s1 + s2) / ((double)omega * s0));  // surfa.f:1186
+}
+
+// Love group velocity (LEIGEN, surfa.f:374-606), float32 like the reference.
+SD_HD float leigen_thread(const ModelView& mv, float T, float c, float fact, unsigned long long& nsubsteps) {
+  const DropResult dr = eigen_drop(mv, c, T, (fact <= 0.f) ? 7.0f : fact, false);
+  const float wvno = SD_TWOPI / (c * T);
+  float ah, bh;
+  mv.ab(dr.jh, ah, bh);
+  const float rhoh = mv.rho(dr.jh);
+  float ut0 = 1.f, ut = 1.f, sumi0 = 0.f, sumi1 = 0.f;
+  for (int attempt = 0; attempt < 16; ++attempt) {
+    ut = ut0;
+    const float covb = c / bh;
+    const float hh = rhoh * bh * bh;
+    const float rbh = wvno * sqrtf(fabsf(covb * covb - 1.f));
+    float tq = -hh * rbh * ut0;
+    float dm = (rbh == 0.f) ? 1.0e25f : 0.5f / rbh;
+    sumi0 = rhoh * dm;
+    sumi1 = hh * dm;
+    bool restart = false;
+    for (int j = dr.jlast; j >= 0 && !restart; --j) {
+      float a, b;
+      mv.ab(j, a, b);
+      if (b == 0.f) continue;
+      const float rho = mv.rho(j);
+      const float cb = c / b;
+      const float rb = wvno * sqrtf(fabsf(cb * cb - 1.f));
+      const float h = rho * b * b;
+      const float dz = mv.dsub(j) / 4.f;
+      const int ns = (j == dr.jlast) ? dr.nlast : mv.nsub(j);
+      for (int s = 0; s < ns; ++s) {
+        if (fabsf(ut) > 1.e10f) { ut0 = ut0 / 1.e5f; restart = true; break; }  // surfa.f:519-522
+        float dmm[5];
+        dmm[0] = ut * ut;
+        float eut = ut, ett = tq;
+#pragma unroll
+        for (int kk = 1; kk < 5; ++kk) {
+          const float q = rb * dz * (float)kk;
+          float y, z, cosq;
+          if (c < b) {
+            const float exqp = expf(q), exqm = 1.f / exqp;
+            y = (exqp - exqm) / (2.f * rb); z = rb * rb * y; cosq = (exqp + exqm) / 2.f;
+          } else if (c == b) {
+            y = dz * (float)kk; z = 0.f; cosq = 1.f;
+          } else {
+            float sn, cs;
+            sincosf(q, &sn, &cs);
+            y = sn / rb; z = -rb * sn; cosq = cs;
+          }
+          eut = cosq * ut - y * tq / h;
+          ett = -h * z * ut + cosq * tq;
+          dmm[kk] = eut * eut;
+        }
+        ut = eut; tq = ett;
+        dm = (dz / 22.5f) * (7.f * (dmm[0] + dmm[4]) + 32.f * (dmm[1] + dmm[3]) + 12.f * dmm[2]);
+        sumi0 = sumi0 + rho * dm;
+        sumi1 = sumi1 + h * dm;
+      }
+      nsubsteps += (unsigned)ns;
+    }
+    if (!restart) break;
+  }
+  return sumi1 / (c * sumi0);  // surfa.f:606 (the 1/ut^2 normalisation cancels)
+}
+
+
+}  // namespace sd

@@ -1,0 +1,582 @@
+// surfdisp_kernels.cu -- sm_100a kernels + C ABI of the batched dispersion forward solver.
+//
+// Data flow of one surfdisp_batch() call (all on one stream):
+//   prep_kernel    thread per model     layers[5][M][Lmax] -> consts[M][8][lpad]   (flat1.f, once per model)
+//   phase1_kernel  G lanes per model    periods sequential (calcul.f:104-220): refresh layer records in
+//                                       shared memory, scan trial velocities G at a time with a ballot
+//                                       for the first sign change, G-section polish, ellipticity
+//                                       -> c[M][K], ratio[M][K], nfound[M]
+//   phase2_kernel  thread per (model, period)   energy integrals -> U[M][K]  (calcul.f:224-404,
+//                                       REIGEN surfa.f:714-1190 in FP64 / LEIGEN surfa.f:374-606 in FP32)
+// No tensor cores: the work is a serial chain of tiny structured propagator products with
+// data-dependent branches.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "surfdisp_core.cuh"
+#include "../../include/surfdisp_b200.h"
+
+namespace {
+
+using namespace sd;
+
+constexpr int kMaxPer = SURFDISP_MAX_PERIODS;
+constexpr int kHdrBytes = 256;  // workspace header: counters + work queues
+
+struct PeriodTab {
+  float per[kMaxPer];
+  float lt[kMaxPer];  // ln(t_base / T), host libm (same logf the reference calls)
+};
+
+struct WsLayout {
+  size_t consts_off, ratio_off, total;
+  int lpad;
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+WsLayout ws_layout(int M, int lmax, int K) {
+  WsLayout w;
+  w.lpad = round_up(lmax, 4);
+  w.consts_off = kHdrBytes;
+  size_t consts = (size_t)M * NCONST * w.lpad * sizeof(float);
+  w.ratio_off = w.consts_off + ((consts + 255) / 256) * 256;
+  size_t ratio = (size_t)M * K * sizeof(float);
+  w.total = w.ratio_off + ((ratio + 255) / 256) * 256;
+  return w;
+}
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return SURFDISP_ECUDA;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+// ------------------------------------------------------------------------------------ prep kernel
+__global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, int kind, int flatten,
+                                                   const int* __restrict__ nlay,
+                                                   const float* __restrict__ layers, float* __restrict__ consts) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int n = nlay[m];
+  if (n < 2 || n > lmax) return;
+  const size_t pl = (size_t)M * lmax;
+  const float* a = layers + 0 * pl + (size_t)m * lmax;
+  const float* b = layers + 1 * pl + (size_t)m * lmax;
+  const float* rho = layers + 2 * pl + (size_t)m * lmax;
+  const float* d = layers + 3 * pl + (size_t)m * lmax;
+  const float* qs = layers + 4 * pl + (size_t)m * lmax;
+  prep_model(n, kind, flatten, a, b, rho, d, qs, consts + (size_t)m * NCONST * lpad, lpad);
+}
+
+// ------------------------------------------------------------------------------------ phase 1
+struct P1Params {
+  int kind, M, lpad, K;
+  const int* nlay;
+  const float* consts;
+  float* c_out;
+  float* ratio_out;
+  int* nfound;
+  int* flags;
+  unsigned long long* counters;
+  unsigned int* queue;
+  float dc, fact;
+  int atten, stale;
+  int mstride;  // float4 units between consecutive groups' shared-memory records
+  PeriodTab tab;
+};
+
+template <int G>
+__device__ __forceinline__ float gshfl(unsigned mask, float v, int src) { return __shfl_sync(mask, v, src, G); }
+template <int G>
+__device__ __forceinline__ int gshfl(unsigned mask, int v, int src) { return __shfl_sync(mask, v, src, G); }
+
+template <int G>
+__global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ P1Params p) {
+  extern __shared__ float4 smem[];
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int gbase = lane & ~(G - 1);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const int grp = threadIdx.x / G;
+  float4* q0 = smem + (size_t)grp * p.mstride;
+  float4* q1 = q0 + p.lpad;
+  const int K = p.K;
+  unsigned long long my_steps = 0, my_sweeps = 0;
+  int my_models = 0;
+
+  for (;;) {
+    int model = 0;
+    if (gl == 0) model = (int)atomicAdd(p.queue, 1u);
+    model = gshfl<G>(gmask, model, 0);
+    if (model >= p.M) break;
+    const int n = p.nlay[model];
+    float* crow = p.c_out + (size_t)model * K;
+    float* rrow = p.ratio_out + (size_t)model * K;
+    if (n < 2 || n > p.lpad) {
+      for (int k = gl; k < K; k += G) { crow[k] = 0.f; rrow[k] = 0.f; }
+      if (gl == 0) { p.nfound[model] = 0; if (p.flags) p.flags[model] = SURFDISP_F_NO_ROOT_FIRST; }
+      continue;
+    }
+    my_models += (gl == 0);
+    const float* cst = p.consts + (size_t)model * NCONST * p.lpad;
+    const int ld = p.lpad;
+    // first start velocity, fast_surf.f:157-171
+    float c1;
+    {
+      const float b0 = cst[C_BREF * ld + 0];
+      const int ilay = (b0 < 0.1f) ? 1 : 0;
+      float b_corr = 0.f;
+      if (p.atten) b_corr = SD_DIV(SD_MUL(cst[C_QS * ld + ilay], p.tab.lt[0]), SD_PI_ATT);
+      float qq = cst[C_BREF * ld + ilay];
+      if (p.kind == 2) qq = SD_MUL(0.9f, qq);
+      c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
+      if (b0 < 0.1f) c1 = 0.5f;
+    }
+    int mm = n;        // reference COMMON mmax carried from period to period
+    int nfound = 0, flag = 0;
+    float c_prev = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float T = p.tab.per[k];
+      const float lt = p.tab.lt[k];
+      // ---- refresh layers 0..mref-1, layer mref-1 flattened as the half-space (calcul.f:112-133)
+      const int mref = p.stale ? mm : n;
+      __syncwarp(gmask);
+      for (int i = gl; i < mref; i += G) {
+        const bool hs = (i == mref - 1);
+        float a, b;
+        layer_ab(cst, ld, i, lt, p.atten, hs, a, b);
+        const float rho = hs ? cst[C_RHOHS * ld + i] : cst[C_RHOFL * ld + i];
+        const float d = hs ? 0.f : cst[C_DFL * ld + i];
+        LayerRec r = make_rec(a, b, rho, d);
+        q0[i] = r.q0;
+        q1[i] = r.q1;
+      }
+      __syncwarp(gmask);
+      if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
+      const float b_top = q1[0].y;
+      // ---- scan: candidates c1, c1+dc, ... evaluated G at a time (calcul.f:155-167)
+      float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
+      int mnew = mm;
+      bool found = false, failed = false;
+      {
+        float cbase = c1;
+        float cl_prev = 0.f, dl_prev = 0.f;
+        bool have_prev = false;
+        for (int round = 0; round < 4096; ++round) {
+          float cj = cbase;
+          for (int t = 0; t < gl; ++t) cj = SD_ADD(cj, p.dc);
+          const int mj = layer_drop(cj, T, p.fact, n, q1);
+          const float dj = (p.kind == 2) ? rayleigh_sweep(cj, T, mj, q0, q1, 1) : love_sweep(cj, T, mj, q0, q1);
+          my_steps += (unsigned)(mj - 1); my_sweeps += 1;
+          float dp = __shfl_up_sync(gmask, dj, 1, G);
+          float cp = __shfl_up_sync(gmask, cj, 1, G);
+          if (gl == 0) { dp = dl_prev; cp = cl_prev; }
+          const bool hasp = (gl > 0) || have_prev;
+          const bool change = hasp && (signbit(dp) != signbit(dj));
+          const float b_hs = q1[mj - 1].y;
+          const bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < b_hs + 0.3f) || !(cj == cj));
+          const unsigned ev = (__ballot_sync(gmask, change || stop) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+          if (ev) {
+            const int j = __ffs(ev) - 1;
+            found = gshfl<G>(gmask, (int)change, j) != 0;
+            lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
+            dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
+            mnew = gshfl<G>(gmask, mj, j);
+            failed = !found;
+            break;
+          }
+          cl_prev = gshfl<G>(gmask, cj, G - 1);
+          dl_prev = gshfl<G>(gmask, dj, G - 1);
+          mnew = gshfl<G>(gmask, mj, G - 1);
+          have_prev = true;
+          cbase = SD_ADD(cl_prev, p.dc);
+          if (round == 4095) { failed = true; flag |= SURFDISP_F_SCAN_LIMIT; }
+        }
+      }
+      mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
+      float croot = 0.f;
+      if (found) {
+        // ---- polish inside [lo,hi] with mmax pinned: G-section until the bracket is
+        // narrow enough for one secant step to land inside float32 noise (replaces NEVILL, surfa.f:2-83)
+        for (int it = 0; it < 12 && (hi - lo) > 2.0e-5f; ++it) {
+          const float step = (hi - lo) / (float)(G + 1);
+          const float pj = lo + (float)(gl + 1) * step;
+          const float dj = (p.kind == 2) ? rayleigh_sweep(pj, T, mm, q0, q1, 1) : love_sweep(pj, T, mm, q0, q1);
+          my_steps += (unsigned)(mm - 1); my_sweeps += 1;
+          float dp = __shfl_up_sync(gmask, dj, 1, G);
+          float pp = __shfl_up_sync(gmask, pj, 1, G);
+          if (gl == 0) { dp = dlo; pp = lo; }
+          const bool change = signbit(dp) != signbit(dj);
+          const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+          if (ev) {
+            const int j = __ffs(ev) - 1;
+            const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
+            hi = gshfl<G>(gmask, pj, j); dhi = gshfl<G>(gmask, dj, j);
+            lo = nlo; dlo = ndlo;
+          } else {
+            lo = gshfl<G>(gmask, pj, G - 1); dlo = gshfl<G>(gmask, dj, G - 1);
+          }
+        }
+        {
+          const float den = dhi - dlo;
+          float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
+          if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
+          croot = cs;
+        }
+        if (croot > q1[mm - 1].y) { found = false; failed = true; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
+      }
+      if (!found) {
+        flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
+        (void)failed;
+        break;
+      }
+      float ratio = 0.f;
+      if (p.kind == 2) {
+        // ellipticity = 0.5 * bb1(e3) / bb1(e2) (surfa.f:360-363); two lanes, one start vector each
+        const float v = rayleigh_sweep(croot, T, mm, q0, q1, 2 + (gl & 1));
+        my_steps += (unsigned)(mm - 1); my_sweeps += 1;
+        const float r12 = gshfl<G>(gmask, v, 0);
+        const float r3 = gshfl<G>(gmask, v, 1);
+        ratio = 0.5f * r3 / r12;
+      }
+      if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
+      c_prev = croot;
+      nfound = k + 1;
+    }
+    for (int k = nfound + gl; k < K; k += G) { crow[k] = 0.f; rrow[k] = 0.f; }
+    if (gl == 0) { p.nfound[model] = nfound; if (p.flags) p.flags[model] = flag; }
+  }
+  // work counters (roofline numerator)
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    my_sweeps += __shfl_xor_sync(0xffffffffu, my_sweeps, o);
+    my_models += __shfl_xor_sync(0xffffffffu, my_models, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&p.counters[0], my_steps);
+    atomicAdd(&p.counters[1], my_sweeps);
+    atomicAdd(&p.counters[3], (unsigned long long)my_models);
+  }
+}
+
+// ------------------------------------------------------------------------------------ phase 2
+struct P2Params {
+  int kind, M, lpad, K, mpb;
+  const int* nlay;
+  const float* consts;
+  const float* c_in;
+  const float* ratio_in;
+  const int* nfound;
+  float* u_out;
+  unsigned long long* counters;
+  float fact;
+  int atten, ndiv, ndiv_cap;
+  PeriodTab tab;
+};
+
+__global__ void __launch_bounds__(256) phase2_kernel(const __grid_constant__ P2Params p) {
+  extern __shared__ float4 smem[];
+  float* sc = reinterpret_cast<float*>(smem);
+  const int K = p.K;
+  const int model0 = blockIdx.x * p.mpb;
+  const int nmod = min(p.mpb, p.M - model0);
+  const int per_model = NCONST * p.lpad;
+  // stage the constants of this block's models (coalesced float4 copies)
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.consts + (size_t)model0 * per_model);
+    const int n4 = nmod * per_model / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) smem[i] = src[i];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  unsigned long long nsub = 0;
+  if (t < nmod * K) {
+    const int ml = t / K, k = t - ml * K;
+    const int model = model0 + ml;
+    float* urow = p.u_out + (size_t)model * K;
+    const int n = p.nlay[model];
+    if (k >= p.nfound[model] || n < 2 || n > p.lpad) {
+      urow[k] = 0.f;
+    } else {
+      ModelView mv;
+      mv.cst = sc + (size_t)ml * per_model;
+      mv.ld = p.lpad; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
+      int ndiv = p.ndiv;
+      const int ivre = p.ndiv_cap / (n - 1);
+      if (ndiv > ivre) ndiv = ivre;
+      mv.ndiv = ndiv;
+      mv.jj0 = (mv.cst[C_BREF * mv.ld + 0] <= 0.1e-10f) ? 1 : 0;
+      const float T = p.tab.per[k];
+      const float c = p.c_in[(size_t)model * K + k];
+      float u;
+      if (p.kind == 2) u = reigen_thread(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
+      else u = leigen_thread(mv, T, c, p.fact, nsub);
+      urow[k] = u;
+    }
+  }
+  // counters: one atomic per warp (all lanes arrive here)
+  for (int o = 16; o > 0; o >>= 1) nsub += __shfl_xor_sync(0xffffffffu, nsub, o);
+  if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(&p.counters[2], nsub);
+}
+
+// ------------------------------------------------------------------------------------ misfit
+struct MisfitParams {
+  int mode, M, K, ncount;
+  const float* c_pred;
+  const int* nfound;
+  float* out;
+  float obs[kMaxPer], isig[kMaxPer], per[kMaxPer];
+  unsigned char use[kMaxPer];
+};
+
+// one warp per model, lanes over periods, shuffle reduction (point.py:15-31, 337-366)
+__global__ void __launch_bounds__(256) misfit_kernel(const __grid_constant__ MisfitParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.M) return;
+  const float* row = p.c_pred + (size_t)warp * p.K;
+  double s1 = 0.0, s2 = 0.0;
+  int n1 = 0, n2 = 0;
+  for (int k = lane; k < p.K; k += 32) {
+    if (!p.use[k]) continue;
+    const double bias = ((double)p.obs[k] - (double)row[k]) * (double)p.isig[k];
+    if (p.mode == 1 && p.per[k] > 40.f) { s2 += bias * bias; n2++; }
+    else { s1 += bias * bias; n1++; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o); n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  if (lane != 0) return;
+  float* o = p.out + (size_t)warp * 3;
+  if (p.nfound[warp] < p.K) { o[0] = 88888.f; o[1] = 88888.f; o[2] = 0.f; return; }  // point.py:20-21
+  const int N = n1 + n2;
+  double chi;
+  if (p.mode == 1) {
+    if (n1 > 0 && n2 > 0) chi = (s1 / n1 + s2 / n2) / 2.0 * N;
+    else if (n2 > 0) chi = s2 / n2 * N;
+    else chi = s1 / (n1 > 0 ? n1 : 1) * N;
+  } else chi = s1;
+  const double misfit = sqrt(chi / (N > 0 ? N : 1));
+  if (!(chi < 50.0)) chi = sqrt(chi * 50.0);  // point.py:29
+  o[0] = (float)misfit; o[1] = (float)chi; o[2] = (float)exp(-0.5 * chi);
+}
+
+int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
+  if (K < 1 || K > kMaxPer) return SURFDISP_EINVAL;
+  memset(&tab, 0, sizeof(tab));
+  for (int k = 0; k < K; ++k) {
+    if (!(periods[k] > 0.f)) return SURFDISP_EINVAL;
+    tab.per[k] = periods[k];
+    tab.lt[k] = logf(t_base / periods[k]);  // host libm, as gfortran's alog (calcul.f:122)
+  }
+  return 0;
+}
+
+template <int G>
+int launch_phase1(const P1Params& p, cudaStream_t st) {
+  const int threads = 128;
+  const int groups = threads / G;
+  P1Params q = p;
+  q.mstride = 2 * p.lpad + 2;  // +2 float4: consecutive groups start 32 B apart mod 128 B (bank spread)
+  size_t smem = (size_t)groups * q.mstride * sizeof(float4);
+  if (smem > 200 * 1024) return SURFDISP_EINVAL;
+  CK(cudaFuncSetAttribute(phase1_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148, occ = 1;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<G>, threads, smem));
+  if (occ < 1) occ = 1;
+  long long need = ((long long)p.M + groups - 1) / groups;
+  long long grid = (long long)sms * occ;  // persistent: one resident wave, models pulled from a queue
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  phase1_kernel<G><<<(unsigned)grid, threads, smem, st>>>(q);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+void surfdisp_default_opts(SurfdispOpts* o) {
+  o->dc = 0.01f; o->fact = 4.0f; o->t_base = 1.0f; o->ndiv = 5; o->ndiv_cap_rayleigh = 99;
+  o->ndiv_cap_love = 999; o->atten = 1; o->flatten = 1; o->stale_mmax = 1; o->compute_group = 1;
+}
+
+size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods) {
+  if (n_models < 0 || n_layers_max < 2 || n_periods < 1) return 0;
+  return ws_layout(n_models, n_layers_max, n_periods).total;
+}
+
+int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                   const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
+                   int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+  SurfdispOpts o;
+  if (opts) o = *opts; else surfdisp_default_opts(&o);
+  if ((kind != 1 && kind != 2) || n_models < 0 || n_layers_max < 2 || n_layers_max > SURFDISP_MAX_LAYERS ||
+      n_periods < 1 || n_periods > kMaxPer || !periods || !(o.dc > 0.f))
+    return SURFDISP_EINVAL;
+  if (n_models == 0) return 0;
+  if (!n_layers || !layers || !c_out || !nfound || !workspace) return SURFDISP_EINVAL;
+  const WsLayout w = ws_layout(n_models, n_layers_max, n_periods);
+  if (workspace_bytes < w.total) return SURFDISP_ENOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  unsigned long long* counters = (unsigned long long*)ws;
+  unsigned int* queue = (unsigned int*)(ws + 64);
+  float* consts = (float*)(ws + w.consts_off);
+  float* ratio = (float*)(ws + w.ratio_off);
+  P1Params p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.kind = kind; p1.M = n_models; p1.lpad = w.lpad; p1.K = n_periods; p1.nlay = n_layers; p1.consts = consts;
+  p1.c_out = c_out; p1.ratio_out = ratio; p1.nfound = nfound; p1.flags = flags; p1.counters = counters;
+  p1.queue = queue; p1.dc = o.dc; p1.fact = o.fact; p1.atten = o.atten; p1.stale = o.stale_mmax;
+  int rc = fill_tab(p1.tab, n_periods, periods, o.t_base);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ws, 0, kHdrBytes, st));
+
+  prep_kernel<<<(n_models + 127) / 128, 128, 0, st>>>(n_models, n_layers_max, w.lpad, kind, o.flatten, n_layers,
+                                                       layers, consts);
+  CK(cudaGetLastError());
+
+  rc = launch_phase1<8>(p1, st);
+  if (rc) return rc;
+
+  if (u_out && o.compute_group) {
+    P2Params p2;
+    memset(&p2, 0, sizeof(p2));
+    p2.kind = kind; p2.M = n_models; p2.lpad = w.lpad; p2.K = n_periods; p2.nlay = n_layers; p2.consts = consts;
+    p2.c_in = c_out; p2.ratio_in = ratio; p2.nfound = nfound; p2.u_out = u_out; p2.counters = counters;
+    p2.fact = o.fact; p2.atten = o.atten; p2.ndiv = o.ndiv;
+    p2.ndiv_cap = (kind == 2) ? o.ndiv_cap_rayleigh : o.ndiv_cap_love;
+    p2.tab = p1.tab;
+    const size_t per_model = (size_t)NCONST * w.lpad * sizeof(float);
+    int mpb = 256 / n_periods;
+    if (mpb < 1) mpb = 1;
+    while (mpb > 1 && mpb * per_model > 96 * 1024) --mpb;
+    if (mpb * per_model > 200 * 1024) return SURFDISP_EINVAL;
+    p2.mpb = mpb;
+    int threads = round_up(mpb * n_periods, 32);
+    if (threads > 256) threads = 256;  // K > 256 cannot happen (K <= 200)
+    size_t smem = mpb * per_model;
+    CK(cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (n_models + mpb - 1) / mpb;
+    phase2_kernel<<<grid, threads, smem, st>>>(p2);
+    CK(cudaGetLastError());
+  } else if (u_out) {
+    CK(cudaMemsetAsync(u_out, 0, (size_t)n_models * n_periods * sizeof(float), st));
+  }
+  return 0;
+}
+
+int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_pred, const int* nfound,
+                          const float* obs, const float* sigma, const unsigned char* mask,
+                          const float* periods, float* out, void* stream) {
+  if ((mode != 0 && mode != 1) || n_models < 0 || n_periods < 1 || n_periods > kMaxPer || !obs || !sigma)
+    return SURFDISP_EINVAL;
+  if (mode == 1 && !periods) return SURFDISP_EINVAL;
+  if (n_models == 0) return 0;
+  if (!c_pred || !nfound || !out) return SURFDISP_EINVAL;
+  MisfitParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode; p.M = n_models; p.K = n_periods; p.c_pred = c_pred; p.nfound = nfound; p.out = out;
+  for (int k = 0; k < n_periods; ++k) {
+    p.obs[k] = obs[k];
+    p.isig[k] = 1.0f / sigma[k];
+    p.per[k] = periods ? periods[k] : 0.f;
+    p.use[k] = mask ? (mask[k] != 0) : 1;
+    p.ncount += p.use[k];
+  }
+  if (p.ncount == 0) return SURFDISP_EINVAL;  // point.py:356 raises when everything is masked
+  const int threads = 256;
+  const long long warps = n_models;
+  const unsigned grid = (unsigned)((warps * 32 + threads - 1) / threads);
+  misfit_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_models, int n_layers_max,
+                        const int* n_layers, const float* layers, int n_periods, const float* periods,
+                        float* c_out, float* u_out, int* nfound, int* flags) {
+  if (n_models < 0 || n_layers_max < 2 || n_periods < 1 || n_periods > kMaxPer) return SURFDISP_EINVAL;
+  if (n_models == 0) return 0;
+  if (!n_layers || !layers || !c_out || !nfound || !periods) return SURFDISP_EINVAL;
+  CK(cudaSetDevice(device));
+  const size_t nl = (size_t)5 * n_models * n_layers_max * sizeof(float);
+  const size_t no = (size_t)n_models * n_periods * sizeof(float);
+  const size_t wsb = surfdisp_workspace_bytes(n_models, n_layers_max, n_periods);
+  char* dev = nullptr;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_lay = 0, o_n = o_lay + al(nl), o_c = o_n + al(n_models * sizeof(int)), o_u = o_c + al(no),
+               o_nf = o_u + al(no), o_fl = o_nf + al(n_models * sizeof(int)), o_ws = o_fl + al(n_models * sizeof(int)),
+               total = o_ws + wsb;
+  CK(cudaMalloc(&dev, total));
+  cudaStream_t st;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { cudaFree(dev); return cuda_fail(e, "cudaStreamCreate"); }
+  int rc = 0;
+  do {
+    if ((e = cudaMemcpyAsync(dev + o_lay, layers, nl, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D layers"); break; }
+    if ((e = cudaMemcpyAsync(dev + o_n, n_layers, n_models * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D nlay"); break; }
+    rc = surfdisp_batch(opts, kind, n_models, n_layers_max, (const int*)(dev + o_n), (const float*)(dev + o_lay),
+                        n_periods, periods, (float*)(dev + o_c), u_out ? (float*)(dev + o_u) : nullptr,
+                        (int*)(dev + o_nf), (int*)(dev + o_fl), dev + o_ws, wsb, st);
+    if (rc) break;
+    if ((e = cudaMemcpyAsync(c_out, dev + o_c, no, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H c"); break; }
+    if (u_out && (e = cudaMemcpyAsync(u_out, dev + o_u, no, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H u"); break; }
+    if ((e = cudaMemcpyAsync(nfound, dev + o_nf, n_models * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H nfound"); break; }
+    if (flags && (e = cudaMemcpyAsync(flags, dev + o_fl, n_models * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H flags"); break; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "sync"); break; }
+  } while (0);
+  cudaStreamDestroy(st);
+  cudaFree(dev);
+  return rc;
+}
+
+void fast_surf_(const int* n_layer0, const int* kind0, const float* a_ref0, const float* b_ref0,
+                const float* rho_ref0, const float* d_ref0, const float* qs_ref0, const float* cvper,
+                const int* ncvper, float* uR0, float* uL0, float* cR0, float* cL0) {
+  for (int i = 0; i < kMaxPer; ++i) { uR0[i] = 0.f; uL0[i] = 0.f; cR0[i] = 0.f; cL0[i] = 0.f; }
+  const int n = *n_layer0, kind = *kind0;
+  int K = *ncvper;
+  if (K > kMaxPer) K = kMaxPer;  // init.f:63-66
+  if (n < 2 || n > SURFDISP_MAX_LAYERS || K < 1 || (kind != 1 && kind != 2)) return;
+  float* lay = (float*)malloc((size_t)5 * n * sizeof(float));
+  if (!lay) return;
+  memcpy(lay + 0 * n, a_ref0, n * sizeof(float));
+  memcpy(lay + 1 * n, b_ref0, n * sizeof(float));
+  memcpy(lay + 2 * n, rho_ref0, n * sizeof(float));
+  memcpy(lay + 3 * n, d_ref0, n * sizeof(float));
+  memcpy(lay + 4 * n, qs_ref0, n * sizeof(float));
+  float c[kMaxPer], u[kMaxPer];
+  int nf = 0, fl = 0, dev = 0;
+  cudaGetDevice(&dev);
+  int rc = surfdisp_host_batch(nullptr, dev, kind, 1, n, &n, lay, K, cvper, c, u, &nf, &fl);
+  free(lay);
+  if (rc != 0) return;
+  for (int i = 0; i < nf && i < K; ++i) {  // fast_surf.f:197-208
+    if (kind == 1) { cL0[i] = c[i]; uL0[i] = u[i]; }
+    else { cR0[i] = c[i]; uR0[i] = u[i]; }
+  }
+}
+
+int surfdisp_read_counters(const void* workspace, unsigned long long out[4], void* stream) {
+  if (!workspace || !out) return SURFDISP_EINVAL;
+  CK(cudaMemcpyAsync(out, workspace, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+const char* surfdisp_version(void) { return "surfdisp_b200 0.1 (sm_100a)"; }
+const char* surfdisp_last_cuda_error(void) { return g_cuda_err; }
+
+}  // extern "C"

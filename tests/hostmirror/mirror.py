@@ -1,0 +1,41 @@
+"""TEST ONLY: builds and wraps tests/hostmirror/hostmirror.cpp (g++ build of the CUDA kernels' per-lane math)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libhostmirror.so")
+        src = os.path.join(_HERE, "hostmirror.cpp")
+        hdr = os.path.join(_HERE, "..", "..", "pysurfinv_b200", "csrc", "surfdisp_core.cuh")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so, src, "-lm"])
+        L = C.CDLL(so)
+        fp = C.POINTER(C.c_float)
+        L.hm_forward.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_int, fp, C.c_float, C.c_float,
+                                 C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp,
+                                 C.POINTER(C.c_longlong)]
+        L.hm_forward.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def forward(kind, vp, vs, rho, h, qsinv, periods, G=8, stale=1, ndiv=5, ndiv_cap=None):
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
+    a, b, r, d, q, per = f(vp), f(vs), f(rho), f(h), f(qsinv), f(periods)
+    K = len(per)
+    c = np.zeros(K, np.float32); u = np.zeros(K, np.float32); rt = np.zeros(K, np.float32)
+    p = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    sw = C.c_longlong(0)
+    if ndiv_cap is None:
+        ndiv_cap = 99 if kind == 2 else 999
+    nf = lib().hm_forward(G, kind, len(b), p(a), p(b), p(r), p(d), p(q), K, p(per), 0.01, 4.0, 1.0, 1, 1, stale,
+                          ndiv, ndiv_cap, p(c), p(u), p(rt), C.byref(sw))
+    return dict(c=c, u=u, ratio=rt, nfound=nf, sweeps=sw.value)
