@@ -39,6 +39,8 @@ extern "C" {
 #define SURFDISP_F_NO_ROOT_AT_K 2    /* scan failed at a later period (calcul.f:218-219): nfound = k-1 */
 #define SURFDISP_F_ROOT_ABOVE_HS 4   /* polished root above the half-space velocity (calcul.f:191) */
 #define SURFDISP_F_SCAN_LIMIT 8      /* scan hit the iteration guard (non-finite secular function) */
+#define SURFDISP_F_LSTOP 16          /* sequential polish did not converge in 50 cycles: the reference aborts
+                                        the call there (surfa.f:17-28, calcul.f:173-189); nfound = 0 */
 
 /* Solver options; defaults are the constants hard-coded in the reference (init.f:25,43-58). */
 typedef struct SurfdispOpts {
@@ -111,6 +113,17 @@ void fast_surf_(const int* n_layer0, const int* kind0, const float* a_ref0, cons
  * numerator): out[0] = secular layer-steps, out[1] = secular sweeps,
  * out[2] = group-velocity sub-layer integrations, out[3] = models processed.  Host pointer. */
 int surfdisp_read_counters(const void* workspace, unsigned long long out[4], void* stream);
+
+/* surfdisp_batch plus CUDA-event timing of its three kernels (prep, phase 1 = root search, phase 2 = group
+ * velocity); synchronises the stream.  kernel_ms is a HOST float[3]. */
+int surfdisp_batch_profiled(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
+                            const int* n_layers, const float* layers, int n_periods, const float* periods,
+                            float* c_out, float* u_out, int* nfound, int* flags, void* workspace,
+                            size_t workspace_bytes, void* stream, float kernel_ms[3]);
+
+/* Register-resident micro-benchmarks on the current device: out[0] = FP32 FMA TFLOP/s,
+ * out[1] = FP64 FMA TFLOP/s, out[2] = MUFU.EX2 T-op/s.  Denominators of the FP-pipe roofline. */
+int surfdisp_measure_peaks(double out[3]);
 
 const char* surfdisp_version(void);
 const char* surfdisp_last_cuda_error(void);

@@ -30,6 +30,8 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 extern "C" {
 
@@ -920,6 +922,7 @@ struct Solver {
           else { if (!(c1 - (b[mmax] + R(0.3f)) < R(0))) { fail = true; break; } }
           if (!(c1 == c1)) { fail = true; break; }  // NaN guard (reference would spin)
         }
+        if (getenv("ORACLE_DEBUG")) fprintf(stderr, "k=%d iq=%d T=%g found=%d fail=%d c1=%.7f c2=%.7f del1=%g del2=%g mmax=%d b1=%.6f bmm=%.6f\n", k, iq, (double)t1, (int)found, (int)fail, (double)c1, (double)c2, (double)del1, (double)del2, mmax, (double)b[1], (double)b[mmax]);
         if (found) {
           R cn = 0;
           if (!nevill(t1, c1, c2, del1, del2, ifunc, cn)) {

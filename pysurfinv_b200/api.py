@@ -60,6 +60,10 @@ def load_library():
     L.fast_surf_.restype = None
     L.surfdisp_read_counters.argtypes = [vp, C.POINTER(C.c_ulonglong), vp]
     L.surfdisp_read_counters.restype = C.c_int
+    L.surfdisp_batch_profiled.argtypes = L.surfdisp_batch.argtypes + [fp]
+    L.surfdisp_batch_profiled.restype = C.c_int
+    L.surfdisp_measure_peaks.argtypes = [C.POINTER(C.c_double)]
+    L.surfdisp_measure_peaks.restype = C.c_int
     L.surfdisp_version.restype = C.c_char_p
     L.surfdisp_last_cuda_error.restype = C.c_char_p
     _lib = L
@@ -114,7 +118,14 @@ class DispersionSolver:
             self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, out=None):
+    def measure_peaks(self):
+        """(FP32 FMA TFLOP/s, FP64 FMA TFLOP/s, MUFU ex2 Top/s) measured with register-resident chains."""
+        arr = (C.c_double * 3)()
+        with self.torch.cuda.device(self.device):
+            _check(self.lib.surfdisp_measure_peaks(arr), "surfdisp_measure_peaks")
+        return tuple(float(x) for x in arr)
+
+    def forward(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, out=None, kernel_ms=None):
         """layers: float32 device tensor [5, M, Lmax]; nlay: int32 device tensor [M]; periods: host
         sequence.  Returns dict of device tensors c[M,K], u[M,K], nfound[M], flags[M].  Asynchronous on
         the current torch stream."""
@@ -139,11 +150,16 @@ class DispersionSolver:
         ws = self.workspace(M, lmax, K)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = self.lib.surfdisp_batch(C.byref(self.opts), int(kind), M, lmax, nlay.data_ptr(), layers.data_ptr(),
-                                         K, _fptr(per), out["c"].data_ptr(),
-                                         out["u"].data_ptr() if (group and out.get("u") is not None) else None,
-                                         out["nfound"].data_ptr(), out["flags"].data_ptr(), ws.data_ptr(),
-                                         ws.numel(), stream)
+            args = [C.byref(self.opts), int(kind), M, lmax, nlay.data_ptr(), layers.data_ptr(),
+                    K, _fptr(per), out["c"].data_ptr(),
+                    out["u"].data_ptr() if (group and out.get("u") is not None) else None,
+                    out["nfound"].data_ptr(), out["flags"].data_ptr(), ws.data_ptr(), ws.numel(), stream]
+            if kernel_ms is None:
+                rc = self.lib.surfdisp_batch(*args)
+            else:  # list that receives [prep_ms, phase1_ms, phase2_ms]; synchronises
+                ms = (C.c_float * 3)()
+                rc = self.lib.surfdisp_batch_profiled(*args, ms)
+                kernel_ms[:] = [float(x) for x in ms]
         _check(rc, "surfdisp_batch")
         return out
 

@@ -316,6 +316,63 @@ SD_HD float love_sweep(float c, float T, int mmax, const float4* q0, const float
   return -tt;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Sequential root polish exactly as the reference does it (NEVILL, surfa.f:2-83): interval halving that
+// switches to Neville inverse interpolation when the bracket values are monotone and within 10x.
+// Only used when the G-section samples show more than one sign change inside the scan bracket (a kink at
+// the half-space velocity can put three roots in one 0.01 km/s bracket): which of them the reference
+// lands on -- and therefore whether it accepts the period -- depends on this exact evaluation order.
+// F: float(float c) evaluates the secular function with mmax pinned.  Returns false on "too many cycles".
+template <typename F>
+SD_HD bool nevill_seq(F f, float c1, float c2, float del1, float del2, float& cc, int& evals) {
+  const float accur1 = 0.1e-5f, accur2 = 0.1e-7f;
+  float x[12], y[12];
+  int ic = 0, nev = 1, m = 1;
+  float c3 = (c1 + c2) / 2.f;
+  float del3 = f(c3); evals++;
+  for (;;) {
+    ic++;
+    if (!(ic < 50)) return false;
+    const bool inside = (c1 <= c3) ? (c2 > c3) : (c2 < c3);
+    bool bisect = !inside;
+    if (inside) {
+      const float s13 = del1 - del3, s32 = del3 - del2;
+      if (signbit(del3) != signbit(del1)) { c2 = c3; del2 = del3; } else { c1 = c3; del1 = del3; }
+      if (fabsf(c1 - c2) <= accur1) { cc = c3; return true; }
+      if (signbit(s13) != signbit(s32)) nev = 0;
+      const float ss1 = fabsf(del1), ss2 = fabsf(del2);
+      if (0.1f * ss1 > ss2 || 0.1f * ss2 > ss1 || nev == 0) bisect = true;
+      else {
+        if (nev == 2) { x[m + 1] = c3; y[m + 1] = del3; }
+        else { x[1] = c1; y[1] = del1; x[2] = c2; y[2] = del2; m = 1; }
+        bool fail = false;
+        for (int kk = 1; kk <= m; ++kk) {
+          const int j = m - kk + 1;
+          const float den = SD_SUB(y[m + 1], y[j]);
+          if (fabsf(den) <= accur2) { fail = true; break; }
+          x[j] = SD_DIV(SD_ADD(SD_MUL(-y[j], x[j + 1]), SD_MUL(y[m + 1], x[j])), den);
+        }
+        if (fail) bisect = true;
+        else {
+          c3 = x[1];
+          del3 = f(c3); evals++;
+          nev = 2;
+          m = m + 1;
+          if (m > 10) m = 10;
+          continue;
+        }
+      }
+    }
+    if (bisect) {
+      c3 = (c1 + c2) / 2.f;
+      del3 = f(c3); evals++;
+      nev = 1;
+      m = 1;
+    }
+  }
+}
+
 // ==============================================================================================
 // Group velocity (phase 2 of calcul.f:224-404)
 // On-the-fly view of the period-T model of calcul.f:325-337 (all n layers refreshed, flat1 with n).

@@ -49,6 +49,7 @@ WsLayout ws_layout(int M, int lmax, int K) {
 }
 
 thread_local char g_cuda_err[256] = "";
+thread_local cudaEvent_t* g_prof_events = nullptr;  // set by surfdisp_batch_profiled: 4 events around the 3 kernels
 
 int cuda_fail(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       // ---- scan: candidates c1, c1+dc, ... evaluated G at a time (calcul.f:155-167)
       float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
       int mnew = mm;
-      bool found = false, failed = false;
+      bool found = false, failed = false, lstop = false;
       {
         float cbase = c1;
         float cl_prev = 0.f, dl_prev = 0.f;
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       if (found) {
         // ---- polish inside [lo,hi] with mmax pinned: G-section until the bracket is
         // narrow enough for one secant step to land inside float32 noise (replaces NEVILL, surfa.f:2-83)
+        const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
+        bool multi = false;
         for (int it = 0; it < 12 && (hi - lo) > 2.0e-5f; ++it) {
           const float step = (hi - lo) / (float)(G + 1);
           const float pj = lo + (float)(gl + 1) * step;
@@ -213,23 +216,36 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
           if (gl == 0) { dp = dlo; pp = lo; }
           const bool change = signbit(dp) != signbit(dj);
           const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+          const float dlast = gshfl<G>(gmask, dj, G - 1);
+          if (it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
           if (ev) {
             const int j = __ffs(ev) - 1;
             const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
             hi = gshfl<G>(gmask, pj, j); dhi = gshfl<G>(gmask, dj, j);
             lo = nlo; dlo = ndlo;
           } else {
-            lo = gshfl<G>(gmask, pj, G - 1); dlo = gshfl<G>(gmask, dj, G - 1);
+            lo = gshfl<G>(gmask, pj, G - 1); dlo = dlast;
           }
         }
-        {
+        if (!multi) {
           const float den = dhi - dlo;
           float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
           if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
           croot = cs;
+        } else {
+          // several roots inside the scan bracket: follow the reference's own sequential polish so the
+          // same one is picked (all lanes of the group run it redundantly, no divergence)
+          int ev_n = 0;
+          auto f = [&](float cc) {
+            return (p.kind == 2) ? rayleigh_sweep(cc, T, mm, q0, q1, 1) : love_sweep(cc, T, mm, q0, q1);
+          };
+          const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
+          if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
+          if (!okp) { found = false; lstop = true; }
         }
-        if (croot > q1[mm - 1].y) { found = false; failed = true; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
+        if (found && croot > q1[mm - 1].y) { found = false; failed = true; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
       }
+      if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; break; }  // reference aborts the whole call (calcul.f:173-189)
       if (!found) {
         flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
         (void)failed;
@@ -367,6 +383,36 @@ __global__ void __launch_bounds__(256) misfit_kernel(const __grid_constant__ Mis
   o[0] = (float)misfit; o[1] = (float)chi; o[2] = (float)exp(-0.5 * chi);
 }
 
+
+// ------------------------------------------------------------------------------------ pipe peaks
+// Register-resident FMA / MUFU chains: the denominators of the FP-pipe roofline (MEASURED_PEAKS.json
+// only has HBM and bf16 tensor figures, neither of which bounds this path).
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
+  T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+  T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+  const T m = (T)0.999999, c = (T)1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+      a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, int iters) {
+  float a0 = 1.0f + threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = __expf(a0) * 0.1f; a1 = __expf(a1) * 0.1f; a2 = __expf(a2) * 0.1f; a3 = __expf(a3) * 0.1f;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
+
 int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
   if (K < 1 || K > kMaxPer) return SURFDISP_EINVAL;
   memset(&tab, 0, sizeof(tab));
@@ -442,13 +488,16 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   int rc = fill_tab(p1.tab, n_periods, periods, o.t_base);
   if (rc) return rc;
   CK(cudaMemsetAsync(ws, 0, kHdrBytes, st));
+  if (g_prof_events) CK(cudaEventRecord(g_prof_events[0], st));
 
   prep_kernel<<<(n_models + 127) / 128, 128, 0, st>>>(n_models, n_layers_max, w.lpad, kind, o.flatten, n_layers,
                                                        layers, consts);
   CK(cudaGetLastError());
 
+  if (g_prof_events) CK(cudaEventRecord(g_prof_events[1], st));
   rc = launch_phase1<8>(p1, st);
   if (rc) return rc;
+  if (g_prof_events) CK(cudaEventRecord(g_prof_events[2], st));
 
   if (u_out && o.compute_group) {
     P2Params p2;
@@ -474,6 +523,7 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   } else if (u_out) {
     CK(cudaMemsetAsync(u_out, 0, (size_t)n_models * n_periods * sizeof(float), st));
   }
+  if (g_prof_events) CK(cudaEventRecord(g_prof_events[3], st));
   return 0;
 }
 
@@ -573,6 +623,57 @@ int surfdisp_read_counters(const void* workspace, unsigned long long out[4], voi
   if (!workspace || !out) return SURFDISP_EINVAL;
   CK(cudaMemcpyAsync(out, workspace, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+
+int surfdisp_batch_profiled(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                            const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
+                            int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream,
+                            float kernel_ms[3]) {
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev[i]));
+  g_prof_events = ev;
+  int rc = surfdisp_batch(opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out, u_out,
+                          nfound, flags, workspace, workspace_bytes, stream);
+  g_prof_events = nullptr;
+  if (rc == 0) {
+    cudaError_t e = cudaEventSynchronize(ev[3]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+    for (int i = 0; i < 3 && rc == 0; ++i) {
+      kernel_ms[i] = 0.f;
+      cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]);
+    }
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
+int surfdisp_measure_peaks(double out[3]) {
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  void* buf = nullptr;
+  CK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float ms = 0.f;
+  for (int which = 0; which < 3; ++which) {
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaEventRecord(e0, 0));
+      if (which == 0) fma_peak_kernel<float><<<blocks, threads>>>((float*)buf, iters);
+      else if (which == 1) fma_peak_kernel<double><<<blocks, threads>>>((double*)buf, iters / 4);
+      else mufu_peak_kernel<<<blocks, threads>>>((float*)buf, iters);
+      CK(cudaEventRecord(e1, 0));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double n = (double)blocks * threads * (which == 1 ? iters / 4 : iters) * 8.0 * (which == 2 ? 4.0 : 8.0);
+      const double rate = (which == 2 ? n : 2.0 * n) / (ms * 1e-3) * 1e-12;  // TFLOP/s, or T-ex2/s
+      if (rep > 0 && rate > best) best = rate;
+    }
+    out[which] = best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
   return 0;
 }
 

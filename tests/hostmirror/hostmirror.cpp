@@ -81,23 +81,33 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     mm = mnew;
     float croot = 0;
     if (found) {
+      const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
+      bool multi = false;
       for (int it = 0; it < 12 && (hi - lo) > 2.0e-5f; ++it) {
         const float step = (hi - lo) / (float)(G + 1);
         for (int g = 0; g < G; ++g) { cj[g] = lo + (float)(g + 1) * step; dj[g] = sweep(cj[g], T, mm); }
-        int j = -1;
+        int j = -1, nchg = 0;
         for (int g = 0; g < G; ++g) {
           const float dp = g ? dj[g - 1] : dlo;
-          if (std::signbit(dp) != std::signbit(dj[g])) { j = g; break; }
+          if (std::signbit(dp) != std::signbit(dj[g])) { if (j < 0) j = g; nchg++; }
         }
+        if (std::signbit(dj[G - 1]) != std::signbit(dhi)) nchg++;
+        if (it == 0 && nchg > 1) { multi = true; break; }
         if (j >= 0) {
           const float nlo = j ? cj[j - 1] : lo, ndlo = j ? dj[j - 1] : dlo;
           hi = cj[j]; dhi = dj[j]; lo = nlo; dlo = ndlo;
         } else { lo = cj[G - 1]; dlo = dj[G - 1]; }
       }
-      const float den = dhi - dlo;
-      float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
-      if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
-      croot = cs;
+      if (!multi) {
+        const float den = dhi - dlo;
+        float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
+        if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
+        croot = cs;
+      } else {
+        int ev_n = 0;
+        auto f = [&](float cc) { return sweep(cc, T, mm); };
+        if (!nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n)) { nfound = 0; break; }
+      }
       if (croot > q1[mm - 1].y) found = false;
     }
     if (!found) break;
