@@ -196,12 +196,14 @@ def test_full_size_properties(solver):
     perm = torch.randperm(M, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     b = solver.forward(dl[:, perm].contiguous(), dn[perm].contiguous(), per, kind=2)
     assert torch.equal(b["c"], c_a[perm]) and torch.equal(b["u"], u_a[perm]) and torch.equal(b["nfound"], nf_a[perm])
-    assert int((nf_a == len(per)).sum()) == M
+    full = nf_a == len(per)
+    assert int(full.sum()) >= M - max(4, M // 10000)     # a handful of stacks lose the root at the longest periods
     vs_half = dl[1, :, 76]
     assert bool((c_a.max(dim=1).values <= vs_half * 1.05).all())
-    assert bool((c_a > 0.5).all()) and bool(torch.isfinite(u_a).all())
-    assert float((u_a[:, -8:] < c_a[:, -8:]).float().mean()) > 0.999
+    assert bool((c_a[full] > 0.5).all()) and bool(torch.isfinite(u_a).all())
+    assert float((u_a[full][:, -8:] < c_a[full][:, -8:]).float().mean()) > 0.999
     # oracle spot check on a strided subset at the full layout
-    idx = np.arange(0, M, M // 256)
+    idx = np.unique(np.concatenate([np.arange(0, M, M // 256), np.nonzero(~full.cpu().numpy())[0]]))
     c0, u0, nf0, st0 = O.forward_batch(2, lay[:, idx], nl[idx], per, opts=O.make_opts(precision=0), nthreads=8)
+    assert np.array_equal(nf_a.cpu().numpy()[idx], nf0)
     assert np.abs(c_a.cpu().numpy()[idx] - c0).max() <= TOL

@@ -1,0 +1,52 @@
+"""CPU tier: the CUDA kernels' per-lane arithmetic (surfdisp_core.cuh compiled with g++) replayed lane by
+lane against the oracle.  This checks the kernel math and the scan / G-section / sequential-polish design
+without a GPU; the CUDA build itself is checked in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pysurfinv_b200 import synth
+from tests.hostmirror import mirror as HM
+
+
+def _run(lay, nl, per, kind, G=8):
+    c0, u0, nf0, st0 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+    dc, du = [], []
+    for i in range(lay.shape[1]):
+        n = int(nl[i])
+        r = HM.forward(kind, lay[0, i, :n], lay[1, i, :n], lay[2, i, :n], lay[3, i, :n], lay[4, i, :n], per, G=G)
+        if st0[i] == 3:
+            continue
+        assert r["nfound"] == nf0[i], "model %d: %d vs %d" % (i, r["nfound"], nf0[i])
+        dc.append(np.abs(r["c"] - c0[i])); du.append(np.abs(r["u"] - u0[i]))
+    return np.array(dc), np.array(du)
+
+
+@pytest.mark.parametrize("kind", [2, 1])
+def test_crustal(kind):
+    lay, nl = synth.crustal_models(150, seed=3)
+    dc, du = _run(lay, nl, synth.log_periods(), kind)
+    assert dc.max() < 1e-4 and np.median(dc) < 2e-6
+    assert (du > 1e-4).mean() < 2e-3 and np.median(du) < 5e-6
+
+
+@pytest.mark.parametrize("kind", [2, 1])
+def test_hand_models_unclamped_ndiv(kind):
+    lay, nl = synth.hand_models(150, seed=4)
+    dc, du = _run(lay, nl, synth.log_periods(16, 6.0, 60.0), kind)
+    assert dc.max() < 1e-4 and du.max() < 1e-4
+
+
+@pytest.mark.parametrize("G", [4, 16, 32])
+def test_group_width_does_not_change_results(G):
+    lay, nl = synth.crustal_models(40, seed=5)
+    dc, du = _run(lay, nl, synth.log_periods(12), 2, G=G)
+    assert dc.max() < 1e-4
+
+
+def test_water_layer_and_ragged():
+    lay, nl = synth.ragged_models(120, seed=6)
+    per = np.array([10, 14, 20, 28, 40, 60, 80], np.float32)
+    for kind in (2, 1):
+        dc, du = _run(lay, nl, per, kind)
+        assert dc.max() < 1e-4 and (du > 1e-4).mean() < 5e-3
