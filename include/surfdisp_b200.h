@@ -57,6 +57,10 @@ typedef struct SurfdispOpts {
   int stale_mmax;          /* 1: period k refreshes only the layers kept by period k-1, as the
                               reference does (calcul.f:112-133); 0: refresh all layers */
   int compute_group;       /* 1: also group velocity (REIGEN/LEIGEN); 0: phase velocity only */
+  int exact_scan;          /* 0 (default): coarse-to-fine scan (every 8th grid point, then the interior of the
+                              first interval with a sign change) and clustered polish; 1: evaluate every grid
+                              point c1 + i*dc like calcul.f:155-167 and polish by uniform section (slower,
+                              identical results unless two roots hide inside one 0.08 km/s coarse interval) */
 } SurfdispOpts;
 
 void surfdisp_default_opts(SurfdispOpts* o);

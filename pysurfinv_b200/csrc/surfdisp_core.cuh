@@ -141,11 +141,64 @@ SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* q1) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Fast scalar primitives of the secular-function inner loop.  On the device they map to single MUFU
+// instructions (1-2 ulp): the secular function only has to be good to the float32 noise of the
+// reference's own evaluation (root noise 1e-6 km/s, tolerance 1e-4).  On the host (tests/hostmirror)
+// they are the exact libm functions.
+#if defined(__CUDA_ARCH__)
+SD_HD float sd_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SD_HD float sd_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SD_HD float sd_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SD_HD void sd_sincos(float x, float& s, float& c) {
+  // two-constant Cody-Waite reduction to [-pi, pi], then MUFU.SIN / MUFU.COS (abs err 2^-21.4 there)
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-n, 6.28318548202514648f, x);
+  r = fmaf(-n, -1.74845553146951715e-7f, r);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(r));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(r));
+}
+#else
+SD_HD float sd_rsqrt(float x) { return 1.0f / sqrtf(x); }
+SD_HD float sd_rcp(float x) { return 1.0f / x; }
+SD_HD float sd_ex2(float x) { return exp2f(x); }
+SD_HD void sd_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
+#endif
+#define SD_LOG2E 1.4426950408889634f
+
+// One "half" of a layer propagator: for r = sqrt(|arg|) and x = kd*r returns
+//   (r sin x, sin x / r, cos x)  when arg < 0 (oscillatory, c above the layer velocity)
+//   (-r sinh x, sinh x / r, cosh x) when arg > 0 (evanescent)          surfa.f:262-288
+//   (0, kd, 1) when |arg| < 1e-16 (|r| < 1e-8, surfa.f:275 / exact zero surfa.f:262)
+SD_HD void half_terms(float arg, float kd, float& rsin, float& sinr, float& cs) {
+  const float t = fabsf(arg);
+  if (t < 1.e-16f) { rsin = 0.f; sinr = kd; cs = 1.f; return; }
+  const float ir = sd_rsqrt(t);
+  const float r = t * ir;
+  const float x = kd * r;
+  if (arg > 0.f) {
+    const float xl = x * SD_LOG2E;
+    const float ex = sd_ex2(xl), em = sd_ex2(-xl);
+    const float sh = 0.5f * (ex - em);
+    cs = 0.5f * (ex + em);
+    rsin = -r * sh;
+    sinr = sh * ir;
+  } else {
+    float sn, c_;
+    sd_sincos(x, sn, c_);
+    cs = c_;
+    rsin = r * sn;
+    sinr = sn * ir;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Rayleigh secular function: Dunkin compound-matrix vector propagated top-down through layers
 // 1..mmax-1 and contracted with the half-space row (surfa.f:193-357).
 //   start = 1: dispersion function (returns -bb1)
 //   start = 2 / 3: the two ellipticity sweeps (returns bb1); liquid layers are skipped there
 //   (surfa.f:220).
+// The 15 matrix entries of surfa.f:289-320 are formed from shared sub-expressions
+// (w = 2 g g1 (1-cc) + g^2 rr + g1^2 ss gives a11 = cc - w and a33 = 1 + 2w, etc.).
 SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const float4* q1, int start) {
   const float wvno = SD_TWOPI / (c * T);
   const float csq = c * c;
@@ -157,90 +210,45 @@ SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const f
     const float4 L = q0[m];
     const float4 E = q1[m];
     const float kd = wvno * E.x;
-    const float arga = 1.0f - csq * L.x;
-    const float ta = fabsf(arga);
     float rsinp, sinpr, cosp;
-    if (arga > 0.f) {            // c < a : evanescent P (surfa.f:267-269 / 228-230)
-      float s = sqrtf(ta);
-      float ex = expf(kd * s);
-      float em = 1.0f / ex;
-      float sh = 0.5f * (ex - em);
-      cosp = 0.5f * (ex + em);
-      rsinp = -s * sh;
-      sinpr = sh / s;
-    } else if (arga < 0.f) {     // c > a : oscillatory P (surfa.f:271-273 / 232-234)
-      float s = sqrtf(ta);
-      float sn, cs;
-      sincosf(kd * s, &sn, &cs);
-      cosp = cs;
-      rsinp = s * sn;
-      sinpr = sn / s;
-    } else {                     // surfa.f:263-265
-      rsinp = 0.f; sinpr = kd; cosp = 1.f;
-    }
+    half_terms(1.0f - csq * L.x, kd, rsinp, sinpr, cosp);
     if (L.y == 0.f) {
       // liquid layer (surfa.f:219-251): only a11 = cosp, a21 = rho c^2 sinpr are non-zero
       if (start != 1) continue;
-      if (ta < 1.e-8f * 1.e-8f) { sinpr = kd; cosp = 1.f; }
       const float a21 = L.w * csq * sinpr;
-      const float n1 = cosp * b1;
-      const float n2 = a21 * b1;
-      const float n5 = cosp * b5;
-      const float n4 = -a21 * b4;
-      // bb3 = 0.5*a13*b5 = 0 ; bb4 = a22*b4 - a12*b5 = 0 ; full form of surfa.f:326-330 with zeros
-      b1 = n1; b2 = n2; b3 = 0.f; b4 = 0.f; b5 = n4 + n5;
+      const float n1 = cosp * b1, n2 = a21 * b1, n5 = cosp * b5 - a21 * b4;
+      b1 = n1; b2 = n2; b3 = 0.f; b4 = 0.f; b5 = n5;
       continue;
     }
-    const float argb = 1.0f - csq * L.y;
-    const float tb = fabsf(argb);
     float rsinq, sinqr, cosq;
-    if (tb < 1.e-16f) {          // |rb| < 1e-8 (surfa.f:275,285-287)
-      rsinq = 0.f; sinqr = kd; cosq = 1.f;
-    } else if (argb > 0.f) {     // c < b : evanescent S (surfa.f:277-279)
-      float s = sqrtf(tb);
-      float ex = expf(kd * s);
-      float em = 1.0f / ex;
-      float sh = 0.5f * (ex - em);
-      cosq = 0.5f * (ex + em);
-      rsinq = -s * sh;
-      sinqr = sh / s;
-    } else {                     // c > b (surfa.f:281-283)
-      float s = sqrtf(tb);
-      float sn, cs;
-      sincosf(kd * s, &sn, &cs);
-      cosq = cs;
-      rsinq = s * sn;
-      sinqr = sn / s;
-    }
+    half_terms(1.0f - csq * L.y, kd, rsinq, sinqr, cosq);
     const float g = L.z * icsq;
     const float g1 = g - 1.0f;
     const float rhoc = L.w * csq;
     const float irhoc = E.z * icsq;
-    // surfa.f:289-320
     const float rr = rsinp * rsinq, ss = sinpr * sinqr, cc = cosp * cosq;
     const float rs1 = rsinp * cosq, rs2 = sinqr * cosp, rs3 = sinpr * cosq, rs4 = rsinq * cosp;
-    const float gm = 2.f * g - 1.f, gs = g * g, g1s = g1 * g1, ccm = 1.f - cc, gg1 = g * g1;
+    const float a24 = sinpr * rsinq, a42 = rsinp * sinqr;
+    const float gm = g + g1, gs = g * g, g1s = g1 * g1, gg1 = g * g1, ccm = 1.0f - cc;
     const float suu = gs * rr + g1s * ss;
-    const float a11 = (2.f * gs - gm) * cc - suu - 2.f * gg1;
+    const float w = 2.f * gg1 * ccm + suu;
+    const float a11 = cc - w;
+    const float a33 = 1.f + 2.f * w;
     const float a12 = -(rs1 + rs2) * irhoc;
-    const float a13 = -2.f * (gm * ccm + g1 * ss + g * rr) * irhoc;
     const float a14 = (rs3 + rs4) * irhoc;
-    const float a15 = (2.f * ccm + rr + ss) * irhoc * irhoc;
+    const float a13h = -(gm * ccm + g1 * ss + g * rr) * irhoc;          // = 0.5 * a13
+    const float a15 = (2.f * ccm + rr + ss) * (irhoc * irhoc);
     const float a21 = rhoc * (g1s * rs3 + gs * rs4);
-    const float a22 = cc;
-    const float a23 = 2.f * (g * rs4 + g1 * rs3);
-    const float a24 = sinpr * rsinq;
-    const float a31 = rhoc * (gg1 * gm * ccm + g1s * g1 * ss + gs * g * rr);
-    const float a32 = g1 * rs2 + g * rs1;
-    const float a33 = 1.f + 2.f * (2.f * gg1 * ccm + suu);
     const float a41 = -rhoc * (g1s * rs2 + gs * rs1);
-    const float a42 = rsinp * sinqr;
-    const float a51 = rhoc * rhoc * (2.f * gs * g1s * ccm + gs * gs * rr + g1s * g1s * ss);
+    const float a23h = g * rs4 + g1 * rs3;                               // = 0.5 * a23
+    const float a32 = g1 * rs2 + g * rs1;
+    const float a31 = rhoc * (gg1 * gm * ccm + (g1s * g1) * ss + (gs * g) * rr);
+    const float a51 = (rhoc * rhoc) * (2.f * (gg1 * gg1) * ccm + (gs * gs) * rr + (g1s * g1s) * ss);
     // surfa.f:326-330
-    const float n1 = a11 * b1 + a12 * b2 + a13 * b3 + a14 * b4 + a15 * b5;
-    const float n2 = a21 * b1 + a22 * b2 + a23 * b3 + a24 * b4 - a14 * b5;
-    const float n3 = a31 * b1 + a32 * b2 + a33 * b3 - 0.5f * a23 * b4 + 0.5f * a13 * b5;
-    const float n4 = a41 * b1 + a42 * b2 - 2.f * a32 * b3 + a22 * b4 - a12 * b5;
+    const float n1 = a11 * b1 + a12 * b2 + 2.f * a13h * b3 + a14 * b4 + a15 * b5;
+    const float n2 = a21 * b1 + cc * b2 + 2.f * a23h * b3 + a24 * b4 - a14 * b5;
+    const float n3 = a31 * b1 + a32 * b2 + a33 * b3 - a23h * b4 + a13h * b5;
+    const float n4 = a41 * b1 + a42 * b2 - 2.f * a32 * b3 + cc * b4 - a12 * b5;
     const float n5 = a51 * b1 - a41 * b2 + 2.f * a31 * b3 - a21 * b4 + a11 * b5;
     b1 = n1; b2 = n2; b3 = n3; b4 = n4; b5 = n5;
   }

@@ -86,10 +86,16 @@ struct P1Params {
   unsigned long long* counters;
   unsigned int* queue;
   float dc, fact;
-  int atten, stale;
+  int atten, stale, exact_scan;
   int mstride;  // float4 units between consecutive groups' shared-memory records
   PeriodTab tab;
 };
+
+// One copy of the secular-function loop for all call sites (scan, polish, sequential polish, ellipticity):
+// inlining it five times made the kernel ~95 KB of SASS and the warps stalled on instruction fetch.
+__device__ __noinline__ float secular(int kind, float c, float T, int mm, const float4* q0, const float4* q1, int start) {
+  return (kind == 2) ? rayleigh_sweep(c, T, mm, q0, q1, start) : love_sweep(c, T, mm, q0, q1);
+}
 
 template <int G>
 __device__ __forceinline__ float gshfl(unsigned mask, float v, int src) { return __shfl_sync(mask, v, src, G); }
@@ -103,6 +109,7 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
   const int gl = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
   const int grp = threadIdx.x / G;
   float4* q0 = smem + (size_t)grp * p.mstride;
   float4* q1 = q0 + p.lpad;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
     }
     int mm = n;        // reference COMMON mmax carried from period to period
     int nfound = 0, flag = 0;
-    float c_prev = 0.f;
+    float c_prev = 0.f, c_prev2 = 0.f;
     for (int k = 0; k < K; ++k) {
       const float T = p.tab.per[k];
       const float lt = p.tab.lt[k];
@@ -160,64 +167,137 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       __syncwarp(gmask);
       if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
       const float b_top = q1[0].y;
-      // ---- scan: candidates c1, c1+dc, ... evaluated G at a time (calcul.f:155-167)
-      float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
-      int mnew = mm;
+      // ---- scan (calcul.f:155-167): first sign change of the secular function on the grid c1 + i*dc.
+      // Coarse-to-fine: the G lanes evaluate every S-th grid point (S = G); the first coarse interval with
+      // an event is then resolved by its S-1 interior points in one more round.  S = 1 (exact_scan, or a
+      // start below 0.8*b(1) where the reference's stop test fires on the first step) is the plain scan.
+      // The coarse scan cannot see two roots inside one coarse interval (fundamental and first overtone
+      // osculate for thick slow sediments at short periods).  Guard: the first two periods are scanned point
+      // by point; later ones are re-scanned point by point whenever the coarse result fails or jumps above
+      // the log-period extrapolation of the previous two roots (a skipped pair lands on a much higher mode).
+      const int mm_in = mm, flag_in = flag;
+      float croot = 0.f;
       bool found = false, failed = false, lstop = false;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+      mm = mm_in; flag = flag_in; found = false; failed = false; lstop = false; croot = 0.f;
+      const bool coarse = !(p.exact_scan || k < 2 || attempt == 1);
+      float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, xn = 0.f, yn = 0.f;
+      int mnew = mm;
+      bool have_n = false;
       {
-        float cbase = c1;
-        float cl_prev = 0.f, dl_prev = 0.f;
+        const float c_1 = SD_ADD(c1, p.dc);
+        int S = (!coarse || c_1 < 0.8f * b_top) ? 1 : G;
+        float cbase = c1, cP = 0.f, dP = 0.f;
         bool have_prev = false;
         for (int round = 0; round < 4096; ++round) {
           float cj = cbase;
-          for (int t = 0; t < gl; ++t) cj = SD_ADD(cj, p.dc);
-          const int mj = layer_drop(cj, T, p.fact, n, q1);
-          const float dj = (p.kind == 2) ? rayleigh_sweep(cj, T, mj, q0, q1, 1) : love_sweep(cj, T, mj, q0, q1);
+          for (int t = 0; t < gl * S; ++t) cj = SD_ADD(cj, p.dc);
+          int mj = layer_drop(cj, T, p.fact, n, q1);
+          float dj = secular(p.kind, cj, T, mj, q0, q1, 1);
           my_steps += (unsigned)(mj - 1); my_sweeps += 1;
           float dp = __shfl_up_sync(gmask, dj, 1, G);
           float cp = __shfl_up_sync(gmask, cj, 1, G);
-          if (gl == 0) { dp = dl_prev; cp = cl_prev; }
+          if (gl == 0) { dp = dP; cp = cP; }
           const bool hasp = (gl > 0) || have_prev;
-          const bool change = hasp && (signbit(dp) != signbit(dj));
-          const float b_hs = q1[mj - 1].y;
-          const bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < b_hs + 0.3f) || !(cj == cj));
-          const unsigned ev = (__ballot_sync(gmask, change || stop) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
-          if (ev) {
-            const int j = __ffs(ev) - 1;
-            found = gshfl<G>(gmask, (int)change, j) != 0;
-            lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
-            dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
-            mnew = gshfl<G>(gmask, mj, j);
-            failed = !found;
-            break;
+          bool change = hasp && (signbit(dp) != signbit(dj));
+          bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
+          // above the half-space velocity the secular function can change sign twice inside one coarse
+          // interval (kink at c = b(mmax)): such intervals are resolved point by point
+          const bool risky = hasp && S > 1 && !(cj < q1[mj - 1].y);
+          unsigned ev = (__ballot_sync(gmask, change || stop || risky) >> gbase) & gbits;
+          if (!ev) {
+            cP = gshfl<G>(gmask, cj, G - 1);
+            dP = gshfl<G>(gmask, dj, G - 1);
+            mnew = gshfl<G>(gmask, mj, G - 1);
+            have_prev = true;
+            cbase = cP;
+            for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, p.dc);
+            if (round == 4095) { failed = true; flag |= SURFDISP_F_SCAN_LIMIT; }
+            continue;
           }
-          cl_prev = gshfl<G>(gmask, cj, G - 1);
-          dl_prev = gshfl<G>(gmask, dj, G - 1);
-          mnew = gshfl<G>(gmask, mj, G - 1);
-          have_prev = true;
-          cbase = SD_ADD(cl_prev, p.dc);
-          if (round == 4095) { failed = true; flag |= SURFDISP_F_SCAN_LIMIT; }
+          int j = __ffs(ev) - 1;
+          if (S > 1) {
+            // fine round: lanes 0..G-2 take the interior grid points, lane G-1 keeps the coarse end point
+            const float c_hi = gshfl<G>(gmask, cj, j), d_hi = gshfl<G>(gmask, dj, j);
+            const int m_hi = gshfl<G>(gmask, mj, j);
+            const float c_lo = gshfl<G>(gmask, cp, j), d_lo = gshfl<G>(gmask, dp, j);
+            if (gl < G - 1) {
+              cj = c_lo;
+              for (int t = 0; t <= gl; ++t) cj = SD_ADD(cj, p.dc);
+              mj = layer_drop(cj, T, p.fact, n, q1);
+              dj = secular(p.kind, cj, T, mj, q0, q1, 1);
+              my_steps += (unsigned)(mj - 1); my_sweeps += 1;
+            } else { cj = c_hi; dj = d_hi; mj = m_hi; }
+            dp = __shfl_up_sync(gmask, dj, 1, G);
+            cp = __shfl_up_sync(gmask, cj, 1, G);
+            if (gl == 0) { dp = d_lo; cp = c_lo; }
+            change = signbit(dp) != signbit(dj);
+            stop = !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
+            ev = (__ballot_sync(gmask, change || stop) >> gbase) & gbits;
+            if (!ev) {  // only the 'risky' flag fired: go on from the end of this interval with the plain scan
+              S = 1; cP = c_hi; dP = d_hi; mnew = m_hi; have_prev = true; cbase = SD_ADD(c_hi, p.dc);
+              continue;
+            }
+            j = __ffs(ev) - 1;
+            // a third point next to the bracket for the first root estimate
+            const int jb = (j >= 1) ? j - 1 : 0, ja = (j < G - 1) ? j + 1 : G - 1;
+            const float xb = gshfl<G>(gmask, cp, jb), yb = gshfl<G>(gmask, dp, jb);   // seq point before lo
+            const float xa = gshfl<G>(gmask, cj, ja), ya = gshfl<G>(gmask, dj, ja);   // seq point after hi
+            const float d_at_hi = gshfl<G>(gmask, dj, j), d_at_lo = gshfl<G>(gmask, dp, j);
+            have_n = false;
+            if (j >= 1) { xn = xb; yn = yb; have_n = true; }
+            if (j < G - 1 && (!have_n || fabsf(d_at_hi) < fabsf(d_at_lo))) { xn = xa; yn = ya; have_n = true; }
+          }
+          found = gshfl<G>(gmask, (int)change, j) != 0;
+          lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
+          dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
+          mnew = gshfl<G>(gmask, mj, j);
+          failed = !found;
+          break;
         }
       }
       mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
-      float croot = 0.f;
       if (found) {
-        // ---- polish inside [lo,hi] with mmax pinned: G-section until the bracket is
-        // narrow enough for one secant step to land inside float32 noise (replaces NEVILL, surfa.f:2-83)
+        // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83).
+        // Fast path: G points clustered geometrically (1,4,16,64 x delta) around the inverse-quadratic /
+        // secant estimate; ends when the bracket is <= 2e-5 (one secant step then lands inside float32
+        // noise).  Careful path (half-space velocity within a step of the bracket, where a kink can put
+        // several roots in one bracket): uniform G-section whose first round counts the sign changes and
+        // hands over to the reference's own sequential bisection/Neville sequence if there are several.
         const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
+        const float b_hs = q1[mm - 1].y;
+        const bool careful = !coarse || (b_hs > lo - 0.011f && b_hs < hi + 0.011f);
         bool multi = false;
-        for (int it = 0; it < 12 && (hi - lo) > 2.0e-5f; ++it) {
-          const float step = (hi - lo) / (float)(G + 1);
-          const float pj = lo + (float)(gl + 1) * step;
-          const float dj = (p.kind == 2) ? rayleigh_sweep(pj, T, mm, q0, q1, 1) : love_sweep(pj, T, mm, q0, q1);
+        for (int it = 0; it < 16 && (hi - lo) > 2.0e-5f; ++it) {
+          const float w = hi - lo;
+          float pj;
+          if (careful || it >= 4) {
+            pj = lo + (float)(gl + 1) * (w / (float)(G + 1));
+          } else {
+            const float den = dhi - dlo;
+            float e = (den != 0.f) ? lo - dlo * w / den : 0.5f * (lo + hi);
+            if (it == 0 && have_n) {
+              const float d01 = dlo - dhi, d02 = dlo - yn, d12 = dhi - yn;
+              if (d01 != 0.f && d02 != 0.f && d12 != 0.f) {
+                const float q = lo * (dhi * yn) / (d01 * d02) - hi * (dlo * yn) / (d01 * d12) + xn * (dlo * dhi) / (d02 * d12);
+                if (q > lo && q < hi) e = q;
+              }
+            }
+            const float dl = fmaxf(0.5e-5f, w * (1.0f / 2048.f));
+            const int h = gl - G / 2;
+            const float mag = (h >= 0) ? (float)(1 << (2 * (h & 7))) : -(float)(1 << (2 * ((-h - 1) & 7)));
+            const float eps = w * 1.0e-3f;
+            pj = fminf(fmaxf(e + mag * dl, lo + eps), hi - eps);
+          }
+          const float dj = secular(p.kind, pj, T, mm, q0, q1, 1);
           my_steps += (unsigned)(mm - 1); my_sweeps += 1;
           float dp = __shfl_up_sync(gmask, dj, 1, G);
           float pp = __shfl_up_sync(gmask, pj, 1, G);
           if (gl == 0) { dp = dlo; pp = lo; }
           const bool change = signbit(dp) != signbit(dj);
-          const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+          const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & gbits;
           const float dlast = gshfl<G>(gmask, dj, G - 1);
-          if (it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
+          if (careful && it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
           if (ev) {
             const int j = __ffs(ev) - 1;
             const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
@@ -236,15 +316,22 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
           // several roots inside the scan bracket: follow the reference's own sequential polish so the
           // same one is picked (all lanes of the group run it redundantly, no divergence)
           int ev_n = 0;
-          auto f = [&](float cc) {
-            return (p.kind == 2) ? rayleigh_sweep(cc, T, mm, q0, q1, 1) : love_sweep(cc, T, mm, q0, q1);
-          };
+          auto f = [&](float cc) { return secular(p.kind, cc, T, mm, q0, q1, 1); };
           const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
           if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
           if (!okp) { found = false; lstop = true; }
         }
         if (found && croot > q1[mm - 1].y) { found = false; failed = true; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
       }
+      if (!coarse) break;
+      bool suspicious = !found || lstop;
+      if (!suspicious) {
+        const float r = (p.tab.lt[k - 1] - p.tab.lt[k]) / (p.tab.lt[k - 2] - p.tab.lt[k - 1]);
+        const float stepp = (c_prev - c_prev2) * r;
+        suspicious = !(croot - (c_prev + stepp) <= fmaxf(0.1f, fabsf(stepp)));
+      }
+      if (!suspicious) break;
+      }  // attempt
       if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; break; }  // reference aborts the whole call (calcul.f:173-189)
       if (!found) {
         flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
@@ -254,13 +341,14 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       float ratio = 0.f;
       if (p.kind == 2) {
         // ellipticity = 0.5 * bb1(e3) / bb1(e2) (surfa.f:360-363); two lanes, one start vector each
-        const float v = rayleigh_sweep(croot, T, mm, q0, q1, 2 + (gl & 1));
+        const float v = secular(2, croot, T, mm, q0, q1, 2 + (gl & 1));
         my_steps += (unsigned)(mm - 1); my_sweeps += 1;
         const float r12 = gshfl<G>(gmask, v, 0);
         const float r3 = gshfl<G>(gmask, v, 1);
         ratio = 0.5f * r3 / r12;
       }
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
+      c_prev2 = c_prev;
       c_prev = croot;
       nfound = k + 1;
     }
@@ -454,7 +542,7 @@ extern "C" {
 
 void surfdisp_default_opts(SurfdispOpts* o) {
   o->dc = 0.01f; o->fact = 4.0f; o->t_base = 1.0f; o->ndiv = 5; o->ndiv_cap_rayleigh = 99;
-  o->ndiv_cap_love = 999; o->atten = 1; o->flatten = 1; o->stale_mmax = 1; o->compute_group = 1;
+  o->ndiv_cap_love = 999; o->atten = 1; o->flatten = 1; o->stale_mmax = 1; o->compute_group = 1; o->exact_scan = 0;
 }
 
 size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods) {
@@ -484,7 +572,7 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   memset(&p1, 0, sizeof(p1));
   p1.kind = kind; p1.M = n_models; p1.lpad = w.lpad; p1.K = n_periods; p1.nlay = n_layers; p1.consts = consts;
   p1.c_out = c_out; p1.ratio_out = ratio; p1.nfound = nfound; p1.flags = flags; p1.counters = counters;
-  p1.queue = queue; p1.dc = o.dc; p1.fact = o.fact; p1.atten = o.atten; p1.stale = o.stale_mmax;
+  p1.queue = queue; p1.dc = o.dc; p1.fact = o.fact; p1.atten = o.atten; p1.stale = o.stale_mmax; p1.exact_scan = o.exact_scan;
   int rc = fill_tab(p1.tab, n_periods, periods, o.t_base);
   if (rc) return rc;
   CK(cudaMemsetAsync(ws, 0, kHdrBytes, st));
