@@ -168,10 +168,22 @@ SD_HD void sd_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
 // One "half" of a layer propagator: for r = sqrt(|arg|) and x = kd*r returns
 //   (r sin x, sin x / r, cos x)  when arg < 0 (oscillatory, c above the layer velocity)
 //   (-r sinh x, sinh x / r, cosh x) when arg > 0 (evanescent)          surfa.f:262-288
-//   (0, kd, 1) when |arg| < 1e-16 (|r| < 1e-8, surfa.f:275 / exact zero surfa.f:262)
-SD_HD void half_terms(float arg, float kd, float& rsin, float& sinr, float& cs) {
+//   (0, kd, 1) in the limit arg -> 0 (surfa.f:262-265, 275, 285-287)
+// With u = kd^2 * arg (signed) all three are entire functions of u:
+//   sin x / r = kd S(u),  r sin x = -kd arg S(u),  cos x = C(u),   S(u) = sum u^n/(2n+1)!,  C(u) = sum u^n/(2n)!
+// For |u| < 0.5 (thin layers / long periods: the vast majority of layer steps) the series are used: no
+// square root, no MUFU, no branch on the sign of arg, and none of the cancellation that
+// (exp(x)-exp(-x))/2 suffers for small x (the reference's float32 form loses ~x^-1 ulps there).
+SD_HD void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float& cs) {
+  const float u = kd2 * arg;
+  if (fabsf(u) < 0.5f) {
+    const float S = 1.f + u * (1.6666667e-1f + u * (8.3333333e-3f + u * (1.9841270e-4f + u * 2.7557319e-6f)));
+    cs = 1.f + u * (0.5f + u * (4.1666667e-2f + u * (1.3888889e-3f + u * (2.4801587e-5f + u * 2.7557319e-7f))));
+    sinr = kd * S;
+    rsin = -arg * sinr;
+    return;
+  }
   const float t = fabsf(arg);
-  if (t < 1.e-16f) { rsin = 0.f; sinr = kd; cs = 1.f; return; }
   const float ir = sd_rsqrt(t);
   const float r = t * ir;
   const float x = kd * r;
@@ -210,8 +222,9 @@ SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const f
     const float4 L = q0[m];
     const float4 E = q1[m];
     const float kd = wvno * E.x;
+    const float kd2 = kd * kd;
     float rsinp, sinpr, cosp;
-    half_terms(1.0f - csq * L.x, kd, rsinp, sinpr, cosp);
+    half_terms(1.0f - csq * L.x, kd, kd2, rsinp, sinpr, cosp);
     if (L.y == 0.f) {
       // liquid layer (surfa.f:219-251): only a11 = cosp, a21 = rho c^2 sinpr are non-zero
       if (start != 1) continue;
@@ -221,7 +234,7 @@ SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const f
       continue;
     }
     float rsinq, sinqr, cosq;
-    half_terms(1.0f - csq * L.y, kd, rsinq, sinqr, cosq);
+    half_terms(1.0f - csq * L.y, kd, kd2, rsinq, sinqr, cosq);
     const float g = L.z * icsq;
     const float g1 = g - 1.0f;
     const float rhoc = L.w * csq;
@@ -298,32 +311,20 @@ SD_HD float love_sweep(float c, float T, int mmax, const float4* q0, const float
     const float4 L = q0[m];
     if (L.y == 0.f) continue;  // liquid layer skipped (surfa.f:152)
     const float4 E = q1[m];
-    const float x = csq * L.y - 1.0f;
-    const float rb = sqrtf(fabsf(x));
-    const float h = L.w * 0.5f * L.z;
     const float kd = wvno * E.x;
-    float y, z, cosq;
-    if (rb < 0.1e-20f || x == 0.f) {      // surfa.f:164-166
-      y = -kd; z = 0.f; cosq = 1.f;
-    } else if (x > 0.f) {                 // c > b (surfa.f:159-162), q = -k d rb
-      float sn, cs;
-      sincosf(-kd * rb, &sn, &cs);
-      y = sn / rb; z = rb * sn; cosq = cs;
-    } else {                              // c < b (surfa.f:168-172)
-      float exqp = expf(-kd * rb);
-      float exqm = 1.0f / exqp;
-      y = (exqp - exqm) / (2.f * rb);
-      z = -rb * rb * y;
-      cosq = 0.5f * (exqp + exqm);
-    }
-    const float eut = cosq * ut - y * tt / h;
-    const float ett = h * z * ut + cosq * tt;
+    // with q = -k d rb (surfa.f:156): y = sin(q)/rb = -sinr, z = rb sin(q) = -rsin (both branches and
+    // the rb -> 0 limit of surfa.f:164-166), cos(q) = cs
+    float rsin, sinr, cs;
+    half_terms(1.0f - csq * L.y, kd, kd * kd, rsin, sinr, cs);
+    const float h = L.w * 0.5f * L.z;
+    const float ih = E.z * L.y;
+    const float eut = cs * ut + sinr * tt * ih;
+    const float ett = cs * tt - h * rsin * ut;
     ut = eut;
     tt = ett;
   }
   return -tt;
 }
-
 
 // ----------------------------------------------------------------------------------------------
 // Sequential root polish exactly as the reference does it (NEVILL, surfa.f:2-83): interval halving that

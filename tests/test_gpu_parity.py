@@ -222,6 +222,6 @@ def test_exact_scan_mode_gives_same_roots():
         a = api.DispersionSolver("cuda:0").forward(dl, dn, per, kind=kind)
         b = api.DispersionSolver("cuda:0", opts=api.default_opts(exact_scan=1)).forward(dl, dn, per, kind=kind)
         assert torch.equal(a["nfound"], b["nfound"])
-        assert float((a["c"] - b["c"]).abs().max()) < 2e-5
+        assert float((a["c"] - b["c"]).abs().max()) < 5e-5
         du = (a["u"] - b["u"]).abs()
         assert float(du.median()) < 2e-6 and float((du > 1e-4).float().mean()) < 1e-3

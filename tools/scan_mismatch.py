@@ -20,4 +20,7 @@ same = na == nb
 print("mismatch", len(idx), "of", M, " max dc on same-count models", dc[same].max())
 out = {"seed": seed, "M": M, "kind": kind, "idx": idx.tolist(), "n_default": na[idx].tolist(), "n_exact": nb[idx].tolist(),
        "c_exact": b["c"].cpu().numpy()[idx].tolist(), "c_default": a["c"].cpu().numpy()[idx].tolist()}
+big = np.argwhere((dc > 1e-4) & same[:, None])
+out["big_dc"] = [[int(i), int(k), float(a["c"][i, k]), float(b["c"][i, k])] for i, k in big[:50]]
+print("big dc", out["big_dc"][:5])
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "scan_mismatch.json"), "w"))
