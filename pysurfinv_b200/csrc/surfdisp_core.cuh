@@ -552,7 +552,6 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
     double yur = 1.0, yuz = 0.0, ytz = y0tz, ytr = y0tr;
     double zur = zs_ur, zuz = zs_uz, ztz = zs_tz, ztr = zs_tr;
     Q.i0yy = Q.i0yz = Q.i0zz = Q.i1yy = Q.i1yz = Q.i1zz = Q.i2yy = Q.i2yz = Q.i2zz = 0.0;
-    const bool acc = (pass == 1);
     for (int j = dr.jlast; j >= jfirst; --j) {
       float a, b;
       mv.ab(j, a, b);
@@ -572,26 +571,31 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
       kc.h = (double)ddz;
       const StepMat sm = make_stepmat(kc);
       const int ns = (j == dr.jlast) ? dr.nlast : mv.nsub(j);
-      const double qw = (double)SD_DIV(SD_DIV(ds, 4.f), 22.5f);
-      const double dk = (double)wvno, dlam = (double)xlamb, dmu = (double)xmu, drho = (double)rho;
-      const double l2m = (double)SD_ADD(xlamb, SD_MUL(2.f, xmu));
+      const double dk = (double)wvno, dlam = (double)xlamb, dmu = (double)xmu;
+      const double dkl = dk * dlam;
+      // Boole-weighted raw sums over the knots of this layer's sub-layers (weights 7,32,12,32,7; the
+      // common factor dz/22.5 and the material constants are applied once per layer)
+      double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0, r8 = 0, r9 = 0, r10 = 0, r11 = 0;
       for (int s = 0; s < ns; ++s) {
 #pragma unroll
         for (int kk = 0; kk < 5; ++kk) {
-          if (acc) {
-            const double wq = qw * ((kk == 0 || kk == 4) ? 7.0 : ((kk == 2) ? 12.0 : 32.0));
-            const double ydur = ytr * kc.a34 - dk * yuz, yduz = (ytz + dk * dlam * yur) * kc.a12;
-            const double zdur = ztr * kc.a34 - dk * zuz, zduz = (ztz + dk * dlam * zur) * kc.a12;
-            const double rr_yy = yur * yur, rr_yz = 2.0 * yur * zur, rr_zz = zur * zur;
-            const double zz_yy = yuz * yuz, zz_yz = 2.0 * yuz * zuz, zz_zz = zuz * zuz;
-            Q.i0yy += wq * drho * (rr_yy + zz_yy); Q.i0yz += wq * drho * (rr_yz + zz_yz); Q.i0zz += wq * drho * (rr_zz + zz_zz);
-            Q.i1yy += wq * (l2m * rr_yy + dmu * zz_yy); Q.i1yz += wq * (l2m * rr_yz + dmu * zz_yz); Q.i1zz += wq * (l2m * rr_zz + dmu * zz_zz);
-            Q.i2yy += wq * (dmu * yuz * ydur - dlam * yur * yduz);
-            Q.i2yz += wq * (dmu * (yuz * zdur + zuz * ydur) - dlam * (yur * zduz + zur * yduz));
-            Q.i2zz += wq * (dmu * zuz * zdur - dlam * zur * zduz);
-          }
+          const double w = (kk == 0 || kk == 4) ? 7.0 : ((kk == 2) ? 12.0 : 32.0);
+          const double ydur = ytr * kc.a34 - dk * yuz, yduz = (ytz + dkl * yur) * kc.a12;
+          const double zdur = ztr * kc.a34 - dk * zuz, zduz = (ztz + dkl * zur) * kc.a12;
+          const double ay = w * yur, by = w * yuz, az = w * zur, bz = w * zuz;
+          r0 += ay * yur; r1 += ay * zur; r2 += az * zur;
+          r3 += by * yuz; r4 += by * zuz; r5 += bz * zuz;
+          r6 += by * ydur; r7 += by * zdur + bz * ydur; r8 += bz * zdur;
+          r9 += ay * yduz; r10 += ay * zduz + az * yduz; r11 += az * zduz;
           if (kk < 4) { rk4_step(sm, yur, yuz, ytz, ytr); rk4_step(sm, zur, zuz, ztz, ztr); }
         }
+      }
+      {
+        const double qw = (double)SD_DIV(SD_DIV(ds, 4.f), 22.5f);
+        const double qr = qw * (double)rho, l2m = (double)SD_ADD(xlamb, SD_MUL(2.f, xmu));
+        Q.i0yy += qr * (r0 + r3); Q.i0yz += 2.0 * qr * (r1 + r4); Q.i0zz += qr * (r2 + r5);
+        Q.i1yy += qw * (l2m * r0 + dmu * r3); Q.i1yz += 2.0 * qw * (l2m * r1 + dmu * r4); Q.i1zz += qw * (l2m * r2 + dmu * r5);
+        Q.i2yy += qw * (dmu * r6 - dlam * r9); Q.i2yz += qw * (dmu * r7 - dlam * r10); Q.i2zz += qw * (dmu * r8 - dlam * r11);
       }
       nsubsteps += (unsigned)ns;
     }
@@ -605,9 +609,9 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
     if (pass == 0) {
       const float ampur = (float)((xnorm * yur + zur) / bb);
       const float xtest = fabsf(ampur / ratio - 1.f);
-      if (xtest >= 0.00001f) {  // second iteration of the reference (surfa.f:1066-1069, 986-998)
-        zs_ur = 0.0 + xnorm * 1.0; zs_uz = 1.0 + xnorm * 0.0; zs_tz = z0tz + xnorm * y0tz; zs_tr = z0tr + xnorm * y0tr;
-      }
+      if (!(xtest >= 0.00001f)) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
+      // second iteration of the reference (surfa.f:986-998): solution 2 restarted from z + xnorm*y
+      zs_ur = 0.0 + xnorm * 1.0; zs_uz = 1.0 + xnorm * 0.0; zs_tz = z0tz + xnorm * y0tz; zs_tr = z0tr + xnorm * y0tr;
     }
   }
   const double ib2 = 1.0 / (bb * bb);
