@@ -514,12 +514,15 @@ int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
 
 template <int G>
 int launch_phase1(const P1Params& p, cudaStream_t st) {
-  const int threads = 128;
-  const int groups = threads / G;
   P1Params q = p;
   q.mstride = 2 * p.lpad + 2;  // +2 float4: consecutive groups start 32 B apart mod 128 B (bank spread)
+  // 128-thread CTAs (16 models) for ordinary stacks; deep stacks (up to 1000 layers, 32 KB of layer records
+  // per model) shrink the CTA until the records of its models fit in shared memory
+  int threads = 128;
+  while (threads > 32 && (size_t)(threads / G) * q.mstride * sizeof(float4) > 100 * 1024) threads /= 2;
+  const int groups = threads / G;
   size_t smem = (size_t)groups * q.mstride * sizeof(float4);
-  if (smem > 200 * 1024) return SURFDISP_EINVAL;
+  if (smem > 220 * 1024) return SURFDISP_EINVAL;
   CK(cudaFuncSetAttribute(phase1_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148, occ = 1;
   CK(cudaGetDevice(&dev));

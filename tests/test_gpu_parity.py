@@ -225,3 +225,42 @@ def test_exact_scan_mode_gives_same_roots():
         assert float((a["c"] - b["c"]).abs().max()) < 5e-5
         du = (a["u"] - b["u"]).abs()
         assert float(du.median()) < 2e-6 and float((du > 1e-4).float().mean()) < 1e-3
+
+
+def test_config4_deep_stacks_ndiv_zero(solver):
+    """BASELINE config 4 shape: ~150 fine layers, Rayleigh 10-150 s.  n >= 101 clamps ndiv to 99/(n-1) = 0
+    (no sub-division, surfa.f:783-787)."""
+    lay, nl = synth.crustal_models(300, seed=71, n_crust=15, n_mantle=130, zmax=400.0)
+    assert lay.shape[2] == 147
+    per = np.arange(10.0, 151.0, 10.0, dtype=np.float32)
+    g = _gpu(solver, lay, nl, per, 2)
+    _check(g, lay, nl, per, 2, max_noisy_frac=0.02)
+
+
+def test_very_deep_stack_and_many_periods(solver):
+    """Shared-memory sizing path: 500-layer stacks (CTA shrinks) and the maximum of 200 periods."""
+    lay, nl = synth.crustal_models(24, seed=72, n_crust=60, n_mantle=438, zmax=600.0)
+    assert lay.shape[2] == 500
+    per = np.linspace(8.0, 100.0, 200).astype(np.float32)
+    for kind in (2, 1):
+        g = _gpu(solver, lay, nl, per, kind)
+        c0, u0, nf0, st0 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+        ok = st0 != 3
+        assert np.array_equal(g["nfound"][ok], nf0[ok])
+        assert np.abs(g["c"] - c0)[ok].max() <= TOL
+        assert np.median(np.abs(g["u"] - u0)[ok]) < 1e-5
+
+
+def test_config3_joint_rayleigh_love_anisotropy(solver):
+    """BASELINE config 3: Love on Vsh, Rayleigh on Vsv of the same stacks (radial anisotropy is outside the
+    reference; parity is per wave type)."""
+    lay, nl = synth.crustal_models(600, seed=73)
+    rng = np.random.default_rng(73)
+    xi = 1.0 + rng.uniform(-0.05, 0.05, (600, 1)).astype(np.float32)
+    lay_sh = lay.copy()
+    lay_sh[1, :, 16:] *= xi          # Vsh = xi * Vsv in the mantle
+    per = synth.log_periods(24)
+    gr = _gpu(solver, lay, nl, per, 2)
+    gl = _gpu(solver, np.ascontiguousarray(lay_sh), nl, per, 1)
+    _check(gr, lay, nl, per, 2)
+    _check(gl, np.ascontiguousarray(lay_sh), nl, per, 1)
