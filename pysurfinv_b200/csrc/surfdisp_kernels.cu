@@ -383,7 +383,11 @@ struct P2Params {
   PeriodTab tab;
 };
 
-__global__ void __launch_bounds__(256) phase2_kernel(const __grid_constant__ P2Params p) {
+#ifndef P2_THREADS
+#define P2_THREADS 128
+#define P2_MINBLK 3
+#endif
+__global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __grid_constant__ P2Params p) {
   extern __shared__ float4 smem[];
   float* sc = reinterpret_cast<float*>(smem);
   const int K = p.K;
@@ -397,9 +401,8 @@ __global__ void __launch_bounds__(256) phase2_kernel(const __grid_constant__ P2P
     for (int i = threadIdx.x; i < n4; i += blockDim.x) smem[i] = src[i];
   }
   __syncthreads();
-  const int t = threadIdx.x;
   unsigned long long nsub = 0;
-  if (t < nmod * K) {
+  for (int t = threadIdx.x; t < nmod * K; t += blockDim.x) {
     const int ml = t / K, k = t - ml * K;
     const int model = model0 + ml;
     float* urow = p.u_out + (size_t)model * K;
@@ -599,13 +602,13 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
     p2.ndiv_cap = (kind == 2) ? o.ndiv_cap_rayleigh : o.ndiv_cap_love;
     p2.tab = p1.tab;
     const size_t per_model = (size_t)NCONST * w.lpad * sizeof(float);
-    int mpb = 256 / n_periods;
+    int mpb = P2_THREADS / n_periods;
     if (mpb < 1) mpb = 1;
     while (mpb > 1 && mpb * per_model > 96 * 1024) --mpb;
     if (mpb * per_model > 200 * 1024) return SURFDISP_EINVAL;
     p2.mpb = mpb;
     int threads = round_up(mpb * n_periods, 32);
-    if (threads > 256) threads = 256;  // K > 256 cannot happen (K <= 200)
+    if (threads > P2_THREADS) threads = P2_THREADS;
     size_t smem = mpb * per_model;
     CK(cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (n_models + mpb - 1) / mpb;
