@@ -1,0 +1,165 @@
+"""Stack templates: the reference's layered-model description (YAML/dict settings of reference
+models.py:41-51 + layers.py:573-604) compiled into a fixed-size record the device-side model builder
+(``surfdisp_build_stacks``) consumes, plus the free-parameter table of the Monte-Carlo walk.
+
+A setting is an ordered dict ``{layerType: parm, ..., 'Info': {...}}`` exactly like the reference's.  Every
+numeric entry written as a Brownian spec -- ``[v, 'abs'|'abs_pos'|'rel'|'rel_pos', width, step]`` or
+``[v, vmin, vmax, step]`` (layers.py:583-598) -- becomes one free parameter; the parameter order is the order
+of ``MCinv._brownians`` (models.py:227-240), i.e. the column order of ``mcTrack`` rows (point.py:57,73).
+Supported layer types: Sediment, Crust, Mantle/OceanMantle, OceanWater, OceanSediment, OceanCrust,
+OceanSedimentCascadia, ReferenceMantle (``Info.refLayer``).  The thermal OceanMantleHybrid is out of scope
+(SURVEY 8 f-4).
+"""
+import ctypes as C
+
+import numpy as np
+
+MAX_GROUPS = 8
+MAX_COEF = 8
+
+# group kinds (Vs profile)                       reference class
+G_WATER, G_CONST, G_LINEAR, G_BSPLINE, G_CASCADIA, G_REFMANTLE = 0, 1, 2, 3, 4, 5
+# fine-layer rules
+N_FIXED, N_CRUST, N_OCRUST = 0, 1, 2
+# density rules
+R_QUARTIC, R_OCEAN, R_MANTLE, R_CONST = 0, 1, 2, 3
+
+
+class Group(C.Structure):
+    _fields_ = [("kind", C.c_int), ("nfine_rule", C.c_int), ("nfine", C.c_int), ("h_mode", C.c_int),
+                ("h_param", C.c_int), ("ncoef", C.c_int), ("rho_rule", C.c_int), ("_pad", C.c_int),
+                ("v_param", C.c_int * MAX_COEF), ("v_fixed", C.c_double * MAX_COEF),
+                ("h_fixed", C.c_double), ("vp_a", C.c_double), ("vp_b", C.c_double), ("rho_const", C.c_double),
+                ("qs", C.c_double), ("slope", C.c_double)]
+
+
+class StackTemplateC(C.Structure):
+    _fields_ = [("ngroups", C.c_int), ("nparams", C.c_int), ("topo", C.c_double), ("groups", Group * MAX_GROUPS)]
+
+
+_TYPES = {
+    # name: (kind, nfine_rule, nfine, vp_a, vp_b, rho_rule, rho_const, qs)
+    "Sediment": (None, N_FIXED, 1, 2.0, 0.0, R_QUARTIC, 0.0, 80.0),                    # layers.py:139-156
+    "Crust": (G_BSPLINE, N_CRUST, 0, 1.80, 0.0, R_QUARTIC, 0.0, 600.0),                # layers.py:158-189
+    "Mantle": (G_BSPLINE, N_CRUST, 0, 1.76, 0.0, R_MANTLE, 0.0, 150.0),                # layers.py:239-265
+    "OceanMantle": (G_BSPLINE, N_CRUST, 0, 1.76, 0.0, R_MANTLE, 0.0, 150.0),
+    "OceanWater": (G_WATER, N_FIXED, 1, 0.0, 1.475, R_CONST, 1.027, 10000.0),          # layers.py:191-204
+    "OceanSediment": (G_CONST, N_FIXED, 1, 1.23, 1.28, R_OCEAN, 0.0, 80.0),            # layers.py:206-219
+    "OceanSedimentCascadia": (G_CASCADIA, N_FIXED, 1, 1.23, 1.28, R_OCEAN, 0.0, 80.0), # layers.py:289-295
+    "OceanCrust": (None, N_OCRUST, 0, 1.8, 0.0, R_OCEAN, 0.0, 350.0),                  # layers.py:221-237
+}
+
+
+def _is_spec(v):
+    if isinstance(v, (list, tuple)) and len(v) >= 2:
+        if v[1] in ("fixed", "total", "abs", "abs_pos", "rel", "rel_pos"):
+            return True
+        if len(v) == 4 and all(isinstance(x, (int, float)) for x in v):
+            return True
+    return False
+
+
+class Param:
+    """One free parameter with the bounds/step of BrownianVar / BrownianVarMC (brownian.py:3-68)."""
+
+    def __init__(self, spec, where):
+        v = float(spec[0])
+        if spec[1] in ("abs", "abs_pos", "rel", "rel_pos"):
+            w = float(spec[2])
+            lo, hi = (v - w, v + w) if spec[1].startswith("abs") else (v * (1 - w / 100), v * (1 + w / 100))
+            if spec[1].endswith("_pos"):
+                lo, hi = max(lo, 0.0), max(hi, 0.0)
+            step = float(spec[3])
+        else:
+            lo, hi, step = float(spec[1]), float(spec[2]), float(spec[3])
+        self.v0, self.vmin, self.vmax = v, lo, hi
+        self.step = abs(hi - lo) / 2 if step > abs(hi - lo) / 2 else step
+        self.where = where
+
+    def __repr__(self):
+        return "Param(%s v=%g [%g,%g] step=%g)" % (self.where, self.v0, self.vmin, self.vmax, self.step)
+
+
+class StackTemplate:
+    def __init__(self, setting):
+        self.params = []
+        self.groups = []
+        info = dict(setting.get("Info", {}))
+        self.topo = float(info.get("topo", 0.0))
+        for name, parm in setting.items():
+            if name == "Info":
+                continue
+            if name not in _TYPES:
+                raise ValueError("layer type %r is not supported by the device-side builder" % name)
+            self.groups.append(self._group(name, dict(parm)))
+        if info.get("refLayer", False):     # models.py:111-113: H = 300 km, slope 0.35/200
+            g = self._blank()
+            g.kind, g.nfine_rule, g.nfine, g.h_mode, g.h_param, g.h_fixed = G_REFMANTLE, N_FIXED, 20, 0, -1, 300.0
+            g.vp_a, g.vp_b, g.rho_rule, g.qs, g.slope = 1.76, 0.0, R_MANTLE, 150.0, 0.35 / 200
+            self.groups.append(g)
+        if len(self.groups) > MAX_GROUPS:
+            raise ValueError("at most %d layer groups" % MAX_GROUPS)
+
+    @staticmethod
+    def _blank():
+        g = Group()
+        for i in range(MAX_COEF):
+            g.v_param[i] = -1
+        g.h_param = -1
+        return g
+
+    def _value(self, v, where):
+        """Returns (param_index, fixed_value)."""
+        if _is_spec(v):
+            if v[1] in ("fixed", "total"):
+                return -1, float(v[0])
+            self.params.append(Param(v, where))
+            return len(self.params) - 1, float(v[0])
+        return -1, float(v)
+
+    def _group(self, name, parm):
+        kind, nrule, nfine, vp_a, vp_b, rrule, rconst, qs = _TYPES[name]
+        g = self._blank()
+        g.nfine_rule, g.nfine, g.vp_a, g.vp_b, g.rho_rule, g.rho_const, g.qs = nrule, nfine, vp_a, vp_b, rrule, rconst, qs
+        # parameter order follows the parm dict order, like MCinv._brownians
+        for key, val in parm.items():
+            if key in ("H", "BottomDepth"):
+                g.h_mode = 0 if key == "H" else 1
+                g.h_param, g.h_fixed = self._value(val, "%s.%s" % (name, key))
+            elif key == "Vs":
+                vals = val if (isinstance(val, (list, tuple)) and not _is_spec(val)) else [val]
+                if len(vals) > MAX_COEF:
+                    raise ValueError("at most %d Vs coefficients per group" % MAX_COEF)
+                g.ncoef = len(vals)
+                for i, x in enumerate(vals):
+                    g.v_param[i], g.v_fixed[i] = self._value(x, "%s.Vs[%d]" % (name, i))
+        if kind is None:   # Sediment / OceanCrust: constant or linear (layers.py:146-149, 228-231)
+            kind = G_LINEAR if g.ncoef == 2 else G_CONST
+            if g.ncoef not in (1, 2):
+                raise ValueError("%s takes one Vs or [top, bottom]" % name)
+        g.kind = kind
+        return g
+
+    @property
+    def nparams(self):
+        return len(self.params)
+
+    def to_c(self):
+        t = StackTemplateC()
+        t.ngroups, t.nparams, t.topo = len(self.groups), self.nparams, self.topo
+        for i, g in enumerate(self.groups):
+            t.groups[i] = g
+        return t
+
+    def start_values(self):
+        return np.array([p.v0 for p in self.params], dtype=np.float32)
+
+    def bounds(self):
+        return (np.array([p.vmin for p in self.params], np.float32), np.array([p.vmax for p in self.params], np.float32),
+                np.array([p.step for p in self.params], np.float32))
+
+    def max_layers(self):
+        n = 0
+        for g in self.groups:
+            n += {N_FIXED: g.nfine, N_CRUST: 60, N_OCRUST: 10}[g.nfine_rule]
+        return n

@@ -1,0 +1,54 @@
+"""CPU tier: the numpy restatement of the reference's model assembly against fixtures produced by running the
+reference's own classes (tests/golden/make_golden_layers.py), and the template compiler."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import model_builder as MB
+from pysurfinv_b200 import stack as S
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "layers_reference.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def test_bspline_bases_match_reference(gold):
+    for b in gold["bspline"]:
+        ref = np.array(b["basis"])
+        mine = MB.bspl_basis(b["N"] + 1, b["nbasis"])
+        assert mine.shape == ref.shape
+        np.testing.assert_allclose(mine, ref, rtol=0, atol=2e-13)
+
+
+def test_stacks_match_reference(gold):
+    for st in gold["stacks"]:
+        t = S.StackTemplate(st["setting"])
+        assert t.nparams == 0
+        h, vs, vp, rho, qs = MB.build_one(t, np.zeros(0))
+        assert len(h) == len(st["h"])
+        for mine, key in ((h, "h"), (vs, "vs"), (vp, "vp"), (rho, "rho"), (qs, "qs")):
+            np.testing.assert_allclose(mine, np.array(st[key]), rtol=1e-11, atol=1e-11)
+
+
+def test_template_parameter_order_and_bounds():
+    setting = {"Sediment": {"H": [2.0, "abs_pos", 1.5, 0.1], "Vs": [1.5, 0.8, 2.6, 0.05]},
+               "Crust": {"H": [30.0, "abs", 10.0, 1.0], "Vs": [[3.3, "rel", 10, 0.02], [3.5, "fixed"], [3.7, "rel", 10, 0.02], 3.9]},
+               "Mantle": {"BottomDepth": 200.0, "Vs": [[4.4, "abs", 0.3, 0.02], [4.3, "abs", 0.3, 0.02], [4.5, "abs", 0.3, 5.0]]},
+               "Info": {"refLayer": True}}
+    t = S.StackTemplate(setting)
+    where = [p.where for p in t.params]
+    assert where == ["Sediment.H", "Sediment.Vs[0]", "Crust.H", "Crust.Vs[0]", "Crust.Vs[2]", "Mantle.Vs[0]", "Mantle.Vs[1]", "Mantle.Vs[2]"]
+    lo, hi, step = t.bounds()
+    assert np.allclose(lo[:3], [0.5, 0.8, 20.0]) and np.allclose(hi[:3], [3.5, 2.6, 40.0])
+    assert np.isclose(lo[3], 3.3 * 0.9) and np.isclose(step[7], 0.3)      # step clamped to half the range (brownian.py:8)
+    assert len(t.groups) == 4 and t.groups[3].kind == S.G_REFMANTLE and t.max_layers() == 1 + 60 + 60 + 20
+    c = t.to_c()
+    assert c.ngroups == 4 and c.nparams == 8 and c.groups[1].v_param[1] == -1 and abs(c.groups[1].v_fixed[3] - 3.9) < 1e-12
+    lay, nl = MB.build_stacks(t, t.start_values()[None, :], 96)
+    assert nl[0] == 1 + 15 + 60 + 20 and abs(lay[3, 0, :nl[0]].sum() - 500.0) < 1e-3
