@@ -9,6 +9,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include "sd_libm.cuh"
 
 #if defined(__CUDACC__)
 #define SD_HD __host__ __device__ __forceinline__
@@ -57,11 +58,11 @@ struct LayerRec { float4 q0, q1; };
 // ----------------------------------------------------------------------------------------------
 // Model preparation.  flat1.f:33-69 evaluated once per model: radii by sequential float32 prefix sum,
 // velocity factor dif(i), density factor, flattened thickness, plus the factors layer i would get if it
-// were the (effective) half-space.  logs and powers go through double to be as close to a correctly
-// rounded float result as possible (the reference uses glibc logf/powf).
+// were the (effective) half-space.  logs and powers follow glibc's logf / powf bit by bit (sd_libm.cuh):
+// r_i**p - r_(i+1)**p cancels 3-4 digits, so even a 1-ulp difference in a power shows up as 1e-5 km/s in c.
 // Arrays are indexed [0..n-1]; out rows have stride ld.
-SD_HD float sd_logf_cr(float x) { return (float)log((double)x); }
-SD_HD float sd_powf_cr(float x, float p) { return (float)pow((double)x, (double)p); }
+SD_HD float sd_logf_cr(float x) { return sdm::logf_glibc(x); }
+SD_HD float sd_powf_cr(float x, float p) { return sdm::powf_glibc(x, p); }
 
 SD_HD void prep_model(int n, int kind, int flatten, const float* a, const float* b, const float* rho,
                       const float* d, const float* qs, float* out, int ld) {
@@ -291,6 +292,143 @@ SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const f
     const float bb1 = h11 * b1 + h12 * b2 + 2.f * h13 * b3 + h14 * b4 + h15 * b5;
     return (start == 1) ? -bb1 : bb1;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Rayleigh secular function, adjoint form.  The dispersion function and the two ellipticity sweeps of the
+// reference are h^T P e1, h^T P e2 and h^T P e3 with the same layer product P = A(mmax-1) ... A(1) and the
+// same half-space row h (surfa.f:341-354); propagating the ROW vector r^T = h^T A(mmax-1) ... upwards
+// (r <- r A(m), m = mmax-1 .. 1) yields all three from one sweep: Delta = -r1, ellipticity = 0.5 r3 / r2
+// with (e2, e3) = (r2, r3) returned separately (the caller interpolates them to the root before dividing)
+// (surfa.f:360-363).  Same 25 multiply-adds per layer as the column form, but every trial velocity of the
+// root polish now carries its ellipticity, so the two extra sweeps per period disappear.
+// A liquid top layer (surfa.f:219-251) closes the sweep: the ellipticity is taken below it (the reference
+// skips liquid layers there, surfa.f:220), the dispersion function includes it.  Liquid layers deeper in the
+// stack get dispersion-function semantics; for such stacks (e2, e3) must come from a second sweep with
+// ell_only = true, which skips every liquid layer like the reference's ellipticity sweeps do.
+SD_HD float rayleigh_adjoint(float c, float T, int mmax, const float4* q0, const float4* q1, bool ell_only,
+                             float& e2, float& e3) {
+  const float wvno = SD_TWOPI / (c * T);
+  const float csq = c * c;
+  const float icsq = 1.0f / csq;
+  const int last = mmax - 1;
+  float r1, r2, r3, r4, r5;
+  {
+    const float4 L = q0[last];
+    const float4 E = q1[last];
+    const float arga = 1.0f - csq * L.x;
+    const float argb = 1.0f - csq * L.y;
+    float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
+    float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
+    const float g = L.z * icsq;
+    const float g1 = g - 1.0f;
+    const float pp = E.w;
+    const float sss = 0.5f * L.z;
+    const float ppp = pp * pp;
+    const float rhp = L.w * pp;
+    const float gra = g * ra;
+    const float g1s = g1 * g1;
+    const float rba = rb - 1.0f / ra;
+    const float h12 = rhp * pp;
+    r1 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
+    r3 = 2.f * (-rb / h12 + g1 / h12 / gra);
+    r4 = rb / h12 / gra;
+    r5 = rba / rhp / rhp / csq / g;
+    r2 = -1.0f / g / h12;
+  }
+  for (int m = last - 1; m >= 0; --m) {
+    const float4 L = q0[m];
+    const float4 E = q1[m];
+    const float kd = wvno * E.x;
+    const float kd2 = kd * kd;
+    float rsinp, sinpr, cosp;
+    half_terms(1.0f - csq * L.x, kd, kd2, rsinp, sinpr, cosp);
+    if (L.y == 0.f) {
+      if (ell_only) continue;
+      const float a21 = L.w * csq * sinpr;
+      if (m == 0) {
+        e2 = r2; e3 = r3;
+        return -(r1 * cosp + r2 * a21);
+      }
+      const float n1 = r1 * cosp + r2 * a21, n4 = -r5 * a21, n5 = r5 * cosp;
+      r1 = n1; r2 = 0.f; r3 = 0.f; r4 = n4; r5 = n5;
+      continue;
+    }
+    float rsinq, sinqr, cosq;
+    half_terms(1.0f - csq * L.y, kd, kd2, rsinq, sinqr, cosq);
+    const float g = L.z * icsq;
+    const float g1 = g - 1.0f;
+    const float rhoc = L.w * csq;
+    const float irhoc = E.z * icsq;
+    const float rr = rsinp * rsinq, ss = sinpr * sinqr, cc = cosp * cosq;
+    const float rs1 = rsinp * cosq, rs2 = sinqr * cosp, rs3 = sinpr * cosq, rs4 = rsinq * cosp;
+    const float a24 = sinpr * rsinq, a42 = rsinp * sinqr;
+    const float gm = g + g1, gs = g * g, g1s = g1 * g1, gg1 = g * g1, ccm = 1.0f - cc;
+    const float suu = gs * rr + g1s * ss;
+    const float w = 2.f * gg1 * ccm + suu;
+    const float a11 = cc - w;
+    const float a33 = 1.f + 2.f * w;
+    const float a12 = -(rs1 + rs2) * irhoc;
+    const float a14 = (rs3 + rs4) * irhoc;
+    const float a13h = -(gm * ccm + g1 * ss + g * rr) * irhoc;
+    const float a15 = (2.f * ccm + rr + ss) * (irhoc * irhoc);
+    const float a21 = rhoc * (g1s * rs3 + gs * rs4);
+    const float a41 = -rhoc * (g1s * rs2 + gs * rs1);
+    const float a23h = g * rs4 + g1 * rs3;
+    const float a32 = g1 * rs2 + g * rs1;
+    const float a31 = rhoc * (gg1 * gm * ccm + (g1s * g1) * ss + (gs * g) * rr);
+    const float a51 = (rhoc * rhoc) * (2.f * (gg1 * gg1) * ccm + (gs * gs) * rr + (g1s * g1s) * ss);
+    // r <- r A with A the matrix of surfa.f:326-330 (rows as in rayleigh_sweep)
+    const float n1 = r1 * a11 + r2 * a21 + r3 * a31 + r4 * a41 + r5 * a51;
+    const float n2 = r1 * a12 + r2 * cc + r3 * a32 + r4 * a42 - r5 * a41;
+    const float n3 = 2.f * (r1 * a13h + r2 * a23h - r4 * a32 + r5 * a31) + r3 * a33;
+    const float n4 = r1 * a14 + r2 * a24 - r3 * a23h + r4 * cc - r5 * a21;
+    const float n5 = r1 * a15 - r2 * a14 + r3 * a13h - r4 * a12 + r5 * a11;
+    r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5;
+  }
+  e2 = r2; e3 = r3;
+  return -r1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Root of a sampled function by inverse polynomial interpolation: Neville's tableau for x(y) at y = 0 through
+// 6 points (x relative to some nearby origin, y the secular-function samples, ordered by x).  e6 uses all six,
+// e4 the four contiguous points starting at i4 (0..2), which is a level-3 entry of the same tableau.
+SD_HD void inv_interp6(const float* xin, const float* y, int i4, float& e4, float& e6) {
+  float x[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 6; ++i) x[i] = xin[i];
+  float l3[3] = {0.f, 0.f, 0.f};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int lev = 1; lev < 6; ++lev) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6 - lev; ++i) x[i] = (y[i + lev] * x[i] - y[i] * x[i + 1]) / (y[i + lev] - y[i]);
+    if (lev == 3) { l3[0] = x[0]; l3[1] = x[1]; l3[2] = x[2]; }
+  }
+  e6 = x[0];
+  e4 = (i4 == 0) ? l3[0] : ((i4 == 1) ? l3[1] : l3[2]);
+}
+
+// 4-point Lagrange weights at x (abscissae xs[0..3])
+SD_HD void lagrange4(const float* xs, float x, float* w) {
+  const float d0 = x - xs[0], d1 = x - xs[1], d2 = x - xs[2], d3 = x - xs[3];
+  w[0] = d1 * d2 * d3 / ((xs[0] - xs[1]) * (xs[0] - xs[2]) * (xs[0] - xs[3]));
+  w[1] = d0 * d2 * d3 / ((xs[1] - xs[0]) * (xs[1] - xs[2]) * (xs[1] - xs[3]));
+  w[2] = d0 * d1 * d3 / ((xs[2] - xs[0]) * (xs[2] - xs[1]) * (xs[2] - xs[3]));
+  w[3] = d0 * d1 * d2 / ((xs[3] - xs[0]) * (xs[3] - xs[1]) * (xs[3] - xs[2]));
+}
+
+// Offsets (in units of s0) of the G = 8 points of a refinement round around the root estimate
+SD_HD float refine_offset8(int g) {
+  const int h = (g >= 4) ? g - 4 : 3 - g;
+  const float m = (h == 0) ? 0.5f : ((h == 1) ? 1.5f : ((h == 2) ? 4.f : 12.f));
+  return (g >= 4) ? m : -m;
 }
 
 // ----------------------------------------------------------------------------------------------

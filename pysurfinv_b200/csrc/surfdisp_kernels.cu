@@ -91,10 +91,16 @@ struct P1Params {
   PeriodTab tab;
 };
 
-// One copy of the secular-function loop for all call sites (scan, polish, sequential polish, ellipticity):
-// inlining it five times made the kernel ~95 KB of SASS and the warps stalled on instruction fetch.
-__device__ __noinline__ float secular(int kind, float c, float T, int mm, const float4* q0, const float4* q1, int start) {
-  return (kind == 2) ? rayleigh_sweep(c, T, mm, q0, q1, start) : love_sweep(c, T, mm, q0, q1);
+// One copy of the secular-function loop for all call sites (window, refinement, scan, polish, ellipticity):
+// inlining it at every site made the kernel ~95 KB of SASS and the warps stalled on instruction fetch.
+// Returns (Delta, e2, e3, -): Rayleigh sweeps are done in the adjoint form, which carries the two
+// ellipticity minors along with the dispersion function.
+__device__ __noinline__ float4 secular(int kind, float c, float T, int mm, const float4* q0, const float4* q1,
+                                       int ell_only) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kind == 2) r.x = rayleigh_adjoint(c, T, mm, q0, q1, ell_only != 0, r.y, r.z);
+  else r.x = love_sweep(c, T, mm, q0, q1);
+  return r;
 }
 
 template <int G>
@@ -102,14 +108,21 @@ __device__ __forceinline__ float gshfl(unsigned mask, float v, int src) { return
 template <int G>
 __device__ __forceinline__ int gshfl(unsigned mask, int v, int src) { return __shfl_sync(mask, v, src, G); }
 
+struct SamplePt { float c, d, e2, e3; };
+
+constexpr float kInterpTol = 1.0e-5f;   // agreement of the 4- and 6-point root estimates that ends the refinement
+constexpr float kWindowTol = 5.0e-7f;   // same, on the 0.01 km/s grid of the window round (agreement there is a weak error bound)
+constexpr float kBracketTol = 2.0e-5f;  // bracket width below which a secant step is final
+
 template <int G>
 __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ P1Params p) {
+  static_assert(G == 8, "the refinement rounds are laid out for 8 lanes per model");
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
-  const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  const unsigned gmask = ((1u << G) - 1u) << gbase;
+  const unsigned gbits = (1u << G) - 1u;
   const int grp = threadIdx.x / G;
   float4* q0 = smem + (size_t)grp * p.mstride;
   float4* q1 = q0 + p.lpad;
@@ -145,9 +158,17 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
       if (b0 < 0.1f) c1 = 0.5f;
     }
+    // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks
+    bool mid_liquid = false;
+    {
+      bool l = false;
+      for (int i = 1 + gl; i < n; i += G) l |= !(cst[C_BREF * ld + i] > 0.f);
+      mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
+    }
     int mm = n;        // reference COMMON mmax carried from period to period
     int nfound = 0, flag = 0;
-    float c_prev = 0.f, c_prev2 = 0.f;
+    bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
+    float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f;
     for (int k = 0; k < K; ++k) {
       const float T = p.tab.per[k];
       const float lt = p.tab.lt[k];
@@ -167,187 +188,249 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       __syncwarp(gmask);
       if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
       const float b_top = q1[0].y;
-      // ---- scan (calcul.f:155-167): first sign change of the secular function on the grid c1 + i*dc.
-      // Coarse-to-fine: the G lanes evaluate every S-th grid point (S = G); the first coarse interval with
-      // an event is then resolved by its S-1 interior points in one more round.  S = 1 (exact_scan, or a
-      // start below 0.8*b(1) where the reference's stop test fires on the first step) is the plain scan.
-      // The coarse scan cannot see two roots inside one coarse interval (fundamental and first overtone
-      // osculate for thick slow sediments at short periods).  Guard: the first two periods are scanned point
-      // by point; later ones are re-scanned point by point whenever the coarse result fails or jumps above
-      // the log-period extrapolation of the previous two roots (a skipped pair lands on a much higher mode).
-      const int mm_in = mm, flag_in = flag;
-      float croot = 0.f;
-      bool found = false, failed = false, lstop = false;
-      for (int attempt = 0; attempt < 2; ++attempt) {
-      mm = mm_in; flag = flag_in; found = false; failed = false; lstop = false; croot = 0.f;
-      const bool coarse = !(p.exact_scan || k < 2 || attempt == 1);
-      float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, xn = 0.f, yn = 0.f;
-      int mnew = mm;
-      bool have_n = false;
-      {
-        const float c_1 = SD_ADD(c1, p.dc);
-        int S = (!coarse || c_1 < 0.8f * b_top) ? 1 : G;
-        float cbase = c1, cP = 0.f, dP = 0.f;
-        bool have_prev = false;
-        for (int round = 0; round < 4096; ++round) {
-          float cj = cbase;
-          for (int t = 0; t < gl * S; ++t) cj = SD_ADD(cj, p.dc);
-          int mj = layer_drop(cj, T, p.fact, n, q1);
-          float dj = secular(p.kind, cj, T, mj, q0, q1, 1);
-          my_steps += (unsigned)(mj - 1); my_sweeps += 1;
-          float dp = __shfl_up_sync(gmask, dj, 1, G);
-          float cp = __shfl_up_sync(gmask, cj, 1, G);
-          if (gl == 0) { dp = dP; cp = cP; }
-          const bool hasp = (gl > 0) || have_prev;
-          bool change = hasp && (signbit(dp) != signbit(dj));
-          bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
-          // above the half-space velocity the secular function can change sign twice inside one coarse
-          // interval (kink at c = b(mmax)): such intervals are resolved point by point
-          const bool risky = hasp && S > 1 && !(cj < q1[mj - 1].y);
-          unsigned ev = (__ballot_sync(gmask, change || stop || risky) >> gbase) & gbits;
-          if (!ev) {
-            cP = gshfl<G>(gmask, cj, G - 1);
-            dP = gshfl<G>(gmask, dj, G - 1);
-            mnew = gshfl<G>(gmask, mj, G - 1);
-            have_prev = true;
-            cbase = cP;
-            for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, p.dc);
-            if (round == 4095) { failed = true; flag |= SURFDISP_F_SCAN_LIMIT; }
-            continue;
-          }
-          int j = __ffs(ev) - 1;
-          if (S > 1) {
-            // fine round: lanes 0..G-2 take the interior grid points, lane G-1 keeps the coarse end point
-            const float c_hi = gshfl<G>(gmask, cj, j), d_hi = gshfl<G>(gmask, dj, j);
-            const int m_hi = gshfl<G>(gmask, mj, j);
-            const float c_lo = gshfl<G>(gmask, cp, j), d_lo = gshfl<G>(gmask, dp, j);
-            if (gl < G - 1) {
-              cj = c_lo;
-              for (int t = 0; t <= gl; ++t) cj = SD_ADD(cj, p.dc);
-              mj = layer_drop(cj, T, p.fact, n, q1);
-              dj = secular(p.kind, cj, T, mj, q0, q1, 1);
-              my_steps += (unsigned)(mj - 1); my_sweeps += 1;
-            } else { cj = c_hi; dj = d_hi; mj = m_hi; }
-            dp = __shfl_up_sync(gmask, dj, 1, G);
-            cp = __shfl_up_sync(gmask, cj, 1, G);
-            if (gl == 0) { dp = d_lo; cp = c_lo; }
-            change = signbit(dp) != signbit(dj);
-            stop = !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
-            ev = (__ballot_sync(gmask, change || stop) >> gbase) & gbits;
-            if (!ev) {  // only the 'risky' flag fired: go on from the end of this interval with the plain scan
-              S = 1; cP = c_hi; dP = d_hi; mnew = m_hi; have_prev = true; cbase = SD_ADD(c_hi, p.dc);
-              continue;
-            }
-            j = __ffs(ev) - 1;
-            // a third point next to the bracket for the first root estimate
-            const int jb = (j >= 1) ? j - 1 : 0, ja = (j < G - 1) ? j + 1 : G - 1;
-            const float xb = gshfl<G>(gmask, cp, jb), yb = gshfl<G>(gmask, dp, jb);   // seq point before lo
-            const float xa = gshfl<G>(gmask, cj, ja), ya = gshfl<G>(gmask, dj, ja);   // seq point after hi
-            const float d_at_hi = gshfl<G>(gmask, dj, j), d_at_lo = gshfl<G>(gmask, dp, j);
-            have_n = false;
-            if (j >= 1) { xn = xb; yn = yb; have_n = true; }
-            if (j < G - 1 && (!have_n || fabsf(d_at_hi) < fabsf(d_at_lo))) { xn = xa; yn = ya; have_n = true; }
-          }
-          found = gshfl<G>(gmask, (int)change, j) != 0;
-          lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
-          dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
-          mnew = gshfl<G>(gmask, mj, j);
-          failed = !found;
-          break;
+      float croot = 0.f, ratio = 0.f;
+      bool found = false, lstop = false, have_ratio = false, fast_done = false;
+
+      // ---- fast path (every period after the first, unless exact_scan).  The reference scans
+      // c1, c1+dc, ... for the first sign change (calcul.f:155-167) and polishes inside that bracket
+      // (NEVILL, surfa.f:2-83).  The root it ends on is the fundamental-mode root; consecutive periods move
+      // it by a few grid steps, so the G lanes evaluate the G grid points around the log-period extrapolation
+      // of the previous roots.  The window is accepted when c1 itself, a point half way and the lowest window
+      // point have the same sign (no odd number of roots was skipped; a model whose root ever leaves the
+      // extrapolation by more than 0.1 km/s -- mode hopping -- is scanned point by point from then on), none
+      // of the reference's stop tests fires up to the bracket and the half-space velocity (kink of the secular
+      // function) is not nearby; anything else goes to the point-by-point path below.  All window points are evaluated on the window's deepest
+      // truncation (layer dropping, surfa.f:92-106) so that they sample ONE smooth function -- each
+      // truncation depth scales the unnormalised secular function differently but has the same root to
+      // ~1e-10 -- and the root is taken by inverse polynomial interpolation; if the 4- and 6-point estimates
+      // disagree, G more points are clustered around the estimate and the test is repeated.
+      float c_pred = c_prev;
+      if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
+      else if (k >= 2) {
+        // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
+        const float x0 = p.tab.lt[k - 1], x1 = p.tab.lt[k - 2], x = lt;
+        c_pred = c_prev + (c_prev - c_prev2) * ((x - x0) / (x0 - x1));
+        if (k >= 3) {
+          const float x2 = p.tab.lt[k - 3];
+          const float d01 = (c_prev - c_prev2) / (x0 - x1), d12 = (c_prev2 - c_prev3) / (x1 - x2);
+          c_pred += (d01 - d12) / (x0 - x2) * (x - x0) * (x - x1);
         }
       }
-      mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
-      if (found) {
-        // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83).
-        // Fast path: G points clustered geometrically (1,4,16,64 x delta) around the inverse-quadratic /
-        // secant estimate; ends when the bracket is <= 2e-5 (one secant step then lands inside float32
-        // noise).  Careful path (half-space velocity within a step of the bracket, where a kink can put
-        // several roots in one bracket): uniform G-section whose first round counts the sign changes and
-        // hands over to the reference's own sequential bisection/Neville sequence if there are several.
-        const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
-        const float b_hs = q1[mm - 1].y;
-        const bool careful = !coarse || (b_hs > lo - 0.011f && b_hs < hi + 0.011f);
-        bool multi = false;
-        for (int it = 0; it < 16 && (hi - lo) > 2.0e-5f; ++it) {
-          const float w = hi - lo;
-          float pj;
-          if (careful || it >= 4) {
-            pj = lo + (float)(gl + 1) * (w / (float)(G + 1));
-          } else {
-            const float den = dhi - dlo;
-            float e = (den != 0.f) ? lo - dlo * w / den : 0.5f * (lo + hi);
-            if (it == 0 && have_n) {
-              const float d01 = dlo - dhi, d02 = dlo - yn, d12 = dhi - yn;
-              if (d01 != 0.f && d02 != 0.f && d12 != 0.f) {
-                const float q = lo * (dhi * yn) / (d01 * d02) - hi * (dlo * yn) / (d01 * d12) + xn * (dlo * dhi) / (d02 * d12);
-                if (q > lo && q < hi) e = q;
+      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top)) {
+        int j0 = (int)floorf((c_pred - c1) / p.dc) - 2;
+        if (j0 < 2) j0 = 2;
+        if (j0 < 1000) {
+          float pc = c1, pd = 0.f, pe2 = 0.f, pe3 = 0.f;
+          int mj = n, mw = n, jev = -1, dir = 0, w0 = 2, sign0 = 0;
+          bool win_ok = false;
+          for (int wtry = 0; wtry < 4; ++wtry) {
+            // first try: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = window (grid
+            // indices j0..j0+5); an odd number of roots below the window shows as a sign difference between
+            // them.  Later tries (window moved up or down): all 8 lanes are window points.
+            const int idx = (gl < w0) ? ((gl == 0) ? 0 : j0 / 2) : j0 + (gl - w0);
+            pc = c1;
+            for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, p.dc);
+            mj = layer_drop(pc, T, p.fact, n, q1);
+            mw = gshfl<G>(gmask, mj, G - 1);
+            const float4 sv = secular(p.kind, pc, T, mw, q0, q1, 0);
+            my_steps += (unsigned)(mw - 1); my_sweeps += 1;
+            pd = sv.x; pe2 = sv.y; pe3 = sv.z;
+            if (wtry == 0) sign0 = (int)signbit(gshfl<G>(gmask, pd, 0));
+            const float dpw = __shfl_up_sync(gmask, pd, 1, G);
+            const bool changew = (gl > w0) && (signbit(dpw) != signbit(pd));
+            const bool badw = (gl >= w0) && ((pc < 0.8f * b_top) || !(pc < q1[mj - 1].y) || !(pc == pc));
+            const bool wrong = ((int)signbit(pd) != sign0);
+            const unsigned evc = (__ballot_sync(gmask, changew) >> gbase) & gbits;
+            const unsigned evb = (__ballot_sync(gmask, badw) >> gbase) & gbits;
+            const unsigned evw = (__ballot_sync(gmask, wrong) >> gbase) & gbits;
+            const bool below_ok = !(evw & ((2u << w0) - 1u));     // lanes 0..w0 have the sign of c1
+            jev = __ffs(evc) - 1;
+            if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) { win_ok = true; break; }
+            if (evb) break;
+            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; continue; }   // root above the window
+            if (!below_ok && dir <= 0) {
+              // root below the window: only if it is between the half-way point and the window
+              const bool lower_ok = !(evw & ((1u << w0) - 1u));
+              const int jmin = (wtry == 0) ? j0 / 2 : 0;
+              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - 7, jmin); w0 = 0; continue; }
+            }
+            break;
+          }
+          if (win_ok) {
+            const int mnew = gshfl<G>(gmask, mj, jev);
+            // the half-space velocity is a kink of the secular function (of the window's truncation, bh2, and
+            // of the reference's own, bh1): not within a grid step of the bracket, and the interpolation only
+            // uses window points below it
+            const float bh1 = q1[mnew - 1].y, bh2 = q1[mw - 1].y, bh = fminf(bh1, bh2);
+            const float br_lo = gshfl<G>(gmask, pc, jev - 1), br_hi = gshfl<G>(gmask, pc, jev);
+            const int nvalid = __popc((__ballot_sync(gmask, gl >= w0 && pc < bh) >> gbase) & gbits);  // window points below the kink
+            const bool kink = (bh1 > br_lo - 0.011f && bh1 < br_hi + 0.011f) || (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) ||
+                              nvalid < 6 || jev - w0 > nvalid - 1;
+            if (!kink) {
+              bool has_ends = false;
+              int jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
+              SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = {0.f, 0.f, 0.f, 0.f};
+              auto sample = [&](int i) {
+                // i-th entry of the ordered list: [lane w0 .. lane G-1] or [E0, lane 0 .. lane G-1, E1]
+                const int src = has_ends ? i - 1 : i + w0;
+                const int sl = min(max(src, 0), G - 1);
+                SamplePt s;
+                s.c = gshfl<G>(gmask, pc, sl); s.d = gshfl<G>(gmask, pd, sl);
+                s.e2 = gshfl<G>(gmask, pe2, sl); s.e3 = gshfl<G>(gmask, pe3, sl);
+                if (has_ends && i == 0) s = E0;
+                if (has_ends && i == G + 1) s = E1;
+                return s;
+              };
+              for (int it = 0; it < 4; ++it) {
+                const int np = has_ends ? G + 2 : nvalid;
+                const int s6 = min(max(jb - 3, 0), np - 6), s4 = min(max(jb - 2, 0), np - 4);
+                const SamplePt B0 = sample(jb - 1), B1 = sample(jb);
+                float x[6], y[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { const SamplePt s = sample(s6 + i); x[i] = s.c - B0.c; y[i] = s.d; }
+                float e4, e6;
+                inv_interp6(x, y, s4 - s6, e4, e6);
+                const float w = B1.c - B0.c;
+                const bool inside = (e6 > 0.f && e6 < w);
+                const float delta = fabsf(e6 - e4);
+                float e = e6;
+                if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
+                if ((inside && delta <= ((it == 0) ? kWindowTol : kInterpTol)) || w <= kBracketTol) {
+                  croot = B0.c + e;
+                  if (p.kind == 2) {
+                    float xs[4], f2[4], f3[4], wl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const SamplePt s = sample(s4 + i); xs[i] = s.c - B0.c; f2[i] = s.e2; f3[i] = s.e3; }
+                    lagrange4(xs, e, wl);
+                    const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
+                    const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
+                    ratio = 0.5f * se3 / se2;
+                  }
+                  fast_done = true;
+                  break;
+                }
+                if (it == 3) break;
+                // one more round: G points around the estimate, spaced by the disagreement of the two orders
+                const float s0 = fmaxf(inside ? 0.5f * delta : w, 1.0e-5f);
+                const bool uni = !(e - 12.5f * s0 > 0.f && e + 12.5f * s0 < w);
+                E0 = B0; E1 = B1;
+                pc = B0.c + (uni ? (float)(gl + 1) * (w / (float)(G + 1)) : e + refine_offset8(gl) * s0);
+                const float4 sr = secular(p.kind, pc, T, mw, q0, q1, 0);
+                my_steps += (unsigned)(mw - 1); my_sweeps += 1;
+                pd = sr.x; pe2 = sr.y; pe3 = sr.z;
+                has_ends = true;
+                float dp = __shfl_up_sync(gmask, pd, 1, G);
+                if (gl == 0) dp = E0.d;
+                const unsigned ev = (__ballot_sync(gmask, signbit(dp) != signbit(pd)) >> gbase) & gbits;
+                const float dlast = gshfl<G>(gmask, pd, G - 1);
+                if (ev) jb = __ffs(ev);                                   // lane g is list entry g + 1
+                else if (signbit(dlast) != signbit(E1.d)) jb = G + 1;
+                else break;
+              }
+              if (fast_done) {
+                if (croot > q1[mnew - 1].y) fast_done = false;   // calcul.f:191 decided by the point-by-point path
+                else { mm = mnew; found = true; have_ratio = (p.kind == 2) && !mid_liquid; }
               }
             }
-            const float dl = fmaxf(0.5e-5f, w * (1.0f / 2048.f));
-            const int h = gl - G / 2;
-            const float mag = (h >= 0) ? (float)(1 << (2 * (h & 7))) : -(float)(1 << (2 * ((-h - 1) & 7)));
-            const float eps = w * 1.0e-3f;
-            pj = fminf(fmaxf(e + mag * dl, lo + eps), hi - eps);
           }
-          const float dj = secular(p.kind, pj, T, mm, q0, q1, 1);
-          my_steps += (unsigned)(mm - 1); my_sweeps += 1;
-          float dp = __shfl_up_sync(gmask, dj, 1, G);
-          float pp = __shfl_up_sync(gmask, pj, 1, G);
-          if (gl == 0) { dp = dlo; pp = lo; }
-          const bool change = signbit(dp) != signbit(dj);
-          const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & gbits;
-          const float dlast = gshfl<G>(gmask, dj, G - 1);
-          if (careful && it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
-          if (ev) {
+        }
+      }
+
+      if (!fast_done) {
+        // ---- point-by-point scan (calcul.f:155-167), G consecutive grid points per round
+        float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
+        int mnew = mm;
+        {
+          float cbase = c1, cP = 0.f, dP = 0.f;
+          bool have_prev = false;
+          for (int round = 0; round < 4096; ++round) {
+            float cj = cbase;
+            for (int t = 0; t < gl; ++t) cj = SD_ADD(cj, p.dc);
+            const int mj = layer_drop(cj, T, p.fact, n, q1);
+            const float dj = secular(p.kind, cj, T, mj, q0, q1, 0).x;
+            my_steps += (unsigned)(mj - 1); my_sweeps += 1;
+            float dp = __shfl_up_sync(gmask, dj, 1, G);
+            float cp = __shfl_up_sync(gmask, cj, 1, G);
+            if (gl == 0) { dp = dP; cp = cP; }
+            const bool hasp = (gl > 0) || have_prev;
+            const bool change = hasp && (signbit(dp) != signbit(dj));
+            const bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
+            const unsigned ev = (__ballot_sync(gmask, change || stop) >> gbase) & gbits;
+            if (!ev) {
+              cP = gshfl<G>(gmask, cj, G - 1);
+              dP = gshfl<G>(gmask, dj, G - 1);
+              mnew = gshfl<G>(gmask, mj, G - 1);
+              have_prev = true;
+              cbase = SD_ADD(cP, p.dc);
+              if (round == 4095) flag |= SURFDISP_F_SCAN_LIMIT;
+              continue;
+            }
             const int j = __ffs(ev) - 1;
-            const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
-            hi = gshfl<G>(gmask, pj, j); dhi = gshfl<G>(gmask, dj, j);
-            lo = nlo; dlo = ndlo;
-          } else {
-            lo = gshfl<G>(gmask, pj, G - 1); dlo = dlast;
+            found = gshfl<G>(gmask, (int)change, j) != 0;
+            lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
+            dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
+            mnew = gshfl<G>(gmask, mj, j);
+            break;
           }
         }
-        if (!multi) {
-          const float den = dhi - dlo;
-          float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
-          if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
-          croot = cs;
-        } else {
-          // several roots inside the scan bracket: follow the reference's own sequential polish so the
-          // same one is picked (all lanes of the group run it redundantly, no divergence)
-          int ev_n = 0;
-          auto f = [&](float cc) { return secular(p.kind, cc, T, mm, q0, q1, 1); };
-          const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
-          if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
-          if (!okp) { found = false; lstop = true; }
+        mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
+        if (found) {
+          // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
+          // G-section until the bracket is <= 2e-5, then one secant step.  The first round counts the sign
+          // changes: with several roots inside the scan bracket (kink at the half-space velocity) the group
+          // runs the reference's own sequential bisection/Neville sequence so that the same root is picked.
+          const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
+          bool multi = false;
+          for (int it = 0; it < 16 && (hi - lo) > kBracketTol; ++it) {
+            const float w = hi - lo;
+            const float pj = lo + (float)(gl + 1) * (w / (float)(G + 1));
+            const float dj = secular(p.kind, pj, T, mm, q0, q1, 0).x;
+            my_steps += (unsigned)(mm - 1); my_sweeps += 1;
+            float dp = __shfl_up_sync(gmask, dj, 1, G);
+            float pp = __shfl_up_sync(gmask, pj, 1, G);
+            if (gl == 0) { dp = dlo; pp = lo; }
+            const bool change = signbit(dp) != signbit(dj);
+            const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & gbits;
+            const float dlast = gshfl<G>(gmask, dj, G - 1);
+            if (it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
+            if (ev) {
+              const int j = __ffs(ev) - 1;
+              const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
+              hi = gshfl<G>(gmask, pj, j); dhi = gshfl<G>(gmask, dj, j);
+              lo = nlo; dlo = ndlo;
+            } else {
+              lo = gshfl<G>(gmask, pj, G - 1); dlo = dlast;
+            }
+          }
+          if (!multi) {
+            const float den = dhi - dlo;
+            float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
+            if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
+            croot = cs;
+          } else {
+            int ev_n = 0;
+            auto f = [&](float cc) { return secular(p.kind, cc, T, mm, q0, q1, 0).x; };
+            const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
+            if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
+            if (!okp) { found = false; lstop = true; }
+          }
+          if (found && croot > q1[mm - 1].y) { found = false; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
         }
-        if (found && croot > q1[mm - 1].y) { found = false; failed = true; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
       }
-      if (!coarse) break;
-      bool suspicious = !found || lstop;
-      if (!suspicious) {
-        const float r = (p.tab.lt[k - 1] - p.tab.lt[k]) / (p.tab.lt[k - 2] - p.tab.lt[k - 1]);
-        const float stepp = (c_prev - c_prev2) * r;
-        suspicious = !(croot - (c_prev + stepp) <= fmaxf(0.1f, fabsf(stepp)));
-      }
-      if (!suspicious) break;
-      }  // attempt
       if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; break; }  // reference aborts the whole call (calcul.f:173-189)
       if (!found) {
         flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
-        (void)failed;
         break;
       }
-      float ratio = 0.f;
-      if (p.kind == 2) {
-        // ellipticity = 0.5 * bb1(e3) / bb1(e2) (surfa.f:360-363); two lanes, one start vector each
-        const float v = secular(2, croot, T, mm, q0, q1, 2 + (gl & 1));
+      if (p.kind == 2 && !have_ratio) {
+        // ellipticity = 0.5 * bb1(e3) / bb1(e2) at the root (surfa.f:360-363)
+        const float4 v = secular(2, croot, T, mm, q0, q1, 1);
         my_steps += (unsigned)(mm - 1); my_sweeps += 1;
-        const float r12 = gshfl<G>(gmask, v, 0);
-        const float r3 = gshfl<G>(gmask, v, 1);
-        ratio = 0.5f * r3 / r12;
+        ratio = 0.5f * v.z / v.y;
       }
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
+      if (k >= 2 && fabsf(croot - c_pred) > 0.1f) hopped = true;
+      c_prev3 = c_prev2;
       c_prev2 = c_prev;
       c_prev = croot;
       nfound = k + 1;

@@ -6,18 +6,28 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
+#include <cstdio>
+#include <algorithm>
 #include "../../pysurfinv_b200/csrc/surfdisp_core.cuh"
 
 using namespace sd;
 
+namespace {
+struct Pt { float c, d, e2, e3; };
+constexpr float kInterpTol = 1.0e-5f;
+constexpr float kWindowTol = 5.0e-7f;
+constexpr float kBracketTol = 2.0e-5f;
+}
+
 extern "C" {
 
-// one model, shared periods; returns nfound
+// one model, shared periods; returns nfound.  `exact` = SurfdispOpts.exact_scan.
 int hm_forward(int G, int kind, int n, const float* a, const float* b, const float* rho, const float* d,
                const float* qs, int K, const float* per, float dc, float fact, float t_base, int atten,
                int flatten, int stale, int ndiv0, int ndiv_cap, float* c_out, float* u_out, float* ratio_out,
-               long long* sweeps, int algo, float delta0, float wfin, long long* rounds_out) {
-  long long nrounds = 0, npolish = 0;
+               long long* sweeps, int exact, long long* rounds_out) {
+  long long nrounds = 0, nwin = 0, nwin_ok = 0, ndirect = 0, nslow = 0;
   const int ld = n;
   std::vector<float> cst((size_t)NCONST * ld);
   prep_model(n, kind, flatten, a, b, rho, d, qs, cst.data(), ld);
@@ -35,14 +45,18 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
     if (b0 < 0.1f) c1 = 0.5f;
   }
+  bool mid_liquid = false;
+  for (int i = 1; i < n; ++i) mid_liquid |= !(cst[C_BREF * ld + i] > 0.f);
   int mm = n, nfound = 0;
-  float c_prev = 0.f, c_prev2 = 0.f;
+  bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
+  float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f;
   long long nsw = 0;
-  std::vector<float> cj(G), dj(G);
-  std::vector<int> mj(G);
-  auto sweep = [&](float c, float T, int m) {
+  auto sweep = [&](float c, float T, int m, bool ell_only) {
     nsw++;
-    return (kind == 2) ? rayleigh_sweep(c, T, m, q0.data(), q1.data(), 1) : love_sweep(c, T, m, q0.data(), q1.data());
+    Pt r = {c, 0.f, 0.f, 0.f};
+    if (kind == 2) r.d = rayleigh_adjoint(c, T, m, q0.data(), q1.data(), ell_only, r.e2, r.e3);
+    else r.d = love_sweep(c, T, m, q0.data(), q1.data());
+    return r;
   };
   for (int k = 0; k < K; ++k) {
     const float T = per[k];
@@ -58,151 +72,224 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     }
     if (k > 0) c1 = SD_MUL(0.90f, c_prev);
     const float b_top = q1[0].y;
-    const int mm_in = mm;
-    float croot = 0;
-    bool found = false, lstop = false;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-    mm = mm_in; found = false; lstop = false; croot = 0;
-    const bool coarse = !(algo == 0 || k < 2 || attempt == 1);
-    float lo = 0, hi = 0, dlo = 0, dhi = 0;
-    float xn = 0, yn = 0; bool have_n = false;   // a third scan point next to the bracket
-    bool done = false;
-    int mnew = mm;
-    auto stopc = [&](float c, int m) { return (c < 0.8f * b_top) || !(c < q1[m - 1].y + 0.3f) || !(c == c); };
-    {
-      // coarse-to-fine scan: coarse points every S grid steps, then the S-1 interior points of the first
-      // coarse interval that shows an event.  S = 1 reproduces the plain scan.
-      const float c_1 = SD_ADD(c1, dc);
-      int S = (!coarse || c_1 < 0.8f * b_top) ? 1 : G;
-      float cbase = c1;             // grid value of the first coarse point of this round
-      float cP = 0, dP = 0; int have_prev = 0;
-      for (int round = 0; round < 4096 && !done; ++round) {
-        nrounds++;
-        for (int g = 0; g < G; ++g) {
-          float c = cbase;
-          for (int t = 0; t < g * S; ++t) c = SD_ADD(c, dc);
-          cj[g] = c; mj[g] = layer_drop(c, T, fact, n, q1.data()); dj[g] = sweep(c, T, mj[g]);
-        }
-        int jev = -1;
-        for (int g = 0; g < G; ++g) {
-          const bool hasp = (g > 0) || have_prev;
-          const float dp = g ? dj[g - 1] : dP;
-          const bool change = hasp && (std::signbit(dp) != std::signbit(dj[g]));
-          const bool stop = hasp && !change && stopc(cj[g], mj[g]);
-          // above the half-space velocity the secular function can change sign twice inside one coarse
-          // interval (kink at c = b(mmax)): force such intervals to be resolved point by point
-          const bool risky = hasp && S > 1 && !(cj[g] < q1[mj[g] - 1].y);
-          if (change || stop || risky) { jev = g; break; }
-        }
-        if (jev < 0) { cP = cj[G - 1]; dP = dj[G - 1]; have_prev = 1; cbase = cP; for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, dc); continue; }
-        // sequence of S+1 fine points from the previous coarse point to the event point
-        std::vector<float> sc(S + 1), sd(S + 1); std::vector<int> sm(S + 1);
-        sc[0] = jev ? cj[jev - 1] : cP; sd[0] = jev ? dj[jev - 1] : dP; sm[0] = 0;
-        sc[S] = cj[jev]; sd[S] = dj[jev]; sm[S] = mj[jev];
-        if (S > 1) {
-          nrounds++;
-          for (int q = 1; q < S; ++q) {
-            float c = sc[0];
-            for (int t = 0; t < q; ++t) c = SD_ADD(c, dc);
-            sc[q] = c; sm[q] = layer_drop(c, T, fact, n, q1.data()); sd[q] = sweep(c, T, sm[q]);
-          }
-        }
-        for (int q = 1; q <= S; ++q) {
-          const bool change = std::signbit(sd[q - 1]) != std::signbit(sd[q]);
-          const bool stop = !change && stopc(sc[q], sm[q]);
-          if (change || stop) {
-            found = change; lo = sc[q - 1]; hi = sc[q]; dlo = sd[q - 1]; dhi = sd[q]; mnew = sm[q]; done = true;
-            // neighbour: prefer the side whose |value| is smaller (closer to the root)
-            have_n = false;
-            if (q >= 2) { xn = sc[q - 2]; yn = sd[q - 2]; have_n = true; }
-            if (q < S && (!have_n || fabsf(sd[q]) < fabsf(sd[q - 1]))) { xn = sc[q + 1]; yn = sd[q + 1]; have_n = true; }
-            break;
-          }
-        }
-        if (!done) {  // only the 'risky' flag fired: go on from the end of this interval with the plain scan
-          S = 1; cP = sc[sc.size() - 1]; dP = sd[sd.size() - 1]; have_prev = 1; cbase = SD_ADD(cP, dc);
-        }
+    float croot = 0.f, ratio = 0.f;
+    bool found = false, lstop = false, have_ratio = false, fast_done = false;
+
+    // ---- fast path: window of G grid points around the extrapolated root, inverse interpolation
+    float c_pred = c_prev;
+    if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
+    else if (k >= 2) {
+      // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
+      const float x0 = lt[k - 1], x1 = lt[k - 2], x = lt[k];
+      c_pred = c_prev + (c_prev - c_prev2) * ((x - x0) / (x0 - x1));
+      if (k >= 3) {
+        const float x2 = lt[k - 3];
+        const float d01 = (c_prev - c_prev2) / (x0 - x1), d12 = (c_prev2 - c_prev3) / (x1 - x2);
+        c_pred += (d01 - d12) / (x0 - x2) * (x - x0) * (x - x1);
       }
     }
-    mm = mnew;
-    if (found) {
-      const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
-      bool multi = false;
-      const float b_hs = q1[mm - 1].y;
-      const bool careful = !coarse || (b_hs > lo - 0.011f && b_hs < hi + 0.011f);
-      for (int it = 0; it < 16 && (hi - lo) > wfin; ++it) {
-        nrounds++; npolish++;
-        const float w = hi - lo;
-        if (careful || it >= 4) {
-          const float step = w / (float)(G + 1);
-          for (int g = 0; g < G; ++g) cj[g] = lo + (float)(g + 1) * step;
-        } else {
-          // points clustered geometrically around the secant estimate
-          const float den = dhi - dlo;
-          float e = (den != 0.f) ? lo - dlo * w / den : 0.5f * (lo + hi);
-          if (it == 0 && have_n && algo >= 2) {
-            // inverse quadratic interpolation through (lo, hi, neighbour) evaluated at y = 0
-            const float y0 = dlo, y1 = dhi, y2 = yn;
-            const float d01 = y0 - y1, d02 = y0 - y2, d12 = y1 - y2;
-            if (d01 != 0.f && d02 != 0.f && d12 != 0.f) {
-              const float q = lo * (y1 * y2) / (d01 * d02) - hi * (y0 * y2) / (d01 * d12) + xn * (y0 * y1) / (d02 * d12);
-              if (q > lo && q < hi) e = q;
+    if (G == 8 && !exact && k >= 1 && !hopped && !(SD_ADD(c1, dc) < 0.8f * b_top)) {
+      int j0 = (int)floorf((c_pred - c1) / dc) - 2;
+      if (j0 < 2) j0 = 2;
+      if (j0 < 1000) {
+        nwin++;
+        std::vector<Pt> lane(G);
+        std::vector<int> mj(G);
+        int mw = 0, jev = -1, dir = 0, w0 = 2, sign0 = 0;
+        bool win_ok = false;
+        for (int wtry = 0; wtry < 4; ++wtry) {
+          nrounds++;
+          // first try: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = window (grid indices
+          // j0..j0+5); an odd number of roots below the window shows as a sign difference between them.
+          // Later tries (window moved up or down): all 8 lanes are window points.
+          for (int g = 0; g < G; ++g) {
+            const int idx = (g < w0) ? ((g == 0) ? 0 : j0 / 2) : j0 + (g - w0);
+            float pc = c1;
+            for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, dc);
+            lane[g].c = pc; mj[g] = layer_drop(pc, T, fact, n, q1.data());
+          }
+          mw = mj[G - 1];
+          for (int g = 0; g < G; ++g) lane[g] = sweep(lane[g].c, T, mw, false);
+          if (wtry == 0) sign0 = (int)std::signbit(lane[0].d);
+          unsigned evc = 0, evb = 0;
+          bool below_ok = true;
+          for (int g = 0; g <= w0; ++g) below_ok &= ((int)std::signbit(lane[g].d) == sign0);
+          for (int g = w0 + 1; g < G; ++g)
+            if (std::signbit(lane[g - 1].d) != std::signbit(lane[g].d)) evc |= 1u << g;
+          for (int g = w0; g < G; ++g) {
+            const float pc = lane[g].c;
+            if ((pc < 0.8f * b_top) || !(pc < q1[mj[g] - 1].y) || !(pc == pc)) evb |= 1u << g;
+          }
+          jev = evc ? __builtin_ctz(evc) : -1;
+          if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) { win_ok = true; break; }
+          if (evb) break;
+          if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; continue; }      // root above the window
+          if (!below_ok && dir <= 0) {
+            // root below the window: only if it is between the half-way point and the window
+            bool lower_ok = true;
+            for (int g = 0; g < w0; ++g) lower_ok &= ((int)std::signbit(lane[g].d) == sign0);
+            const int jmin = (wtry == 0) ? j0 / 2 : 0;
+            if (lower_ok && j0 > jmin) { dir = -1; j0 = std::max(j0 - 7, jmin); w0 = 0; continue; }
+          }
+          break;
+        }
+        if (!win_ok && getenv("HM_DEBUG")) fprintf(stderr, "winmiss k=%d T=%g jev=%d dir=%d c_pred=%g c1=%g lane0=%g\n", k, T, jev, dir, c_pred, c1, lane[0].c);
+        if (win_ok) {
+          const int mnew = mj[jev];
+          // the half-space velocity is a kink of the secular function (of the window's truncation, bh2, and of
+          // the reference's own, bh1): not within a grid step of the bracket, and the interpolation only
+          // uses window points below it
+          const float bh1 = q1[mnew - 1].y, bh2 = q1[mw - 1].y, bh = fminf(bh1, bh2);
+          const float br_lo = lane[jev - 1].c, br_hi = lane[jev].c;   // jev > w0: both are window points
+          int nvalid = 0;   // window points below the kink
+          for (int g = w0; g < G; ++g) nvalid += (lane[g].c < bh);
+          const bool kink = (bh1 > br_lo - 0.011f && bh1 < br_hi + 0.011f) || (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) ||
+                            nvalid < 6 || jev - w0 > nvalid - 1;
+          if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh1=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh1, bh2, br_lo, br_hi, nvalid);
+          if (!kink) {
+            nwin_ok++;
+            bool has_ends = false;
+            int jb = jev - w0;
+            Pt E0 = {0, 0, 0, 0}, E1 = {0, 0, 0, 0};
+            auto sample = [&](int i) {
+              const int src = has_ends ? i - 1 : i + w0;
+              const int sl = std::min(std::max(src, 0), G - 1);
+              Pt s = lane[sl];
+              if (has_ends && i == 0) s = E0;
+              if (has_ends && i == G + 1) s = E1;
+              return s;
+            };
+            for (int it = 0; it < 4; ++it) {
+              const int np = has_ends ? G + 2 : nvalid;
+              const int s6 = std::min(std::max(jb - 3, 0), np - 6), s4 = std::min(std::max(jb - 2, 0), np - 4);
+              const Pt B0 = sample(jb - 1), B1 = sample(jb);
+              float x[6], y[6];
+              for (int i = 0; i < 6; ++i) { const Pt s = sample(s6 + i); x[i] = s.c - B0.c; y[i] = s.d; }
+              float e4, e6;
+              inv_interp6(x, y, s4 - s6, e4, e6);
+              const float w = B1.c - B0.c;
+              const bool inside = (e6 > 0.f && e6 < w);
+              const float delta = fabsf(e6 - e4);
+              float e = e6;
+              if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
+              if ((inside && delta <= ((it == 0) ? kWindowTol : kInterpTol)) || w <= kBracketTol) {
+                croot = B0.c + e;
+                if (getenv("HM_DEBUG2")) fprintf(stderr, "acc k=%d it=%d w=%g delta=%g e4=%g e6=%g inside=%d c=%.7f s6=%d jb=%d np=%d\n", k, it, w, delta, e4, e6, (int)inside, croot, s6, jb, np);
+                if (kind == 2) {
+                  float xs[4], f2[4], f3[4], wl[4];
+                  for (int i = 0; i < 4; ++i) { const Pt s = sample(s4 + i); xs[i] = s.c - B0.c; f2[i] = s.e2; f3[i] = s.e3; }
+                  lagrange4(xs, e, wl);
+                  const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
+                  const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
+                  ratio = 0.5f * se3 / se2;
+                }
+                fast_done = true;
+                ndirect += (it == 0);
+                break;
+              }
+              if (it == 3) break;
+              const float s0 = fmaxf(inside ? 0.5f * delta : w, 1.0e-5f);
+              const bool uni = !(e - 12.5f * s0 > 0.f && e + 12.5f * s0 < w);
+              E0 = B0; E1 = B1;
+              nrounds++;
+              for (int g = 0; g < G; ++g) {
+                const float pc = B0.c + (uni ? (float)(g + 1) * (w / (float)(G + 1)) : e + refine_offset8(g) * s0);
+                lane[g] = sweep(pc, T, mw, false);
+              }
+              has_ends = true;
+              unsigned ev = 0;
+              for (int g = 0; g < G; ++g) {
+                const float dp = g ? lane[g - 1].d : E0.d;
+                if (std::signbit(dp) != std::signbit(lane[g].d)) ev |= 1u << g;
+              }
+              if (ev) jb = __builtin_ctz(ev) + 1;
+              else if (std::signbit(lane[G - 1].d) != std::signbit(E1.d)) jb = G + 1;
+              else break;
+            }
+            if (fast_done) {
+              if (croot > q1[mnew - 1].y) fast_done = false;
+              else { mm = mnew; found = true; have_ratio = (kind == 2) && !mid_liquid; }
             }
           }
-          const float dl = fmaxf(delta0, w * (1.0f / 2048.f));
+        }
+      }
+    }
+
+    if (!fast_done) {
+      nslow++;
+      // ---- point-by-point scan, G grid points per round
+      float lo = 0, hi = 0, dlo = 0, dhi = 0;
+      int mnew = mm;
+      {
+        float cbase = c1, cP = 0, dP = 0;
+        bool have_prev = false, done = false;
+        std::vector<float> cj(G), dj(G);
+        std::vector<int> mj(G);
+        for (int round = 0; round < 4096 && !done; ++round) {
+          nrounds++;
           for (int g = 0; g < G; ++g) {
-            const int h = g - G / 2;                       // -4..3 for G = 8
-            const float mag = (h >= 0) ? (float)(1 << (2 * h)) : -(float)(1 << (2 * (-h - 1)));
-            float pnt = e + mag * dl;
-            const float eps = w * 1.0e-3f;
-            pnt = fminf(fmaxf(pnt, lo + eps), hi - eps);
-            cj[g] = pnt;
+            float c = cbase;
+            for (int t = 0; t < g; ++t) c = SD_ADD(c, dc);
+            cj[g] = c; mj[g] = layer_drop(c, T, fact, n, q1.data()); dj[g] = sweep(c, T, mj[g], false).d;
           }
+          int jev = -1; bool chg = false;
+          for (int g = 0; g < G; ++g) {
+            const bool hasp = (g > 0) || have_prev;
+            const float dp = g ? dj[g - 1] : dP;
+            const bool change = hasp && (std::signbit(dp) != std::signbit(dj[g]));
+            const bool stop = hasp && !change && ((cj[g] < 0.8f * b_top) || !(cj[g] < q1[mj[g] - 1].y + 0.3f) || !(cj[g] == cj[g]));
+            if (change || stop) { jev = g; chg = change; break; }
+          }
+          if (jev < 0) { cP = cj[G - 1]; dP = dj[G - 1]; mnew = mj[G - 1]; have_prev = true; cbase = SD_ADD(cP, dc); continue; }
+          found = chg;
+          lo = jev ? cj[jev - 1] : cP; hi = cj[jev]; dlo = jev ? dj[jev - 1] : dP; dhi = dj[jev]; mnew = mj[jev];
+          done = true;
         }
-        for (int g = 0; g < G; ++g) dj[g] = sweep(cj[g], T, mm);
-        int j = -1, nchg = 0;
-        for (int g = 0; g < G; ++g) {
-          const float dp = g ? dj[g - 1] : dlo;
-          if (std::signbit(dp) != std::signbit(dj[g])) { if (j < 0) j = g; nchg++; }
+      }
+      mm = mnew;
+      if (found) {
+        const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
+        bool multi = false;
+        std::vector<float> pj(G), dj(G);
+        for (int it = 0; it < 16 && (hi - lo) > kBracketTol; ++it) {
+          nrounds++;
+          const float w = hi - lo;
+          for (int g = 0; g < G; ++g) { pj[g] = lo + (float)(g + 1) * (w / (float)(G + 1)); dj[g] = sweep(pj[g], T, mm, false).d; }
+          int j = -1, nchg = 0;
+          for (int g = 0; g < G; ++g) {
+            const float dp = g ? dj[g - 1] : dlo;
+            if (std::signbit(dp) != std::signbit(dj[g])) { if (j < 0) j = g; nchg++; }
+          }
+          if (std::signbit(dj[G - 1]) != std::signbit(dhi)) nchg++;
+          if (it == 0 && nchg > 1) { multi = true; break; }
+          if (j >= 0) {
+            const float nlo = j ? pj[j - 1] : lo, ndlo = j ? dj[j - 1] : dlo;
+            hi = pj[j]; dhi = dj[j]; lo = nlo; dlo = ndlo;
+          } else { lo = pj[G - 1]; dlo = dj[G - 1]; }
         }
-        if (std::signbit(dj[G - 1]) != std::signbit(dhi)) nchg++;
-        if (careful && it == 0 && nchg > 1) { multi = true; break; }
-        if (j >= 0) {
-          const float nlo = j ? cj[j - 1] : lo, ndlo = j ? dj[j - 1] : dlo;
-          hi = cj[j]; dhi = dj[j]; lo = nlo; dlo = ndlo;
-        } else { lo = cj[G - 1]; dlo = dj[G - 1]; }
+        if (!multi) {
+          const float den = dhi - dlo;
+          float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
+          if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
+          croot = cs;
+        } else {
+          int ev_n = 0;
+          auto f = [&](float cc) { return sweep(cc, T, mm, false).d; };
+          if (!nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n)) { found = false; lstop = true; }
+        }
+        if (found && croot > q1[mm - 1].y) found = false;
       }
-      if (!multi) {
-        const float den = dhi - dlo;
-        float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
-        if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
-        croot = cs;
-      } else {
-        int ev_n = 0;
-        auto f = [&](float cc) { return sweep(cc, T, mm); };
-        if (!nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n)) { found = false; lstop = true; }
-      }
-      if (found && croot > q1[mm - 1].y) found = false;
     }
-    if (!coarse) break;
-    bool suspicious = !found || lstop;
-    if (!suspicious) {
-      const float r = (lt[k - 1] - lt[k]) / (lt[k - 2] - lt[k - 1]);
-      const float stepp = (c_prev - c_prev2) * r;
-      suspicious = !(croot - (c_prev + stepp) <= fmaxf(0.1f, fabsf(stepp)));
-    }
-    if (!suspicious) break;
-    }  // attempt
     if (lstop) { nfound = 0; break; }
     if (!found) break;
-    float ratio = 0;
-    if (kind == 2) {
-      const float r12 = rayleigh_sweep(croot, T, mm, q0.data(), q1.data(), 2);
-      const float r3 = rayleigh_sweep(croot, T, mm, q0.data(), q1.data(), 3);
-      nsw += 2; nrounds++;
-      ratio = 0.5f * r3 / r12;
+    if (kind == 2 && !have_ratio) {
+      const Pt v = sweep(croot, T, mm, true);
+      nrounds++;
+      ratio = 0.5f * v.e3 / v.e2;
     }
-    c_out[k] = croot; ratio_out[k] = ratio; c_prev2 = c_prev; c_prev = croot; nfound = k + 1;
+    if (getenv("HM_PRED") && k >= 1) fprintf(stderr, "pred %d %g %g\n", k, croot - c_pred, (croot - c1) / dc);
+    if (k >= 2 && fabsf(croot - c_pred) > 0.1f) hopped = true;
+    c_out[k] = croot; ratio_out[k] = ratio; c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot; nfound = k + 1;
   }
   // phase 2
   for (int k = 0; k < nfound; ++k) {
@@ -218,7 +305,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
                            : leigen_thread(mv, per[k], c_out[k], fact, ns);
   }
   if (sweeps) *sweeps += nsw;
-  if (rounds_out) { rounds_out[0] += nrounds; rounds_out[1] += npolish; }
+  if (rounds_out) { rounds_out[0] += nrounds; rounds_out[1] += nslow; rounds_out[2] += nwin; rounds_out[3] += nwin_ok; rounds_out[4] += ndirect; }
   return nfound;
 }
 

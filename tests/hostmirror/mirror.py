@@ -21,22 +21,22 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.hm_forward.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_int, fp, C.c_float, C.c_float,
                                  C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp,
-                                 C.POINTER(C.c_longlong), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_longlong)]
+                                 C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong)]
         L.hm_forward.restype = C.c_int
         _LIB = L
     return _LIB
 
 
-def forward(kind, vp, vs, rho, h, qsinv, periods, G=8, stale=1, ndiv=5, ndiv_cap=None, algo=1, delta0=1e-5, wfin=2e-5):
+def forward(kind, vp, vs, rho, h, qsinv, periods, G=8, stale=1, ndiv=5, ndiv_cap=None, exact_scan=0):
     f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
     a, b, r, d, q, per = f(vp), f(vs), f(rho), f(h), f(qsinv), f(periods)
     K = len(per)
     c = np.zeros(K, np.float32); u = np.zeros(K, np.float32); rt = np.zeros(K, np.float32)
     p = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
     sw = C.c_longlong(0)
-    rounds = (C.c_longlong * 2)(0, 0)
+    rounds = (C.c_longlong * 5)(0, 0, 0, 0, 0)
     if ndiv_cap is None:
         ndiv_cap = 99 if kind == 2 else 999
     nf = lib().hm_forward(G, kind, len(b), p(a), p(b), p(r), p(d), p(q), K, p(per), 0.01, 4.0, 1.0, 1, 1, stale,
-                          ndiv, ndiv_cap, p(c), p(u), p(rt), C.byref(sw), algo, delta0, wfin, rounds)
-    return dict(c=c, u=u, ratio=rt, nfound=nf, sweeps=sw.value, rounds=rounds[0], polish_rounds=rounds[1])
+                          ndiv, ndiv_cap, p(c), p(u), p(rt), C.byref(sw), exact_scan, rounds)
+    return dict(c=c, u=u, ratio=rt, nfound=nf, sweeps=sw.value, rounds=rounds[0], slow_periods=rounds[1], windows=rounds[2], windows_ok=rounds[3], direct=rounds[4])
