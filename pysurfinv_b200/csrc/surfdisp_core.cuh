@@ -424,6 +424,13 @@ SD_HD void lagrange4(const float* xs, float x, float* w) {
   w[3] = d0 * d1 * d2 / ((xs[3] - xs[0]) * (xs[3] - xs[1]) * (xs[3] - xs[2]));
 }
 
+// Offsets (in units of the cluster spacing) of the 6 points of the first round around the predicted root
+SD_HD float cluster_offset6(int i) {
+  const int h = (i >= 3) ? i - 3 : 2 - i;
+  const float m = (h == 0) ? 0.5f : ((h == 1) ? 1.5f : 4.f);
+  return (i >= 3) ? m : -m;
+}
+
 // Offsets (in units of s0) of the G = 8 points of a refinement round around the root estimate
 SD_HD float refine_offset8(int g) {
   const int h = (g >= 4) ? g - 4 : 3 - g;

@@ -111,7 +111,7 @@ __device__ __forceinline__ int gshfl(unsigned mask, int v, int src) { return __s
 struct SamplePt { float c, d, e2, e3; };
 
 constexpr float kInterpTol = 1.0e-5f;   // agreement of the 4- and 6-point root estimates that ends the refinement
-constexpr float kWindowTol = 5.0e-7f;   // same, on the 0.01 km/s grid of the window round (agreement there is a weak error bound)
+constexpr float kClusterTol = 2.0e-6f;  // same, for the first round (cluster around the predicted root, bracket <= 3e-3 km/s)
 constexpr float kBracketTol = 2.0e-5f;  // bracket width below which a secant step is final
 
 template <int G>
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
     int mm = n;        // reference COMMON mmax carried from period to period
     int nfound = 0, flag = 0;
     bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
-    float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f;
+    float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f;
     for (int k = 0; k < K; ++k) {
       const float T = p.tab.per[k];
       const float lt = p.tab.lt[k];
@@ -222,20 +222,27 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
         if (j0 < 1000) {
           float pc = c1, pd = 0.f, pe2 = 0.f, pe3 = 0.f;
           int mj = n, mw = n, jev = -1, dir = 0, w0 = 2, sign0 = 0;
+          // stage 0 (from the third period on): 6 points clustered around the predicted root, spaced by the
+          // last prediction error; stage 1: window of 6 grid points around it; stage 2: window moved up or down.
+          int stage = (k >= 2 && j0 >= 4) ? 0 : 1;
+          const float hd = fminf(fmaxf(1.5f * pred_err, 5.0e-4f), 4.0e-3f);
           bool win_ok = false;
-          for (int wtry = 0; wtry < 4; ++wtry) {
-            // first try: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = window (grid
-            // indices j0..j0+5); an odd number of roots below the window shows as a sign difference between
-            // them.  Later tries (window moved up or down): all 8 lanes are window points.
-            const int idx = (gl < w0) ? ((gl == 0) ? 0 : j0 / 2) : j0 + (gl - w0);
-            pc = c1;
-            for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, p.dc);
+          for (int wtry = 0; wtry < 5; ++wtry) {
+            // stages 0/1: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = cluster / window
+            // (grid indices j0..j0+5); an odd number of roots below shows as a sign difference between them.
+            // stage 2: all 8 lanes are window points.
+            if (gl >= w0 && stage == 0) pc = c_pred + cluster_offset6(gl - 2) * hd;
+            else {
+              const int idx = (gl < w0) ? ((gl == 0) ? 0 : j0 / 2) : j0 + (gl - w0);
+              pc = c1;
+              for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, p.dc);
+            }
             mj = layer_drop(pc, T, p.fact, n, q1);
             mw = gshfl<G>(gmask, mj, G - 1);
             const float4 sv = secular(p.kind, pc, T, mw, q0, q1, 0);
             my_steps += (unsigned)(mw - 1); my_sweeps += 1;
             pd = sv.x; pe2 = sv.y; pe3 = sv.z;
-            if (wtry == 0) sign0 = (int)signbit(gshfl<G>(gmask, pd, 0));
+            if (w0) sign0 = (int)signbit(gshfl<G>(gmask, pd, 0));
             const float dpw = __shfl_up_sync(gmask, pd, 1, G);
             const bool changew = (gl > w0) && (signbit(dpw) != signbit(pd));
             const bool badw = (gl >= w0) && ((pc < 0.8f * b_top) || !(pc < q1[mj - 1].y) || !(pc == pc));
@@ -245,27 +252,28 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
             const unsigned evw = (__ballot_sync(gmask, wrong) >> gbase) & gbits;
             const bool below_ok = !(evw & ((2u << w0) - 1u));     // lanes 0..w0 have the sign of c1
             jev = __ffs(evc) - 1;
-            if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) { win_ok = true; break; }
+            if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) {
+              if (stage == 0 && (evc & (evc - 1u))) break;     // several sign changes inside the cluster
+              win_ok = true; break;
+            }
             if (evb) break;
-            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; continue; }   // root above the window
+            if (stage == 0) { stage = 1; continue; }           // the cluster does not bracket the root
+            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; stage = 2; continue; }   // root above the window
             if (!below_ok && dir <= 0) {
               // root below the window: only if it is between the half-way point and the window
               const bool lower_ok = !(evw & ((1u << w0) - 1u));
-              const int jmin = (wtry == 0) ? j0 / 2 : 0;
-              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - 7, jmin); w0 = 0; continue; }
+              const int jmin = w0 ? j0 / 2 : 0;
+              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - 7, jmin); w0 = 0; stage = 2; continue; }
             }
             break;
           }
           if (win_ok) {
-            const int mnew = gshfl<G>(gmask, mj, jev);
-            // the half-space velocity is a kink of the secular function (of the window's truncation, bh2, and
-            // of the reference's own, bh1): not within a grid step of the bracket, and the interpolation only
-            // uses window points below it
-            const float bh1 = q1[mnew - 1].y, bh2 = q1[mw - 1].y, bh = fminf(bh1, bh2);
+            // the half-space velocity of the window's truncation is a kink of the sampled function: not within
+            // a grid step of the bracket, and the interpolation only uses points below it
+            const float bh2 = q1[mw - 1].y;
             const float br_lo = gshfl<G>(gmask, pc, jev - 1), br_hi = gshfl<G>(gmask, pc, jev);
-            const int nvalid = __popc((__ballot_sync(gmask, gl >= w0 && pc < bh) >> gbase) & gbits);  // window points below the kink
-            const bool kink = (bh1 > br_lo - 0.011f && bh1 < br_hi + 0.011f) || (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) ||
-                              nvalid < 6 || jev - w0 > nvalid - 1;
+            const int nvalid = __popc((__ballot_sync(gmask, gl >= w0 && pc < bh2) >> gbase) & gbits);  // points below the kink
+            const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jev - w0 > nvalid - 1;
             if (!kink) {
               bool has_ends = false;
               int jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
@@ -295,7 +303,11 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
                 const float delta = fabsf(e6 - e4);
                 float e = e6;
                 if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
-                if ((inside && delta <= ((it == 0) ? kWindowTol : kInterpTol)) || w <= kBracketTol) {
+                // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
+                // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
+                const bool interior = (jb >= 2 && jb <= np - 2);
+                const float tol = (it > 0) ? kInterpTol : ((stage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
+                if ((inside && interior && delta <= tol) || w <= kBracketTol) {
                   croot = B0.c + e;
                   if (p.kind == 2) {
                     float xs[4], f2[4], f3[4], wl[4];
@@ -328,7 +340,12 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
                 else break;
               }
               if (fast_done) {
-                if (croot > q1[mnew - 1].y) fast_done = false;   // calcul.f:191 decided by the point-by-point path
+                // the reference's bracket is the grid interval around the root; its upper end fixes mmax
+                float hg = c1;
+                for (int t = 0; t < 4096 && !(hg > croot); ++t) hg = SD_ADD(hg, p.dc);
+                const int mnew = layer_drop(hg, T, p.fact, n, q1);
+                const float bh1 = q1[mnew - 1].y;
+                if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
                 else { mm = mnew; found = true; have_ratio = (p.kind == 2) && !mid_liquid; }
               }
             }
@@ -429,7 +446,7 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
         ratio = 0.5f * v.z / v.y;
       }
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
-      if (k >= 2 && fabsf(croot - c_pred) > 0.1f) hopped = true;
+      if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
       c_prev3 = c_prev2;
       c_prev2 = c_prev;
       c_prev = croot;

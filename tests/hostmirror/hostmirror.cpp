@@ -16,7 +16,7 @@ using namespace sd;
 namespace {
 struct Pt { float c, d, e2, e3; };
 constexpr float kInterpTol = 1.0e-5f;
-constexpr float kWindowTol = 5.0e-7f;
+constexpr float kClusterTol = 2.0e-6f;
 constexpr float kBracketTol = 2.0e-5f;
 }
 
@@ -49,7 +49,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   for (int i = 1; i < n; ++i) mid_liquid |= !(cst[C_BREF * ld + i] > 0.f);
   int mm = n, nfound = 0;
   bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
-  float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f;
+  float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f;
   long long nsw = 0;
   auto sweep = [&](float c, float T, int m, bool ell_only) {
     nsw++;
@@ -96,21 +96,29 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         std::vector<Pt> lane(G);
         std::vector<int> mj(G);
         int mw = 0, jev = -1, dir = 0, w0 = 2, sign0 = 0;
+        // stage 0 (from the third period on): 6 points clustered around the predicted root, spaced by the last
+        // prediction error; stage 1: window of 6 grid points around it; stage 2: window moved up or down.
+        int stage = (k >= 2 && j0 >= 4) ? 0 : 1;
+        const float hd = fminf(fmaxf(1.5f * pred_err, 5.0e-4f), 4.0e-3f);
         bool win_ok = false;
-        for (int wtry = 0; wtry < 4; ++wtry) {
+        for (int wtry = 0; wtry < 5; ++wtry) {
           nrounds++;
-          // first try: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = window (grid indices
-          // j0..j0+5); an odd number of roots below the window shows as a sign difference between them.
-          // Later tries (window moved up or down): all 8 lanes are window points.
+          // stages 0/1: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = cluster / window (grid
+          // indices j0..j0+5); an odd number of roots below shows as a sign difference between them.
+          // stage 2: all 8 lanes are window points.
           for (int g = 0; g < G; ++g) {
-            const int idx = (g < w0) ? ((g == 0) ? 0 : j0 / 2) : j0 + (g - w0);
-            float pc = c1;
-            for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, dc);
+            float pc;
+            if (g >= w0 && stage == 0) pc = c_pred + cluster_offset6(g - 2) * hd;
+            else {
+              const int idx = (g < w0) ? ((g == 0) ? 0 : j0 / 2) : j0 + (g - w0);
+              pc = c1;
+              for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, dc);
+            }
             lane[g].c = pc; mj[g] = layer_drop(pc, T, fact, n, q1.data());
           }
           mw = mj[G - 1];
           for (int g = 0; g < G; ++g) lane[g] = sweep(lane[g].c, T, mw, false);
-          if (wtry == 0) sign0 = (int)std::signbit(lane[0].d);
+          if (w0) sign0 = (int)std::signbit(lane[0].d);
           unsigned evc = 0, evb = 0;
           bool below_ok = true;
           for (int g = 0; g <= w0; ++g) below_ok &= ((int)std::signbit(lane[g].d) == sign0);
@@ -121,31 +129,32 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             if ((pc < 0.8f * b_top) || !(pc < q1[mj[g] - 1].y) || !(pc == pc)) evb |= 1u << g;
           }
           jev = evc ? __builtin_ctz(evc) : -1;
-          if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) { win_ok = true; break; }
+          if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) {
+            if (stage == 0 && (evc & (evc - 1u))) break;     // several sign changes inside the cluster
+            win_ok = true; break;
+          }
           if (evb) break;
-          if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; continue; }      // root above the window
+          if (stage == 0) { stage = 1; continue; }           // the cluster does not bracket the root
+          if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; stage = 2; continue; }      // root above the window
           if (!below_ok && dir <= 0) {
             // root below the window: only if it is between the half-way point and the window
             bool lower_ok = true;
             for (int g = 0; g < w0; ++g) lower_ok &= ((int)std::signbit(lane[g].d) == sign0);
-            const int jmin = (wtry == 0) ? j0 / 2 : 0;
-            if (lower_ok && j0 > jmin) { dir = -1; j0 = std::max(j0 - 7, jmin); w0 = 0; continue; }
+            const int jmin = w0 ? j0 / 2 : 0;
+            if (lower_ok && j0 > jmin) { dir = -1; j0 = std::max(j0 - 7, jmin); w0 = 0; stage = 2; continue; }
           }
           break;
         }
         if (!win_ok && getenv("HM_DEBUG")) fprintf(stderr, "winmiss k=%d T=%g jev=%d dir=%d c_pred=%g c1=%g lane0=%g\n", k, T, jev, dir, c_pred, c1, lane[0].c);
         if (win_ok) {
-          const int mnew = mj[jev];
-          // the half-space velocity is a kink of the secular function (of the window's truncation, bh2, and of
-          // the reference's own, bh1): not within a grid step of the bracket, and the interpolation only
-          // uses window points below it
-          const float bh1 = q1[mnew - 1].y, bh2 = q1[mw - 1].y, bh = fminf(bh1, bh2);
-          const float br_lo = lane[jev - 1].c, br_hi = lane[jev].c;   // jev > w0: both are window points
-          int nvalid = 0;   // window points below the kink
-          for (int g = w0; g < G; ++g) nvalid += (lane[g].c < bh);
-          const bool kink = (bh1 > br_lo - 0.011f && bh1 < br_hi + 0.011f) || (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) ||
-                            nvalid < 6 || jev - w0 > nvalid - 1;
-          if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh1=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh1, bh2, br_lo, br_hi, nvalid);
+          // the half-space velocity of the window's truncation is a kink of the sampled function: not within a
+          // grid step of the bracket, and the interpolation only uses points below it
+          const float bh2 = q1[mw - 1].y;
+          const float br_lo = lane[jev - 1].c, br_hi = lane[jev].c;   // jev > w0: both are cluster / window points
+          int nvalid = 0;   // points below the kink
+          for (int g = w0; g < G; ++g) nvalid += (lane[g].c < bh2);
+          const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jev - w0 > nvalid - 1;
+          if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh2, br_lo, br_hi, nvalid);
           if (!kink) {
             nwin_ok++;
             bool has_ends = false;
@@ -172,7 +181,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               const float delta = fabsf(e6 - e4);
               float e = e6;
               if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
-              if ((inside && delta <= ((it == 0) ? kWindowTol : kInterpTol)) || w <= kBracketTol) {
+              // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
+              // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
+              const bool interior = (jb >= 2 && jb <= np - 2);
+              const float tol = (it > 0) ? kInterpTol : ((stage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
+              if ((inside && interior && delta <= tol) || w <= kBracketTol) {
                 croot = B0.c + e;
                 if (getenv("HM_DEBUG2")) fprintf(stderr, "acc k=%d it=%d w=%g delta=%g e4=%g e6=%g inside=%d c=%.7f s6=%d jb=%d np=%d\n", k, it, w, delta, e4, e6, (int)inside, croot, s6, jb, np);
                 if (kind == 2) {
@@ -207,7 +220,12 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               else break;
             }
             if (fast_done) {
-              if (croot > q1[mnew - 1].y) fast_done = false;
+              // the reference's bracket is the grid interval around the root; its upper end fixes mmax
+              float hg = c1;
+              for (int t = 0; t < 4096 && !(hg > croot); ++t) hg = SD_ADD(hg, dc);
+              const int mnew = layer_drop(hg, T, fact, n, q1.data());
+              const float bh1 = q1[mnew - 1].y;
+              if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
               else { mm = mnew; found = true; have_ratio = (kind == 2) && !mid_liquid; }
             }
           }
@@ -288,7 +306,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       ratio = 0.5f * v.e3 / v.e2;
     }
     if (getenv("HM_PRED") && k >= 1) fprintf(stderr, "pred %d %g %g\n", k, croot - c_pred, (croot - c1) / dc);
-    if (k >= 2 && fabsf(croot - c_pred) > 0.1f) hopped = true;
+    if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
     c_out[k] = croot; ratio_out[k] = ratio; c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot; nfound = k + 1;
   }
   // phase 2
@@ -307,6 +325,21 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   if (sweeps) *sweeps += nsw;
   if (rounds_out) { rounds_out[0] += nrounds; rounds_out[1] += nslow; rounds_out[2] += nwin; rounds_out[3] += nwin_ok; rounds_out[4] += ndirect; }
   return nfound;
+}
+
+// Bit-for-bit comparison of the glibc logf / powf restatement (sd_libm.cuh) with the host libm over every
+// float in [lo, hi).  out = {count, logf mismatches, powf(x, 2.275) mismatches, powf(x, 5) mismatches}.
+void hm_libm_check(float lo, float hi, long long* out) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (float x = lo; x < hi; x = nextafterf(x, 3.0e38f)) {
+    out[0]++;
+    const float a = logf(x), b = sdm::logf_glibc(x);
+    out[1] += (memcmp(&a, &b, 4) != 0);
+    const float c = powf(x, 2.2750f), d = sdm::powf_glibc(x, 2.2750f);
+    out[2] += (memcmp(&c, &d, 4) != 0);
+    const float e = powf(x, 5.0f), f = sdm::powf_glibc(x, 5.0f);
+    out[3] += (memcmp(&e, &f, 4) != 0);
+  }
 }
 
 }  // extern "C"
