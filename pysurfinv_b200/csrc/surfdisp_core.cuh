@@ -131,13 +131,24 @@ SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* q1) {
   const float dmax = SD_MUL(SD_MUL(fact, c), T);
   float sum = 0.f;
   int mmax = nmax;
-  for (int ii = 0; ii < nmax; ++ii) {
-    float4 e = q1[ii];
+  // four layers per shared-memory round trip (the loop is latency bound: load -> compare -> add -> compare);
+  // the additions stay in the reference's order
+  int ii = 0;
+  for (; ii + 4 <= nmax; ii += 4) {
+    const float4 e0 = q1[ii], e1 = q1[ii + 1], e2 = q1[ii + 2], e3 = q1[ii + 3];
+    if (c < e0.y) { sum = SD_ADD(sum, e0.x); if (sum > dmax) { mmax = ii + 1; goto done; } }
+    if (c < e1.y) { sum = SD_ADD(sum, e1.x); if (sum > dmax) { mmax = ii + 2; goto done; } }
+    if (c < e2.y) { sum = SD_ADD(sum, e2.x); if (sum > dmax) { mmax = ii + 3; goto done; } }
+    if (c < e3.y) { sum = SD_ADD(sum, e3.x); if (sum > dmax) { mmax = ii + 4; goto done; } }
+  }
+  for (; ii < nmax; ++ii) {
+    const float4 e = q1[ii];
     if (c < e.y) {
       sum = SD_ADD(sum, e.x);
       if (sum > dmax) { mmax = ii + 1; break; }
     }
   }
+done:
   return mmax < 2 ? 2 : mmax;
 }
 

@@ -233,9 +233,10 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
             // stage 2: all 8 lanes are window points.
             if (gl >= w0 && stage == 0) pc = c_pred + cluster_offset6(gl - 2) * hd;
             else {
+              // grid points in closed form: the fast path only needs the signs there (the reference's own
+              // sequentially accumulated grid differs by a few ulps, i.e. 1e-4 of a grid step)
               const int idx = (gl < w0) ? ((gl == 0) ? 0 : j0 / 2) : j0 + (gl - w0);
-              pc = c1;
-              for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, p.dc);
+              pc = c1 + (float)idx * p.dc;
             }
             mj = layer_drop(pc, T, p.fact, n, q1);
             mw = gshfl<G>(gmask, mj, G - 1);
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
               }
               if (fast_done) {
                 // the reference's bracket is the grid interval around the root; its upper end fixes mmax
-                float hg = c1;
-                for (int t = 0; t < 4096 && !(hg > croot); ++t) hg = SD_ADD(hg, p.dc);
+                float hg = c1 + (floorf((croot - c1) / p.dc) + 1.f) * p.dc;
+                if (!(hg > croot)) hg += p.dc;
                 const int mnew = layer_drop(hg, T, p.fact, n, q1);
                 const float bh1 = q1[mnew - 1].y;
                 if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path

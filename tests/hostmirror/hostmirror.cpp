@@ -111,8 +111,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             if (g >= w0 && stage == 0) pc = c_pred + cluster_offset6(g - 2) * hd;
             else {
               const int idx = (g < w0) ? ((g == 0) ? 0 : j0 / 2) : j0 + (g - w0);
-              pc = c1;
-              for (int t = 0; t < idx; ++t) pc = SD_ADD(pc, dc);
+              pc = c1 + (float)idx * dc;
             }
             lane[g].c = pc; mj[g] = layer_drop(pc, T, fact, n, q1.data());
           }
@@ -221,8 +220,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             }
             if (fast_done) {
               // the reference's bracket is the grid interval around the root; its upper end fixes mmax
-              float hg = c1;
-              for (int t = 0; t < 4096 && !(hg > croot); ++t) hg = SD_ADD(hg, dc);
+              float hg = c1 + (floorf((croot - c1) / dc) + 1.f) * dc;
+              if (!(hg > croot)) hg += dc;
               const int mnew = layer_drop(hg, T, fact, n, q1.data());
               const float bh1 = q1[mnew - 1].y;
               if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
