@@ -50,10 +50,10 @@ namespace sd {
 // calcul.f:112-133 + flat1.f).  One row of NCONST arrays per model.
 enum { C_AREF = 0, C_BREF = 1, C_QS = 2, C_DIF = 3, C_RHOFL = 4, C_DFL = 5, C_HSF = 6, C_RHOHS = 7, NCONST = 8 };
 
-// Working layer record in shared memory (what one secular-function layer step reads).
-//   q0 = (1/a^2, 1/b^2, 2 b^2, rho)      b == 0 (liquid) is flagged by q0.y == 0
-//   q1 = (d, b, 1/rho, a)
-struct LayerRec { float4 q0, q1; };
+// Working layer record in shared memory: one float4 (a, b, rho, d) per layer for the current period
+// (attenuation-corrected, flattened).  b == 0 flags a liquid layer.  The reciprocals the layer step needs
+// (1/a^2, 1/b^2, 1/rho) are MUFU.RCP results formed on the fly: 16 bytes per layer instead of 32 lets twice
+// as many models stay resident per SM.
 
 // ----------------------------------------------------------------------------------------------
 // Model preparation.  flat1.f:33-69 evaluated once per model: radii by sequential float32 prefix sum,
@@ -118,16 +118,11 @@ SD_HD void layer_ab(const float* cst, int ld, int i, float lt, int atten, bool a
   b = SD_MUL(b, f);
 }
 
-SD_HD LayerRec make_rec(float a, float b, float rho, float d) {
-  LayerRec r;
-  r.q0 = make_float4(1.0f / (a * a), (b > 0.f) ? 1.0f / (b * b) : 0.f, 2.0f * b * b, rho);
-  r.q1 = make_float4(d, b, 1.0f / rho, a);
-  return r;
-}
+SD_HD float4 make_rec(float a, float b, float rho, float d) { return make_float4(a, b, rho, d); }
 
 // ----------------------------------------------------------------------------------------------
 // Layer dropping, surfa.f:92-106.  Returns mmax (1-based count of layers kept, >= 2).
-SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* q1) {
+SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* rec) {
   const float dmax = SD_MUL(SD_MUL(fact, c), T);
   float sum = 0.f;
   int mmax = nmax;
@@ -135,16 +130,16 @@ SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* q1) {
   // the additions stay in the reference's order
   int ii = 0;
   for (; ii + 4 <= nmax; ii += 4) {
-    const float4 e0 = q1[ii], e1 = q1[ii + 1], e2 = q1[ii + 2], e3 = q1[ii + 3];
-    if (c < e0.y) { sum = SD_ADD(sum, e0.x); if (sum > dmax) { mmax = ii + 1; goto done; } }
-    if (c < e1.y) { sum = SD_ADD(sum, e1.x); if (sum > dmax) { mmax = ii + 2; goto done; } }
-    if (c < e2.y) { sum = SD_ADD(sum, e2.x); if (sum > dmax) { mmax = ii + 3; goto done; } }
-    if (c < e3.y) { sum = SD_ADD(sum, e3.x); if (sum > dmax) { mmax = ii + 4; goto done; } }
+    const float4 e0 = rec[ii], e1 = rec[ii + 1], e2 = rec[ii + 2], e3 = rec[ii + 3];
+    if (c < e0.y) { sum = SD_ADD(sum, e0.w); if (sum > dmax) { mmax = ii + 1; goto done; } }
+    if (c < e1.y) { sum = SD_ADD(sum, e1.w); if (sum > dmax) { mmax = ii + 2; goto done; } }
+    if (c < e2.y) { sum = SD_ADD(sum, e2.w); if (sum > dmax) { mmax = ii + 3; goto done; } }
+    if (c < e3.y) { sum = SD_ADD(sum, e3.w); if (sum > dmax) { mmax = ii + 4; goto done; } }
   }
   for (; ii < nmax; ++ii) {
-    const float4 e = q1[ii];
+    const float4 e = rec[ii];
     if (c < e.y) {
-      sum = SD_ADD(sum, e.x);
+      sum = SD_ADD(sum, e.w);
       if (sum > dmax) { mmax = ii + 1; break; }
     }
   }
@@ -216,189 +211,189 @@ SD_HD void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// Rayleigh secular function: Dunkin compound-matrix vector propagated top-down through layers
-// 1..mmax-1 and contracted with the half-space row (surfa.f:193-357).
-//   start = 1: dispersion function (returns -bb1)
-//   start = 2 / 3: the two ellipticity sweeps (returns bb1); liquid layers are skipped there
-//   (surfa.f:220).
+// Rayleigh secular function (surfa.f:193-357), adjoint form.  The reference propagates the Dunkin
+// compound-matrix COLUMN vector top-down through layers 1..mmax-1 and contracts it with the half-space row h
+// (surfa.f:341-354): the dispersion function and the two ellipticity sweeps are h^T P e1, h^T P e2 and
+// h^T P e3 with the same layer product P = A(mmax-1) ... A(1).  Propagating the ROW vector upwards instead
+// (r <- r A(m), m = mmax-1 .. 1) yields all three from one sweep: Delta = -r1, ellipticity = 0.5 r3 / r2
+// (surfa.f:360-363), with (e2, e3) = (r2, r3) returned separately (the caller interpolates them to the root
+// before dividing).  Same 25 multiply-adds per layer as the column form, but every trial velocity of the root
+// search carries its ellipticity, so the reference's two extra sweeps per period disappear.
 // The 15 matrix entries of surfa.f:289-320 are formed from shared sub-expressions
 // (w = 2 g g1 (1-cc) + g^2 rr + g1^2 ss gives a11 = cc - w and a33 = 1 + 2w, etc.).
-SD_HD float rayleigh_sweep(float c, float T, int mmax, const float4* q0, const float4* q1, int start) {
-  const float wvno = SD_TWOPI / (c * T);
-  const float csq = c * c;
-  const float icsq = 1.0f / csq;
-  float b1 = (start == 1) ? 1.f : 0.f, b2 = (start == 2) ? 1.f : 0.f, b3 = (start == 3) ? 1.f : 0.f;
-  float b4 = 0.f, b5 = 0.f;
-  const int last = mmax - 1;
-  for (int m = 0; m < last; ++m) {
-    const float4 L = q0[m];
-    const float4 E = q1[m];
-    const float kd = wvno * E.x;
-    const float kd2 = kd * kd;
-    float rsinp, sinpr, cosp;
-    half_terms(1.0f - csq * L.x, kd, kd2, rsinp, sinpr, cosp);
-    if (L.y == 0.f) {
-      // liquid layer (surfa.f:219-251): only a11 = cosp, a21 = rho c^2 sinpr are non-zero
-      if (start != 1) continue;
-      const float a21 = L.w * csq * sinpr;
-      const float n1 = cosp * b1, n2 = a21 * b1, n5 = cosp * b5 - a21 * b4;
-      b1 = n1; b2 = n2; b3 = 0.f; b4 = 0.f; b5 = n5;
-      continue;
-    }
-    float rsinq, sinqr, cosq;
-    half_terms(1.0f - csq * L.y, kd, kd2, rsinq, sinqr, cosq);
-    const float g = L.z * icsq;
-    const float g1 = g - 1.0f;
-    const float rhoc = L.w * csq;
-    const float irhoc = E.z * icsq;
-    const float rr = rsinp * rsinq, ss = sinpr * sinqr, cc = cosp * cosq;
-    const float rs1 = rsinp * cosq, rs2 = sinqr * cosp, rs3 = sinpr * cosq, rs4 = rsinq * cosp;
-    const float a24 = sinpr * rsinq, a42 = rsinp * sinqr;
-    const float gm = g + g1, gs = g * g, g1s = g1 * g1, gg1 = g * g1, ccm = 1.0f - cc;
-    const float suu = gs * rr + g1s * ss;
-    const float w = 2.f * gg1 * ccm + suu;
-    const float a11 = cc - w;
-    const float a33 = 1.f + 2.f * w;
-    const float a12 = -(rs1 + rs2) * irhoc;
-    const float a14 = (rs3 + rs4) * irhoc;
-    const float a13h = -(gm * ccm + g1 * ss + g * rr) * irhoc;          // = 0.5 * a13
-    const float a15 = (2.f * ccm + rr + ss) * (irhoc * irhoc);
-    const float a21 = rhoc * (g1s * rs3 + gs * rs4);
-    const float a41 = -rhoc * (g1s * rs2 + gs * rs1);
-    const float a23h = g * rs4 + g1 * rs3;                               // = 0.5 * a23
-    const float a32 = g1 * rs2 + g * rs1;
-    const float a31 = rhoc * (gg1 * gm * ccm + (g1s * g1) * ss + (gs * g) * rr);
-    const float a51 = (rhoc * rhoc) * (2.f * (gg1 * gg1) * ccm + (gs * gs) * rr + (g1s * g1s) * ss);
-    // surfa.f:326-330
-    const float n1 = a11 * b1 + a12 * b2 + 2.f * a13h * b3 + a14 * b4 + a15 * b5;
-    const float n2 = a21 * b1 + cc * b2 + 2.f * a23h * b3 + a24 * b4 - a14 * b5;
-    const float n3 = a31 * b1 + a32 * b2 + a33 * b3 - a23h * b4 + a13h * b5;
-    const float n4 = a41 * b1 + a42 * b2 - 2.f * a32 * b3 + cc * b4 - a12 * b5;
-    const float n5 = a51 * b1 - a41 * b2 + 2.f * a31 * b3 - a21 * b4 + a11 * b5;
-    b1 = n1; b2 = n2; b3 = n3; b4 = n4; b5 = n5;
-  }
-  // half-space row (surfa.f:341-354)
-  {
-    const float4 L = q0[last];
-    const float4 E = q1[last];
-    const float arga = 1.0f - csq * L.x;
-    const float argb = 1.0f - csq * L.y;
-    float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
-    float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
-    const float g = L.z * icsq;
-    const float g1 = g - 1.0f;
-    const float pp = E.w;
-    const float sss = 0.5f * L.z;
-    const float ppp = pp * pp;
-    const float rhp = L.w * pp;
-    const float gra = g * ra;
-    const float g1s = g1 * g1;
-    const float rba = rb - 1.0f / ra;
-    const float h11 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
-    float h12 = rhp * pp;
-    const float h13 = -rb / h12 + g1 / h12 / gra;
-    const float h14 = rb / h12 / gra;
-    const float h15 = rba / rhp / rhp / csq / g;
-    h12 = -1.0f / g / h12;
-    const float bb1 = h11 * b1 + h12 * b2 + 2.f * h13 * b3 + h14 * b4 + h15 * b5;
-    return (start == 1) ? -bb1 : bb1;
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
-// Rayleigh secular function, adjoint form.  The dispersion function and the two ellipticity sweeps of the
-// reference are h^T P e1, h^T P e2 and h^T P e3 with the same layer product P = A(mmax-1) ... A(1) and the
-// same half-space row h (surfa.f:341-354); propagating the ROW vector r^T = h^T A(mmax-1) ... upwards
-// (r <- r A(m), m = mmax-1 .. 1) yields all three from one sweep: Delta = -r1, ellipticity = 0.5 r3 / r2
-// with (e2, e3) = (r2, r3) returned separately (the caller interpolates them to the root before dividing)
-// (surfa.f:360-363).  Same 25 multiply-adds per layer as the column form, but every trial velocity of the
-// root polish now carries its ellipticity, so the two extra sweeps per period disappear.
 // A liquid top layer (surfa.f:219-251) closes the sweep: the ellipticity is taken below it (the reference
 // skips liquid layers there, surfa.f:220), the dispersion function includes it.  Liquid layers deeper in the
 // stack get dispersion-function semantics; for such stacks (e2, e3) must come from a second sweep with
 // ell_only = true, which skips every liquid layer like the reference's ellipticity sweeps do.
-SD_HD float rayleigh_adjoint(float c, float T, int mmax, const float4* q0, const float4* q1, bool ell_only,
-                             float& e2, float& e3) {
-  const float wvno = SD_TWOPI / (c * T);
-  const float csq = c * c;
-  const float icsq = 1.0f / csq;
-  const int last = mmax - 1;
-  float r1, r2, r3, r4, r5;
-  {
-    const float4 L = q0[last];
-    const float4 E = q1[last];
-    const float arga = 1.0f - csq * L.x;
-    const float argb = 1.0f - csq * L.y;
-    float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
-    float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
-    const float g = L.z * icsq;
-    const float g1 = g - 1.0f;
-    const float pp = E.w;
-    const float sss = 0.5f * L.z;
-    const float ppp = pp * pp;
-    const float rhp = L.w * pp;
-    const float gra = g * ra;
-    const float g1s = g1 * g1;
-    const float rba = rb - 1.0f / ra;
-    const float h12 = rhp * pp;
-    r1 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
-    r3 = 2.f * (-rb / h12 + g1 / h12 / gra);
-    r4 = rb / h12 / gra;
-    r5 = rba / rhp / rhp / csq / g;
-    r2 = -1.0f / g / h12;
+
+// ----------------------------------------------------------------------------------------------
+// Two trial velocities per lane.  sm_100 has packed FP32 arithmetic (fma/mul/add.rn.f32x2 -> FFMA2 / FMUL2 /
+// FADD2): one issue slot for two lanes' worth of work, and the packed multiply / add also run at twice the
+// scalar rate (tools/microbench/ffma2_bench.cu).  The secular-function loop is issue bound, and everything
+// in it is elementwise in the trial velocity (the layer data are shared), so each lane carries a PAIR of
+// velocities through the sweep.
+#if defined(__CUDACC__)
+typedef float2 V2;
+#else
+typedef struct float2 V2;   // the host mirror's plain struct (top of this file)
+#endif
+SD_HD V2 v2(float a, float b) { V2 r; r.x = a; r.y = b; return r; }
+#if defined(__CUDA_ARCH__)
+SD_HD V2 vmul(V2 a, V2 b) { return __fmul2_rn(a, b); }
+SD_HD V2 vadd(V2 a, V2 b) { return __fadd2_rn(a, b); }
+SD_HD V2 vfma(V2 a, V2 b, V2 c) { return __ffma2_rn(a, b, c); }
+#else
+SD_HD V2 vmul(V2 a, V2 b) { return v2(a.x * b.x, a.y * b.y); }
+SD_HD V2 vadd(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+SD_HD V2 vfma(V2 a, V2 b, V2 c) { return v2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+SD_HD V2 vs(float s) { return v2(s, s); }
+SD_HD V2 vneg(V2 a) { return v2(-a.x, -a.y); }
+SD_HD V2 vsub(V2 a, V2 b) { return vfma(b, vs(-1.f), a); }
+
+// half_terms for a pair; the series branch is taken only if both velocities qualify
+SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
+  const V2 u = vmul(kd2, arg);
+  if (fmaxf(fabsf(u.x), fabsf(u.y)) < 0.5f) {
+    V2 S = vfma(u, vs(2.7557319e-6f), vs(1.9841270e-4f));
+    S = vfma(u, S, vs(8.3333333e-3f));
+    S = vfma(u, S, vs(1.6666667e-1f));
+    S = vfma(u, S, vs(1.f));
+    V2 C = vfma(u, vs(2.7557319e-7f), vs(2.4801587e-5f));
+    C = vfma(u, C, vs(1.3888889e-3f));
+    C = vfma(u, C, vs(4.1666667e-2f));
+    C = vfma(u, C, vs(0.5f));
+    cs = vfma(u, C, vs(1.f));
+    sinr = vmul(kd, S);
+    rsin = vmul(vneg(arg), sinr);
+    return;
   }
+  half_terms(arg.x, kd.x, kd2.x, rsin.x, sinr.x, cs.x);
+  half_terms(arg.y, kd.y, kd2.y, rsin.y, sinr.y, cs.y);
+}
+
+// Half-space row of the Rayleigh secular function (surfa.f:341-354) for one velocity; R = (a, b, rho, d)
+SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, float& r2, float& r3, float& r4, float& r5) {
+  const float pp = R.x, b2 = 2.0f * R.y * R.y;
+  const float arga = 1.0f - csq / (pp * pp);
+  const float argb = 1.0f - csq / (R.y * R.y);
+  float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
+  float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
+  const float g = b2 * icsq;
+  const float g1 = g - 1.0f;
+  const float sss = 0.5f * b2;
+  const float ppp = pp * pp;
+  const float rhp = R.z * pp;
+  const float gra = g * ra;
+  const float g1s = g1 * g1;
+  const float rba = rb - 1.0f / ra;
+  const float h12 = rhp * pp;
+  r1 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
+  r3 = 2.f * (-rb / h12 + g1 / h12 / gra);
+  r4 = rb / h12 / gra;
+  r5 = rba / rhp / rhp / csq / g;
+  r2 = -1.0f / g / h12;
+}
+
+// Rayleigh sweep for a pair of trial velocities (same truncation depth mmax, same period)
+SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_only, V2& e2, V2& e3) {
+  const V2 csq = vmul(c, c);
+  const V2 icsq = v2(1.0f / csq.x, 1.0f / csq.y);
+  const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
+  const V2 ncsq = vneg(csq);
+  const int last = mmax - 1;
+  V2 r1, r2, r3, r4, r5;
+  rayleigh_hs_row(csq.x, icsq.x, rec[last], r1.x, r2.x, r3.x, r4.x, r5.x);
+  rayleigh_hs_row(csq.y, icsq.y, rec[last], r1.y, r2.y, r3.y, r4.y, r5.y);
+  const V2 one = vs(1.f), two = vs(2.f);
   for (int m = last - 1; m >= 0; --m) {
-    const float4 L = q0[m];
-    const float4 E = q1[m];
-    const float kd = wvno * E.x;
-    const float kd2 = kd * kd;
-    float rsinp, sinpr, cosp;
-    half_terms(1.0f - csq * L.x, kd, kd2, rsinp, sinpr, cosp);
-    if (L.y == 0.f) {
+    const float4 R = rec[m];
+    const float ia = sd_rcp(R.x), ia2 = ia * ia;
+    const V2 kd = vmul(wvno, vs(R.w));
+    const V2 kd2 = vmul(kd, kd);
+    V2 rsinp, sinpr, cosp;
+    half_terms2(vfma(ncsq, vs(ia2), one), kd, kd2, rsinp, sinpr, cosp);
+    if (R.y == 0.f) {
       if (ell_only) continue;
-      const float a21 = L.w * csq * sinpr;
+      const V2 a21 = vmul(vmul(vs(R.z), csq), sinpr);
+      const V2 n1 = vfma(r1, cosp, vmul(r2, a21));
       if (m == 0) {
         e2 = r2; e3 = r3;
-        return -(r1 * cosp + r2 * a21);
+        return vneg(n1);
       }
-      const float n1 = r1 * cosp + r2 * a21, n4 = -r5 * a21, n5 = r5 * cosp;
-      r1 = n1; r2 = 0.f; r3 = 0.f; r4 = n4; r5 = n5;
+      const V2 n4 = vneg(vmul(r5, a21)), n5 = vmul(r5, cosp);
+      r1 = n1; r2 = vs(0.f); r3 = vs(0.f); r4 = n4; r5 = n5;
       continue;
     }
-    float rsinq, sinqr, cosq;
-    half_terms(1.0f - csq * L.y, kd, kd2, rsinq, sinqr, cosq);
-    const float g = L.z * icsq;
-    const float g1 = g - 1.0f;
-    const float rhoc = L.w * csq;
-    const float irhoc = E.z * icsq;
-    const float rr = rsinp * rsinq, ss = sinpr * sinqr, cc = cosp * cosq;
-    const float rs1 = rsinp * cosq, rs2 = sinqr * cosp, rs3 = sinpr * cosq, rs4 = rsinq * cosp;
-    const float a24 = sinpr * rsinq, a42 = rsinp * sinqr;
-    const float gm = g + g1, gs = g * g, g1s = g1 * g1, gg1 = g * g1, ccm = 1.0f - cc;
-    const float suu = gs * rr + g1s * ss;
-    const float w = 2.f * gg1 * ccm + suu;
-    const float a11 = cc - w;
-    const float a33 = 1.f + 2.f * w;
-    const float a12 = -(rs1 + rs2) * irhoc;
-    const float a14 = (rs3 + rs4) * irhoc;
-    const float a13h = -(gm * ccm + g1 * ss + g * rr) * irhoc;
-    const float a15 = (2.f * ccm + rr + ss) * (irhoc * irhoc);
-    const float a21 = rhoc * (g1s * rs3 + gs * rs4);
-    const float a41 = -rhoc * (g1s * rs2 + gs * rs1);
-    const float a23h = g * rs4 + g1 * rs3;
-    const float a32 = g1 * rs2 + g * rs1;
-    const float a31 = rhoc * (gg1 * gm * ccm + (g1s * g1) * ss + (gs * g) * rr);
-    const float a51 = (rhoc * rhoc) * (2.f * (gg1 * gg1) * ccm + (gs * gs) * rr + (g1s * g1s) * ss);
-    // r <- r A with A the matrix of surfa.f:326-330 (rows as in rayleigh_sweep)
-    const float n1 = r1 * a11 + r2 * a21 + r3 * a31 + r4 * a41 + r5 * a51;
-    const float n2 = r1 * a12 + r2 * cc + r3 * a32 + r4 * a42 - r5 * a41;
-    const float n3 = 2.f * (r1 * a13h + r2 * a23h - r4 * a32 + r5 * a31) + r3 * a33;
-    const float n4 = r1 * a14 + r2 * a24 - r3 * a23h + r4 * cc - r5 * a21;
-    const float n5 = r1 * a15 - r2 * a14 + r3 * a13h - r4 * a12 + r5 * a11;
+    const float ib = sd_rcp(R.y), ib2 = ib * ib, b2 = 2.0f * R.y * R.y, irho = sd_rcp(R.z);
+    V2 rsinq, sinqr, cosq;
+    half_terms2(vfma(ncsq, vs(ib2), one), kd, kd2, rsinq, sinqr, cosq);
+    const V2 g = vmul(vs(b2), icsq);
+    const V2 g1 = vadd(g, vs(-1.f));
+    const V2 rhoc = vmul(vs(R.z), csq);
+    const V2 irhoc = vmul(vs(irho), icsq);
+    const V2 rr = vmul(rsinp, rsinq), ss = vmul(sinpr, sinqr), cc = vmul(cosp, cosq);
+    const V2 rs1 = vmul(rsinp, cosq), rs2 = vmul(sinqr, cosp), rs3 = vmul(sinpr, cosq), rs4 = vmul(rsinq, cosp);
+    const V2 a24 = vmul(sinpr, rsinq), a42 = vmul(rsinp, sinqr);
+    const V2 gm = vadd(g, g1), gs = vmul(g, g), g1s = vmul(g1, g1), gg1 = vmul(g, g1);
+    const V2 ccm = vsub(one, cc);
+    const V2 suu = vfma(gs, rr, vmul(g1s, ss));
+    const V2 w = vfma(vmul(two, gg1), ccm, suu);
+    const V2 a11 = vsub(cc, w);
+    const V2 a33 = vfma(two, w, one);
+    const V2 nirhoc = vneg(irhoc);
+    const V2 a12 = vmul(vadd(rs1, rs2), nirhoc);
+    const V2 a14 = vmul(vadd(rs3, rs4), irhoc);
+    const V2 a13h = vmul(vfma(gm, ccm, vfma(g1, ss, vmul(g, rr))), nirhoc);          // = 0.5 * a13
+    const V2 a15 = vmul(vfma(two, ccm, vadd(rr, ss)), vmul(irhoc, irhoc));
+    const V2 a21 = vmul(rhoc, vfma(g1s, rs3, vmul(gs, rs4)));
+    const V2 a41 = vmul(vneg(rhoc), vfma(g1s, rs2, vmul(gs, rs1)));
+    const V2 a23h = vfma(g, rs4, vmul(g1, rs3));                                       // = 0.5 * a23
+    const V2 a32 = vfma(g1, rs2, vmul(g, rs1));
+    const V2 a31 = vmul(rhoc, vfma(vmul(gg1, gm), ccm, vfma(vmul(g1s, g1), ss, vmul(vmul(gs, g), rr))));
+    const V2 a51 = vmul(vmul(rhoc, rhoc), vfma(vmul(two, vmul(gg1, gg1)), ccm, vfma(vmul(gs, gs), rr, vmul(vmul(g1s, g1s), ss))));
+    // r <- r A (rows of A as in surfa.f:326-330)
+    const V2 n1 = vfma(r1, a11, vfma(r2, a21, vfma(r3, a31, vfma(r4, a41, vmul(r5, a51)))));
+    const V2 n2 = vfma(r1, a12, vfma(r2, cc, vfma(r3, a32, vfma(r4, a42, vmul(vneg(r5), a41)))));
+    const V2 n3 = vfma(two, vfma(r1, a13h, vfma(r2, a23h, vfma(vneg(r4), a32, vmul(r5, a31)))), vmul(r3, a33));
+    const V2 n4 = vfma(r1, a14, vfma(r2, a24, vfma(vneg(r3), a23h, vfma(r4, cc, vmul(vneg(r5), a21)))));
+    const V2 n5 = vfma(r1, a15, vfma(vneg(r2), a14, vfma(r3, a13h, vfma(vneg(r4), a12, vmul(r5, a11)))));
     r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5;
   }
   e2 = r2; e3 = r3;
-  return -r1;
+  return vneg(r1);
+}
+
+// Love secular function for a pair of trial velocities: (displacement, stress) propagated from the half-space
+// up (surfa.f:143-182).  With q = -k d rb (surfa.f:156): y = sin(q)/rb = -sinr, z = rb sin(q) = -rsin (both
+// branches and the rb -> 0 limit of surfa.f:164-166), cos(q) = cs.
+SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec) {
+  const V2 csq = vmul(c, c);
+  const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
+  const V2 ncsq = vneg(csq);
+  const int last = mmax - 1;
+  V2 ut, tt;
+  {
+    const float4 R = rec[last];
+    const float h = R.z * R.y * R.y, ib2 = 1.0f / (R.y * R.y);
+    ut = vs(1.f);
+    tt = v2(h * sqrtf(fabsf(csq.x * ib2 - 1.0f)), h * sqrtf(fabsf(csq.y * ib2 - 1.0f)));
+  }
+  for (int m = last - 1; m >= 0; --m) {
+    const float4 R = rec[m];
+    if (R.y == 0.f) continue;  // liquid layer skipped (surfa.f:152)
+    const float ib = sd_rcp(R.y), ib2 = ib * ib;
+    const V2 kd = vmul(wvno, vs(R.w));
+    V2 rsin, sinr, cs;
+    half_terms2(vfma(ncsq, vs(ib2), vs(1.f)), kd, vmul(kd, kd), rsin, sinr, cs);
+    const float h = R.z * R.y * R.y;
+    const float ih = sd_rcp(R.z) * ib2;
+    const V2 eut = vfma(cs, ut, vmul(vmul(sinr, tt), vs(ih)));
+    const V2 ett = vfma(cs, tt, vmul(vmul(vs(-h), rsin), ut));
+    ut = eut;
+    tt = ett;
+  }
+  return vneg(tt);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -435,51 +430,14 @@ SD_HD void lagrange4(const float* xs, float x, float* w) {
   w[3] = d0 * d1 * d2 / ((xs[3] - xs[0]) * (xs[3] - xs[1]) * (xs[3] - xs[2]));
 }
 
-// Offsets (in units of the cluster spacing) of the 6 points of the first round around the predicted root
-SD_HD float cluster_offset6(int i) {
-  const int h = (i >= 3) ? i - 3 : 2 - i;
-  const float m = (h == 0) ? 0.5f : ((h == 1) ? 1.5f : 4.f);
-  return (i >= 3) ? m : -m;
-}
-
-// Offsets (in units of s0) of the G = 8 points of a refinement round around the root estimate
-SD_HD float refine_offset8(int g) {
-  const int h = (g >= 4) ? g - 4 : 3 - g;
-  const float m = (h == 0) ? 0.5f : ((h == 1) ? 1.5f : ((h == 2) ? 4.f : 12.f));
-  return (g >= 4) ? m : -m;
-}
-
-// ----------------------------------------------------------------------------------------------
-// Love secular function: (displacement, stress) propagated from the half-space up (surfa.f:143-182).
-SD_HD float love_sweep(float c, float T, int mmax, const float4* q0, const float4* q1) {
-  const float wvno = SD_TWOPI / (c * T);
-  const float csq = c * c;
-  const int last = mmax - 1;
-  float ut, tt;
-  {
-    const float4 L = q0[last];
-    const float h = L.w * 0.5f * L.z;
-    const float rb = sqrtf(fabsf(csq * L.y - 1.0f));
-    ut = 1.f;
-    tt = h * rb;
-  }
-  for (int m = last - 1; m >= 0; --m) {
-    const float4 L = q0[m];
-    if (L.y == 0.f) continue;  // liquid layer skipped (surfa.f:152)
-    const float4 E = q1[m];
-    const float kd = wvno * E.x;
-    // with q = -k d rb (surfa.f:156): y = sin(q)/rb = -sinr, z = rb sin(q) = -rsin (both branches and
-    // the rb -> 0 limit of surfa.f:164-166), cos(q) = cs
-    float rsin, sinr, cs;
-    half_terms(1.0f - csq * L.y, kd, kd * kd, rsin, sinr, cs);
-    const float h = L.w * 0.5f * L.z;
-    const float ih = E.z * L.y;
-    const float eut = cs * ut + sinr * tt * ih;
-    const float ett = cs * tt - h * rsin * ut;
-    ut = eut;
-    tt = ett;
-  }
-  return -tt;
+// Offsets of the points of a clustered round around a root estimate, in units of the innermost half spacing:
+// +-(0.5, 1.5, 3.5, 7.5, 15.5, ...) for i = 0 .. n-1 in ascending order (n even): every interval is twice as
+// wide as its inner neighbour, so a bracket found at distance e from the estimate is about e/2 wide.
+SD_HD float geometric_offset(int i, int n) {
+  const int half = n / 2;
+  const int h = (i >= half) ? i - half : half - 1 - i;
+  const float m = (float)(1 << h) - 0.5f;
+  return (i >= half) ? m : -m;
 }
 
 // ----------------------------------------------------------------------------------------------

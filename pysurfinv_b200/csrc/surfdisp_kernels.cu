@@ -91,15 +91,18 @@ struct P1Params {
   PeriodTab tab;
 };
 
-// One copy of the secular-function loop for all call sites (window, refinement, scan, polish, ellipticity):
-// inlining it at every site made the kernel ~95 KB of SASS and the warps stalled on instruction fetch.
-// Returns (Delta, e2, e3, -): Rayleigh sweeps are done in the adjoint form, which carries the two
-// ellipticity minors along with the dispersion function.
-__device__ __noinline__ float4 secular(int kind, float c, float T, int mm, const float4* q0, const float4* q1,
-                                       int ell_only) {
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (kind == 2) r.x = rayleigh_adjoint(c, T, mm, q0, q1, ell_only != 0, r.y, r.z);
-  else r.x = love_sweep(c, T, mm, q0, q1);
+// One copy of the secular-function loop for all call sites (cluster / window, refinement, scan, polish,
+// ellipticity): inlining it at every site made the kernel ~95 KB of SASS and the warps stalled on instruction
+// fetch.  Every lane carries a PAIR of trial velocities (packed FP32 arithmetic, see surfdisp_core.cuh);
+// Rayleigh sweeps are done in the adjoint form, which yields the two ellipticity minors along with the
+// dispersion function.
+struct Sec2 { float2 d, e2, e3; };
+
+__device__ __noinline__ Sec2 secular2(int kind, float2 c, float T, int mm, const float4* rec, int ell_only) {
+  Sec2 r;
+  r.e2 = make_float2(0.f, 0.f); r.e3 = r.e2;
+  if (kind == 2) r.d = rayleigh_adjoint2(c, T, mm, rec, ell_only != 0, r.e2, r.e3);
+  else r.d = love_sweep2(c, T, mm, rec);
   return r;
 }
 
@@ -113,10 +116,27 @@ struct SamplePt { float c, d, e2, e3; };
 constexpr float kInterpTol = 1.0e-5f;   // agreement of the 4- and 6-point root estimates that ends the refinement
 constexpr float kClusterTol = 2.0e-6f;  // same, for the first round (cluster around the predicted root, bracket <= 3e-3 km/s)
 constexpr float kBracketTol = 2.0e-5f;  // bracket width below which a secant step is final
+constexpr float kClusterH0 = 2.5e-4f;   // smallest innermost spacing of the first-round cluster
 
+// bit i of the result = bit i/2 of a (i even) or of b (i odd)
 template <int G>
-__global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ P1Params p) {
-  static_assert(G == 8, "the refinement rounds are laid out for 8 lanes per model");
+__device__ __forceinline__ unsigned interleave(unsigned a, unsigned b) {
+  unsigned r = 0;
+#pragma unroll
+  for (int i = 0; i < G; ++i) r |= (((a >> i) & 1u) << (2 * i)) | (((b >> i) & 1u) << (2 * i + 1));
+  return r;
+}
+
+#ifndef P1_G
+#define P1_G 4
+#endif
+#ifndef P1_MINBLK
+#define P1_MINBLK 5
+#endif
+template <int G>
+__global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
+  static_assert(G == 4 || G == 8, "4 or 8 lanes x 2 trial velocities per model");
+  constexpr int P = 2 * G;   // trial velocities per round; point i lives in lane i/2, component i%2
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -124,11 +144,25 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
   const unsigned gmask = ((1u << G) - 1u) << gbase;
   const unsigned gbits = (1u << G) - 1u;
   const int grp = threadIdx.x / G;
-  float4* q0 = smem + (size_t)grp * p.mstride;
-  float4* q1 = q0 + p.lpad;
+  float4* rec = smem + (size_t)grp * p.mstride;   // this model's layer records (a, b, rho, d)
   const int K = p.K;
   unsigned long long my_steps = 0, my_sweeps = 0;
   int my_models = 0;
+
+  // ordered sign-change mask of the 16 points of a round: bit i set <=> sign(point i) != sign(point i-1)
+  // (point -1 = `before`)
+  auto change_mask = [&](float2 d, float before) -> unsigned {
+    float dprev = __shfl_up_sync(gmask, d.y, 1, G);
+    if (gl == 0) dprev = before;
+    const unsigned ex = (__ballot_sync(gmask, signbit(dprev) != signbit(d.x)) >> gbase) & gbits;
+    const unsigned ey = (__ballot_sync(gmask, signbit(d.x) != signbit(d.y)) >> gbase) & gbits;
+    return interleave<G>(ex, ey);
+  };
+  auto pair_mask = [&](bool bx, bool by) -> unsigned {
+    const unsigned ex = (__ballot_sync(gmask, bx) >> gbase) & gbits;
+    const unsigned ey = (__ballot_sync(gmask, by) >> gbase) & gbits;
+    return interleave<G>(ex, ey);
+  };
 
   for (;;) {
     int model = 0;
@@ -181,29 +215,29 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
         layer_ab(cst, ld, i, lt, p.atten, hs, a, b);
         const float rho = hs ? cst[C_RHOHS * ld + i] : cst[C_RHOFL * ld + i];
         const float d = hs ? 0.f : cst[C_DFL * ld + i];
-        LayerRec r = make_rec(a, b, rho, d);
-        q0[i] = r.q0;
-        q1[i] = r.q1;
+        rec[i] = make_rec(a, b, rho, d);
       }
       __syncwarp(gmask);
       if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
-      const float b_top = q1[0].y;
+      const float b_top = rec[0].y;
       float croot = 0.f, ratio = 0.f;
       bool found = false, lstop = false, have_ratio = false, fast_done = false;
 
       // ---- fast path (every period after the first, unless exact_scan).  The reference scans
       // c1, c1+dc, ... for the first sign change (calcul.f:155-167) and polishes inside that bracket
-      // (NEVILL, surfa.f:2-83).  The root it ends on is the fundamental-mode root; consecutive periods move
-      // it by a few grid steps, so the G lanes evaluate the G grid points around the log-period extrapolation
-      // of the previous roots.  The window is accepted when c1 itself, a point half way and the lowest window
-      // point have the same sign (no odd number of roots was skipped; a model whose root ever leaves the
-      // extrapolation by more than 0.1 km/s -- mode hopping -- is scanned point by point from then on), none
-      // of the reference's stop tests fires up to the bracket and the half-space velocity (kink of the secular
-      // function) is not nearby; anything else goes to the point-by-point path below.  All window points are evaluated on the window's deepest
-      // truncation (layer dropping, surfa.f:92-106) so that they sample ONE smooth function -- each
-      // truncation depth scales the unnormalised secular function differently but has the same root to
-      // ~1e-10 -- and the root is taken by inverse polynomial interpolation; if the 4- and 6-point estimates
-      // disagree, G more points are clustered around the estimate and the test is repeated.
+      // (NEVILL, surfa.f:2-83).  The root it ends on moves smoothly with the period, so the P = 2G trial
+      // velocities of the first round are: c1 itself, a point half way, and P-2 points clustered geometrically
+      // around the extrapolation (in ln T) of the previous roots.  The round is accepted when c1, the
+      // half-way point and the lowest cluster point have the same sign (no odd number of roots was skipped;
+      // a model whose root ever leaves the extrapolation by more than 0.1 km/s -- mode hopping -- is scanned
+      // point by point from then on), there is exactly one sign change inside the cluster and the half-space
+      // velocity (kink of the secular function) is not nearby.  If the cluster misses the root, a window of
+      // P-2 grid points takes its place (moved up or down once more if needed); anything else goes to the
+      // point-by-point path below.  All points of a round are evaluated on the round's deepest truncation
+      // (layer dropping, surfa.f:92-106) so that they sample ONE smooth function -- each truncation depth
+      // scales the unnormalised secular function differently but has the same root to ~1e-10 -- and the root
+      // is taken by inverse polynomial interpolation; if the 4- and 6-point estimates disagree, P more points
+      // are clustered around the estimate and the test is repeated.
       float c_pred = c_prev;
       if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
       else if (k >= 2) {
@@ -217,81 +251,84 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
         }
       }
       if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top)) {
-        int j0 = (int)floorf((c_pred - c1) / p.dc) - 2;
+        int j0 = (int)floorf((c_pred - c1) / p.dc) - (P - 4) / 2;
         if (j0 < 2) j0 = 2;
         if (j0 < 1000) {
-          float pc = c1, pd = 0.f, pe2 = 0.f, pe3 = 0.f;
-          int mj = n, mw = n, jev = -1, dir = 0, w0 = 2, sign0 = 0;
-          // stage 0 (from the third period on): 6 points clustered around the predicted root, spaced by the
-          // last prediction error; stage 1: window of 6 grid points around it; stage 2: window moved up or down.
+          float2 pc = make_float2(c1, c1), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
+          int mw = n, jev = -1, dir = 0, w0 = 2;
+          // stage 0 (from the third period on): cluster around the predicted root; stage 1: window of 14 grid
+          // points around it; stage 2: window of 16 grid points moved up or down.
           int stage = (k >= 2 && j0 >= 4) ? 0 : 1;
-          const float hd = fminf(fmaxf(1.5f * pred_err, 5.0e-4f), 4.0e-3f);
+          // cluster spacing: the cluster spans about 6x the last prediction error
+          const float cspan = (float)(1 << ((P - 2) / 2 - 1)) - 0.5f;
+          const float hc = fminf(fmaxf(6.0f * pred_err / cspan, kClusterH0), 16.f * kClusterH0);
           bool win_ok = false;
-          for (int wtry = 0; wtry < 5; ++wtry) {
-            // stages 0/1: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = cluster / window
-            // (grid indices j0..j0+5); an odd number of roots below shows as a sign difference between them.
-            // stage 2: all 8 lanes are window points.
-            if (gl >= w0 && stage == 0) pc = c_pred + cluster_offset6(gl - 2) * hd;
-            else {
-              // grid points in closed form: the fast path only needs the signs there (the reference's own
-              // sequentially accumulated grid differs by a few ulps, i.e. 1e-4 of a grid step)
-              const int idx = (gl < w0) ? ((gl == 0) ? 0 : j0 / 2) : j0 + (gl - w0);
-              pc = c1 + (float)idx * p.dc;
+          for (int wtry = 0; wtry < 4; ++wtry) {
+            // stages 0/1: point 0 = c1 itself, point 1 = half way to the window, points 2..15 = cluster / window;
+            // an odd number of roots below shows as a sign difference between points 0, 1 and 2.
+            {
+              float cc[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int pi = 2 * gl + h;
+                if (pi >= w0 && stage == 0) cc[h] = c_pred + geometric_offset(pi - 2, P - 2) * hc;
+                else {
+                  // grid points in closed form: only the signs matter there (the reference's sequentially
+                  // accumulated grid differs by a few ulps, i.e. 1e-4 of a grid step)
+                  const int idx = (pi < w0) ? ((pi == 0) ? 0 : j0 / 2) : j0 + (pi - w0);
+                  cc[h] = c1 + (float)idx * p.dc;
+                }
+              }
+              pc = make_float2(cc[0], cc[1]);
             }
-            mj = layer_drop(pc, T, p.fact, n, q1);
-            mw = gshfl<G>(gmask, mj, G - 1);
-            const float4 sv = secular(p.kind, pc, T, mw, q0, q1, 0);
-            my_steps += (unsigned)(mw - 1); my_sweeps += 1;
-            pd = sv.x; pe2 = sv.y; pe3 = sv.z;
-            if (w0) sign0 = (int)signbit(gshfl<G>(gmask, pd, 0));
-            const float dpw = __shfl_up_sync(gmask, pd, 1, G);
-            const bool changew = (gl > w0) && (signbit(dpw) != signbit(pd));
-            const bool badw = (gl >= w0) && ((pc < 0.8f * b_top) || !(pc < q1[mj - 1].y) || !(pc == pc));
-            const bool wrong = ((int)signbit(pd) != sign0);
-            const unsigned evc = (__ballot_sync(gmask, changew) >> gbase) & gbits;
-            const unsigned evb = (__ballot_sync(gmask, badw) >> gbase) & gbits;
-            const unsigned evw = (__ballot_sync(gmask, wrong) >> gbase) & gbits;
-            const bool below_ok = !(evw & ((2u << w0) - 1u));     // lanes 0..w0 have the sign of c1
+            mw = layer_drop(gshfl<G>(gmask, pc.y, G - 1), T, p.fact, n, rec);
+            const Sec2 sv = secular2(p.kind, pc, T, mw, rec, 0);
+            my_steps += 2u * (unsigned)(mw - 1); my_sweeps += 2;
+            pd = sv.d; pe2 = sv.e2; pe3 = sv.e3;
+            const float d0 = gshfl<G>(gmask, pd.x, 0);
+            const unsigned evc = change_mask(pd, d0) & ~((2u << w0) - 1u);     // changes between cluster / window points
+            const unsigned evw = pair_mask(signbit(pd.x) != signbit(d0), signbit(pd.y) != signbit(d0));
+            const bool below_ok = !(evw & ((2u << w0) - 1u));     // points 0..w0 have the sign of c1
             jev = __ffs(evc) - 1;
-            if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) {
+            if (below_ok && jev >= 1) {
               if (stage == 0 && (evc & (evc - 1u))) break;     // several sign changes inside the cluster
               win_ok = true; break;
             }
-            if (evb) break;
             if (stage == 0) { stage = 1; continue; }           // the cluster does not bracket the root
-            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; stage = 2; continue; }   // root above the window
+            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? P - 3 : P - 1); w0 = 0; stage = 2; continue; }   // root above the window
             if (!below_ok && dir <= 0) {
               // root below the window: only if it is between the half-way point and the window
               const bool lower_ok = !(evw & ((1u << w0) - 1u));
               const int jmin = w0 ? j0 / 2 : 0;
-              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - 7, jmin); w0 = 0; stage = 2; continue; }
+              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - (P - 1), jmin); w0 = 0; stage = 2; continue; }
             }
             break;
           }
           if (win_ok) {
-            // the half-space velocity of the window's truncation is a kink of the sampled function: not within
+            bool has_ends = false;
+            SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = {0.f, 0.f, 0.f, 0.f};
+            auto sample = [&](int i) {
+              // i-th entry of the ordered list: [point w0 .. point 15] or [E0, point 0 .. point 15, E1]
+              const int pi = min(max(has_ends ? i - 1 : i + w0, 0), P - 1);
+              const int sl = pi >> 1;
+              const bool hi = (pi & 1) != 0;
+              SamplePt s;
+              s.c = gshfl<G>(gmask, hi ? pc.y : pc.x, sl); s.d = gshfl<G>(gmask, hi ? pd.y : pd.x, sl);
+              s.e2 = gshfl<G>(gmask, hi ? pe2.y : pe2.x, sl); s.e3 = gshfl<G>(gmask, hi ? pe3.y : pe3.x, sl);
+              if (has_ends && i == 0) s = E0;
+              if (has_ends && i == P + 1) s = E1;
+              return s;
+            };
+            // the half-space velocity of the round's truncation is a kink of the sampled function: not within
             // a grid step of the bracket, and the interpolation only uses points below it
-            const float bh2 = q1[mw - 1].y;
-            const float br_lo = gshfl<G>(gmask, pc, jev - 1), br_hi = gshfl<G>(gmask, pc, jev);
-            const int nvalid = __popc((__ballot_sync(gmask, gl >= w0 && pc < bh2) >> gbase) & gbits);  // points below the kink
-            const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jev - w0 > nvalid - 1;
+            const float bh2 = rec[mw - 1].y;
+            int jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
+            const float br_lo = sample(jb - 1).c, br_hi = sample(jb).c;
+            const int nvalid = __popc(pair_mask(pc.x < bh2, pc.y < bh2) & ~((1u << w0) - 1u));  // list points below the kink
+            const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jb > nvalid - 1;
             if (!kink) {
-              bool has_ends = false;
-              int jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
-              SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = {0.f, 0.f, 0.f, 0.f};
-              auto sample = [&](int i) {
-                // i-th entry of the ordered list: [lane w0 .. lane G-1] or [E0, lane 0 .. lane G-1, E1]
-                const int src = has_ends ? i - 1 : i + w0;
-                const int sl = min(max(src, 0), G - 1);
-                SamplePt s;
-                s.c = gshfl<G>(gmask, pc, sl); s.d = gshfl<G>(gmask, pd, sl);
-                s.e2 = gshfl<G>(gmask, pe2, sl); s.e3 = gshfl<G>(gmask, pe3, sl);
-                if (has_ends && i == 0) s = E0;
-                if (has_ends && i == G + 1) s = E1;
-                return s;
-              };
               for (int it = 0; it < 4; ++it) {
-                const int np = has_ends ? G + 2 : nvalid;
+                const int np = has_ends ? P + 2 : nvalid;
                 const int s6 = min(max(jb - 3, 0), np - 6), s4 = min(max(jb - 2, 0), np - 4);
                 const SamplePt B0 = sample(jb - 1), B1 = sample(jb);
                 float x[6], y[6];
@@ -323,29 +360,36 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
                   break;
                 }
                 if (it == 3) break;
-                // one more round: G points around the estimate, spaced by the disagreement of the two orders
-                const float s0 = fmaxf(inside ? 0.5f * delta : w, 1.0e-5f);
-                const bool uni = !(e - 12.5f * s0 > 0.f && e + 12.5f * s0 < w);
+                // one more round: 16 points around the estimate, spaced by the disagreement of the two orders
+                const float span = (float)(1 << (P / 2 - 1));   // outermost offset of the round, in units of s0
+                const float s0 = fmaxf(inside ? 0.5f * delta : w / (2.f * span), 1.0e-5f);
+                const bool uni = !(e - span * s0 > 0.f && e + span * s0 < w);
                 E0 = B0; E1 = B1;
-                pc = B0.c + (uni ? (float)(gl + 1) * (w / (float)(G + 1)) : e + refine_offset8(gl) * s0);
-                const float4 sr = secular(p.kind, pc, T, mw, q0, q1, 0);
-                my_steps += (unsigned)(mw - 1); my_sweeps += 1;
-                pd = sr.x; pe2 = sr.y; pe3 = sr.z;
+                {
+                  float cc[2];
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const int pi = 2 * gl + h;
+                    cc[h] = B0.c + (uni ? (float)(pi + 1) * (w / (float)(P + 1)) : e + geometric_offset(pi, P) * s0);
+                  }
+                  pc = make_float2(cc[0], cc[1]);
+                }
+                const Sec2 sr = secular2(p.kind, pc, T, mw, rec, 0);
+                my_steps += 2u * (unsigned)(mw - 1); my_sweeps += 2;
+                pd = sr.d; pe2 = sr.e2; pe3 = sr.e3;
                 has_ends = true;
-                float dp = __shfl_up_sync(gmask, pd, 1, G);
-                if (gl == 0) dp = E0.d;
-                const unsigned ev = (__ballot_sync(gmask, signbit(dp) != signbit(pd)) >> gbase) & gbits;
-                const float dlast = gshfl<G>(gmask, pd, G - 1);
-                if (ev) jb = __ffs(ev);                                   // lane g is list entry g + 1
-                else if (signbit(dlast) != signbit(E1.d)) jb = G + 1;
+                const unsigned ev = change_mask(pd, E0.d);
+                const float dlast = gshfl<G>(gmask, pd.y, G - 1);
+                if (ev) jb = __ffs(ev);                                   // point i is list entry i + 1
+                else if (signbit(dlast) != signbit(E1.d)) jb = P + 1;
                 else break;
               }
               if (fast_done) {
                 // the reference's bracket is the grid interval around the root; its upper end fixes mmax
                 float hg = c1 + (floorf((croot - c1) / p.dc) + 1.f) * p.dc;
                 if (!(hg > croot)) hg += p.dc;
-                const int mnew = layer_drop(hg, T, p.fact, n, q1);
-                const float bh1 = q1[mnew - 1].y;
+                const int mnew = layer_drop(hg, T, p.fact, n, rec);
+                const float bh1 = rec[mnew - 1].y;
                 if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
                 else { mm = mnew; found = true; have_ratio = (p.kind == 2) && !mid_liquid; }
               }
@@ -355,69 +399,74 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       }
 
       if (!fast_done) {
-        // ---- point-by-point scan (calcul.f:155-167), G consecutive grid points per round
+        // ---- point-by-point scan (calcul.f:155-167), 16 consecutive grid points per round.  Each point has
+        // its own layer dropping; the pair of a lane is evaluated on the deeper of the two
+        // truncations (same sign, see above).
         float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
         int mnew = mm;
         {
           float cbase = c1, cP = 0.f, dP = 0.f;
           bool have_prev = false;
-          for (int round = 0; round < 4096; ++round) {
-            float cj = cbase;
-            for (int t = 0; t < gl; ++t) cj = SD_ADD(cj, p.dc);
-            const int mj = layer_drop(cj, T, p.fact, n, q1);
-            const float dj = secular(p.kind, cj, T, mj, q0, q1, 0).x;
-            my_steps += (unsigned)(mj - 1); my_sweeps += 1;
-            float dp = __shfl_up_sync(gmask, dj, 1, G);
-            float cp = __shfl_up_sync(gmask, cj, 1, G);
-            if (gl == 0) { dp = dP; cp = cP; }
-            const bool hasp = (gl > 0) || have_prev;
-            const bool change = hasp && (signbit(dp) != signbit(dj));
-            const bool stop = hasp && !change && ((cj < 0.8f * b_top) || !(cj < q1[mj - 1].y + 0.3f) || !(cj == cj));
-            const unsigned ev = (__ballot_sync(gmask, change || stop) >> gbase) & gbits;
+          for (int round = 0; round < 2048; ++round) {
+            float cx = cbase;
+            for (int t = 0; t < 2 * gl; ++t) cx = SD_ADD(cx, p.dc);
+            const float2 cj = make_float2(cx, SD_ADD(cx, p.dc));
+            const int mjx = layer_drop(cj.x, T, p.fact, n, rec), mjy = layer_drop(cj.y, T, p.fact, n, rec);
+            const float2 dj = secular2(p.kind, cj, T, max(mjx, mjy), rec, 0).d;
+            my_steps += 2u * (unsigned)(max(mjx, mjy) - 1); my_sweeps += 2;
+            // previous point of every point in sequence order
+            float dpx = __shfl_up_sync(gmask, dj.y, 1, G), cpx = __shfl_up_sync(gmask, cj.y, 1, G);
+            if (gl == 0) { dpx = dP; cpx = cP; }
+            const bool haspx = (gl > 0) || have_prev;
+            const bool chx = haspx && (signbit(dpx) != signbit(dj.x));
+            const bool stx = haspx && !chx && ((cj.x < 0.8f * b_top) || !(cj.x < rec[mjx - 1].y + 0.3f) || !(cj.x == cj.x));
+            const bool chy = (signbit(dj.x) != signbit(dj.y));
+            const bool sty = !chy && ((cj.y < 0.8f * b_top) || !(cj.y < rec[mjy - 1].y + 0.3f) || !(cj.y == cj.y));
+            const unsigned ev = pair_mask(chx || stx, chy || sty);
             if (!ev) {
-              cP = gshfl<G>(gmask, cj, G - 1);
-              dP = gshfl<G>(gmask, dj, G - 1);
-              mnew = gshfl<G>(gmask, mj, G - 1);
+              cP = gshfl<G>(gmask, cj.y, G - 1);
+              dP = gshfl<G>(gmask, dj.y, G - 1);
+              mnew = gshfl<G>(gmask, mjy, G - 1);
               have_prev = true;
               cbase = SD_ADD(cP, p.dc);
-              if (round == 4095) flag |= SURFDISP_F_SCAN_LIMIT;
+              if (round == 2047) flag |= SURFDISP_F_SCAN_LIMIT;
               continue;
             }
-            const int j = __ffs(ev) - 1;
-            found = gshfl<G>(gmask, (int)change, j) != 0;
-            lo = gshfl<G>(gmask, cp, j); hi = gshfl<G>(gmask, cj, j);
-            dlo = gshfl<G>(gmask, dp, j); dhi = gshfl<G>(gmask, dj, j);
-            mnew = gshfl<G>(gmask, mj, j);
+            const int j = __ffs(ev) - 1, sl = j >> 1;
+            const bool jy = (j & 1) != 0;
+            found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
+            lo = gshfl<G>(gmask, jy ? cj.x : cpx, sl); hi = gshfl<G>(gmask, jy ? cj.y : cj.x, sl);
+            dlo = gshfl<G>(gmask, jy ? dj.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? dj.y : dj.x, sl);
+            mnew = gshfl<G>(gmask, jy ? mjy : mjx, sl);
             break;
           }
         }
         mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
         if (found) {
           // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
-          // G-section until the bracket is <= 2e-5, then one secant step.  The first round counts the sign
+          // 17-section until the bracket is <= 2e-5, then one secant step.  The first round counts the sign
           // changes: with several roots inside the scan bracket (kink at the half-space velocity) the group
           // runs the reference's own sequential bisection/Neville sequence so that the same root is picked.
           const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
           bool multi = false;
           for (int it = 0; it < 16 && (hi - lo) > kBracketTol; ++it) {
-            const float w = hi - lo;
-            const float pj = lo + (float)(gl + 1) * (w / (float)(G + 1));
-            const float dj = secular(p.kind, pj, T, mm, q0, q1, 0).x;
-            my_steps += (unsigned)(mm - 1); my_sweeps += 1;
-            float dp = __shfl_up_sync(gmask, dj, 1, G);
-            float pp = __shfl_up_sync(gmask, pj, 1, G);
-            if (gl == 0) { dp = dlo; pp = lo; }
-            const bool change = signbit(dp) != signbit(dj);
-            const unsigned ev = (__ballot_sync(gmask, change) >> gbase) & gbits;
-            const float dlast = gshfl<G>(gmask, dj, G - 1);
+            const float w = hi - lo, st = w / (float)(P + 1);
+            const float2 pj = make_float2(lo + (float)(2 * gl + 1) * st, lo + (float)(2 * gl + 2) * st);
+            const float2 dj = secular2(p.kind, pj, T, mm, rec, 0).d;
+            my_steps += 2u * (unsigned)(mm - 1); my_sweeps += 2;
+            const unsigned ev = change_mask(dj, dlo);
+            const float dlast = gshfl<G>(gmask, dj.y, G - 1);
             if (it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
             if (ev) {
-              const int j = __ffs(ev) - 1;
-              const float nlo = gshfl<G>(gmask, pp, j), ndlo = gshfl<G>(gmask, dp, j);
-              hi = gshfl<G>(gmask, pj, j); dhi = gshfl<G>(gmask, dj, j);
+              const int j = __ffs(ev) - 1, sl = j >> 1;
+              const bool jy = (j & 1) != 0;
+              float ppx = __shfl_up_sync(gmask, pj.y, 1, G), dpx = __shfl_up_sync(gmask, dj.y, 1, G);
+              if (gl == 0) { ppx = lo; dpx = dlo; }
+              const float nlo = gshfl<G>(gmask, jy ? pj.x : ppx, sl), ndlo = gshfl<G>(gmask, jy ? dj.x : dpx, sl);
+              hi = gshfl<G>(gmask, jy ? pj.y : pj.x, sl); dhi = gshfl<G>(gmask, jy ? dj.y : dj.x, sl);
               lo = nlo; dlo = ndlo;
             } else {
-              lo = gshfl<G>(gmask, pj, G - 1); dlo = dlast;
+              lo = gshfl<G>(gmask, pj.y, G - 1); dlo = dlast;
             }
           }
           if (!multi) {
@@ -427,12 +476,12 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
             croot = cs;
           } else {
             int ev_n = 0;
-            auto f = [&](float cc) { return secular(p.kind, cc, T, mm, q0, q1, 0).x; };
+            auto f = [&](float cc) { return secular2(p.kind, make_float2(cc, cc), T, mm, rec, 0).d.x; };
             const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
             if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
             if (!okp) { found = false; lstop = true; }
           }
-          if (found && croot > q1[mm - 1].y) { found = false; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
+          if (found && croot > rec[mm - 1].y) { found = false; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
         }
       }
       if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; break; }  // reference aborts the whole call (calcul.f:173-189)
@@ -442,9 +491,9 @@ __global__ void __launch_bounds__(128, 4) phase1_kernel(const __grid_constant__ 
       }
       if (p.kind == 2 && !have_ratio) {
         // ellipticity = 0.5 * bb1(e3) / bb1(e2) at the root (surfa.f:360-363)
-        const float4 v = secular(2, croot, T, mm, q0, q1, 1);
+        const Sec2 v = secular2(2, make_float2(croot, croot), T, mm, rec, 1);
         my_steps += (unsigned)(mm - 1); my_sweeps += 1;
-        ratio = 0.5f * v.z / v.y;
+        ratio = 0.5f * v.e3.x / v.e2.x;
       }
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
       if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
@@ -619,8 +668,8 @@ int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
 template <int G>
 int launch_phase1(const P1Params& p, cudaStream_t st) {
   P1Params q = p;
-  q.mstride = 2 * p.lpad + 2;  // +2 float4: consecutive groups start 32 B apart mod 128 B (bank spread)
-  // 128-thread CTAs (16 models) for ordinary stacks; deep stacks (up to 1000 layers, 32 KB of layer records
+  q.mstride = p.lpad + 1;  // +1 float4: consecutive groups start 16 B apart mod 128 B (bank spread)
+  // 128-thread CTAs (128/G models) for ordinary stacks; deep stacks (up to 1000 layers, 16 KB of layer records
   // per model) shrink the CTA until the records of its models fit in shared memory
   int threads = 128;
   while (threads > 32 && (size_t)(threads / G) * q.mstride * sizeof(float4) > 100 * 1024) threads /= 2;
@@ -690,7 +739,7 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   CK(cudaGetLastError());
 
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[1], st));
-  rc = launch_phase1<8>(p1, st);
+  rc = launch_phase1<P1_G>(p1, st);
   if (rc) return rc;
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[2], st));
 

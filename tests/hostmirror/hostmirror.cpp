@@ -18,20 +18,22 @@ struct Pt { float c, d, e2, e3; };
 constexpr float kInterpTol = 1.0e-5f;
 constexpr float kClusterTol = 2.0e-6f;
 constexpr float kBracketTol = 2.0e-5f;
+constexpr float kClusterH0 = 2.5e-4f;
 }
 
 extern "C" {
 
-// one model, shared periods; returns nfound.  `exact` = SurfdispOpts.exact_scan.
+// one model, shared periods; returns nfound.  `exact` = SurfdispOpts.exact_scan.  G lanes x 2 trial velocities.
 int hm_forward(int G, int kind, int n, const float* a, const float* b, const float* rho, const float* d,
                const float* qs, int K, const float* per, float dc, float fact, float t_base, int atten,
                int flatten, int stale, int ndiv0, int ndiv_cap, float* c_out, float* u_out, float* ratio_out,
                long long* sweeps, int exact, long long* rounds_out) {
   long long nrounds = 0, nwin = 0, nwin_ok = 0, ndirect = 0, nslow = 0;
+  const int P = 2 * G;
   const int ld = n;
   std::vector<float> cst((size_t)NCONST * ld);
   prep_model(n, kind, flatten, a, b, rho, d, qs, cst.data(), ld);
-  std::vector<float4> q0(n + 1), q1(n + 1);
+  std::vector<float4> rec(n + 1);
   std::vector<float> lt(K);
   for (int k = 0; k < K; ++k) { lt[k] = logf(t_base / per[k]); c_out[k] = 0; u_out[k] = 0; ratio_out[k] = 0; }
   float c1;
@@ -51,12 +53,17 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
   float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f;
   long long nsw = 0;
-  auto sweep = [&](float c, float T, int m, bool ell_only) {
-    nsw++;
-    Pt r = {c, 0.f, 0.f, 0.f};
-    if (kind == 2) r.d = rayleigh_adjoint(c, T, m, q0.data(), q1.data(), ell_only, r.e2, r.e3);
-    else r.d = love_sweep(c, T, m, q0.data(), q1.data());
-    return r;
+  // the kernel evaluates pairs (packed arithmetic); the pair functions are used here too so that the same
+  // source is exercised
+  auto sweep2 = [&](float ca, float cb, float T, int m, bool ell_only, Pt& A, Pt& B) {
+    nsw += 2;
+    V2 c = v2(ca, cb), e2 = v2(0.f, 0.f), e3 = v2(0.f, 0.f), dd;
+    if (kind == 2) dd = rayleigh_adjoint2(c, T, m, rec.data(), ell_only, e2, e3);
+    else dd = love_sweep2(c, T, m, rec.data());
+    A = {ca, dd.x, e2.x, e3.x}; B = {cb, dd.y, e2.y, e3.y};
+  };
+  auto sweep_all = [&](std::vector<Pt>& pt, float T, int m) {
+    for (int i = 0; i + 1 < (int)pt.size(); i += 2) sweep2(pt[i].c, pt[i + 1].c, T, m, false, pt[i], pt[i + 1]);
   };
   for (int k = 0; k < K; ++k) {
     const float T = per[k];
@@ -67,19 +74,17 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       layer_ab(cst.data(), ld, i, lt[k], atten, hs, aa, bb);
       const float r = hs ? cst[C_RHOHS * ld + i] : cst[C_RHOFL * ld + i];
       const float dd = hs ? 0.f : cst[C_DFL * ld + i];
-      LayerRec rec = make_rec(aa, bb, r, dd);
-      q0[i] = rec.q0; q1[i] = rec.q1;
+      rec[i] = make_rec(aa, bb, r, dd);
     }
     if (k > 0) c1 = SD_MUL(0.90f, c_prev);
-    const float b_top = q1[0].y;
+    const float b_top = rec[0].y;
     float croot = 0.f, ratio = 0.f;
     bool found = false, lstop = false, have_ratio = false, fast_done = false;
 
-    // ---- fast path: window of G grid points around the extrapolated root, inverse interpolation
+    // ---- fast path: cluster / window of trial velocities around the extrapolated root, inverse interpolation
     float c_pred = c_prev;
-    if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
+    if (k == 1) c_pred = c_prev + 0.02f;
     else if (k >= 2) {
-      // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
       const float x0 = lt[k - 1], x1 = lt[k - 2], x = lt[k];
       c_pred = c_prev + (c_prev - c_prev2) * ((x - x0) / (x0 - x1));
       if (k >= 3) {
@@ -88,87 +93,70 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         c_pred += (d01 - d12) / (x0 - x2) * (x - x0) * (x - x1);
       }
     }
-    if (G == 8 && !exact && k >= 1 && !hopped && !(SD_ADD(c1, dc) < 0.8f * b_top)) {
-      int j0 = (int)floorf((c_pred - c1) / dc) - 2;
+    if (P >= 8 && !exact && k >= 1 && !hopped && !(SD_ADD(c1, dc) < 0.8f * b_top)) {
+      int j0 = (int)floorf((c_pred - c1) / dc) - (P - 4) / 2;
       if (j0 < 2) j0 = 2;
       if (j0 < 1000) {
         nwin++;
-        std::vector<Pt> lane(G);
-        std::vector<int> mj(G);
-        int mw = 0, jev = -1, dir = 0, w0 = 2, sign0 = 0;
-        // stage 0 (from the third period on): 6 points clustered around the predicted root, spaced by the last
-        // prediction error; stage 1: window of 6 grid points around it; stage 2: window moved up or down.
+        std::vector<Pt> pt(P);
+        int mw = 0, jev = -1, dir = 0, w0 = 2;
         int stage = (k >= 2 && j0 >= 4) ? 0 : 1;
-        const float hd = fminf(fmaxf(1.5f * pred_err, 5.0e-4f), 4.0e-3f);
+        const float cspan = (float)(1 << ((P - 2) / 2 - 1)) - 0.5f;
+        const float hc = fminf(fmaxf(6.0f * pred_err / cspan, kClusterH0), 16.f * kClusterH0);
         bool win_ok = false;
-        for (int wtry = 0; wtry < 5; ++wtry) {
+        for (int wtry = 0; wtry < 4; ++wtry) {
           nrounds++;
-          // stages 0/1: lane 0 = c1 itself, lane 1 = half way to the window, lanes 2..7 = cluster / window (grid
-          // indices j0..j0+5); an odd number of roots below shows as a sign difference between them.
-          // stage 2: all 8 lanes are window points.
-          for (int g = 0; g < G; ++g) {
-            float pc;
-            if (g >= w0 && stage == 0) pc = c_pred + cluster_offset6(g - 2) * hd;
+          for (int pi = 0; pi < P; ++pi) {
+            if (pi >= w0 && stage == 0) pt[pi].c = c_pred + geometric_offset(pi - 2, P - 2) * hc;
             else {
-              const int idx = (g < w0) ? ((g == 0) ? 0 : j0 / 2) : j0 + (g - w0);
-              pc = c1 + (float)idx * dc;
+              const int idx = (pi < w0) ? ((pi == 0) ? 0 : j0 / 2) : j0 + (pi - w0);
+              pt[pi].c = c1 + (float)idx * dc;
             }
-            lane[g].c = pc; mj[g] = layer_drop(pc, T, fact, n, q1.data());
           }
-          mw = mj[G - 1];
-          for (int g = 0; g < G; ++g) lane[g] = sweep(lane[g].c, T, mw, false);
-          if (w0) sign0 = (int)std::signbit(lane[0].d);
-          unsigned evc = 0, evb = 0;
-          bool below_ok = true;
-          for (int g = 0; g <= w0; ++g) below_ok &= ((int)std::signbit(lane[g].d) == sign0);
-          for (int g = w0 + 1; g < G; ++g)
-            if (std::signbit(lane[g - 1].d) != std::signbit(lane[g].d)) evc |= 1u << g;
-          for (int g = w0; g < G; ++g) {
-            const float pc = lane[g].c;
-            if ((pc < 0.8f * b_top) || !(pc < q1[mj[g] - 1].y) || !(pc == pc)) evb |= 1u << g;
-          }
+          mw = layer_drop(pt[P - 1].c, T, fact, n, rec.data());
+          sweep_all(pt, T, mw);
+          const float d0 = pt[0].d;
+          unsigned evc = 0, evw = 0;
+          for (int pi = 1; pi < P; ++pi) if (std::signbit(pt[pi - 1].d) != std::signbit(pt[pi].d)) evc |= 1u << pi;
+          evc &= ~((2u << w0) - 1u);
+          for (int pi = 0; pi < P; ++pi) if (std::signbit(pt[pi].d) != std::signbit(d0)) evw |= 1u << pi;
+          const bool below_ok = !(evw & ((2u << w0) - 1u));
           jev = evc ? __builtin_ctz(evc) : -1;
-          if (below_ok && jev >= 1 && !(evb & ((2u << jev) - 1u))) {
-            if (stage == 0 && (evc & (evc - 1u))) break;     // several sign changes inside the cluster
+          if (below_ok && jev >= 1) {
+            if (stage == 0 && (evc & (evc - 1u))) break;
             win_ok = true; break;
           }
-          if (evb) break;
-          if (stage == 0) { stage = 1; continue; }           // the cluster does not bracket the root
-          if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? 5 : 7); w0 = 0; stage = 2; continue; }      // root above the window
+          if (stage == 0) { stage = 1; continue; }
+          if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? P - 3 : P - 1); w0 = 0; stage = 2; continue; }
           if (!below_ok && dir <= 0) {
-            // root below the window: only if it is between the half-way point and the window
-            bool lower_ok = true;
-            for (int g = 0; g < w0; ++g) lower_ok &= ((int)std::signbit(lane[g].d) == sign0);
+            const bool lower_ok = !(evw & ((1u << w0) - 1u));
             const int jmin = w0 ? j0 / 2 : 0;
-            if (lower_ok && j0 > jmin) { dir = -1; j0 = std::max(j0 - 7, jmin); w0 = 0; stage = 2; continue; }
+            if (lower_ok && j0 > jmin) { dir = -1; j0 = std::max(j0 - (P - 1), jmin); w0 = 0; stage = 2; continue; }
           }
           break;
         }
-        if (!win_ok && getenv("HM_DEBUG")) fprintf(stderr, "winmiss k=%d T=%g jev=%d dir=%d c_pred=%g c1=%g lane0=%g\n", k, T, jev, dir, c_pred, c1, lane[0].c);
+        if (!win_ok && getenv("HM_DEBUG")) fprintf(stderr, "winmiss k=%d T=%g jev=%d dir=%d c_pred=%g c1=%g\n", k, T, jev, dir, c_pred, c1);
         if (win_ok) {
-          // the half-space velocity of the window's truncation is a kink of the sampled function: not within a
-          // grid step of the bracket, and the interpolation only uses points below it
-          const float bh2 = q1[mw - 1].y;
-          const float br_lo = lane[jev - 1].c, br_hi = lane[jev].c;   // jev > w0: both are cluster / window points
-          int nvalid = 0;   // points below the kink
-          for (int g = w0; g < G; ++g) nvalid += (lane[g].c < bh2);
-          const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jev - w0 > nvalid - 1;
+          bool has_ends = false;
+          Pt E0 = {0, 0, 0, 0}, E1 = {0, 0, 0, 0};
+          auto sample = [&](int i) {
+            const int pi = std::min(std::max(has_ends ? i - 1 : i + w0, 0), P - 1);
+            Pt s = pt[pi];
+            if (has_ends && i == 0) s = E0;
+            if (has_ends && i == P + 1) s = E1;
+            return s;
+          };
+          const float bh2 = rec[mw - 1].y;
+          int jb = jev - w0;
+          const float br_lo = sample(jb - 1).c, br_hi = sample(jb).c;
+          int nvalid = 0;
+          for (int pi = w0; pi < P; ++pi) nvalid += (pt[pi].c < bh2);
+          const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jb > nvalid - 1;
           if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh2, br_lo, br_hi, nvalid);
           if (!kink) {
             nwin_ok++;
-            bool has_ends = false;
-            int jb = jev - w0;
-            Pt E0 = {0, 0, 0, 0}, E1 = {0, 0, 0, 0};
-            auto sample = [&](int i) {
-              const int src = has_ends ? i - 1 : i + w0;
-              const int sl = std::min(std::max(src, 0), G - 1);
-              Pt s = lane[sl];
-              if (has_ends && i == 0) s = E0;
-              if (has_ends && i == G + 1) s = E1;
-              return s;
-            };
             for (int it = 0; it < 4; ++it) {
-              const int np = has_ends ? G + 2 : nvalid;
+              const int np = has_ends ? P + 2 : nvalid;
               const int s6 = std::min(std::max(jb - 3, 0), np - 6), s4 = std::min(std::max(jb - 2, 0), np - 4);
               const Pt B0 = sample(jb - 1), B1 = sample(jb);
               float x[6], y[6];
@@ -180,8 +168,6 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               const float delta = fabsf(e6 - e4);
               float e = e6;
               if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
-              // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
-              // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
               const bool interior = (jb >= 2 && jb <= np - 2);
               const float tol = (it > 0) ? kInterpTol : ((stage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
               if ((inside && interior && delta <= tol) || w <= kBracketTol) {
@@ -200,31 +186,29 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
                 break;
               }
               if (it == 3) break;
-              const float s0 = fmaxf(inside ? 0.5f * delta : w, 1.0e-5f);
-              const bool uni = !(e - 12.5f * s0 > 0.f && e + 12.5f * s0 < w);
+              const float s0 = fmaxf(inside ? 0.5f * delta : w * (1.f / 256.f), 1.0e-5f);
+              const bool uni = !(e - 128.f * s0 > 0.f && e + 128.f * s0 < w);
               E0 = B0; E1 = B1;
               nrounds++;
-              for (int g = 0; g < G; ++g) {
-                const float pc = B0.c + (uni ? (float)(g + 1) * (w / (float)(G + 1)) : e + refine_offset8(g) * s0);
-                lane[g] = sweep(pc, T, mw, false);
-              }
+              for (int pi = 0; pi < P; ++pi)
+                pt[pi].c = B0.c + (uni ? (float)(pi + 1) * (w / (float)(P + 1)) : e + geometric_offset(pi, P) * s0);
+              sweep_all(pt, T, mw);
               has_ends = true;
               unsigned ev = 0;
-              for (int g = 0; g < G; ++g) {
-                const float dp = g ? lane[g - 1].d : E0.d;
-                if (std::signbit(dp) != std::signbit(lane[g].d)) ev |= 1u << g;
+              for (int pi = 0; pi < P; ++pi) {
+                const float dp = pi ? pt[pi - 1].d : E0.d;
+                if (std::signbit(dp) != std::signbit(pt[pi].d)) ev |= 1u << pi;
               }
               if (ev) jb = __builtin_ctz(ev) + 1;
-              else if (std::signbit(lane[G - 1].d) != std::signbit(E1.d)) jb = G + 1;
+              else if (std::signbit(pt[P - 1].d) != std::signbit(E1.d)) jb = P + 1;
               else break;
             }
             if (fast_done) {
-              // the reference's bracket is the grid interval around the root; its upper end fixes mmax
               float hg = c1 + (floorf((croot - c1) / dc) + 1.f) * dc;
               if (!(hg > croot)) hg += dc;
-              const int mnew = layer_drop(hg, T, fact, n, q1.data());
-              const float bh1 = q1[mnew - 1].y;
-              if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
+              const int mnew = layer_drop(hg, T, fact, n, rec.data());
+              const float bh1 = rec[mnew - 1].y;
+              if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;
               else { mm = mnew; found = true; have_ratio = (kind == 2) && !mid_liquid; }
             }
           }
@@ -234,32 +218,34 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
 
     if (!fast_done) {
       nslow++;
-      // ---- point-by-point scan, G grid points per round
+      // ---- point-by-point scan, P grid points per round
       float lo = 0, hi = 0, dlo = 0, dhi = 0;
       int mnew = mm;
       {
         float cbase = c1, cP = 0, dP = 0;
         bool have_prev = false, done = false;
-        std::vector<float> cj(G), dj(G);
-        std::vector<int> mj(G);
-        for (int round = 0; round < 4096 && !done; ++round) {
+        std::vector<Pt> pt(P);
+        std::vector<int> mj(P);
+        for (int round = 0; round < 2048 && !done; ++round) {
           nrounds++;
-          for (int g = 0; g < G; ++g) {
+          for (int pi = 0; pi < P; ++pi) {
             float c = cbase;
-            for (int t = 0; t < g; ++t) c = SD_ADD(c, dc);
-            cj[g] = c; mj[g] = layer_drop(c, T, fact, n, q1.data()); dj[g] = sweep(c, T, mj[g], false).d;
+            for (int t = 0; t < pi; ++t) c = SD_ADD(c, dc);
+            pt[pi].c = c; mj[pi] = layer_drop(c, T, fact, n, rec.data());
           }
+          for (int pi = 0; pi < P; pi += 2) sweep2(pt[pi].c, pt[pi + 1].c, T, std::max(mj[pi], mj[pi + 1]), false, pt[pi], pt[pi + 1]);
           int jev = -1; bool chg = false;
-          for (int g = 0; g < G; ++g) {
-            const bool hasp = (g > 0) || have_prev;
-            const float dp = g ? dj[g - 1] : dP;
-            const bool change = hasp && (std::signbit(dp) != std::signbit(dj[g]));
-            const bool stop = hasp && !change && ((cj[g] < 0.8f * b_top) || !(cj[g] < q1[mj[g] - 1].y + 0.3f) || !(cj[g] == cj[g]));
-            if (change || stop) { jev = g; chg = change; break; }
+          for (int pi = 0; pi < P; ++pi) {
+            const bool hasp = (pi > 0) || have_prev;
+            const float dp = pi ? pt[pi - 1].d : dP;
+            const float c = pt[pi].c;
+            const bool change = hasp && (std::signbit(dp) != std::signbit(pt[pi].d));
+            const bool stop = hasp && !change && ((c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c));
+            if (change || stop) { jev = pi; chg = change; break; }
           }
-          if (jev < 0) { cP = cj[G - 1]; dP = dj[G - 1]; mnew = mj[G - 1]; have_prev = true; cbase = SD_ADD(cP, dc); continue; }
+          if (jev < 0) { cP = pt[P - 1].c; dP = pt[P - 1].d; mnew = mj[P - 1]; have_prev = true; cbase = SD_ADD(cP, dc); continue; }
           found = chg;
-          lo = jev ? cj[jev - 1] : cP; hi = cj[jev]; dlo = jev ? dj[jev - 1] : dP; dhi = dj[jev]; mnew = mj[jev];
+          lo = jev ? pt[jev - 1].c : cP; hi = pt[jev].c; dlo = jev ? pt[jev - 1].d : dP; dhi = pt[jev].d; mnew = mj[jev];
           done = true;
         }
       }
@@ -267,22 +253,23 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       if (found) {
         const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
         bool multi = false;
-        std::vector<float> pj(G), dj(G);
+        std::vector<Pt> pt(P);
         for (int it = 0; it < 16 && (hi - lo) > kBracketTol; ++it) {
           nrounds++;
-          const float w = hi - lo;
-          for (int g = 0; g < G; ++g) { pj[g] = lo + (float)(g + 1) * (w / (float)(G + 1)); dj[g] = sweep(pj[g], T, mm, false).d; }
+          const float w = hi - lo, st = w / (float)(P + 1);
+          for (int pi = 0; pi < P; ++pi) pt[pi].c = lo + (float)(pi + 1) * st;
+          sweep_all(pt, T, mm);
           int j = -1, nchg = 0;
-          for (int g = 0; g < G; ++g) {
-            const float dp = g ? dj[g - 1] : dlo;
-            if (std::signbit(dp) != std::signbit(dj[g])) { if (j < 0) j = g; nchg++; }
+          for (int pi = 0; pi < P; ++pi) {
+            const float dp = pi ? pt[pi - 1].d : dlo;
+            if (std::signbit(dp) != std::signbit(pt[pi].d)) { if (j < 0) j = pi; nchg++; }
           }
-          if (std::signbit(dj[G - 1]) != std::signbit(dhi)) nchg++;
+          if (std::signbit(pt[P - 1].d) != std::signbit(dhi)) nchg++;
           if (it == 0 && nchg > 1) { multi = true; break; }
           if (j >= 0) {
-            const float nlo = j ? pj[j - 1] : lo, ndlo = j ? dj[j - 1] : dlo;
-            hi = pj[j]; dhi = dj[j]; lo = nlo; dlo = ndlo;
-          } else { lo = pj[G - 1]; dlo = dj[G - 1]; }
+            const float nlo = j ? pt[j - 1].c : lo, ndlo = j ? pt[j - 1].d : dlo;
+            hi = pt[j].c; dhi = pt[j].d; lo = nlo; dlo = ndlo;
+          } else { lo = pt[P - 1].c; dlo = pt[P - 1].d; }
         }
         if (!multi) {
           const float den = dhi - dlo;
@@ -291,18 +278,19 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           croot = cs;
         } else {
           int ev_n = 0;
-          auto f = [&](float cc) { return sweep(cc, T, mm, false).d; };
+          auto f = [&](float cc) { Pt A, B; sweep2(cc, cc, T, mm, false, A, B); return A.d; };
           if (!nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n)) { found = false; lstop = true; }
         }
-        if (found && croot > q1[mm - 1].y) found = false;
+        if (found && croot > rec[mm - 1].y) found = false;
       }
     }
     if (lstop) { nfound = 0; break; }
     if (!found) break;
     if (kind == 2 && !have_ratio) {
-      const Pt v = sweep(croot, T, mm, true);
+      Pt A, B;
+      sweep2(croot, croot, T, mm, true, A, B);
       nrounds++;
-      ratio = 0.5f * v.e3 / v.e2;
+      ratio = 0.5f * A.e3 / A.e2;
     }
     if (getenv("HM_PRED") && k >= 1) fprintf(stderr, "pred %d %g %g\n", k, croot - c_pred, (croot - c1) / dc);
     if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }

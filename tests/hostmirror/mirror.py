@@ -27,7 +27,7 @@ def lib():
     return _LIB
 
 
-def forward(kind, vp, vs, rho, h, qsinv, periods, G=8, stale=1, ndiv=5, ndiv_cap=None, exact_scan=0):
+def forward(kind, vp, vs, rho, h, qsinv, periods, G=4, stale=1, ndiv=5, ndiv_cap=None, exact_scan=0):
     f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
     a, b, r, d, q, per = f(vp), f(vs), f(rho), f(h), f(qsinv), f(periods)
     K = len(per)
