@@ -39,6 +39,14 @@ static inline float sd_div(float a, float b) { volatile float r = a / b; return 
 #define SD_DIV(a, b) sd_div((a), (b))
 #endif
 
+// Division where the last ulp does not matter (interpolation weights, the small attenuation terms): one
+// MUFU.RCP + multiply on the device.
+#if defined(__CUDA_ARCH__)
+#define SD_FDIV(a, b) __fdividef((a), (b))
+#else
+#define SD_FDIV(a, b) ((a) / (b))
+#endif
+
 namespace sd {
 
 // float32 literals of the reference
@@ -104,18 +112,22 @@ SD_HD void prep_model(int n, int kind, int flatten, const float* a, const float*
 
 // Attenuation-corrected, flattened (a, b) of layer i for the period whose log term is lt = ln(t_base/T)
 // (calcul.f:121-127 then flat1 scaling).  as_half selects the half-space flattening factor.
-SD_HD void layer_ab(const float* cst, int ld, int i, float lt, int atten, bool as_half, float& a, float& b) {
-  float ar = cst[C_AREF * ld + i], br = cst[C_BREF * ld + i];
+SD_HD void layer_ab_vals(float ar, float br, float qs, float f, float lt, int atten, float& a, float& b) {
   a = ar; b = br;
   if (atten) {
-    float qsq = SD_DIV(SD_MUL(cst[C_QS * ld + i], lt), SD_PI_ATT);
-    float qpq = SD_DIV(SD_MUL(SD_MUL(qsq, 1.33333333f), SD_MUL(br, br)), SD_MUL(ar, ar));
+    // qsq, qpq ~ 1e-2: an ulp of them is 1e-9 of the velocity, far below float32 resolution
+    const float qsq = SD_FDIV(SD_MUL(qs, lt), SD_PI_ATT);
+    const float qpq = SD_FDIV(SD_MUL(SD_MUL(qsq, 1.33333333f), SD_MUL(br, br)), SD_MUL(ar, ar));
     b = SD_MUL(br, SD_ADD(1.0f, qsq));
     a = SD_MUL(ar, SD_ADD(1.0f, qpq));
   }
-  float f = as_half ? cst[C_HSF * ld + i] : cst[C_DIF * ld + i];
   a = SD_MUL(a, f);
   b = SD_MUL(b, f);
+}
+
+SD_HD void layer_ab(const float* cst, int ld, int i, float lt, int atten, bool as_half, float& a, float& b) {
+  const float f = as_half ? cst[C_HSF * ld + i] : cst[C_DIF * ld + i];
+  layer_ab_vals(cst[C_AREF * ld + i], cst[C_BREF * ld + i], cst[C_QS * ld + i], f, lt, atten, a, b);
 }
 
 SD_HD float4 make_rec(float a, float b, float rho, float d) { return make_float4(a, b, rho, d); }
@@ -251,10 +263,14 @@ SD_HD V2 vs(float s) { return v2(s, s); }
 SD_HD V2 vneg(V2 a) { return v2(-a.x, -a.y); }
 SD_HD V2 vsub(V2 a, V2 b) { return vfma(b, vs(-1.f), a); }
 
-// half_terms for a pair; the series branch is taken only if both velocities qualify
+// half_terms for a pair.  Two series tiers, taken only if both velocities qualify: |u| < 0.5 (thin layers, the
+// vast majority) and |u| < 3 (thick layers at short periods / low trial velocities, e.g. the whole scan of the
+// first period), where the entire functions S and C need 9 / 10 terms for float32 accuracy; beyond that each
+// velocity goes through the MUFU-based scalar form.
 SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
   const V2 u = vmul(kd2, arg);
-  if (fmaxf(fabsf(u.x), fabsf(u.y)) < 0.5f) {
+  const float um = fmaxf(fabsf(u.x), fabsf(u.y));
+  if (um < 0.5f) {
     V2 S = vfma(u, vs(2.7557319e-6f), vs(1.9841270e-4f));
     S = vfma(u, S, vs(8.3333333e-3f));
     S = vfma(u, S, vs(1.6666667e-1f));
@@ -262,6 +278,30 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
     V2 C = vfma(u, vs(2.7557319e-7f), vs(2.4801587e-5f));
     C = vfma(u, C, vs(1.3888889e-3f));
     C = vfma(u, C, vs(4.1666667e-2f));
+    C = vfma(u, C, vs(0.5f));
+    cs = vfma(u, C, vs(1.f));
+    sinr = vmul(kd, S);
+    rsin = vmul(vneg(arg), sinr);
+    return;
+  }
+  if (um < 3.0f) {
+    // S(u) = sum u^n / (2n+1)!,  C(u) = sum u^n / (2n)!;  |u|^10/21! < 2e-15, |u|^10/20! < 3e-14 relative
+    V2 S = vfma(u, vs(8.2206352e-18f), vs(2.8114573e-15f));   // 1/19!, 1/17!
+    S = vfma(u, S, vs(7.6471637e-13f));                         // 1/15!
+    S = vfma(u, S, vs(1.6059044e-10f));                         // 1/13!
+    S = vfma(u, S, vs(2.5052108e-8f));                          // 1/11!
+    S = vfma(u, S, vs(2.7557319e-6f));                          // 1/9!
+    S = vfma(u, S, vs(1.9841270e-4f));                          // 1/7!
+    S = vfma(u, S, vs(8.3333333e-3f));                          // 1/5!
+    S = vfma(u, S, vs(1.6666667e-1f));                          // 1/3!
+    S = vfma(u, S, vs(1.f));
+    V2 C = vfma(u, vs(1.5619207e-16f), vs(4.7794773e-14f));   // 1/18!, 1/16!
+    C = vfma(u, C, vs(1.1470746e-11f));                         // 1/14!
+    C = vfma(u, C, vs(2.0876757e-9f));                          // 1/12!
+    C = vfma(u, C, vs(2.7557319e-7f));                          // 1/10!
+    C = vfma(u, C, vs(2.4801587e-5f));                          // 1/8!
+    C = vfma(u, C, vs(1.3888889e-3f));                          // 1/6!
+    C = vfma(u, C, vs(4.1666667e-2f));                          // 1/4!
     C = vfma(u, C, vs(0.5f));
     cs = vfma(u, C, vs(1.f));
     sinr = vmul(kd, S);
@@ -414,7 +454,7 @@ SD_HD void inv_interp6(const float* xin, const float* y, int i4, float& e4, floa
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 6 - lev; ++i) x[i] = (y[i + lev] * x[i] - y[i] * x[i + 1]) / (y[i + lev] - y[i]);
+    for (int i = 0; i < 6 - lev; ++i) x[i] = SD_FDIV(y[i + lev] * x[i] - y[i] * x[i + 1], y[i + lev] - y[i]);
     if (lev == 3) { l3[0] = x[0]; l3[1] = x[1]; l3[2] = x[2]; }
   }
   e6 = x[0];
@@ -424,10 +464,10 @@ SD_HD void inv_interp6(const float* xin, const float* y, int i4, float& e4, floa
 // 4-point Lagrange weights at x (abscissae xs[0..3])
 SD_HD void lagrange4(const float* xs, float x, float* w) {
   const float d0 = x - xs[0], d1 = x - xs[1], d2 = x - xs[2], d3 = x - xs[3];
-  w[0] = d1 * d2 * d3 / ((xs[0] - xs[1]) * (xs[0] - xs[2]) * (xs[0] - xs[3]));
-  w[1] = d0 * d2 * d3 / ((xs[1] - xs[0]) * (xs[1] - xs[2]) * (xs[1] - xs[3]));
-  w[2] = d0 * d1 * d3 / ((xs[2] - xs[0]) * (xs[2] - xs[1]) * (xs[2] - xs[3]));
-  w[3] = d0 * d1 * d2 / ((xs[3] - xs[0]) * (xs[3] - xs[1]) * (xs[3] - xs[2]));
+  w[0] = SD_FDIV(d1 * d2 * d3, (xs[0] - xs[1]) * (xs[0] - xs[2]) * (xs[0] - xs[3]));
+  w[1] = SD_FDIV(d0 * d2 * d3, (xs[1] - xs[0]) * (xs[1] - xs[2]) * (xs[1] - xs[3]));
+  w[2] = SD_FDIV(d0 * d1 * d3, (xs[2] - xs[0]) * (xs[2] - xs[1]) * (xs[2] - xs[3]));
+  w[3] = SD_FDIV(d0 * d1 * d2, (xs[3] - xs[0]) * (xs[3] - xs[1]) * (xs[3] - xs[2]));
 }
 
 // Offsets of the points of a clustered round around a root estimate, in units of the innermost half spacing:

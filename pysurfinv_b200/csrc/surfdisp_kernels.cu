@@ -106,6 +106,7 @@ __device__ __noinline__ Sec2 secular2(int kind, float2 c, float T, int mm, const
   return r;
 }
 
+struct SecFn;
 template <int G>
 __device__ __forceinline__ float gshfl(unsigned mask, float v, int src) { return __shfl_sync(mask, v, src, G); }
 template <int G>
@@ -127,12 +128,70 @@ __device__ __forceinline__ unsigned interleave(unsigned a, unsigned b) {
   return r;
 }
 
+// Layer dropping (surfa.f:92-106) for ONE trial velocity, computed by the G lanes of a group together: each lane
+// sums the thicknesses of its contiguous chunk of layers (those with c < b), the chunk sums are prefixed across
+// the lanes, and the lane whose chunk crosses dmax = fact c T walks it again to find the layer.  The additions
+// inside a chunk are in the reference's order; the chunked total rounds differently from the reference's
+// single running sum only in the last ulp, i.e. the result can differ by one layer on an exact tie (1e-10 in c).
+template <int G>
+__device__ __noinline__ int layer_drop_coop(float c, float T, float fact, int nmax, const float4* rec, unsigned gmask, int gl) {
+  const float dmax = SD_MUL(SD_MUL(fact, c), T);
+  const int L = (nmax + G - 1) / G;
+  const int i0 = gl * L, i1 = min(i0 + L, nmax);
+  float s = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float4 e = rec[i];
+    if (c < e.y) s = SD_ADD(s, e.w);
+  }
+  // exclusive prefix over the lanes of the group
+  float base = 0.f;
+#pragma unroll
+  for (int j = 0; j < G - 1; ++j) {
+    const float sj = __shfl_sync(gmask, s, j, G);
+    if (gl > j) base = SD_ADD(base, sj);
+  }
+  int found = nmax;
+  if (!(base > dmax) && SD_ADD(base, s) > dmax) {
+    float sum = base;
+    for (int i = i0; i < i1; ++i) {
+      const float4 e = rec[i];
+      if (c < e.y) { sum = SD_ADD(sum, e.w); if (sum > dmax) { found = i + 1; break; } }
+    }
+  }
+  // the first lane that crosses wins
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o, G));
+  return found < 2 ? 2 : found;
+}
+
+struct SecFn {
+  int kind; float T; int mm; const float4* rec;
+  __device__ float operator()(float cc) const;
+};
+
+__device__ float SecFn::operator()(float cc) const { return secular2(kind, make_float2(cc, cc), T, mm, rec, 0).d.x; }
+
+// the reference's sequential polish (rare path), kept out of line
+__device__ __noinline__ bool nevill_out_of_line(const SecFn& f, float c1, float c2, float d1, float d2, float* cc, int* evals) {
+  return nevill_seq(f, c1, c2, d1, d2, *cc, *evals);
+}
+
 #ifndef P1_G
 #define P1_G 4
 #endif
 #ifndef P1_MINBLK
-#define P1_MINBLK 5
+#define P1_MINBLK 4
 #endif
+
+// Stages of a group's (= one model's) state machine.  Every iteration of the kernel's main loop performs ONE
+// sweep of the secular function for every group of the warp, whatever stage each group is in: the groups
+// advance through their periods and models independently, and the expensive code (the sweep) is always
+// executed by all of them together (a structured loop nest would make groups that need an extra round, or
+// that sit in the scan of their first period, serialise the others).
+enum { ST_FETCH = 0, ST_PERIOD, ST_FAST, ST_REFINE, ST_SCAN, ST_POLISH, ST_ELL, ST_DONE };
+// Which trial velocities the next sweep of a group needs (built in ONE place, right before the sweep)
+enum { NB_NONE = 0, NB_FAST, NB_REFINE, NB_SCAN, NB_POLISH, NB_ELL };
+
 template <int G>
 __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
   static_assert(G == 4 || G == 8, "4 or 8 lanes x 2 trial velocities per model");
@@ -146,10 +205,11 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
   const int grp = threadIdx.x / G;
   float4* rec = smem + (size_t)grp * p.mstride;   // this model's layer records (a, b, rho, d)
   const int K = p.K;
+  const int ld = p.lpad;
   unsigned long long my_steps = 0, my_sweeps = 0;
   int my_models = 0;
 
-  // ordered sign-change mask of the 16 points of a round: bit i set <=> sign(point i) != sign(point i-1)
+  // ordered sign-change mask of the P points of a round: bit i set <=> sign(point i) != sign(point i-1)
   // (point -1 = `before`)
   auto change_mask = [&](float2 d, float before) -> unsigned {
     float dprev = __shfl_up_sync(gmask, d.y, 1, G);
@@ -164,65 +224,181 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
     return interleave<G>(ex, ey);
   };
 
+  // ---- per-model state (uniform inside a group)
+  int stage = ST_FETCH;
+  int model = 0, n = 2, k = 0, mm = 2, nfound = 0, flag = 0;
+  const float* cst = p.consts;
+  float* crow = p.c_out;
+  float* rrow = p.ratio_out;
+  float c1 = 1.f, c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f, c_pred = 0.f, b_top = 0.f, T = 1.f;
+  bool hopped = false, mid_liquid = false;
+  // ---- the sweep request of the current iteration (per lane) and its result
+  float2 pc = make_float2(1.f, 1.f), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
+  int meval = 2, ell_only = 0;
+  // ---- fast path (cluster / window / refinement rounds)
+  int j0 = 2, w0 = 2, dir = 0, fstage = 0, wtry = 0, mw = 2, jb = 1, it = 0, nvalid = 0;
+  bool has_ends = false;
+  SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = E0;
+  // ---- point-by-point path (scan, polish)
+  float cbase = 0.f, cP = 0.f, dP = 0.f, lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, lo0 = 0.f, hi0 = 0.f, dlo0 = 0.f, dhi0 = 0.f;
+  int mjx = 2, mjy = 2, round = 0, pit = 0;
+  bool have_prev = false, own_mj = false;
+  float bmin = 0.f;   // smallest b below the top layer (this period's records)
+  // ---- result of the period
+  float croot = 0.f, ratio = 0.f;
+  // ---- what to build before the next sweep; refinement round parameters
+  int need = NB_NONE;
+  float rf_e = 0.f, rf_s0 = 0.f;
+  bool rf_uni = false;
+
+  const float cspan = (float)(1 << ((P - 2) / 2 - 1)) - 0.5f;   // outermost cluster offset in units of the spacing
+
+  // ---- request builders
+  auto build_fast = [&]() {
+    // stages 0/1: point 0 = c1 itself, point 1 = half way to the window, points 2..P-1 = cluster / window; an odd
+    // number of roots below shows as a sign difference between points 0, 1 and 2.  stage 2: P window points.
+    const float hc = fminf(fmaxf(6.0f * pred_err / cspan, kClusterH0), 16.f * kClusterH0);  // cluster spans ~6x the last prediction error
+    float cc[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pi = 2 * gl + h;
+      if (pi >= w0 && fstage == 0) cc[h] = c_pred + geometric_offset(pi - 2, P - 2) * hc;
+      else {
+        // grid points in closed form: only the signs matter there (the reference's sequentially accumulated
+        // grid differs by a few ulps, i.e. 1e-4 of a grid step)
+        const int idx = (pi < w0) ? ((pi == 0) ? 0 : j0 / 2) : j0 + (pi - w0);
+        cc[h] = c1 + (float)idx * p.dc;
+      }
+    }
+    pc = make_float2(cc[0], cc[1]);
+    mw = layer_drop_coop<G>(gshfl<G>(gmask, pc.y, G - 1), T, p.fact, n, rec, gmask, gl);
+    meval = mw; ell_only = 0;
+  };
+  auto build_scan = [&]() {
+    // 2G consecutive grid points, accumulated like the reference does (calcul.f:157).  The reference gives each
+    // point its own layer dropping; here the whole round is evaluated on the deepest of them (same
+    // sign, see below).  The own truncation of a point matters for the stop test c >= b(mmax) + 0.3
+    // (calcul.f:166), which cannot fire while c < min b + 0.3: only then is it computed per point.
+    float cx = cbase;
+    for (int t = 0; t < 2 * gl; ++t) cx = SD_ADD(cx, p.dc);
+    pc = make_float2(cx, SD_ADD(cx, p.dc));
+    const float ctop = gshfl<G>(gmask, pc.y, G - 1);
+    meval = layer_drop_coop<G>(ctop, T, p.fact, n, rec, gmask, gl);
+    own_mj = !(ctop < bmin + 0.3f);
+    if (own_mj) { mjx = layer_drop(pc.x, T, p.fact, n, rec); mjy = layer_drop(pc.y, T, p.fact, n, rec); }
+    ell_only = 0;
+  };
+  auto start_scan = [&]() {
+    cbase = c1; cP = 0.f; dP = 0.f; have_prev = false; round = 0;
+    stage = ST_SCAN; need = NB_SCAN;
+  };
+  auto build_polish = [&]() {
+    const float st = (hi - lo) / (float)(P + 1);
+    pc = make_float2(lo + (float)(2 * gl + 1) * st, lo + (float)(2 * gl + 2) * st);
+    meval = mm; ell_only = 0;
+  };
+  auto build_refine = [&]() {
+    // P points around the root estimate, spaced by the disagreement of the two interpolation orders
+    float cc[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pi = 2 * gl + h;
+      cc[h] = E0.c + (rf_uni ? (float)(pi + 1) * ((E1.c - E0.c) / (float)(P + 1)) : rf_e + geometric_offset(pi, P) * rf_s0);
+    }
+    pc = make_float2(cc[0], cc[1]);
+    meval = mw; ell_only = 0;
+  };
+  auto build_ell = [&]() {
+    pc = make_float2(croot, croot);
+    meval = mm; ell_only = 1;
+  };
+
   for (;;) {
-    int model = 0;
-    if (gl == 0) model = (int)atomicAdd(p.queue, 1u);
-    model = gshfl<G>(gmask, model, 0);
-    if (model >= p.M) break;
-    const int n = p.nlay[model];
-    float* crow = p.c_out + (size_t)model * K;
-    float* rrow = p.ratio_out + (size_t)model * K;
-    if (n < 2 || n > p.lpad) {
-      for (int k = gl; k < K; k += G) { crow[k] = 0.f; rrow[k] = 0.f; }
-      if (gl == 0) { p.nfound[model] = 0; if (p.flags) p.flags[model] = SURFDISP_F_NO_ROOT_FIRST; }
-      continue;
+    // =========================================================== set-up: next model / next period
+    // The groups of a warp start their models together: inside a model they drift apart by a few rounds only,
+    // so that the sweeps issued together have similar depths (the truncation depth grows with the period; a
+    // warp whose groups sit at very different periods would run every sweep to the depth of the deepest one).
+#ifdef P1_SYNC_MODELS
+    const bool warp_fetch = __all_sync(0xffffffffu, stage == ST_FETCH || stage == ST_DONE);
+#else
+    const bool warp_fetch = true;
+#endif
+    if (stage == ST_FETCH && warp_fetch) {
+      if (gl == 0) model = (int)atomicAdd(p.queue, 1u);
+      model = gshfl<G>(gmask, model, 0);
+      if (model >= p.M) stage = ST_DONE;
+      else {
+        n = p.nlay[model];
+        crow = p.c_out + (size_t)model * K;
+        rrow = p.ratio_out + (size_t)model * K;
+        if (n < 2 || n > p.lpad) {
+          for (int kk = gl; kk < K; kk += G) { crow[kk] = 0.f; rrow[kk] = 0.f; }
+          if (gl == 0) { p.nfound[model] = 0; if (p.flags) p.flags[model] = SURFDISP_F_NO_ROOT_FIRST; }
+          n = 2;  // stays in ST_FETCH: sits this iteration's sweep out and pulls another model next time
+        } else {
+          my_models += (gl == 0);
+          cst = p.consts + (size_t)model * NCONST * p.lpad;
+          // first start velocity, fast_surf.f:157-171
+          {
+            const float b0 = cst[C_BREF * ld + 0];
+            const int ilay = (b0 < 0.1f) ? 1 : 0;
+            float b_corr = 0.f;
+            if (p.atten) b_corr = SD_DIV(SD_MUL(cst[C_QS * ld + ilay], p.tab.lt[0]), SD_PI_ATT);
+            float qq = cst[C_BREF * ld + ilay];
+            if (p.kind == 2) qq = SD_MUL(0.9f, qq);
+            c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
+            if (b0 < 0.1f) c1 = 0.5f;
+          }
+          // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks
+          {
+            bool l = false;
+            for (int i = 1 + gl; i < n; i += G) l |= !(cst[C_BREF * ld + i] > 0.f);
+            mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
+          }
+          mm = n;  // reference COMMON mmax carried from period to period
+          nfound = 0; flag = 0; k = 0; hopped = false;
+          c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 2.0e-3f;
+          stage = ST_PERIOD;
+        }
+      }
     }
-    my_models += (gl == 0);
-    const float* cst = p.consts + (size_t)model * NCONST * p.lpad;
-    const int ld = p.lpad;
-    // first start velocity, fast_surf.f:157-171
-    float c1;
-    {
-      const float b0 = cst[C_BREF * ld + 0];
-      const int ilay = (b0 < 0.1f) ? 1 : 0;
-      float b_corr = 0.f;
-      if (p.atten) b_corr = SD_DIV(SD_MUL(cst[C_QS * ld + ilay], p.tab.lt[0]), SD_PI_ATT);
-      float qq = cst[C_BREF * ld + ilay];
-      if (p.kind == 2) qq = SD_MUL(0.9f, qq);
-      c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
-      if (b0 < 0.1f) c1 = 0.5f;
-    }
-    // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks
-    bool mid_liquid = false;
-    {
-      bool l = false;
-      for (int i = 1 + gl; i < n; i += G) l |= !(cst[C_BREF * ld + i] > 0.f);
-      mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
-    }
-    int mm = n;        // reference COMMON mmax carried from period to period
-    int nfound = 0, flag = 0;
-    bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
-    float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f;
-    for (int k = 0; k < K; ++k) {
-      const float T = p.tab.per[k];
+    if (stage == ST_PERIOD) {
+      T = p.tab.per[k];
       const float lt = p.tab.lt[k];
       // ---- refresh layers 0..mref-1, layer mref-1 flattened as the half-space (calcul.f:112-133)
       const int mref = p.stale ? mm : n;
       __syncwarp(gmask);
-      for (int i = gl; i < mref; i += G) {
-        const bool hs = (i == mref - 1);
-        float a, b;
-        layer_ab(cst, ld, i, lt, p.atten, hs, a, b);
-        const float rho = hs ? cst[C_RHOHS * ld + i] : cst[C_RHOFL * ld + i];
-        const float d = hs ? 0.f : cst[C_DFL * ld + i];
-        rec[i] = make_rec(a, b, rho, d);
+      float bm = 3.0e38f;
+      for (int i0 = 4 * gl; i0 < mref; i0 += 4 * G) {
+        // four layers per lane and iteration: six float4 loads of the per-model constants
+        const float4 AR = *reinterpret_cast<const float4*>(cst + C_AREF * ld + i0);
+        const float4 BR = *reinterpret_cast<const float4*>(cst + C_BREF * ld + i0);
+        const float4 QS = *reinterpret_cast<const float4*>(cst + C_QS * ld + i0);
+        const float4 DF = *reinterpret_cast<const float4*>(cst + C_DIF * ld + i0);
+        const float4 RF = *reinterpret_cast<const float4*>(cst + C_RHOFL * ld + i0);
+        const float4 DL = *reinterpret_cast<const float4*>(cst + C_DFL * ld + i0);
+        const float ar[4] = {AR.x, AR.y, AR.z, AR.w}, br[4] = {BR.x, BR.y, BR.z, BR.w}, qs[4] = {QS.x, QS.y, QS.z, QS.w};
+        const float df[4] = {DF.x, DF.y, DF.z, DF.w}, rf[4] = {RF.x, RF.y, RF.z, RF.w}, dl[4] = {DL.x, DL.y, DL.z, DL.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          if (i < mref) {
+            const bool hs = (i == mref - 1);
+            float a, b;
+            layer_ab_vals(ar[j], br[j], qs[j], hs ? cst[C_HSF * ld + i] : df[j], lt, p.atten, a, b);
+            rec[i] = make_rec(a, b, hs ? cst[C_RHOHS * ld + i] : rf[j], hs ? 0.f : dl[j]);
+            if (i >= 1) bm = fminf(bm, b);
+          }
+        }
       }
       __syncwarp(gmask);
+      // smallest b below the top layer: taken at the first period, where all layers are refreshed (mm = n); the
+      // attenuation correction moves b by < 1 % over the period range, which the margin covers
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) bm = fminf(bm, __shfl_xor_sync(gmask, bm, o, G));
+      if (k == 0) bmin = bm - 0.05f;
       if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
-      const float b_top = rec[0].y;
-      float croot = 0.f, ratio = 0.f;
-      bool found = false, lstop = false, have_ratio = false, fast_done = false;
-
+      b_top = rec[0].y;
       // ---- fast path (every period after the first, unless exact_scan).  The reference scans
       // c1, c1+dc, ... for the first sign change (calcul.f:155-167) and polishes inside that bracket
       // (NEVILL, surfa.f:2-83).  The root it ends on moves smoothly with the period, so the P = 2G trial
@@ -233,12 +409,12 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
       // point by point from then on), there is exactly one sign change inside the cluster and the half-space
       // velocity (kink of the secular function) is not nearby.  If the cluster misses the root, a window of
       // P-2 grid points takes its place (moved up or down once more if needed); anything else goes to the
-      // point-by-point path below.  All points of a round are evaluated on the round's deepest truncation
+      // point-by-point path.  All points of a round are evaluated on the round's deepest truncation
       // (layer dropping, surfa.f:92-106) so that they sample ONE smooth function -- each truncation depth
       // scales the unnormalised secular function differently but has the same root to ~1e-10 -- and the root
       // is taken by inverse polynomial interpolation; if the 4- and 6-point estimates disagree, P more points
       // are clustered around the estimate and the test is repeated.
-      float c_pred = c_prev;
+      c_pred = c_prev;
       if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
       else if (k >= 2) {
         // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
@@ -250,260 +426,234 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
           c_pred += (d01 - d12) / (x0 - x2) * (x - x0) * (x - x1);
         }
       }
-      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top)) {
-        int j0 = (int)floorf((c_pred - c1) / p.dc) - (P - 4) / 2;
-        if (j0 < 2) j0 = 2;
-        if (j0 < 1000) {
-          float2 pc = make_float2(c1, c1), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
-          int mw = n, jev = -1, dir = 0, w0 = 2;
-          // stage 0 (from the third period on): cluster around the predicted root; stage 1: window of 14 grid
-          // points around it; stage 2: window of 16 grid points moved up or down.
-          int stage = (k >= 2 && j0 >= 4) ? 0 : 1;
-          // cluster spacing: the cluster spans about 6x the last prediction error
-          const float cspan = (float)(1 << ((P - 2) / 2 - 1)) - 0.5f;
-          const float hc = fminf(fmaxf(6.0f * pred_err / cspan, kClusterH0), 16.f * kClusterH0);
-          bool win_ok = false;
-          for (int wtry = 0; wtry < 4; ++wtry) {
-            // stages 0/1: point 0 = c1 itself, point 1 = half way to the window, points 2..15 = cluster / window;
-            // an odd number of roots below shows as a sign difference between points 0, 1 and 2.
-            {
-              float cc[2];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int pi = 2 * gl + h;
-                if (pi >= w0 && stage == 0) cc[h] = c_pred + geometric_offset(pi - 2, P - 2) * hc;
-                else {
-                  // grid points in closed form: only the signs matter there (the reference's sequentially
-                  // accumulated grid differs by a few ulps, i.e. 1e-4 of a grid step)
-                  const int idx = (pi < w0) ? ((pi == 0) ? 0 : j0 / 2) : j0 + (pi - w0);
-                  cc[h] = c1 + (float)idx * p.dc;
-                }
-              }
-              pc = make_float2(cc[0], cc[1]);
-            }
-            mw = layer_drop(gshfl<G>(gmask, pc.y, G - 1), T, p.fact, n, rec);
-            const Sec2 sv = secular2(p.kind, pc, T, mw, rec, 0);
-            my_steps += 2u * (unsigned)(mw - 1); my_sweeps += 2;
-            pd = sv.d; pe2 = sv.e2; pe3 = sv.e3;
-            const float d0 = gshfl<G>(gmask, pd.x, 0);
-            const unsigned evc = change_mask(pd, d0) & ~((2u << w0) - 1u);     // changes between cluster / window points
-            const unsigned evw = pair_mask(signbit(pd.x) != signbit(d0), signbit(pd.y) != signbit(d0));
-            const bool below_ok = !(evw & ((2u << w0) - 1u));     // points 0..w0 have the sign of c1
-            jev = __ffs(evc) - 1;
-            if (below_ok && jev >= 1) {
-              if (stage == 0 && (evc & (evc - 1u))) break;     // several sign changes inside the cluster
-              win_ok = true; break;
-            }
-            if (stage == 0) { stage = 1; continue; }           // the cluster does not bracket the root
-            if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? P - 3 : P - 1); w0 = 0; stage = 2; continue; }   // root above the window
-            if (!below_ok && dir <= 0) {
-              // root below the window: only if it is between the half-way point and the window
-              const bool lower_ok = !(evw & ((1u << w0) - 1u));
-              const int jmin = w0 ? j0 / 2 : 0;
-              if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - (P - 1), jmin); w0 = 0; stage = 2; continue; }
-            }
-            break;
-          }
-          if (win_ok) {
-            bool has_ends = false;
-            SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = {0.f, 0.f, 0.f, 0.f};
-            auto sample = [&](int i) {
-              // i-th entry of the ordered list: [point w0 .. point 15] or [E0, point 0 .. point 15, E1]
-              const int pi = min(max(has_ends ? i - 1 : i + w0, 0), P - 1);
-              const int sl = pi >> 1;
-              const bool hi = (pi & 1) != 0;
-              SamplePt s;
-              s.c = gshfl<G>(gmask, hi ? pc.y : pc.x, sl); s.d = gshfl<G>(gmask, hi ? pd.y : pd.x, sl);
-              s.e2 = gshfl<G>(gmask, hi ? pe2.y : pe2.x, sl); s.e3 = gshfl<G>(gmask, hi ? pe3.y : pe3.x, sl);
-              if (has_ends && i == 0) s = E0;
-              if (has_ends && i == P + 1) s = E1;
-              return s;
-            };
-            // the half-space velocity of the round's truncation is a kink of the sampled function: not within
-            // a grid step of the bracket, and the interpolation only uses points below it
-            const float bh2 = rec[mw - 1].y;
-            int jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
-            const float br_lo = sample(jb - 1).c, br_hi = sample(jb).c;
-            const int nvalid = __popc(pair_mask(pc.x < bh2, pc.y < bh2) & ~((1u << w0) - 1u));  // list points below the kink
-            const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jb > nvalid - 1;
-            if (!kink) {
-              for (int it = 0; it < 4; ++it) {
-                const int np = has_ends ? P + 2 : nvalid;
-                const int s6 = min(max(jb - 3, 0), np - 6), s4 = min(max(jb - 2, 0), np - 4);
-                const SamplePt B0 = sample(jb - 1), B1 = sample(jb);
-                float x[6], y[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { const SamplePt s = sample(s6 + i); x[i] = s.c - B0.c; y[i] = s.d; }
-                float e4, e6;
-                inv_interp6(x, y, s4 - s6, e4, e6);
-                const float w = B1.c - B0.c;
-                const bool inside = (e6 > 0.f && e6 < w);
-                const float delta = fabsf(e6 - e4);
-                float e = e6;
-                if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
-                // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
-                // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
-                const bool interior = (jb >= 2 && jb <= np - 2);
-                const float tol = (it > 0) ? kInterpTol : ((stage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
-                if ((inside && interior && delta <= tol) || w <= kBracketTol) {
-                  croot = B0.c + e;
-                  if (p.kind == 2) {
-                    float xs[4], f2[4], f3[4], wl[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { const SamplePt s = sample(s4 + i); xs[i] = s.c - B0.c; f2[i] = s.e2; f3[i] = s.e3; }
-                    lagrange4(xs, e, wl);
-                    const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
-                    const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
-                    ratio = 0.5f * se3 / se2;
-                  }
-                  fast_done = true;
-                  break;
-                }
-                if (it == 3) break;
-                // one more round: 16 points around the estimate, spaced by the disagreement of the two orders
-                const float span = (float)(1 << (P / 2 - 1));   // outermost offset of the round, in units of s0
-                const float s0 = fmaxf(inside ? 0.5f * delta : w / (2.f * span), 1.0e-5f);
-                const bool uni = !(e - span * s0 > 0.f && e + span * s0 < w);
-                E0 = B0; E1 = B1;
-                {
-                  float cc[2];
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const int pi = 2 * gl + h;
-                    cc[h] = B0.c + (uni ? (float)(pi + 1) * (w / (float)(P + 1)) : e + geometric_offset(pi, P) * s0);
-                  }
-                  pc = make_float2(cc[0], cc[1]);
-                }
-                const Sec2 sr = secular2(p.kind, pc, T, mw, rec, 0);
-                my_steps += 2u * (unsigned)(mw - 1); my_sweeps += 2;
-                pd = sr.d; pe2 = sr.e2; pe3 = sr.e3;
-                has_ends = true;
-                const unsigned ev = change_mask(pd, E0.d);
-                const float dlast = gshfl<G>(gmask, pd.y, G - 1);
-                if (ev) jb = __ffs(ev);                                   // point i is list entry i + 1
-                else if (signbit(dlast) != signbit(E1.d)) jb = P + 1;
-                else break;
-              }
-              if (fast_done) {
-                // the reference's bracket is the grid interval around the root; its upper end fixes mmax
-                float hg = c1 + (floorf((croot - c1) / p.dc) + 1.f) * p.dc;
-                if (!(hg > croot)) hg += p.dc;
-                const int mnew = layer_drop(hg, T, p.fact, n, rec);
-                const float bh1 = rec[mnew - 1].y;
-                if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;   // calcul.f:191 / kink: point-by-point path
-                else { mm = mnew; found = true; have_ratio = (p.kind == 2) && !mid_liquid; }
-              }
-            }
-          }
+      j0 = (int)floorf((c_pred - c1) / p.dc) - (P - 4) / 2;
+      if (j0 < 2) j0 = 2;
+      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000) {
+        // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
+        // around it; 2: window of P grid points moved up or down
+        fstage = (k >= 2 && j0 >= 4) ? 0 : 1;
+        w0 = 2; dir = 0; wtry = 0;
+        stage = ST_FAST; need = NB_FAST;
+      } else start_scan();
+    }
+    if (__all_sync(0xffffffffu, stage == ST_DONE)) break;
+    // ---- trial velocities of this iteration's sweep
+    if (need == NB_FAST) build_fast();
+    else if (need == NB_REFINE) build_refine();
+    else if (need == NB_SCAN) build_scan();
+    else if (need == NB_POLISH) build_polish();
+    else if (need == NB_ELL) build_ell();
+    need = NB_NONE;
+
+    // =========================================================== the sweep (the only call site)
+    const bool active = (stage >= ST_FAST && stage <= ST_ELL);
+    if (active) {
+      const Sec2 sv = secular2(p.kind, pc, T, meval, rec, ell_only);
+      my_steps += 2u * (unsigned)(meval - 1); my_sweeps += 2;
+      pd = sv.d; pe2 = sv.e2; pe3 = sv.e3;
+    }
+
+#ifdef P1_DEBUG
+    if (active && model == P1_DEBUG && gl == 0 && k < 4)
+      printf("k=%d stage=%d fstage=%d wtry=%d j0=%d w0=%d meval=%d pc=(%.5f,%.5f) pd=(%g,%g) c1=%.5f c_pred=%.5f lo=%.5f hi=%.5f cbase=%.5f round=%d\n",
+             k, stage, fstage, wtry, j0, w0, meval, pc.x, pc.y, pd.x, pd.y, c1, c_pred, lo, hi, cbase, round);
+#endif
+    // =========================================================== what the results mean, per stage
+    bool do_interp = false, period_done = false, model_done = false;
+    auto sample = [&](int i) {
+      // i-th entry of the ordered list: [point w0 .. point P-1] or [E0, point 0 .. point P-1, E1]
+      const int pi = min(max(has_ends ? i - 1 : i + w0, 0), P - 1);
+      const int sl = pi >> 1;
+      const bool hc = (pi & 1) != 0;
+      SamplePt sp;
+      sp.c = gshfl<G>(gmask, hc ? pc.y : pc.x, sl); sp.d = gshfl<G>(gmask, hc ? pd.y : pd.x, sl);
+      sp.e2 = gshfl<G>(gmask, hc ? pe2.y : pe2.x, sl); sp.e3 = gshfl<G>(gmask, hc ? pe3.y : pe3.x, sl);
+      if (has_ends && i == 0) sp = E0;
+      if (has_ends && i == P + 1) sp = E1;
+      return sp;
+    };
+    if (stage == ST_FAST) {
+      const float d0 = gshfl<G>(gmask, pd.x, 0);
+      const unsigned evc = change_mask(pd, d0) & ~((2u << w0) - 1u);     // changes between cluster / window points
+      const unsigned evw = pair_mask(signbit(pd.x) != signbit(d0), signbit(pd.y) != signbit(d0));
+      const bool below_ok = !(evw & ((2u << w0) - 1u));     // points 0..w0 have the sign of c1
+      const int jev = __ffs(evc) - 1;
+      bool retry = false, ok = false;
+      if (below_ok && jev >= 1) ok = !(fstage == 0 && (evc & (evc - 1u)));   // not several sign changes inside the cluster
+      else if (wtry < 3) {
+        if (fstage == 0) { fstage = 1; retry = true; }           // the cluster does not bracket the root
+        else if (below_ok && !evc && dir >= 0) { dir = 1; j0 += (w0 ? P - 3 : P - 1); w0 = 0; fstage = 2; retry = true; }   // root above the window
+        else if (!below_ok && dir <= 0) {
+          // root below the window: only if it is between the half-way point and the window
+          const bool lower_ok = !(evw & ((1u << w0) - 1u));
+          const int jmin = w0 ? j0 / 2 : 0;
+          if (lower_ok && j0 > jmin) { dir = -1; j0 = max(j0 - (P - 1), jmin); w0 = 0; fstage = 2; retry = true; }
         }
       }
-
-      if (!fast_done) {
-        // ---- point-by-point scan (calcul.f:155-167), 16 consecutive grid points per round.  Each point has
-        // its own layer dropping; the pair of a lane is evaluated on the deeper of the two
-        // truncations (same sign, see above).
-        float lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f;
-        int mnew = mm;
-        {
-          float cbase = c1, cP = 0.f, dP = 0.f;
-          bool have_prev = false;
-          for (int round = 0; round < 2048; ++round) {
-            float cx = cbase;
-            for (int t = 0; t < 2 * gl; ++t) cx = SD_ADD(cx, p.dc);
-            const float2 cj = make_float2(cx, SD_ADD(cx, p.dc));
-            const int mjx = layer_drop(cj.x, T, p.fact, n, rec), mjy = layer_drop(cj.y, T, p.fact, n, rec);
-            const float2 dj = secular2(p.kind, cj, T, max(mjx, mjy), rec, 0).d;
-            my_steps += 2u * (unsigned)(max(mjx, mjy) - 1); my_sweeps += 2;
-            // previous point of every point in sequence order
-            float dpx = __shfl_up_sync(gmask, dj.y, 1, G), cpx = __shfl_up_sync(gmask, cj.y, 1, G);
-            if (gl == 0) { dpx = dP; cpx = cP; }
-            const bool haspx = (gl > 0) || have_prev;
-            const bool chx = haspx && (signbit(dpx) != signbit(dj.x));
-            const bool stx = haspx && !chx && ((cj.x < 0.8f * b_top) || !(cj.x < rec[mjx - 1].y + 0.3f) || !(cj.x == cj.x));
-            const bool chy = (signbit(dj.x) != signbit(dj.y));
-            const bool sty = !chy && ((cj.y < 0.8f * b_top) || !(cj.y < rec[mjy - 1].y + 0.3f) || !(cj.y == cj.y));
-            const unsigned ev = pair_mask(chx || stx, chy || sty);
-            if (!ev) {
-              cP = gshfl<G>(gmask, cj.y, G - 1);
-              dP = gshfl<G>(gmask, dj.y, G - 1);
-              mnew = gshfl<G>(gmask, mjy, G - 1);
-              have_prev = true;
-              cbase = SD_ADD(cP, p.dc);
-              if (round == 2047) flag |= SURFDISP_F_SCAN_LIMIT;
-              continue;
-            }
-            const int j = __ffs(ev) - 1, sl = j >> 1;
-            const bool jy = (j & 1) != 0;
-            found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
-            lo = gshfl<G>(gmask, jy ? cj.x : cpx, sl); hi = gshfl<G>(gmask, jy ? cj.y : cj.x, sl);
-            dlo = gshfl<G>(gmask, jy ? dj.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? dj.y : dj.x, sl);
-            mnew = gshfl<G>(gmask, jy ? mjy : mjx, sl);
-            break;
-          }
-        }
-        mm = mnew;  // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
+      if (ok) {
+        // the half-space velocity of the round's truncation is a kink of the sampled function: not within a
+        // grid step of the bracket, and the interpolation only uses points below it
+        has_ends = false;
+        const float bh2 = rec[mw - 1].y;
+        jb = jev - w0;  // index (in the ordered sample list) of the upper end of the bracket
+        const float br_lo = sample(jb - 1).c, br_hi = sample(jb).c;
+        nvalid = __popc(pair_mask(pc.x < bh2, pc.y < bh2) & ~((1u << w0) - 1u));  // list points below the kink
+        const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jb > nvalid - 1;
+        if (kink) start_scan(); else { it = 0; do_interp = true; }
+      } else if (retry) { wtry++; need = NB_FAST; }
+      else start_scan();
+    } else if (stage == ST_REFINE) {
+      const unsigned ev = change_mask(pd, E0.d);
+      const float dlast = gshfl<G>(gmask, pd.y, G - 1);
+      has_ends = true;
+      if (ev) { jb = __ffs(ev); it++; do_interp = true; }                                   // point i is list entry i + 1
+      else if (signbit(dlast) != signbit(E1.d)) { jb = P + 1; it++; do_interp = true; }
+      else start_scan();
+    } else if (stage == ST_SCAN) {
+      // ---- point-by-point scan (calcul.f:155-167): first sign change or stop condition in sequence order
+      float dpx = __shfl_up_sync(gmask, pd.y, 1, G), cpx = __shfl_up_sync(gmask, pc.y, 1, G);
+      if (gl == 0) { dpx = dP; cpx = cP; }
+      const bool haspx = (gl > 0) || have_prev;
+      const bool chx = haspx && (signbit(dpx) != signbit(pd.x));
+      const bool stx = haspx && !chx && ((pc.x < 0.8f * b_top) || (own_mj && !(pc.x < rec[mjx - 1].y + 0.3f)) || !(pc.x == pc.x));
+      const bool chy = (signbit(pd.x) != signbit(pd.y));
+      const bool sty = !chy && ((pc.y < 0.8f * b_top) || (own_mj && !(pc.y < rec[mjy - 1].y + 0.3f)) || !(pc.y == pc.y));
+      const unsigned ev = pair_mask(chx || stx, chy || sty);
+      if (!ev) {
+        cP = gshfl<G>(gmask, pc.y, G - 1);
+        dP = gshfl<G>(gmask, pd.y, G - 1);
+        have_prev = true;
+        cbase = SD_ADD(cP, p.dc);
+        if (++round >= 2048) { flag |= SURFDISP_F_SCAN_LIMIT; flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K; model_done = true; }
+        else need = NB_SCAN;
+      } else {
+        const int j = __ffs(ev) - 1, sl = j >> 1;
+        const bool jy = (j & 1) != 0;
+        const bool found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
+        lo = gshfl<G>(gmask, jy ? pc.x : cpx, sl); hi = gshfl<G>(gmask, jy ? pc.y : pc.x, sl);
+        dlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
+        mm = layer_drop_coop<G>(hi, T, p.fact, n, rec, gmask, gl);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
         if (found) {
           // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
-          // 17-section until the bracket is <= 2e-5, then one secant step.  The first round counts the sign
-          // changes: with several roots inside the scan bracket (kink at the half-space velocity) the group
-          // runs the reference's own sequential bisection/Neville sequence so that the same root is picked.
-          const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
-          bool multi = false;
-          for (int it = 0; it < 16 && (hi - lo) > kBracketTol; ++it) {
-            const float w = hi - lo, st = w / (float)(P + 1);
-            const float2 pj = make_float2(lo + (float)(2 * gl + 1) * st, lo + (float)(2 * gl + 2) * st);
-            const float2 dj = secular2(p.kind, pj, T, mm, rec, 0).d;
-            my_steps += 2u * (unsigned)(mm - 1); my_sweeps += 2;
-            const unsigned ev = change_mask(dj, dlo);
-            const float dlast = gshfl<G>(gmask, dj.y, G - 1);
-            if (it == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) { multi = true; break; }
-            if (ev) {
-              const int j = __ffs(ev) - 1, sl = j >> 1;
-              const bool jy = (j & 1) != 0;
-              float ppx = __shfl_up_sync(gmask, pj.y, 1, G), dpx = __shfl_up_sync(gmask, dj.y, 1, G);
-              if (gl == 0) { ppx = lo; dpx = dlo; }
-              const float nlo = gshfl<G>(gmask, jy ? pj.x : ppx, sl), ndlo = gshfl<G>(gmask, jy ? dj.x : dpx, sl);
-              hi = gshfl<G>(gmask, jy ? pj.y : pj.x, sl); dhi = gshfl<G>(gmask, jy ? dj.y : dj.x, sl);
-              lo = nlo; dlo = ndlo;
-            } else {
-              lo = gshfl<G>(gmask, pj.y, G - 1); dlo = dlast;
-            }
-          }
-          if (!multi) {
-            const float den = dhi - dlo;
-            float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
-            if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
-            croot = cs;
-          } else {
-            int ev_n = 0;
-            auto f = [&](float cc) { return secular2(p.kind, make_float2(cc, cc), T, mm, rec, 0).d.x; };
-            const bool okp = nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n);
-            if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
-            if (!okp) { found = false; lstop = true; }
-          }
-          if (found && croot > rec[mm - 1].y) { found = false; flag |= SURFDISP_F_ROOT_ABOVE_HS; }  // calcul.f:191
+          // (P+1)-section until the bracket is <= 2e-5, then one secant step
+          lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0;
+          stage = ST_POLISH; need = NB_POLISH;
+        } else {
+          flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
+          model_done = true;
         }
       }
-      if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; break; }  // reference aborts the whole call (calcul.f:173-189)
-      if (!found) {
-        flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
-        break;
+    } else if (stage == ST_POLISH) {
+      const unsigned ev = change_mask(pd, dlo);
+      const float dlast = gshfl<G>(gmask, pd.y, G - 1);
+      bool have_root = false, lstop = false;
+      if (pit == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) {
+        // several roots inside the scan bracket (kink at the half-space velocity): follow the reference's own
+        // sequential bisection/Neville sequence so that the same one is picked (all lanes run it redundantly)
+        int ev_n = 0;
+        SecFn f; f.kind = p.kind; f.T = T; f.mm = mm; f.rec = rec;
+        const bool okp = nevill_out_of_line(f, lo0, hi0, dlo0, dhi0, &croot, &ev_n);
+        if (gl == 0) { my_steps += (unsigned long long)ev_n * (unsigned)(mm - 1); my_sweeps += ev_n; }
+        if (okp) have_root = true; else lstop = true;
+      } else {
+        if (ev) {
+          const int j = __ffs(ev) - 1, sl = j >> 1;
+          const bool jy = (j & 1) != 0;
+          float ppx = __shfl_up_sync(gmask, pc.y, 1, G), dpx = __shfl_up_sync(gmask, pd.y, 1, G);
+          if (gl == 0) { ppx = lo; dpx = dlo; }
+          const float nlo = gshfl<G>(gmask, jy ? pc.x : ppx, sl), ndlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl);
+          hi = gshfl<G>(gmask, jy ? pc.y : pc.x, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
+          lo = nlo; dlo = ndlo;
+        } else {
+          lo = gshfl<G>(gmask, pc.y, G - 1); dlo = dlast;
+        }
+        if ((hi - lo) > kBracketTol && ++pit < 16) need = NB_POLISH;
+        else {
+          const float den = dhi - dlo;
+          float cs = (den != 0.f) ? lo - dlo * (hi - lo) / den : 0.5f * (lo + hi);
+          if (!(cs >= lo && cs <= hi)) cs = 0.5f * (lo + hi);
+          croot = cs;
+          have_root = true;
+        }
       }
-      if (p.kind == 2 && !have_ratio) {
-        // ellipticity = 0.5 * bb1(e3) / bb1(e2) at the root (surfa.f:360-363)
-        const Sec2 v = secular2(2, make_float2(croot, croot), T, mm, rec, 1);
-        my_steps += (unsigned)(mm - 1); my_sweeps += 1;
-        ratio = 0.5f * v.e3.x / v.e2.x;
+      if (lstop) { flag |= SURFDISP_F_LSTOP; nfound = 0; model_done = true; }   // reference aborts the whole call (calcul.f:173-189)
+      else if (have_root) {
+        if (croot > rec[mm - 1].y) {   // calcul.f:191
+          flag |= SURFDISP_F_ROOT_ABOVE_HS;
+          flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
+          model_done = true;
+        } else if (p.kind == 2) { stage = ST_ELL; need = NB_ELL; }
+        else { ratio = 0.f; period_done = true; }
       }
+    } else if (stage == ST_ELL) {
+      // ellipticity = 0.5 * bb1(e3) / bb1(e2) at the root (surfa.f:360-363)
+      ratio = 0.5f * pe3.x / pe2.x;
+      period_done = true;
+    }
+
+    if (do_interp) {
+      const int np = has_ends ? P + 2 : nvalid;
+      const int s6 = min(max(jb - 3, 0), np - 6), s4 = min(max(jb - 2, 0), np - 4);
+      const SamplePt B0 = sample(jb - 1), B1 = sample(jb);
+      float x[6], y[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const SamplePt sp = sample(s6 + i); x[i] = sp.c - B0.c; y[i] = sp.d; }
+      float e4, e6;
+      inv_interp6(x, y, s4 - s6, e4, e6);
+      const float w = B1.c - B0.c;
+      const bool inside = (e6 > 0.f && e6 < w);
+      const float delta = fabsf(e6 - e4);
+      float e = e6;
+      if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
+      // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
+      // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
+      const bool interior = (jb >= 2 && jb <= np - 2);
+      const float tol = (it > 0) ? kInterpTol : ((fstage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
+      if ((inside && interior && delta <= tol) || w <= kBracketTol) {
+        croot = B0.c + e;
+        if (p.kind == 2) {
+          float xs[4], f2[4], f3[4], wl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const SamplePt sp = sample(s4 + i); xs[i] = sp.c - B0.c; f2[i] = sp.e2; f3[i] = sp.e3; }
+          lagrange4(xs, e, wl);
+          const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
+          const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
+          ratio = 0.5f * se3 / se2;
+        } else ratio = 0.f;
+        // the reference's bracket is the grid interval around the root; its upper end fixes mmax
+        float hg = c1 + (floorf((croot - c1) / p.dc) + 1.f) * p.dc;
+        if (!(hg > croot)) hg += p.dc;
+        const int mnew = layer_drop_coop<G>(hg, T, p.fact, n, rec, gmask, gl);
+        const float bh1 = rec[mnew - 1].y;
+        if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) start_scan();   // calcul.f:191 / kink: point-by-point path
+        else {
+          mm = mnew;
+          if (p.kind == 2 && mid_liquid) { stage = ST_ELL; need = NB_ELL; } else period_done = true;
+        }
+      } else if (it >= 3) start_scan();
+      else {
+        // one more round: P points around the estimate, spaced by the disagreement of the two orders
+        const float span = (float)(1 << (P / 2 - 1));   // outermost offset of the round, in units of s0
+        const float s0 = fmaxf(inside ? 0.5f * delta : w / (2.f * span), 1.0e-5f);
+        const bool uni = !(e - span * s0 > 0.f && e + span * s0 < w);
+        E0 = B0; E1 = B1;
+        rf_e = e; rf_s0 = s0; rf_uni = uni;   // relative to E0.c
+        stage = ST_REFINE; need = NB_REFINE;
+      }
+    }
+
+    if (period_done) {
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
       if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
-      c_prev3 = c_prev2;
-      c_prev2 = c_prev;
-      c_prev = croot;
-      nfound = k + 1;
+      c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot;
+      nfound = ++k;
+      if (k == K) model_done = true; else stage = ST_PERIOD;
     }
-    for (int k = nfound + gl; k < K; k += G) { crow[k] = 0.f; rrow[k] = 0.f; }
-    if (gl == 0) { p.nfound[model] = nfound; if (p.flags) p.flags[model] = flag; }
+    if (model_done) {
+      for (int kk = nfound + gl; kk < K; kk += G) { crow[kk] = 0.f; rrow[kk] = 0.f; }
+      if (gl == 0) { p.nfound[model] = nfound; if (p.flags) p.flags[model] = flag; }
+      stage = ST_FETCH;
+    }
   }
   // work counters (roofline numerator)
   for (int o = 16; o > 0; o >>= 1) {

@@ -185,6 +185,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
                 ndirect += (it == 0);
                 break;
               }
+              if (it == 0 && getenv("HM_DEBUG3")) fprintf(stderr, "noacc k=%d stage=%d inside=%d interior=%d w=%g delta=%g jb=%d np=%d\n", k, stage, (int)inside, (int)interior, w, delta, jb, np);
               if (it == 3) break;
               const float s0 = fmaxf(inside ? 0.5f * delta : w * (1.f / 256.f), 1.0e-5f);
               const bool uni = !(e - 128.f * s0 > 0.f && e + 128.f * s0 < w);
