@@ -134,7 +134,12 @@ SD_HD float4 make_rec(float a, float b, float rho, float d) { return make_float4
 
 // ----------------------------------------------------------------------------------------------
 // Layer dropping, surfa.f:92-106.  Returns mmax (1-based count of layers kept, >= 2).
-SD_HD int layer_drop(float c, float T, float fact, int nmax, const float4* rec) {
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+int layer_drop(float c, float T, float fact, int nmax, const float4* rec) {
   const float dmax = SD_MUL(SD_MUL(fact, c), T);
   float sum = 0.f;
   int mmax = nmax;
@@ -193,7 +198,12 @@ SD_HD void sd_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
 // For |u| < 0.5 (thin layers / long periods: the vast majority of layer steps) the series are used: no
 // square root, no MUFU, no branch on the sign of arg, and none of the cancellation that
 // (exp(x)-exp(-x))/2 suffers for small x (the reference's float32 form loses ~x^-1 ulps there).
-SD_HD void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float& cs) {
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float& cs) {
   const float u = kd2 * arg;
   if (fabsf(u) < 0.5f) {
     const float S = 1.f + u * (1.6666667e-1f + u * (8.3333333e-3f + u * (1.9841270e-4f + u * 2.7557319e-6f)));
@@ -315,24 +325,24 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
 // Half-space row of the Rayleigh secular function (surfa.f:341-354) for one velocity; R = (a, b, rho, d)
 SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, float& r2, float& r3, float& r4, float& r5) {
   const float pp = R.x, b2 = 2.0f * R.y * R.y;
-  const float arga = 1.0f - csq / (pp * pp);
-  const float argb = 1.0f - csq / (R.y * R.y);
+  const float ippp = SD_FDIV(1.0f, pp * pp);
+  const float arga = 1.0f - csq * ippp;
+  const float argb = 1.0f - SD_FDIV(csq, R.y * R.y);
   float ra = sqrtf(fabsf(arga)); if (arga > 0.f) ra = -ra;
   float rb = sqrtf(fabsf(argb)); if (argb > 0.f) rb = -rb;
   const float g = b2 * icsq;
   const float g1 = g - 1.0f;
   const float sss = 0.5f * b2;
-  const float ppp = pp * pp;
   const float rhp = R.z * pp;
-  const float gra = g * ra;
+  const float igra = SD_FDIV(1.0f, g * ra);
   const float g1s = g1 * g1;
-  const float rba = rb - 1.0f / ra;
-  const float h12 = rhp * pp;
-  r1 = -2.f * rb * sss / ppp + csq * g1s / ppp / gra;
-  r3 = 2.f * (-rb / h12 + g1 / h12 / gra);
-  r4 = rb / h12 / gra;
-  r5 = rba / rhp / rhp / csq / g;
-  r2 = -1.0f / g / h12;
+  const float rba = rb - SD_FDIV(1.0f, ra);
+  const float ih12 = SD_FDIV(1.0f, rhp * pp);
+  r1 = -2.f * rb * sss * ippp + csq * g1s * ippp * igra;
+  r3 = 2.f * (-rb * ih12 + g1 * ih12 * igra);
+  r4 = rb * ih12 * igra;
+  r5 = SD_FDIV(rba, rhp * rhp * csq * g);
+  r2 = -SD_FDIV(ih12, g);
 }
 
 // Rayleigh sweep for a pair of trial velocities (same truncation depth mmax, same period)

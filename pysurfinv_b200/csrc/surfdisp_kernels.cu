@@ -204,6 +204,8 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
   const unsigned gbits = (1u << G) - 1u;
   const int grp = threadIdx.x / G;
   float4* rec = smem + (size_t)grp * p.mstride;   // this model's layer records (a, b, rho, d)
+  // ordered samples of the current round: slot 0 / P+1 = bracket ends of the previous round, 1..P = the points
+  float4* slots = smem + (size_t)(blockDim.x / G) * p.mstride + (size_t)grp * (P + 2);
   const int K = p.K;
   const int ld = p.lpad;
   unsigned long long my_steps = 0, my_sweeps = 0;
@@ -460,16 +462,16 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
 #endif
     // =========================================================== what the results mean, per stage
     bool do_interp = false, period_done = false, model_done = false;
+    if (active) {
+      __syncwarp(gmask);
+      slots[1 + 2 * gl] = make_float4(pc.x, pd.x, pe2.x, pe3.x);
+      slots[2 + 2 * gl] = make_float4(pc.y, pd.y, pe2.y, pe3.y);
+      __syncwarp(gmask);
+    }
     auto sample = [&](int i) {
       // i-th entry of the ordered list: [point w0 .. point P-1] or [E0, point 0 .. point P-1, E1]
-      const int pi = min(max(has_ends ? i - 1 : i + w0, 0), P - 1);
-      const int sl = pi >> 1;
-      const bool hc = (pi & 1) != 0;
-      SamplePt sp;
-      sp.c = gshfl<G>(gmask, hc ? pc.y : pc.x, sl); sp.d = gshfl<G>(gmask, hc ? pd.y : pd.x, sl);
-      sp.e2 = gshfl<G>(gmask, hc ? pe2.y : pe2.x, sl); sp.e3 = gshfl<G>(gmask, hc ? pe3.y : pe3.x, sl);
-      if (has_ends && i == 0) sp = E0;
-      if (has_ends && i == P + 1) sp = E1;
+      const float4 v = slots[has_ends ? i : i + w0 + 1];
+      SamplePt sp; sp.c = v.x; sp.d = v.y; sp.e2 = v.z; sp.e3 = v.w;
       return sp;
     };
     if (stage == ST_FAST) {
@@ -637,6 +639,8 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
         const float s0 = fmaxf(inside ? 0.5f * delta : w / (2.f * span), 1.0e-5f);
         const bool uni = !(e - span * s0 > 0.f && e + span * s0 < w);
         E0 = B0; E1 = B1;
+        __syncwarp(gmask);
+        if (gl == 0) { slots[0] = make_float4(B0.c, B0.d, B0.e2, B0.e3); slots[P + 1] = make_float4(B1.c, B1.d, B1.e2, B1.e3); }
         rf_e = e; rf_s0 = s0; rf_uni = uni;   // relative to E0.c
         stage = ST_REFINE; need = NB_REFINE;
       }
@@ -822,9 +826,9 @@ int launch_phase1(const P1Params& p, cudaStream_t st) {
   // 128-thread CTAs (128/G models) for ordinary stacks; deep stacks (up to 1000 layers, 16 KB of layer records
   // per model) shrink the CTA until the records of its models fit in shared memory
   int threads = 128;
-  while (threads > 32 && (size_t)(threads / G) * q.mstride * sizeof(float4) > 100 * 1024) threads /= 2;
+  while (threads > 32 && (size_t)(threads / G) * (q.mstride + 2 * G + 2) * sizeof(float4) > 100 * 1024) threads /= 2;
   const int groups = threads / G;
-  size_t smem = (size_t)groups * q.mstride * sizeof(float4);
+  size_t smem = (size_t)groups * (q.mstride + 2 * G + 2) * sizeof(float4);   // layer records + sample slots
   if (smem > 220 * 1024) return SURFDISP_EINVAL;
   CK(cudaFuncSetAttribute(phase1_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148, occ = 1;
