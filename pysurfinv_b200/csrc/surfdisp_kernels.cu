@@ -58,12 +58,17 @@ int cuda_fail(cudaError_t e, const char* where) {
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
 
 // ------------------------------------------------------------------------------------ prep kernel
+// One warp per model, lanes over layers (coalesced loads of the five input rows, coalesced stores of the eight
+// constant rows).  Same arithmetic, operation by operation, as prep_model() in surfdisp_core.cuh (the form the
+// host mirror runs): the only sequential part of flat1.f:33-37 is the float32 running sum of the thicknesses,
+// done here with a 32-step shuffle loop per chunk of 32 layers.
 __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, int kind, int flatten,
                                                    const int* __restrict__ nlay,
                                                    const float* __restrict__ layers, float* __restrict__ consts) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (m >= M) return;
-  int n = nlay[m];
+  const int n = nlay[m];
   if (n < 2 || n > lmax) return;
   const size_t pl = (size_t)M * lmax;
   const float* a = layers + 0 * pl + (size_t)m * lmax;
@@ -71,7 +76,52 @@ __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, in
   const float* rho = layers + 2 * pl + (size_t)m * lmax;
   const float* d = layers + 3 * pl + (size_t)m * lmax;
   const float* qs = layers + 4 * pl + (size_t)m * lmax;
-  prep_model(n, kind, flatten, a, b, rho, d, qs, consts + (size_t)m * NCONST * lpad, lpad);
+  float* out = consts + (size_t)m * NCONST * lpad;
+  const int ld = lpad;
+  const float A = SD_R0;
+  const float pwr = (kind == 1) ? 5.0f : 2.2750f;
+  const float apw = sd_powf_cr(A, pwr);
+  float hs = 0.f;       // running sum of thicknesses (uniform across the warp)
+  float zcarry = 0.f;   // z1 of the last layer of the previous chunk
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool act = i < n;
+    const float di = act ? d[i] : 0.f;
+    float my_ht = 0.f, my_hs = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float dj = __shfl_sync(0xffffffffu, di, j);
+      const float ht = hs;
+      hs = SD_ADD(hs, dj);
+      if (lane == j) { my_ht = ht; my_hs = hs; }
+    }
+    float z1 = 0.f;
+    float o_dif = 1.f, o_rhofl = 0.f, o_dfl = 0.f, o_hsf = 1.f, o_rhohs = 0.f;
+    const float ai = act ? a[i] : 0.f, bi = act ? b[i] : 0.f, ri = act ? rho[i] : 0.f, qi = act ? qs[i] : 0.f;
+    if (act && flatten) {
+      const float r_i = SD_SUB(A, my_ht);
+      const float r_n = SD_SUB(A, my_hs);  // radius of the top of layer i+1
+      const float fltd = sd_logf_cr(SD_DIV(r_i, r_n));
+      o_dif = SD_DIV(SD_MUL(SD_SUB(SD_DIV(1.0f, r_n), SD_DIV(1.0f, r_i)), A), fltd);
+      const float difr = SD_SUB(sd_powf_cr(r_i, pwr), sd_powf_cr(r_n, pwr));
+      const float qqq = SD_DIV(difr, SD_MUL(SD_MUL(fltd, apw), pwr));
+      o_rhofl = SD_MUL(ri, qqq);
+      z1 = SD_MUL(A, sd_logf_cr(SD_DIV(A, r_n)));
+      const float fct = SD_DIV(A, r_i);
+      o_hsf = fct;
+      o_rhohs = SD_MUL(ri, sd_powf_cr(SD_DIV(1.0f, fct), pwr));
+    }
+    float z0 = __shfl_up_sync(0xffffffffu, z1, 1);
+    if (lane == 0) z0 = zcarry;
+    zcarry = __shfl_sync(0xffffffffu, z1, 31);
+    if (act) {
+      if (flatten) o_dfl = SD_SUB(z1, z0);
+      else { o_rhofl = ri; o_dfl = di; o_rhohs = ri; }
+      out[C_AREF * ld + i] = ai; out[C_BREF * ld + i] = bi; out[C_QS * ld + i] = qi;
+      out[C_DIF * ld + i] = o_dif; out[C_RHOFL * ld + i] = o_rhofl; out[C_DFL * ld + i] = o_dfl;
+      out[C_HSF * ld + i] = o_hsf; out[C_RHOHS * ld + i] = o_rhohs;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ phase 1
@@ -888,8 +938,8 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   CK(cudaMemsetAsync(ws, 0, kHdrBytes, st));
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[0], st));
 
-  prep_kernel<<<(n_models + 127) / 128, 128, 0, st>>>(n_models, n_layers_max, w.lpad, kind, o.flatten, n_layers,
-                                                       layers, consts);
+  prep_kernel<<<(unsigned)(((size_t)n_models * 32 + 127) / 128), 128, 0, st>>>(n_models, n_layers_max, w.lpad, kind, o.flatten,
+                                                                               n_layers, layers, consts);
   CK(cudaGetLastError());
 
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[1], st));
