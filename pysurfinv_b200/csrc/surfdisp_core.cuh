@@ -318,8 +318,11 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
     rsin = vmul(vneg(arg), sinr);
     return;
   }
-  half_terms(arg.x, kd.x, kd2.x, rsin.x, sinr.x, cs.x);
-  half_terms(arg.y, kd.y, kd2.y, rsin.y, sinr.y, cs.y);
+  // (temporaries: the out-of-line scalar form takes addresses, which must not pin the pair registers to memory)
+  float r0, s0, c0, r1, s1, c1;
+  half_terms(arg.x, kd.x, kd2.x, r0, s0, c0);
+  half_terms(arg.y, kd.y, kd2.y, r1, s1, c1);
+  rsin = v2(r0, r1); sinr = v2(s0, s1); cs = v2(c0, c1);
 }
 
 // Half-space row of the Rayleigh secular function (surfa.f:341-354) for one velocity; R = (a, b, rho, d)

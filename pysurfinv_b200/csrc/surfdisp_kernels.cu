@@ -31,7 +31,7 @@ struct PeriodTab {
 };
 
 struct WsLayout {
-  size_t consts_off, ratio_off, total;
+  size_t consts_off, ratio_off, mm_off, total;
   int lpad;
 };
 
@@ -44,7 +44,8 @@ WsLayout ws_layout(int M, int lmax, int K) {
   size_t consts = (size_t)M * NCONST * w.lpad * sizeof(float);
   w.ratio_off = w.consts_off + ((consts + 255) / 256) * 256;
   size_t ratio = (size_t)M * K * sizeof(float);
-  w.total = w.ratio_off + ((ratio + 255) / 256) * 256;
+  w.mm_off = w.ratio_off + ((ratio + 255) / 256) * 256;
+  w.total = w.mm_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
   return w;
 }
 
@@ -137,6 +138,8 @@ struct P1Params {
   unsigned int* queue;
   float dc, fact;
   int atten, stale, exact_scan;
+  int k_begin, k_end;   // periods [k_begin, k_end) are done by this launch (the first period runs as a launch of its own)
+  int* mm_state;        // layer-dropping depth carried from launch to launch
   int mstride;  // float4 units between consecutive groups' shared-memory records
   PeriodTab tab;
 };
@@ -365,6 +368,39 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
     meval = mm; ell_only = 1;
   };
 
+  // refresh layers 0..mref-1 for the period with log term lt, layer mref-1 flattened as the half-space
+  // (calcul.f:112-133); returns the smallest b below the top layer among them
+  auto refresh = [&](int mref, float lt) -> float {
+    __syncwarp(gmask);
+    float bm = 3.0e38f;
+    for (int i0 = 4 * gl; i0 < mref; i0 += 4 * G) {
+      // four layers per lane and iteration: six float4 loads of the per-model constants
+      const float4 AR = *reinterpret_cast<const float4*>(cst + C_AREF * ld + i0);
+      const float4 BR = *reinterpret_cast<const float4*>(cst + C_BREF * ld + i0);
+      const float4 QS = *reinterpret_cast<const float4*>(cst + C_QS * ld + i0);
+      const float4 DF = *reinterpret_cast<const float4*>(cst + C_DIF * ld + i0);
+      const float4 RF = *reinterpret_cast<const float4*>(cst + C_RHOFL * ld + i0);
+      const float4 DL = *reinterpret_cast<const float4*>(cst + C_DFL * ld + i0);
+      const float ar[4] = {AR.x, AR.y, AR.z, AR.w}, br[4] = {BR.x, BR.y, BR.z, BR.w}, qs[4] = {QS.x, QS.y, QS.z, QS.w};
+      const float df[4] = {DF.x, DF.y, DF.z, DF.w}, rf[4] = {RF.x, RF.y, RF.z, RF.w}, dl[4] = {DL.x, DL.y, DL.z, DL.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i < mref) {
+          const bool hs = (i == mref - 1);
+          float a, b;
+          layer_ab_vals(ar[j], br[j], qs[j], hs ? cst[C_HSF * ld + i] : df[j], lt, p.atten, a, b);
+          rec[i] = make_rec(a, b, hs ? cst[C_RHOHS * ld + i] : rf[j], hs ? 0.f : dl[j]);
+          if (i >= 1) bm = fminf(bm, b);
+        }
+      }
+    }
+    __syncwarp(gmask);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) bm = fminf(bm, __shfl_xor_sync(gmask, bm, o, G));
+    return bm;
+  };
+
   for (;;) {
     // =========================================================== set-up: next model / next period
     // The groups of a warp start their models together: inside a model they drift apart by a few rounds only,
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
           if (gl == 0) { p.nfound[model] = 0; if (p.flags) p.flags[model] = SURFDISP_F_NO_ROOT_FIRST; }
           n = 2;  // stays in ST_FETCH: sits this iteration's sweep out and pulls another model next time
         } else {
-          my_models += (gl == 0);
+          my_models += (gl == 0 && p.k_begin == 0);
           cst = p.consts + (size_t)model * NCONST * p.lpad;
           // first start velocity, fast_surf.f:157-171
           {
@@ -408,46 +444,32 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
             mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
           }
           mm = n;  // reference COMMON mmax carried from period to period
-          nfound = 0; flag = 0; k = 0; hopped = false;
+          nfound = 0; flag = 0; k = p.k_begin; hopped = false;
           c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 2.0e-3f;
           stage = ST_PERIOD;
+          if (k > 0) {
+            // continuing a model whose earlier periods were done by a previous launch
+            nfound = p.nfound[model];
+            if (nfound < k) { stage = ST_FETCH; n = 2; }   // it ended there: nothing to do
+            else {
+              // the layers below the dropping depth keep the values the first period gave them
+              bmin = refresh(n, p.tab.lt[0]) - 0.05f;
+              mm = p.mm_state[model];
+              flag = p.flags ? p.flags[model] : 0;
+              c_prev = crow[k - 1];
+              if (k >= 2) c_prev2 = crow[k - 2];
+              if (k >= 3) c_prev3 = crow[k - 3];
+            }
+          }
         }
       }
     }
     if (stage == ST_PERIOD) {
       T = p.tab.per[k];
       const float lt = p.tab.lt[k];
-      // ---- refresh layers 0..mref-1, layer mref-1 flattened as the half-space (calcul.f:112-133)
-      const int mref = p.stale ? mm : n;
-      __syncwarp(gmask);
-      float bm = 3.0e38f;
-      for (int i0 = 4 * gl; i0 < mref; i0 += 4 * G) {
-        // four layers per lane and iteration: six float4 loads of the per-model constants
-        const float4 AR = *reinterpret_cast<const float4*>(cst + C_AREF * ld + i0);
-        const float4 BR = *reinterpret_cast<const float4*>(cst + C_BREF * ld + i0);
-        const float4 QS = *reinterpret_cast<const float4*>(cst + C_QS * ld + i0);
-        const float4 DF = *reinterpret_cast<const float4*>(cst + C_DIF * ld + i0);
-        const float4 RF = *reinterpret_cast<const float4*>(cst + C_RHOFL * ld + i0);
-        const float4 DL = *reinterpret_cast<const float4*>(cst + C_DFL * ld + i0);
-        const float ar[4] = {AR.x, AR.y, AR.z, AR.w}, br[4] = {BR.x, BR.y, BR.z, BR.w}, qs[4] = {QS.x, QS.y, QS.z, QS.w};
-        const float df[4] = {DF.x, DF.y, DF.z, DF.w}, rf[4] = {RF.x, RF.y, RF.z, RF.w}, dl[4] = {DL.x, DL.y, DL.z, DL.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + j;
-          if (i < mref) {
-            const bool hs = (i == mref - 1);
-            float a, b;
-            layer_ab_vals(ar[j], br[j], qs[j], hs ? cst[C_HSF * ld + i] : df[j], lt, p.atten, a, b);
-            rec[i] = make_rec(a, b, hs ? cst[C_RHOHS * ld + i] : rf[j], hs ? 0.f : dl[j]);
-            if (i >= 1) bm = fminf(bm, b);
-          }
-        }
-      }
-      __syncwarp(gmask);
+      const float bm = refresh(p.stale ? mm : n, lt);
       // smallest b below the top layer: taken at the first period, where all layers are refreshed (mm = n); the
       // attenuation correction moves b by < 1 % over the period range, which the margin covers
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) bm = fminf(bm, __shfl_xor_sync(gmask, bm, o, G));
       if (k == 0) bmin = bm - 0.05f;
       if (k > 0) c1 = SD_MUL(0.90f, c_prev);  // calcul.f:143
       b_top = rec[0].y;
@@ -701,11 +723,12 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
       if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
       c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot;
       nfound = ++k;
-      if (k == K) model_done = true; else stage = ST_PERIOD;
+      if (k == p.k_end) model_done = true; else stage = ST_PERIOD;
     }
     if (model_done) {
-      for (int kk = nfound + gl; kk < K; kk += G) { crow[kk] = 0.f; rrow[kk] = 0.f; }
-      if (gl == 0) { p.nfound[model] = nfound; if (p.flags) p.flags[model] = flag; }
+      if (nfound < p.k_end || p.k_end == K)
+        for (int kk = nfound + gl; kk < K; kk += G) { crow[kk] = 0.f; rrow[kk] = 0.f; }
+      if (gl == 0) { p.nfound[model] = nfound; p.mm_state[model] = mm; if (p.flags) p.flags[model] = flag; }
       stage = ST_FETCH;
     }
   }
@@ -943,8 +966,18 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   CK(cudaGetLastError());
 
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[1], st));
+  // The scan of the first period (calcul.f:155-167 from 0.9 b(1)) consists of many shallow sweeps, the later
+  // periods of one or two deep ones each: run as separate launches, the groups of a warp never mix the two.
+  p1.mm_state = (int*)(ws + w.mm_off);
+  p1.k_begin = 0; p1.k_end = (n_periods > 1 && !o.exact_scan) ? 1 : n_periods;
   rc = launch_phase1<P1_G>(p1, st);
   if (rc) return rc;
+  if (p1.k_end < n_periods) {
+    CK(cudaMemsetAsync(p1.queue, 0, sizeof(unsigned int), st));
+    p1.k_begin = p1.k_end; p1.k_end = n_periods;
+    rc = launch_phase1<P1_G>(p1, st);
+    if (rc) return rc;
+  }
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[2], st));
 
   if (u_out && o.compute_group) {
