@@ -57,10 +57,12 @@ typedef struct SurfdispOpts {
   int stale_mmax;          /* 1: period k refreshes only the layers kept by period k-1, as the
                               reference does (calcul.f:112-133); 0: refresh all layers */
   int compute_group;       /* 1: also group velocity (REIGEN/LEIGEN); 0: phase velocity only */
-  int exact_scan;          /* 0 (default): coarse-to-fine scan (every 8th grid point, then the interior of the
-                              first interval with a sign change) and clustered polish; 1: evaluate every grid
-                              point c1 + i*dc like calcul.f:155-167 and polish by uniform section (slower,
-                              identical results unless two roots hide inside one 0.08 km/s coarse interval) */
+  int exact_scan;          /* 0 (default): after the first period the root is bracketed by trial velocities clustered
+                              around the extrapolation of the previous roots (guard points at c1 and half way
+                              rule out an odd number of skipped roots) and taken by inverse interpolation;
+                              1: every period evaluates every grid point c1 + i*dc like calcul.f:155-167 and
+                              polishes by uniform section (slower; differs only where two roots of different
+                              modes lie between c1 and the tracked root) */
 } SurfdispOpts;
 
 void surfdisp_default_opts(SurfdispOpts* o);
@@ -128,6 +130,55 @@ int surfdisp_batch_profiled(const SurfdispOpts* opts, int kind, int n_models, in
 /* Register-resident micro-benchmarks on the current device: out[0] = FP32 FMA TFLOP/s,
  * out[1] = FP64 FMA TFLOP/s, out[2] = MUFU.EX2 T-op/s.  Denominators of the FP-pipe roofline. */
 int surfdisp_measure_peaks(double out[3]);
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-side model builder: free parameters of a Monte-Carlo walk -> layer stacks in the layout
+ * surfdisp_batch reads.  It replaces, for M models at once, the reference's per-model Python assembly:
+ * B-spline basis x coefficients on the fine grid of every layer group (layers.py:4-45, 104-136), the per-class
+ * Vp / density / Q rules (layers.py:139-295), the stacking of the groups (models.py:72-91), mid-point
+ * averaging to layers and the h > 0.01 km filter (models.py:93-102, models.py:20).
+ * A template describes the groups (top to bottom); every numeric entry is either fixed or refers to one of
+ * the P free parameters of a model (column order = MCinv._brownians order, models.py:227-240).
+ */
+#define SURFDISP_MAX_GROUPS 8
+#define SURFDISP_MAX_COEF 8
+
+/* group kinds (Vs profile inside the group)                                   reference class            */
+#define SURFDISP_G_WATER 0      /* Vs = 0                                        OceanWater  layers.py:191  */
+#define SURFDISP_G_CONST 1      /* constant                                      Sediment / OceanSediment    */
+#define SURFDISP_G_LINEAR 2     /* linear top..bottom                            Sediment / OceanCrust       */
+#define SURFDISP_G_BSPLINE 3    /* B-spline, ncoef coefficients                  Crust / Mantle  :158, :239  */
+#define SURFDISP_G_CASCADIA 4   /* (0.02 H^2 + 1.27 H + 0.029) / (H + 0.29)      OceanSedimentCascadia :289  */
+#define SURFDISP_G_REFMANTLE 5  /* linear continuation below the model           ReferenceMantle :267        */
+/* number of fine layers of a group */
+#define SURFDISP_N_FIXED 0
+#define SURFDISP_N_CRUST 1      /* 5/10/15/30/60 by thickness, layers.py:161-173 */
+#define SURFDISP_N_OCRUST 2     /* min(max(round(H/2), 2), 10), layers.py:226 */
+/* density rules */
+#define SURFDISP_R_QUARTIC 0    /* quartic in Vs, layers.py:152 */
+#define SURFDISP_R_OCEAN 1      /* 0.541 + 0.3601 Vp, layers.py:216 */
+#define SURFDISP_R_MANTLE 2     /* 3.4268 + (Vs - 4.5) / 4.5, layers.py:262 */
+#define SURFDISP_R_CONST 3
+
+typedef struct SurfdispStackGroup {
+  int kind, nfine_rule, nfine, h_mode;      /* h_mode 0: parameter is the thickness H, 1: BottomDepth */
+  int h_param, ncoef, rho_rule, pad_;       /* h_param: index of the free parameter or -1 (h_fixed) */
+  int v_param[SURFDISP_MAX_COEF];           /* per Vs coefficient: free-parameter index or -1 (v_fixed) */
+  double v_fixed[SURFDISP_MAX_COEF];
+  double h_fixed, vp_a, vp_b, rho_const, qs, slope;   /* Vp = vp_a Vs + vp_b; slope: km/s per km (REFMANTLE) */
+} SurfdispStackGroup;
+
+typedef struct SurfdispStackTemplate {
+  int ngroups, nparams;
+  double topo;                               /* km, negative below sea level (models.py:76) */
+  SurfdispStackGroup groups[SURFDISP_MAX_GROUPS];
+} SurfdispStackTemplate;
+
+/* params: device float[M][nparams]; layers: device float[5][M][n_layers_max]; n_layers: device int[M]
+ * (0 if a stack would need more than n_layers_max layers).  Asynchronous on `stream`. */
+int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params,
+                          int n_layers_max, float* layers, int* n_layers, void* stream);
 
 const char* surfdisp_version(void);
 const char* surfdisp_last_cuda_error(void);

@@ -64,6 +64,9 @@ def load_library():
     L.surfdisp_batch_profiled.restype = C.c_int
     L.surfdisp_measure_peaks.argtypes = [C.POINTER(C.c_double)]
     L.surfdisp_measure_peaks.restype = C.c_int
+    from . import stack as _stack
+    L.surfdisp_build_stacks.argtypes = [C.POINTER(_stack.StackTemplateC), C.c_int, vp, C.c_int, vp, vp, vp]
+    L.surfdisp_build_stacks.restype = C.c_int
     L.surfdisp_version.restype = C.c_char_p
     L.surfdisp_last_cuda_error.restype = C.c_char_p
     _lib = L
@@ -187,6 +190,30 @@ class DispersionSolver:
                                                 _fptr(s), None if mk is None else mk.ctypes.data_as(C.POINTER(C.c_ubyte)),
                                                 None if pr is None else _fptr(pr), out.data_ptr(), stream)
         _check(rc, "surfdisp_misfit_batch")
+        return out
+
+    def build_stacks(self, template, params, lmax=None, out=None):
+        """Device-side model assembly (reference models.py:72-102 + layers.py, for M models at once).
+        template: pysurfinv_b200.stack.StackTemplate; params: float32 device tensor [M, template.nparams]
+        (column order = order of the free parameters in the setting, like MCinv._brownians).
+        Returns (layers [5, M, lmax], nlay [M]) device tensors ready for forward()."""
+        torch = self.torch
+        P = template.nparams
+        if params.dtype != torch.float32 or params.dim() != 2 or params.shape[1] != P or not params.is_contiguous():
+            raise ValueError("params must be a contiguous float32 tensor [M, %d]" % P)
+        if params.device != self.device:
+            raise ValueError("params must live on %s" % self.device)
+        M = int(params.shape[0])
+        lmax = int(lmax) if lmax is not None else template.max_layers()
+        if out is None:
+            out = (torch.empty((5, M, lmax), dtype=torch.float32, device=self.device),
+                   torch.empty(M, dtype=torch.int32, device=self.device))
+        tc = template.to_c()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_build_stacks(C.byref(tc), M, params.data_ptr() if P else None, lmax,
+                                                out[0].data_ptr(), out[1].data_ptr(), stream)
+        _check(rc, "surfdisp_build_stacks")
         return out
 
     # -- host path (what a reference-side caller uses): pinned staging, H2D, solve, D2H --------------

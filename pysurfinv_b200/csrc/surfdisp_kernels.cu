@@ -852,6 +852,129 @@ __global__ void __launch_bounds__(256) misfit_kernel(const __grid_constant__ Mis
 }
 
 
+
+// ------------------------------------------------------------------------------------ model builder
+// Thread per model.  All arithmetic in double like the reference's numpy code; results are rounded to float32
+// when stored (that is what f2py does to the arrays handed to fast_surf, fast_surf.pyf:6-19).
+__device__ double bspl_profile(const double* coef, int n, double z) {
+  // value at z in [0, 1] of sum_i coef_i B_i(z) with the basis of reference layers.py:4-45: degree 3 (n = 3) or
+  // 4 (n >= 4) de Boor recursion on the knot vector [-eps x (deg-1), 0, geometric interior knots, 1, 1+eps ...]
+  const double eps = 2.220446049250313e-16;
+  const int deg = 3 + (n >= 4);
+  double x[SURFDISP_MAX_COEF + 4];
+  for (int i = 0; i < deg - 1; ++i) x[i] = -eps;
+  x[deg - 1] = 0.0;
+  {
+    const int m = n - deg;            // number of interior knots
+    const double den = pow(2.0, (double)(m + 1)) - 1.0;
+    for (int kk = 0; kk < m; ++kk) x[deg + kk] = pow(2.0, (double)kk) * (2.0 - 1.0) / den;
+  }
+  x[n] = 1.0;
+  for (int i = n + 1; i < n + deg; ++i) x[i] = 1.0 + eps;
+  const int nc = n + deg - 1;
+  double b0[SURFDISP_MAX_COEF + 3], b1[SURFDISP_MAX_COEF + 3];
+  for (int i = 0; i < nc; ++i) { b0[i] = (z >= x[i] && z < x[i + 1]) ? 1.0 : 0.0; b1[i] = b0[i]; }
+  for (int r = 0; r < deg - 1; ++r) {
+    for (int i = 0; i < nc - r - 1; ++i) {
+      double col = 0.0;
+      const double d1 = x[i + r + 1] - x[i], d2 = x[i + r + 2] - x[i + 1];
+      if (d1 != 0.0) col += b0[i] * (z - x[i]) / d1;
+      if (d2 != 0.0) col += b0[i + 1] * (x[i + r + 2] - z) / d2;
+      b1[i] = col;
+    }
+    for (int i = 0; i < nc; ++i) b0[i] = b1[i];
+  }
+  double v = 0.0;
+  for (int i = 0; i < n; ++i) v += coef[i] * b1[i];
+  return v;
+}
+
+__device__ double stack_rho(int rule, double cst, double vs, double vp) {
+  if (rule == SURFDISP_R_QUARTIC) return 1.22679 + 1.53201 * vs - 0.83668 * vs * vs + 0.20673 * vs * vs * vs - 0.01656 * vs * vs * vs * vs;
+  if (rule == SURFDISP_R_OCEAN) return 0.541 + 0.3601 * vp;
+  if (rule == SURFDISP_R_MANTLE) return 3.4268 + (vs - 4.5) / 4.5;
+  return cst;
+}
+
+__global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
+                                                           const float* __restrict__ params, int lmax,
+                                                           float* __restrict__ layers, int* __restrict__ nlay) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* pm = params + (size_t)m * t.nparams;
+  const size_t pl = (size_t)M * lmax;
+  float* o_vp = layers + 0 * pl + (size_t)m * lmax;
+  float* o_vs = layers + 1 * pl + (size_t)m * lmax;
+  float* o_rho = layers + 2 * pl + (size_t)m * lmax;
+  float* o_h = layers + 3 * pl + (size_t)m * lmax;
+  float* o_qs = layers + 4 * pl + (size_t)m * lmax;
+  int nl = 0;
+  bool overflow = false, any = false;
+  double z0 = -fmax(t.topo, 0.0);        // depth of the top of the next group (models.py:76-77)
+  double ztop_prev = 0.0;                 // bottom depth of the stack so far, for BottomDepth groups (0 if none)
+  double last_vs = 0.0, last_vp = 0.0, last_rho = 0.0, last_qs = 0.0;   // deepest grid values so far
+  for (int gi = 0; gi < t.ngroups; ++gi) {
+    const SurfdispStackGroup& g = t.groups[gi];
+    const double hv = (g.h_param >= 0) ? (double)pm[g.h_param] : g.h_fixed;
+    double H = hv;
+    if (g.h_mode == 1 && any) H = hv - ztop_prev;
+    int N = g.nfine;
+    if (g.nfine_rule == SURFDISP_N_CRUST) N = (H >= 150.0) ? 60 : ((H > 60.0) ? 30 : ((H > 20.0) ? 15 : ((H > 10.0) ? 10 : 5)));
+    else if (g.nfine_rule == SURFDISP_N_OCRUST) N = min(max((int)rint(H / 2.0), 2), 10);
+    double coef[SURFDISP_MAX_COEF];
+    for (int i = 0; i < g.ncoef; ++i) coef[i] = (g.v_param[i] >= 0) ? (double)pm[g.v_param[i]] : g.v_fixed[i];
+    // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
+    if (H - 0.0 < 0.01) continue;
+    const double zstep = H / (double)N, ustep = 1.0 / (double)N;
+    double p_z = 0.0, p_vs = 0.0, p_vp = 0.0, p_rho = 0.0, p_qs = 0.0;   // previous grid point
+    double vs0_ref = last_vs, vp_first = 0.0, rho_first = 0.0, qs_first = 0.0;
+    for (int j = 0; j <= N; ++j) {
+      const double zz = (j == N) ? H : (double)j * zstep;
+      const double u = (j == N) ? 1.0 : (double)j * ustep;
+      double vs;
+      if (g.kind == SURFDISP_G_WATER) vs = 0.0;
+      else if (g.kind == SURFDISP_G_CONST) vs = coef[0];
+      else if (g.kind == SURFDISP_G_LINEAR) vs = (j == N) ? coef[1] : coef[0] + (double)j * ((coef[1] - coef[0]) / (double)N);
+      else if (g.kind == SURFDISP_G_BSPLINE) {
+        if (g.ncoef == 1) vs = coef[0];
+        else if (g.ncoef == 2) vs = coef[0] * ((j == N) ? 0.0 : 1.0 + (double)j * ((0.0 - 1.0) / (double)N)) + coef[1] * u;
+        else vs = bspl_profile(coef, g.ncoef, u);
+      } else if (g.kind == SURFDISP_G_CASCADIA) vs = (0.02 * H * H + 1.27 * H + 0.29 * 0.1) / (H + 0.29);
+      else {  // reference mantle: linear continuation of the deepest Vs (layers.py:267-285)
+        const double vend = vs0_ref + H * g.slope;
+        vs = (j == N) ? vend : vs0_ref + (double)j * ((vend - vs0_ref) / (double)N);
+      }
+      double vp = g.vp_a * vs + g.vp_b;
+      double rho = stack_rho(g.rho_rule, g.rho_const, vs, vp);
+      double qs = g.qs;
+      if (g.kind == SURFDISP_G_REFMANTLE) {
+        // Vp, rho, Qs continue from the deepest values above (layers.py:279-283)
+        if (j == 0) { vp_first = vp; rho_first = rho; qs_first = qs; }
+        vp = last_vp + (vp - vp_first); rho = last_rho + (rho - rho_first); qs = last_qs + (qs - qs_first);
+      }
+      if (j > 0) {
+        const double h = (zz + z0) - (p_z + z0);
+        if (h > 0.01) {   // models.py:102 (and models.py:20: h > 1e-3)
+          if (nl < lmax) {
+            o_vp[nl] = (float)(0.5 * (vp + p_vp)); o_vs[nl] = (float)(0.5 * (vs + p_vs));
+            o_rho[nl] = (float)(0.5 * (rho + p_rho)); o_h[nl] = (float)h;
+            o_qs[nl] = (float)(1.0 / (0.5 * (qs + p_qs)));
+            nl++;
+          } else overflow = true;
+        }
+      }
+      p_z = zz; p_vs = vs; p_vp = vp; p_rho = rho; p_qs = qs;
+    }
+    // REFMANTLE reads the values of the group above before they are replaced
+    last_vs = p_vs; last_vp = p_vp; last_rho = p_rho; last_qs = p_qs;
+    z0 = z0 + H;
+    ztop_prev = z0;
+    any = true;
+  }
+  for (int j = nl; j < lmax; ++j) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
+  nlay[m] = overflow ? 0 : nl;
+}
+
 // ------------------------------------------------------------------------------------ pipe peaks
 // Register-resident FMA / MUFU chains: the denominators of the FP-pipe roofline (MEASURED_PEAKS.json
 // only has HBM and bf16 tensor figures, neither of which bounds this path).
@@ -1155,6 +1278,26 @@ int surfdisp_measure_peaks(double out[3]) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(buf);
+  return 0;
+}
+
+
+int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int n_layers_max,
+                          float* layers, int* n_layers, void* stream) {
+  if (!tmpl || n_models < 0 || n_layers_max < 2 || n_layers_max > SURFDISP_MAX_LAYERS) return SURFDISP_EINVAL;
+  if (tmpl->ngroups < 1 || tmpl->ngroups > SURFDISP_MAX_GROUPS || tmpl->nparams < 0) return SURFDISP_EINVAL;
+  for (int g = 0; g < tmpl->ngroups; ++g) {
+    const SurfdispStackGroup& G = tmpl->groups[g];
+    if (G.ncoef < 0 || G.ncoef > SURFDISP_MAX_COEF || G.h_param >= tmpl->nparams) return SURFDISP_EINVAL;
+    if (G.kind < SURFDISP_G_WATER || G.kind > SURFDISP_G_REFMANTLE) return SURFDISP_EINVAL;
+    if (G.nfine_rule == SURFDISP_N_FIXED && G.nfine < 1) return SURFDISP_EINVAL;
+    if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
+    for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;
+  }
+  if (n_models == 0) return 0;
+  if (!layers || !n_layers || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
+  build_stacks_kernel<<<(n_models + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
+  CK(cudaGetLastError());
   return 0;
 }
 
