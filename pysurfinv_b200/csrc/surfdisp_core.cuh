@@ -325,6 +325,30 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
   rsin = v2(r0, r1); sinr = v2(s0, s1); cs = v2(c0, c1);
 }
 
+// P and SV terms of one Rayleigh layer step together.  When all four arguments are in the thin-layer tier
+// (the common case) the four Horner chains are interleaved in one basic block: no branch between them and four
+// independent dependency chains for the scheduler.
+SD_HD void half_terms2x2(V2 argp, V2 argq, V2 kd, V2 kd2, V2& rsinp, V2& sinpr, V2& cosp, V2& rsinq, V2& sinqr, V2& cosq) {
+  const V2 up = vmul(kd2, argp), uq = vmul(kd2, argq);
+  const float um = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(uq.x), fabsf(uq.y)));
+  if (um < 0.5f) {
+    V2 Sp = vfma(up, vs(2.7557319e-6f), vs(1.9841270e-4f)), Sq = vfma(uq, vs(2.7557319e-6f), vs(1.9841270e-4f));
+    V2 Cp = vfma(up, vs(2.7557319e-7f), vs(2.4801587e-5f)), Cq = vfma(uq, vs(2.7557319e-7f), vs(2.4801587e-5f));
+    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
+    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
+    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
+    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
+    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
+    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
+    cosp = vfma(up, Cp, vs(1.f)); cosq = vfma(uq, Cq, vs(1.f));
+    sinpr = vmul(kd, Sp); sinqr = vmul(kd, Sq);
+    rsinp = vmul(vneg(argp), sinpr); rsinq = vmul(vneg(argq), sinqr);
+    return;
+  }
+  half_terms2(argp, kd, kd2, rsinp, sinpr, cosp);
+  half_terms2(argq, kd, kd2, rsinq, sinqr, cosq);
+}
+
 // Half-space row of the Rayleigh secular function (surfa.f:341-354) for one velocity; R = (a, b, rho, d)
 SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, float& r2, float& r3, float& r4, float& r5) {
   const float pp = R.x, b2 = 2.0f * R.y * R.y;
@@ -365,8 +389,8 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
     const V2 kd = vmul(wvno, vs(R.w));
     const V2 kd2 = vmul(kd, kd);
     V2 rsinp, sinpr, cosp;
-    half_terms2(vfma(ncsq, vs(ia2), one), kd, kd2, rsinp, sinpr, cosp);
     if (R.y == 0.f) {
+      half_terms2(vfma(ncsq, vs(ia2), one), kd, kd2, rsinp, sinpr, cosp);
       if (ell_only) continue;
       const V2 a21 = vmul(vmul(vs(R.z), csq), sinpr);
       const V2 n1 = vfma(r1, cosp, vmul(r2, a21));
@@ -380,7 +404,7 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
     }
     const float ib = sd_rcp(R.y), ib2 = ib * ib, b2 = 2.0f * R.y * R.y, irho = sd_rcp(R.z);
     V2 rsinq, sinqr, cosq;
-    half_terms2(vfma(ncsq, vs(ib2), one), kd, kd2, rsinq, sinqr, cosq);
+    half_terms2x2(vfma(ncsq, vs(ia2), one), vfma(ncsq, vs(ib2), one), kd, kd2, rsinp, sinpr, cosp, rsinq, sinqr, cosq);
     const V2 g = vmul(vs(b2), icsq);
     const V2 g1 = vadd(g, vs(-1.f));
     const V2 rhoc = vmul(vs(R.z), csq);
