@@ -225,11 +225,14 @@ def main():
 
     if rank == 0:
         flop_p1 = steps_ctr * F_R
-        roof = {"bound": "fp32", "kernel": "phase1_kernel<8> (scan + polish + ellipticity)",
+        roof = {"bound": "fp32", "kernel": "phase1_kernel<4> (root search: 2 launches, first period / later periods)",
                 "achieved": flop_p1 / (kms[1] * 1e-3) * 1e-12, "peak": peaks[0], "unit": "TFLOP/s",
-                "frac": flop_p1 / (kms[1] * 1e-3) * 1e-12 / peaks[0] if peaks[0] else None, "traffic": None,
+                "frac": flop_p1 / (kms[1] * 1e-3) * 1e-12 / peaks[0] if peaks[0] else None,
                 "peak_source": "surfdisp_measure_peaks(): register-resident FFMA chain, this run "
-                               "(MEASURED_PEAKS.json has no FP32 figure)",
+                               "(MEASURED_PEAKS.json has no FP32 figure; the path is FP-pipe bound, not HBM or tensor)",
+                "work_unit": "secular-function layer-step of one trial velocity = %.0f FLOP-equivalents (SURVEY 8d); "
+                             "counted on the device" % F_R,
+                "traffic": None,
                 "kernel_ms": {"prep": float(kms[0]), "phase1": float(kms[1]), "phase2": float(kms[2])},
                 "layer_steps_per_eval": steps_ctr / (M * K), "sweeps_per_eval": sweeps_ctr / (M * K),
                 "u_sublayers_per_eval": subu_ctr / (M * K),
@@ -255,7 +258,7 @@ def main():
                            "l2_policy": "inputs (%.2f GB layers + %.2f GB workspace per step) exceed the 126 MB L2"
                                         % (lay.nbytes / 1e9, solver._ws.numel() / 1e9),
                            "roots_found_frac": nfound_ok / M},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

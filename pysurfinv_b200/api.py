@@ -224,7 +224,7 @@ class DispersionSolver:
             self._pinned[key] = t
         return t
 
-    def forward_host(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True):
+    def forward_host(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, chunks=None):
         """numpy in, numpy out.  Inputs are staged through pinned memory, copied to the GPU, solved and
         copied back; returns dict(c, u, nfound, flags) of numpy arrays."""
         torch = self.torch
@@ -234,26 +234,79 @@ class DispersionSolver:
         hn = self._pin("nl", nl.shape, torch.int32)
         hl.numpy()[...] = lay
         hn.numpy()[...] = nl
-        return self.forward_pinned(hl, hn, periods, kind, group)
+        return self.forward_pinned(hl, hn, periods, kind, group, chunks)
 
-    def forward_pinned(self, hl, hn, periods, kind=KIND_RAYLEIGH, group=True):
-        """Same as forward_host but the caller already holds pinned host tensors."""
+    def forward_pinned(self, hl, hn, periods, kind=KIND_RAYLEIGH, group=True, chunks=None):
+        """Same as forward_host but the caller already holds pinned host tensors.  With chunks > 1 the batch is cut
+        into chunks whose host->device / device->host copies run on a copy stream while the neighbouring chunk is
+        being solved.  Measured on B200 (tools/e2e_chunks.py, 2^20 models x 40 periods): the copies are 35 ms of a
+        400 ms step (55 GB/s), while every extra launch of the persistent kernels costs ~10 ms of tail, so one
+        chunk is fastest; chunking is the default only for batches that would not fit device memory at once."""
         torch = self.torch
-        dl = hl.to(self.device, non_blocking=True)
-        dn = hn.to(self.device, non_blocking=True)
-        out = self.forward(dl, dn, periods, kind, group)
-        M, K = out["c"].shape
+        M, lmax = int(hl.shape[1]), int(hl.shape[2])
+        K = int(np.asarray(periods).size)
+        if chunks is None:
+            chunks = 1 if M <= (1 << 21) else (M + (1 << 20) - 1) >> 20
+        chunks = max(1, min(int(chunks), M if M > 0 else 1))
         hc = self._pin("c", (M, K), torch.float32)
         hf = self._pin("nf", (M,), torch.int32)
         hg = self._pin("fl", (M,), torch.int32)
-        hc.copy_(out["c"], non_blocking=True)
-        hf.copy_(out["nfound"], non_blocking=True)
-        hg.copy_(out["flags"], non_blocking=True)
-        hu = None
-        if group:
-            hu = self._pin("u", (M, K), torch.float32)
-            hu.copy_(out["u"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        hu = self._pin("u", (M, K), torch.float32) if group else None
+        if M == 0:
+            return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+        compute = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = self._copy_stream
+        bounds = [(i * M) // chunks for i in range(chunks + 1)]
+        mc = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
+        key = (mc, lmax, K, bool(group))
+        if getattr(self, "_chunk_key", None) != key:
+            # double-buffered device staging for inputs and outputs
+            self._chunk_buf = [dict(lay=torch.empty((5, mc, lmax), dtype=torch.float32, device=self.device),
+                                    nl=torch.empty(mc, dtype=torch.int32, device=self.device),
+                                    c=torch.empty((mc, K), dtype=torch.float32, device=self.device),
+                                    u=torch.empty((mc, K), dtype=torch.float32, device=self.device) if group else None,
+                                    nfound=torch.empty(mc, dtype=torch.int32, device=self.device),
+                                    flags=torch.empty(mc, dtype=torch.int32, device=self.device)) for _ in range(2)]
+            self._chunk_key = key
+        copy.wait_stream(compute)
+        h2d_done, solved, d2h_done = [None] * chunks, [None] * chunks, [None] * chunks
+
+        def upload(i):
+            a, b = bounds[i], bounds[i + 1]
+            buf = self._chunk_buf[i % 2]
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(d2h_done[i - 2])     # the buffer's previous results have left
+                for comp in range(5):
+                    buf["lay"][comp, :b - a].copy_(hl[comp, a:b], non_blocking=True)
+                buf["nl"][:b - a].copy_(hn[a:b], non_blocking=True)
+                h2d_done[i] = torch.cuda.Event(); h2d_done[i].record(copy)
+
+        upload(0)
+        for i in range(chunks):
+            a, b = bounds[i], bounds[i + 1]
+            n = b - a
+            buf = self._chunk_buf[i % 2]
+            if i + 1 < chunks:
+                upload(i + 1)
+            compute.wait_event(h2d_done[i])
+            lay = buf["lay"] if n == mc else buf["lay"][:, :n].contiguous()
+            out = dict(c=buf["c"][:n], u=None if buf["u"] is None else buf["u"][:n], nfound=buf["nfound"][:n],
+                       flags=buf["flags"][:n])
+            self.forward(lay, buf["nl"][:n], periods, kind, group, out=out)
+            solved[i] = torch.cuda.Event(); solved[i].record(compute)
+            with torch.cuda.stream(copy):
+                copy.wait_event(solved[i])
+                hc[a:b].copy_(out["c"], non_blocking=True)
+                hf[a:b].copy_(out["nfound"], non_blocking=True)
+                hg[a:b].copy_(out["flags"], non_blocking=True)
+                if group:
+                    hu[a:b].copy_(out["u"], non_blocking=True)
+                d2h_done[i] = torch.cuda.Event(); d2h_done[i].record(copy)
+        compute.wait_stream(copy)
+        compute.synchronize()
         return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
 
 

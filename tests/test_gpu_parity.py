@@ -264,3 +264,17 @@ def test_config3_joint_rayleigh_love_anisotropy(solver):
     gl = _gpu(solver, np.ascontiguousarray(lay_sh), nl, per, 1)
     _check(gr, lay, nl, per, 2)
     _check(gl, np.ascontiguousarray(lay_sh), nl, per, 1)
+
+
+def test_chunked_host_path_matches_device_path(solver):
+    """forward_host cuts large batches into chunks whose PCIe copies overlap the kernels: same results as one
+    device-resident call, for a chunk count that does not divide the batch."""
+    import torch
+    lay, nl = synth.crustal_models(1001, seed=77)
+    per = synth.log_periods(12)
+    d = solver.forward(torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda(), per, kind=2)
+    torch.cuda.synchronize()
+    for chunks in (1, 3, 8):
+        h = solver.forward_host(lay, nl, per, 2, chunks=chunks)
+        assert np.array_equal(h["c"], d["c"].cpu().numpy()) and np.array_equal(h["u"], d["u"].cpu().numpy())
+        assert np.array_equal(h["nfound"], d["nfound"].cpu().numpy()) and np.array_equal(h["flags"], d["flags"].cpu().numpy())
