@@ -160,10 +160,23 @@ int surfdisp_measure_peaks(double out[3]);
 #define SURFDISP_R_OCEAN 1      /* 0.541 + 0.3601 Vp, layers.py:216 */
 #define SURFDISP_R_MANTLE 2     /* 3.4268 + (Vs - 4.5) / 4.5, layers.py:262 */
 #define SURFDISP_R_CONST 3
+/* group classes (layers.py prop['Group']) used by the prior checks */
+#define SURFDISP_C_WATER 0
+#define SURFDISP_C_SEDIMENT 1
+#define SURFDISP_C_CRUST 2
+#define SURFDISP_C_MANTLE 3
+#define SURFDISP_C_OTHER 4
+/* prior checks of CascadiaPrism.isgood (models.py:294-360), bits of SurfdispStackTemplate.prior_mask and of the
+ * per-model result */
+#define SURFDISP_P_JUMP 1        /* Vs jump between groups must not be negative (models.py:305-307) */
+#define SURFDISP_P_VSMAX 2       /* all Vs <= 4.9 km/s (models.py:312-313) */
+#define SURFDISP_P_MONO 4        /* Vs strictly increasing inside sediment and crust (models.py:318-321) */
+#define SURFDISP_P_BOTTOM 8      /* positive Vs gradient at the bottom of the mantle (models.py:355-356) */
 
 typedef struct SurfdispStackGroup {
   int kind, nfine_rule, nfine, h_mode;      /* h_mode 0: parameter is the thickness H, 1: BottomDepth */
-  int h_param, ncoef, rho_rule, pad_;       /* h_param: index of the free parameter or -1 (h_fixed) */
+  int h_param, ncoef, rho_rule, gclass;     /* h_param: index of the free parameter or -1 (h_fixed);
+                                               gclass: SURFDISP_C_* group of the reference (layer.prop['Group']) */
   int v_param[SURFDISP_MAX_COEF];           /* per Vs coefficient: free-parameter index or -1 (v_fixed) */
   double v_fixed[SURFDISP_MAX_COEF];
   double h_fixed, vp_a, vp_b, rho_const, qs, slope;   /* Vp = vp_a Vs + vp_b; slope: km/s per km (REFMANTLE) */
@@ -171,6 +184,7 @@ typedef struct SurfdispStackGroup {
 
 typedef struct SurfdispStackTemplate {
   int ngroups, nparams;
+  int prior_mask, pad_;                      /* which SURFDISP_P_* rules the Monte-Carlo walk enforces (0: none, MCinv.isgood) */
   double topo;                               /* km, negative below sea level (models.py:76) */
   SurfdispStackGroup groups[SURFDISP_MAX_GROUPS];
 } SurfdispStackTemplate;
@@ -179,6 +193,34 @@ typedef struct SurfdispStackTemplate {
  * (0 if a stack would need more than n_layers_max layers).  Asynchronous on `stream`. */
 int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params,
                           int n_layers_max, float* layers, int* n_layers, void* stream);
+
+/* Prior checks only: priors device int[M] = SURFDISP_P_* bits violated (all four rules are evaluated,
+ * whatever prior_mask says). */
+int surfdisp_check_priors(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int* priors,
+                          void* stream);
+
+/* One Monte-Carlo proposal per chain, replacing MCinv.perturb / reset (models.py:190-219) with
+ * BrownianVar.move / reset (brownian.py:17-27): every free parameter gets a Gaussian step, redrawn (up to 1000
+ * times, then a uniform redraw) until it is inside (vmin, vmax); the whole proposal is redrawn (up to 1000 times,
+ * then uniform resets, up to 10000) until the enabled priors hold.
+ *   lo, hi, step   HOST float[P]  (BrownianVar vmin, vmax, step)
+ *   cur            device float[M][P] current models; reset_mask device unsigned char[M] or NULL: chains that
+ *                  start over from a uniform draw (chain restarts, point.py:47-57)
+ *   prop           device float[M][P] proposals (out); status device int[M] or NULL: tries used, negative if no
+ *                  admissible model was found (the reference raises there)
+ *   seed, step_index  counter-based generator (Philox4x32-10): chain m at step s always draws the same numbers
+ */
+int surfdisp_mc_propose(const SurfdispStackTemplate* tmpl, int n_chains, const float* lo, const float* hi,
+                        const float* step, const float* cur, const unsigned char* reset_mask, float* prop,
+                        int* status, unsigned long long seed, unsigned int step_index, void* stream);
+
+/* Metropolis rule of point.py:34-37 for every chain: accept if chi1 < chi0, else if u > 1 - exp(-(chi1-chi0)/2).
+ * chi0 / cur are updated in place where the proposal is accepted; accepted device unsigned char[M] (out).
+ * force_mask device unsigned char[M] or NULL: chains whose proposal is taken unconditionally (first sample of a
+ * chain, point.py:57). */
+int surfdisp_mc_accept(int n_chains, int n_params, const float* chi1, const float* prop, float* chi0, float* cur,
+                       const unsigned char* force_mask, unsigned char* accepted, unsigned long long seed,
+                       unsigned int step_index, void* stream);
 
 const char* surfdisp_version(void);
 const char* surfdisp_last_cuda_error(void);

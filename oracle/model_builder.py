@@ -118,3 +118,54 @@ def build_stacks(tmpl, params, lmax):
         out[0, m, :n] = vp; out[1, m, :n] = vs; out[2, m, :n] = rho; out[3, m, :n] = h; out[4, m, :n] = 1.0 / qs
         nl[m] = n
     return out, nl
+
+
+def grids_one(tmpl, p):
+    """Fine grid (z, vs, group class) of models.py:72-91 without the reference mantle (the default of
+    Model1D.seisPropGrids, which is what the prior checks look at)."""
+    z_all, vs_all, vp_all, rho_all, qs_all, cls = [], [], [], [], [], []
+    z0 = -max(tmpl.topo, 0.0)
+    for g in tmpl.groups:
+        if g.kind == S.G_REFMANTLE:
+            continue
+        hv = p[g.h_param] if g.h_param >= 0 else g.h_fixed
+        top = z_all[-1] if z_all else 0.0
+        H = float(hv) if (g.h_mode == 0 or not z_all) else float(hv) - top
+        N = nfine(g.nfine_rule, g.nfine, H)
+        z = np.linspace(0, H, N + 1)
+        coef = np.array([p[g.v_param[i]] if g.v_param[i] >= 0 else g.v_fixed[i] for i in range(g.ncoef)], dtype=np.float64)
+        if g.kind == S.G_WATER:
+            vs = np.zeros(N + 1)
+        elif g.kind == S.G_CONST:
+            vs = np.full(N + 1, coef[0])
+        elif g.kind == S.G_LINEAR:
+            vs = np.linspace(coef[0], coef[1], N + 1)
+        elif g.kind == S.G_BSPLINE:
+            vs = coef @ bspl_basis(N + 1, g.ncoef)
+        else:
+            vs = np.full(N + 1, (0.02 * H ** 2 + 1.27 * H + 0.29 * 0.1) / (H + 0.29))
+        if z[-1] - z[0] < 0.01:
+            continue
+        z_all += list(z + z0); vs_all += list(vs); cls += [g.gclass] * (N + 1)
+        z0 = z_all[-1]
+    return np.array(z_all), np.array(vs_all), np.array(cls)
+
+
+def priors(tmpl, p):
+    """Bits of the violated rules of CascadiaPrism.isgood (reference models.py:294-360)."""
+    z, vs, cls = grids_one(tmpl, np.asarray(p, dtype=np.float64))
+    eps = np.finfo(float).eps
+    bad = 0
+    for i in np.where(cls[1:] != cls[:-1])[0]:
+        if vs[i + 1] < vs[i]:
+            bad |= S.P_JUMP
+    if np.any(vs > 4.9):
+        bad |= S.P_VSMAX
+    for c in (S.C_SEDIMENT, S.C_CRUST):
+        v = vs[cls == c]
+        if not np.all(np.diff(v) >= eps):
+            bad |= S.P_MONO
+    zm, vm = z[cls == S.C_MANTLE], vs[cls == S.C_MANTLE]
+    if len(vm) >= 2 and (vm[-1] - vm[-2]) / (zm[-1] - zm[-2]) <= 0:
+        bad |= S.P_BOTTOM
+    return bad

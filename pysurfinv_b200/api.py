@@ -67,6 +67,14 @@ def load_library():
     from . import stack as _stack
     L.surfdisp_build_stacks.argtypes = [C.POINTER(_stack.StackTemplateC), C.c_int, vp, C.c_int, vp, vp, vp]
     L.surfdisp_build_stacks.restype = C.c_int
+    ub = C.POINTER(C.c_ubyte)
+    L.surfdisp_check_priors.argtypes = [C.POINTER(_stack.StackTemplateC), C.c_int, vp, vp, vp]
+    L.surfdisp_check_priors.restype = C.c_int
+    L.surfdisp_mc_propose.argtypes = [C.POINTER(_stack.StackTemplateC), C.c_int, fp, fp, fp, vp, vp, vp, vp,
+                                      C.c_ulonglong, C.c_uint, vp]
+    L.surfdisp_mc_propose.restype = C.c_int
+    L.surfdisp_mc_accept.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_ulonglong, C.c_uint, vp]
+    L.surfdisp_mc_accept.restype = C.c_int
     L.surfdisp_version.restype = C.c_char_p
     L.surfdisp_last_cuda_error.restype = C.c_char_p
     _lib = L
@@ -215,6 +223,50 @@ class DispersionSolver:
                                                 out[0].data_ptr(), out[1].data_ptr(), stream)
         _check(rc, "surfdisp_build_stacks")
         return out
+
+    def check_priors(self, template, params):
+        """SURFDISP P_* bits of the prior rules (CascadiaPrism.isgood, reference models.py:294-360) each model
+        violates; int32 device tensor [M]."""
+        torch = self.torch
+        M = int(params.shape[0])
+        out = torch.empty(M, dtype=torch.int32, device=self.device)
+        tc = template.to_c()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_check_priors(C.byref(tc), M, params.data_ptr() if template.nparams else None,
+                                                out.data_ptr(), stream)
+        _check(rc, "surfdisp_check_priors")
+        return out
+
+    def mc_propose(self, template, cur, seed, step_index, reset_mask=None, out=None, status=None):
+        """One proposal per chain (MCinv.perturb / reset, reference models.py:190-219, brownian.py:17-27)."""
+        torch = self.torch
+        lo, hi, st = template.bounds()
+        M, P = int(cur.shape[0]), template.nparams
+        if out is None:
+            out = torch.empty_like(cur)
+        tc = template.to_c()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_mc_propose(C.byref(tc), M, _fptr(lo), _fptr(hi), _fptr(st), cur.data_ptr(),
+                                              None if reset_mask is None else reset_mask.data_ptr(), out.data_ptr(),
+                                              None if status is None else status.data_ptr(), int(seed), int(step_index), stream)
+        _check(rc, "surfdisp_mc_propose")
+        return out
+
+    def mc_accept(self, chi1, prop, chi0, cur, seed, step_index, force_mask=None, accepted=None):
+        """Metropolis rule of reference point.py:34-37; chi0 and cur are updated in place where accepted."""
+        torch = self.torch
+        M, P = int(cur.shape[0]), int(cur.shape[1])
+        if accepted is None:
+            accepted = torch.empty(M, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_mc_accept(M, P, chi1.data_ptr(), prop.data_ptr(), chi0.data_ptr(), cur.data_ptr(),
+                                             None if force_mask is None else force_mask.data_ptr(), accepted.data_ptr(),
+                                             int(seed), int(step_index), stream)
+        _check(rc, "surfdisp_mc_accept")
+        return accepted
 
     # -- host path (what a reference-side caller uses): pinned staging, H2D, solve, D2H --------------
     def _pin(self, key, shape, dtype):

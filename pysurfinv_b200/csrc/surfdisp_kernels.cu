@@ -896,23 +896,19 @@ __device__ double stack_rho(int rule, double cst, double vs, double vp) {
   return cst;
 }
 
-__global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
-                                                           const float* __restrict__ params, int lmax,
-                                                           float* __restrict__ layers, int* __restrict__ nlay) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const float* pm = params + (size_t)m * t.nparams;
-  const size_t pl = (size_t)M * lmax;
-  float* o_vp = layers + 0 * pl + (size_t)m * lmax;
-  float* o_vs = layers + 1 * pl + (size_t)m * lmax;
-  float* o_rho = layers + 2 * pl + (size_t)m * lmax;
-  float* o_h = layers + 3 * pl + (size_t)m * lmax;
-  float* o_qs = layers + 4 * pl + (size_t)m * lmax;
-  int nl = 0;
+// Assembles one model from its parameter vector.  EMIT: write the layers; always returns the SURFDISP_P_* bits
+// of the violated prior rules (CascadiaPrism.isgood, models.py:294-360, evaluated on the fine grid without the
+// reference mantle like Model1D.seisPropGrids() does by default).
+template <bool EMIT>
+__device__ int assemble_stack(const SurfdispStackTemplate& t, const float* pm, int lmax, float* o_vp, float* o_vs,
+                              float* o_rho, float* o_h, float* o_qs, int* nl_out) {
+  int nl = 0, bad = 0;
   bool overflow = false, any = false;
   double z0 = -fmax(t.topo, 0.0);        // depth of the top of the next group (models.py:76-77)
   double ztop_prev = 0.0;                 // bottom depth of the stack so far, for BottomDepth groups (0 if none)
   double last_vs = 0.0, last_vp = 0.0, last_rho = 0.0, last_qs = 0.0;   // deepest grid values so far
+  int last_class = -1;
+  double bot_grad = 1.0;                  // Vs gradient at the bottom of the deepest mantle group
   for (int gi = 0; gi < t.ngroups; ++gi) {
     const SurfdispStackGroup& g = t.groups[gi];
     const double hv = (g.h_param >= 0) ? (double)pm[g.h_param] : g.h_fixed;
@@ -925,9 +921,11 @@ __global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant
     for (int i = 0; i < g.ncoef; ++i) coef[i] = (g.v_param[i] >= 0) ? (double)pm[g.v_param[i]] : g.v_fixed[i];
     // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
     if (H - 0.0 < 0.01) continue;
+    const bool is_ref = (g.kind == SURFDISP_G_REFMANTLE);
     const double zstep = H / (double)N, ustep = 1.0 / (double)N;
     double p_z = 0.0, p_vs = 0.0, p_vp = 0.0, p_rho = 0.0, p_qs = 0.0;   // previous grid point
-    double vs0_ref = last_vs, vp_first = 0.0, rho_first = 0.0, qs_first = 0.0;
+    const double vs0_ref = last_vs;
+    double vp_first = 0.0, rho_first = 0.0, qs_first = 0.0;
     for (int j = 0; j <= N; ++j) {
       const double zz = (j == N) ? H : (double)j * zstep;
       const double u = (j == N) ? 1.0 : (double)j * ustep;
@@ -947,12 +945,23 @@ __global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant
       double vp = g.vp_a * vs + g.vp_b;
       double rho = stack_rho(g.rho_rule, g.rho_const, vs, vp);
       double qs = g.qs;
-      if (g.kind == SURFDISP_G_REFMANTLE) {
+      if (is_ref) {
         // Vp, rho, Qs continue from the deepest values above (layers.py:279-283)
         if (j == 0) { vp_first = vp; rho_first = rho; qs_first = qs; }
         vp = last_vp + (vp - vp_first); rho = last_rho + (rho - rho_first); qs = last_qs + (qs - qs_first);
       }
-      if (j > 0) {
+      if (!is_ref) {
+        // ---- prior rules on the grid (models.py:301-356)
+        if (vs > 4.9) bad |= SURFDISP_P_VSMAX;
+        if (j == 0 && any && g.gclass != last_class && vs < last_vs) bad |= SURFDISP_P_JUMP;
+        if (j > 0 && (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST) && !(vs - p_vs >= 2.220446049250313e-16))
+          bad |= SURFDISP_P_MONO;
+        if (j == 0 && any && g.gclass == last_class && (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST) &&
+            !(vs - last_vs >= 2.220446049250313e-16))
+          bad |= SURFDISP_P_MONO;   // two groups of the same class form one array in the reference's test
+        if (j == N && g.gclass == SURFDISP_C_MANTLE) bot_grad = (vs - p_vs) / (zz - p_z);
+      }
+      if (EMIT && j > 0) {
         const double h = (zz + z0) - (p_z + z0);
         if (h > 0.01) {   // models.py:102 (and models.py:20: h > 1e-3)
           if (nl < lmax) {
@@ -965,14 +974,137 @@ __global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant
       }
       p_z = zz; p_vs = vs; p_vp = vp; p_rho = rho; p_qs = qs;
     }
-    // REFMANTLE reads the values of the group above before they are replaced
     last_vs = p_vs; last_vp = p_vp; last_rho = p_rho; last_qs = p_qs;
+    if (!is_ref) last_class = g.gclass;
     z0 = z0 + H;
     ztop_prev = z0;
     any = true;
   }
-  for (int j = nl; j < lmax; ++j) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
-  nlay[m] = overflow ? 0 : nl;
+  if (!(bot_grad > 0.0)) bad |= SURFDISP_P_BOTTOM;
+  if (EMIT) *nl_out = overflow ? -1 : nl;
+  return bad;
+}
+
+__global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
+                                                           const float* __restrict__ params, int lmax,
+                                                           float* __restrict__ layers, int* __restrict__ nlay) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* pm = params + (size_t)m * t.nparams;
+  const size_t pl = (size_t)M * lmax;
+  float* o_vp = layers + 0 * pl + (size_t)m * lmax;
+  float* o_vs = layers + 1 * pl + (size_t)m * lmax;
+  float* o_rho = layers + 2 * pl + (size_t)m * lmax;
+  float* o_h = layers + 3 * pl + (size_t)m * lmax;
+  float* o_qs = layers + 4 * pl + (size_t)m * lmax;
+  int nl = 0;
+  assemble_stack<true>(t, pm, lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl);
+  const int nz = nl < 0 ? 0 : nl;
+  for (int j = nz; j < lmax; ++j) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
+  nlay[m] = nz;
+}
+
+__global__ void __launch_bounds__(128) check_priors_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
+                                                           const float* __restrict__ params, int* __restrict__ priors) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  priors[m] = assemble_stack<false>(t, params + (size_t)m * t.nparams, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------------------------ Monte-Carlo step
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so chain m at step s draws the same numbers whatever
+// the launch geometry.  counter = (chain, step, draw, stream id), key = seed.
+struct Philox {
+  unsigned int c0, c1, c2, c3, k0, k1;
+  unsigned int buf[4];
+  int have;
+  __device__ Philox(unsigned long long seed, unsigned int chain, unsigned int step, unsigned int stream_id)
+      : c0(chain), c1(step), c2(0u), c3(stream_id), k0((unsigned int)seed), k1((unsigned int)(seed >> 32)), have(0) {}
+  __device__ void block() {
+    unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const unsigned int h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
+      const unsigned int h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
+      const unsigned int y0 = h1 ^ x1 ^ a, y1 = l1, y2 = h0 ^ x3 ^ b, y3 = l0;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+    c2++;
+    have = 4;
+  }
+  __device__ unsigned int next() { if (!have) block(); return buf[--have]; }
+  __device__ float uniform() { return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+  __device__ float gauss() {   // Box-Muller
+    const float u1 = uniform(), u2 = uniform();
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  }
+};
+
+struct McBounds { float lo[64], hi[64], step[64]; };
+constexpr int kMaxParams = 64;
+
+__global__ void __launch_bounds__(128) mc_propose_kernel(const __grid_constant__ SurfdispStackTemplate t,
+                                                         const __grid_constant__ McBounds bd, int M,
+                                                         const float* __restrict__ cur,
+                                                         const unsigned char* __restrict__ reset_mask,
+                                                         float* __restrict__ prop, int* __restrict__ status,
+                                                         unsigned long long seed, unsigned int step_index) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int P = t.nparams;
+  Philox rng(seed, (unsigned int)m, step_index, 1u);
+  const float* c = cur + (size_t)m * P;
+  float* q = prop + (size_t)m * P;
+  const bool restart = reset_mask && reset_mask[m];
+  int tries = 0, result = -1;
+  // MCinv.perturb (models.py:190-205): up to 1000 proposals, then MCinv.reset (models.py:206-219): up to 10000
+  for (int phase = restart ? 1 : 0; phase < 2 && result < 0; ++phase) {
+    const int limit = phase == 0 ? 1000 : 10000;
+    for (int a = 0; a < limit; ++a) {
+      ++tries;
+      for (int i = 0; i < P; ++i) {
+        const float lo = bd.lo[i], hi = bd.hi[i];
+        float v = 0.f;
+        bool ok = false;
+        if (phase == 0) {
+          // BrownianVar.move (brownian.py:20-27): Gaussian step, redrawn until strictly inside the bounds
+          for (int r = 0; r < 1000 && !ok; ++r) {
+            v = c[i] + bd.step[i] * rng.gauss();
+            ok = (v < hi && v > lo);
+          }
+        }
+        if (!ok) v = lo + (hi - lo) * rng.uniform();   // BrownianVar.reset (brownian.py:17-19)
+        q[i] = v;
+      }
+      const int bad = t.prior_mask ? (assemble_stack<false>(t, q, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) & t.prior_mask) : 0;
+      if (!bad) { result = tries; break; }
+    }
+  }
+  if (status) status[m] = result;
+}
+
+__global__ void __launch_bounds__(256) mc_accept_kernel(int M, int P, const float* __restrict__ chi1,
+                                                        const float* __restrict__ prop, float* __restrict__ chi0,
+                                                        float* __restrict__ cur, const unsigned char* __restrict__ force,
+                                                        unsigned char* __restrict__ accepted, unsigned long long seed,
+                                                        unsigned int step_index) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  Philox rng(seed, (unsigned int)m, step_index, 2u);
+  const float x0 = chi0[m], x1 = chi1[m];
+  bool acc = force && force[m];
+  if (!acc) {
+    // point.py:34-37: accept if chi1 < chi0, else if u > 1 - exp(-(chi1 - chi0) / 2)   (= (L0 - L1) / L0)
+    if (x1 < x0) acc = true;
+    else acc = (double)rng.uniform() > 1.0 - exp(-0.5 * ((double)x1 - (double)x0));
+  }
+  if (acc) {
+    chi0[m] = x1;
+    for (int i = 0; i < P; ++i) cur[(size_t)m * P + i] = prop[(size_t)m * P + i];
+  }
+  accepted[m] = acc ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------ pipe peaks
@@ -1282,9 +1414,8 @@ int surfdisp_measure_peaks(double out[3]) {
 }
 
 
-int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int n_layers_max,
-                          float* layers, int* n_layers, void* stream) {
-  if (!tmpl || n_models < 0 || n_layers_max < 2 || n_layers_max > SURFDISP_MAX_LAYERS) return SURFDISP_EINVAL;
+static int check_template(const SurfdispStackTemplate* tmpl) {
+  if (!tmpl) return SURFDISP_EINVAL;
   if (tmpl->ngroups < 1 || tmpl->ngroups > SURFDISP_MAX_GROUPS || tmpl->nparams < 0) return SURFDISP_EINVAL;
   for (int g = 0; g < tmpl->ngroups; ++g) {
     const SurfdispStackGroup& G = tmpl->groups[g];
@@ -1294,9 +1425,59 @@ int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const
     if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
     for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;
   }
+  return 0;
+}
+
+int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int n_layers_max,
+                          float* layers, int* n_layers, void* stream) {
+  if (n_models < 0 || n_layers_max < 2 || n_layers_max > SURFDISP_MAX_LAYERS) return SURFDISP_EINVAL;
+  if (int rc = check_template(tmpl)) return rc;
   if (n_models == 0) return 0;
   if (!layers || !n_layers || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
   build_stacks_kernel<<<(n_models + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int surfdisp_check_priors(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int* priors, void* stream) {
+  if (n_models < 0) return SURFDISP_EINVAL;
+  if (int rc = check_template(tmpl)) return rc;
+  if (n_models == 0) return 0;
+  if (!priors || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
+  check_priors_kernel<<<(n_models + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int surfdisp_mc_propose(const SurfdispStackTemplate* tmpl, int n_chains, const float* lo, const float* hi,
+                        const float* step, const float* cur, const unsigned char* reset_mask, float* prop,
+                        int* status, unsigned long long seed, unsigned int step_index, void* stream) {
+  if (n_chains < 0) return SURFDISP_EINVAL;
+  if (int rc = check_template(tmpl)) return rc;
+  const int P = tmpl->nparams;
+  if (P < 1 || P > kMaxParams || !lo || !hi || !step) return SURFDISP_EINVAL;
+  if (n_chains == 0) return 0;
+  if (!cur || !prop) return SURFDISP_EINVAL;
+  McBounds bd;
+  memset(&bd, 0, sizeof(bd));
+  for (int i = 0; i < P; ++i) {
+    if (!(hi[i] > lo[i]) || !(step[i] > 0.f)) return SURFDISP_EINVAL;
+    bd.lo[i] = lo[i]; bd.hi[i] = hi[i]; bd.step[i] = step[i];
+  }
+  mc_propose_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, bd, n_chains, cur, reset_mask, prop,
+                                                                              status, seed, step_index);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int surfdisp_mc_accept(int n_chains, int n_params, const float* chi1, const float* prop, float* chi0, float* cur,
+                       const unsigned char* force_mask, unsigned char* accepted, unsigned long long seed,
+                       unsigned int step_index, void* stream) {
+  if (n_chains < 0 || n_params < 1) return SURFDISP_EINVAL;
+  if (n_chains == 0) return 0;
+  if (!chi1 || !prop || !chi0 || !cur || !accepted) return SURFDISP_EINVAL;
+  mc_accept_kernel<<<(n_chains + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_chains, n_params, chi1, prop, chi0, cur,
+                                                                             force_mask, accepted, seed, step_index);
   CK(cudaGetLastError());
   return 0;
 }

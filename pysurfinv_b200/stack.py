@@ -23,18 +23,25 @@ G_WATER, G_CONST, G_LINEAR, G_BSPLINE, G_CASCADIA, G_REFMANTLE = 0, 1, 2, 3, 4, 
 N_FIXED, N_CRUST, N_OCRUST = 0, 1, 2
 # density rules
 R_QUARTIC, R_OCEAN, R_MANTLE, R_CONST = 0, 1, 2, 3
+# group classes (layer.prop['Group']) and prior rules (CascadiaPrism.isgood, reference models.py:294-360)
+C_WATER, C_SEDIMENT, C_CRUST, C_MANTLE, C_OTHER = 0, 1, 2, 3, 4
+P_JUMP, P_VSMAX, P_MONO, P_BOTTOM = 1, 2, 4, 8
+P_ALL = 15
+_CLASS = {'Sediment': C_SEDIMENT, 'Crust': C_CRUST, 'Mantle': C_MANTLE, 'OceanMantle': C_MANTLE, 'OceanWater': C_WATER,
+          'OceanSediment': C_SEDIMENT, 'OceanSedimentCascadia': C_SEDIMENT, 'OceanCrust': C_CRUST}
 
 
 class Group(C.Structure):
     _fields_ = [("kind", C.c_int), ("nfine_rule", C.c_int), ("nfine", C.c_int), ("h_mode", C.c_int),
-                ("h_param", C.c_int), ("ncoef", C.c_int), ("rho_rule", C.c_int), ("_pad", C.c_int),
+                ("h_param", C.c_int), ("ncoef", C.c_int), ("rho_rule", C.c_int), ("gclass", C.c_int),
                 ("v_param", C.c_int * MAX_COEF), ("v_fixed", C.c_double * MAX_COEF),
                 ("h_fixed", C.c_double), ("vp_a", C.c_double), ("vp_b", C.c_double), ("rho_const", C.c_double),
                 ("qs", C.c_double), ("slope", C.c_double)]
 
 
 class StackTemplateC(C.Structure):
-    _fields_ = [("ngroups", C.c_int), ("nparams", C.c_int), ("topo", C.c_double), ("groups", Group * MAX_GROUPS)]
+    _fields_ = [("ngroups", C.c_int), ("nparams", C.c_int), ("prior_mask", C.c_int), ("_pad", C.c_int),
+                ("topo", C.c_double), ("groups", Group * MAX_GROUPS)]
 
 
 _TYPES = {
@@ -81,7 +88,8 @@ class Param:
 
 
 class StackTemplate:
-    def __init__(self, setting):
+    def __init__(self, setting, prior_mask=0):
+        self.prior_mask = int(prior_mask)   # which prior rules proposals must satisfy (0 = MCinv.isgood: none)
         self.params = []
         self.groups = []
         info = dict(setting.get("Info", {}))
@@ -96,6 +104,7 @@ class StackTemplate:
             g = self._blank()
             g.kind, g.nfine_rule, g.nfine, g.h_mode, g.h_param, g.h_fixed = G_REFMANTLE, N_FIXED, 20, 0, -1, 300.0
             g.vp_a, g.vp_b, g.rho_rule, g.qs, g.slope = 1.76, 0.0, R_MANTLE, 150.0, 0.35 / 200
+            g.gclass = C_MANTLE
             self.groups.append(g)
         if len(self.groups) > MAX_GROUPS:
             raise ValueError("at most %d layer groups" % MAX_GROUPS)
@@ -121,6 +130,7 @@ class StackTemplate:
         kind, nrule, nfine, vp_a, vp_b, rrule, rconst, qs = _TYPES[name]
         g = self._blank()
         g.nfine_rule, g.nfine, g.vp_a, g.vp_b, g.rho_rule, g.rho_const, g.qs = nrule, nfine, vp_a, vp_b, rrule, rconst, qs
+        g.gclass = _CLASS[name]
         # parameter order follows the parm dict order, like MCinv._brownians
         for key, val in parm.items():
             if key in ("H", "BottomDepth"):
@@ -146,7 +156,7 @@ class StackTemplate:
 
     def to_c(self):
         t = StackTemplateC()
-        t.ngroups, t.nparams, t.topo = len(self.groups), self.nparams, self.topo
+        t.ngroups, t.nparams, t.topo, t.prior_mask = len(self.groups), self.nparams, self.topo, self.prior_mask
         for i, g in enumerate(self.groups):
             t.groups[i] = g
         return t

@@ -80,9 +80,30 @@ def main():
         out["stacks"].append({"setting": s2, "refLayer": ref, "h": h.tolist(), "vs": vs.tolist(), "vp": vp.tolist(),
                               "rho": rho.tolist(), "qs": qs.tolist(), "groups": list(grp),
                               "grid_z": z.tolist(), "grid_vs": gvs.tolist()})
+    # prior checks: the reference's own CascadiaPrism.isgood (models.py:294-360) on perturbed models
+    out["priors"] = []
+    base = {"Sediment": {"H": 2.0, "Vs": [1.2, 2.0]}, "Crust": {"H": 30.0, "Vs": [3.3, 3.5, 3.7, 3.9]},
+            "Mantle": {"BottomDepth": 200.0, "Vs": [4.4, 4.3, 4.5, 4.4, 4.6]}, "Info": {"modelType": "MCInv"}}
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        s2 = json.loads(json.dumps(base))
+        s2["Sediment"]["H"] = float(rng.uniform(0.5, 4.0))
+        s2["Sediment"]["Vs"] = [float(x) for x in rng.uniform(0.9, 2.6, 2)]
+        s2["Crust"]["H"] = float(rng.uniform(18.0, 45.0))
+        s2["Crust"]["Vs"] = [float(x) for x in np.sort(rng.uniform(3.1, 4.1, 4)) + rng.normal(0, 0.08, 4)]
+        s2["Mantle"]["Vs"] = [float(x) for x in rng.uniform(4.0, 5.0, 5)]
+        s3 = json.loads(json.dumps(s2))
+        for k, parm in s3.items():
+            if k != "Info" and "Vs" in parm:
+                parm["Vs"] = fix(parm["Vs"])
+        # CascadiaPrism cannot be instantiated through buildModel1D (its _loadLocalInfo refers to an undefined
+        # name, models.py:279); its isgood only needs seisPropGrids, so it is applied to the MCinv model
+        mod = models.buildModel1D(s3)
+        out["priors"].append({"setting": s3, "isgood": bool(models.CascadiaPrism.isgood(mod))})
     with open(OUT, "w") as f:
         json.dump(out, f)
-    print("wrote", OUT, len(out["bspline"]), "bases,", len(out["stacks"]), "stacks")
+    print("wrote", OUT, len(out["bspline"]), "bases,", len(out["stacks"]), "stacks,", len(out["priors"]), "prior cases,",
+          sum(p["isgood"] for p in out["priors"]), "good")
 
 
 if __name__ == "__main__":

@@ -52,3 +52,15 @@ def test_template_parameter_order_and_bounds():
     assert c.ngroups == 4 and c.nparams == 8 and c.groups[1].v_param[1] == -1 and abs(c.groups[1].v_fixed[3] - 3.9) < 1e-12
     lay, nl = MB.build_stacks(t, t.start_values()[None, :], 96)
     assert nl[0] == 1 + 15 + 60 + 20 and abs(lay[3, 0, :nl[0]].sum() - 500.0) < 1e-3
+
+
+def test_priors_match_reference_isgood(gold):
+    """The numpy restatement of the prior rules against the reference's own CascadiaPrism.isgood, run on 60
+    perturbed models by make_golden_layers.py."""
+    n_good = 0
+    for case in gold["priors"]:
+        t = S.StackTemplate(case["setting"])
+        bad = MB.priors(t, np.zeros(0))
+        assert (bad == 0) == case["isgood"], (case["setting"], bad)
+        n_good += case["isgood"]
+    assert 0 < n_good < len(gold["priors"])
