@@ -766,21 +766,24 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
       const double dkl = dk * dlam;
       // Boole-weighted raw sums over the knots of this layer's sub-layers (weights 7,32,12,32,7; the
       // common factor dz/22.5 and the material constants are applied once per layer)
-      double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0, r8 = 0, r9 = 0, r10 = 0, r11 = 0;
+      // Raw Boole-weighted sums of products of the state components; the derivative terms of the integrands
+      // (ur' = tr/mu - k uz, uz' = (tz + k lambda ur)/(lambda + 2 mu), surfa.f:1100-1110) are linear in the state
+      // with layer-constant coefficients, so they are applied once per layer instead of once per knot.
+      double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, q6 = 0, q7 = 0, q8 = 0, q9 = 0, q10 = 0, q11 = 0;
       for (int s = 0; s < ns; ++s) {
 #pragma unroll
         for (int kk = 0; kk < 5; ++kk) {
           const double w = (kk == 0 || kk == 4) ? 7.0 : ((kk == 2) ? 12.0 : 32.0);
-          const double ydur = ytr * kc.a34 - dk * yuz, yduz = (ytz + dkl * yur) * kc.a12;
-          const double zdur = ztr * kc.a34 - dk * zuz, zduz = (ztz + dkl * zur) * kc.a12;
           const double ay = w * yur, by = w * yuz, az = w * zur, bz = w * zuz;
           r0 += ay * yur; r1 += ay * zur; r2 += az * zur;
           r3 += by * yuz; r4 += by * zuz; r5 += bz * zuz;
-          r6 += by * ydur; r7 += by * zdur + bz * ydur; r8 += bz * zdur;
-          r9 += ay * yduz; r10 += ay * zduz + az * yduz; r11 += az * zduz;
+          q6 += by * ytr; q7 += by * ztr + bz * ytr; q8 += bz * ztr;
+          q9 += ay * ytz; q10 += ay * ztz + az * ytz; q11 += az * ztz;
           if (kk < 4) { rk4_step(sm, yur, yuz, ytz, ytr); rk4_step(sm, zur, zuz, ztz, ztr); }
         }
       }
+      const double r6 = kc.a34 * q6 - dk * r3, r7 = kc.a34 * q7 - 2.0 * dk * r4, r8 = kc.a34 * q8 - dk * r5;
+      const double r9 = kc.a12 * (q9 + dkl * r0), r10 = kc.a12 * (q10 + 2.0 * dkl * r1), r11 = kc.a12 * (q11 + dkl * r2);
       {
         const double qw = (double)SD_DIV(SD_DIV(ds, 4.f), 22.5f);
         const double qr = qw * (double)rho, l2m = (double)SD_ADD(xlamb, SD_MUL(2.f, xmu));

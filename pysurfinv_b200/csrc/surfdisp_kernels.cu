@@ -437,12 +437,6 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
             c1 = SD_MUL(qq, SD_ADD(1.0f, b_corr));
             if (b0 < 0.1f) c1 = 0.5f;
           }
-          // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks
-          {
-            bool l = false;
-            for (int i = 1 + gl; i < n; i += G) l |= !(cst[C_BREF * ld + i] > 0.f);
-            mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
-          }
           mm = n;  // reference COMMON mmax carried from period to period
           nfound = 0; flag = 0; k = p.k_begin; hopped = false;
           c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 2.0e-3f;
@@ -468,6 +462,13 @@ __global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_con
       T = p.tab.per[k];
       const float lt = p.tab.lt[k];
       const float bm = refresh(p.stale ? mm : n, lt);
+      if (k == p.k_begin) {
+        // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks (all n records
+        // are in shared memory at a model's first period here)
+        bool l = false;
+        for (int i = 1 + gl; i < n; i += G) l |= !(rec[i].y > 0.f);
+        mid_liquid = (__ballot_sync(gmask, l) & gmask) != 0u;
+      }
       // smallest b below the top layer: taken at the first period, where all layers are refreshed (mm = n); the
       // attenuation correction moves b by < 1 % over the period range, which the margin covers
       if (k == 0) bmin = bm - 0.05f;
