@@ -217,6 +217,22 @@ def main():
     nfound_ok = int((out["nfound"] == K).sum().item())
     steps_ctr, sweeps_ctr, subu_ctr, models_ctr = solver.counters()
 
+    # ---- the same sweep for Love waves (kind = 1; the headline stays the Rayleigh configuration of BASELINE.json)
+    out_l = solver.forward(d_lay, d_nl, per, kind=1)
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(args.steps):
+        solver.forward(d_lay, d_nl, per, kind=1, out=out_l)
+    l1.record()
+    barrier()
+    tl = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    love = {"value": world * M * K * args.steps / (float(tl.item()) * 1e-3), "unit": UNIT,
+            "ms_per_step": float(tl.item()) / args.steps, "roots_found_frac": int((out_l["nfound"] == K).sum().item()) / M}
+    del out_l
+
     # ---- per-kernel durations (CUDA events inside the library, same workload) for the roofline
     kms = []
     for _ in range(max(1, args.steps)):
@@ -280,7 +296,8 @@ def main():
                            "l2_policy": "inputs (%.2f GB layers + %.2f GB workspace per step) exceed the 126 MB L2"
                                         % (lay.nbytes / 1e9, solver._ws.numel() / 1e9),
                            "roots_found_frac": nfound_ok / M},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "love": love}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -2,7 +2,7 @@
 //
 // Everything here is written from the physics/algorithm of the reference hot path
 // (fast_surf_src/{flat1,calcul,surfa}.f of 001cat/pySurfInv; line numbers cited per function), laid
-// out for one GPU lane evaluating one trial phase velocity (or one period) against a layer stack
+// out for one GPU lane evaluating a pair of trial phase velocities (or one period) against a layer stack
 // staged in shared memory.  The functions are __host__ __device__ so that tests/hostmirror can compile
 // the same source with g++ and check the math against the CPU oracle without a GPU; the product only
 // ever runs the __device__ instantiation (see surfdisp_kernels.cu).

@@ -1,13 +1,16 @@
 // surfdisp_kernels.cu -- sm_100a kernels + C ABI of the batched dispersion forward solver.
 //
 // Data flow of one surfdisp_batch() call (all on one stream):
-//   prep_kernel    thread per model     layers[5][M][Lmax] -> consts[M][8][lpad]   (flat1.f, once per model)
-//   phase1_kernel  G lanes per model    periods sequential (calcul.f:104-220): refresh layer records in
-//                                       shared memory, scan trial velocities G at a time with a ballot
-//                                       for the first sign change, G-section polish, ellipticity
-//                                       -> c[M][K], ratio[M][K], nfound[M]
-//   phase2_kernel  thread per (model, period)   energy integrals -> U[M][K]  (calcul.f:224-404,
+//   prep_kernel    warp per model, lanes over layers   layers[5][M][Lmax] -> consts[M][8][lpad]  (flat1.f, once per model)
+//   phase1_kernel  4 lanes x 2 packed trial velocities per model, 8 models per warp; every group is a state
+//                  machine and one loop iteration = one sweep of the secular function for every group.
+//                  Launch 1: first period (the reference's scan, calcul.f:155-167).  Launch 2: later periods
+//                  (cluster of trial velocities around the extrapolated root, inverse interpolation, scan as
+//                  fall-back)                           -> c[M][K], ratio[M][K], nfound[M], flags[M]
+//   phase2_kernel  thread per (model, period)          energy integrals -> U[M][K]  (calcul.f:224-404,
 //                                       REIGEN surfa.f:714-1190 in FP64 / LEIGEN surfa.f:374-606 in FP32)
+//   build_stacks / check_priors / mc_propose / mc_accept / misfit kernels: the callers on either side of the
+//   solver (model assembly, Monte-Carlo step), thread or warp per model.
 // No tensor cores: the work is a serial chain of tiny structured propagator products with
 // data-dependent branches.
 #include <cuda_runtime.h>
