@@ -238,6 +238,9 @@ __device__ __noinline__ bool nevill_out_of_line(const SecFn& f, float c1, float 
 #ifndef P1_MINBLK
 #define P1_MINBLK 4
 #endif
+#ifndef P1_THREADS
+#define P1_THREADS 128
+#endif
 
 // Stages of a group's (= one model's) state machine.  Every iteration of the kernel's main loop performs ONE
 // sweep of the secular function for every group of the warp, whatever stage each group is in: the groups
@@ -249,7 +252,7 @@ enum { ST_FETCH = 0, ST_PERIOD, ST_FAST, ST_REFINE, ST_SCAN, ST_POLISH, ST_ELL, 
 enum { NB_NONE = 0, NB_FAST, NB_REFINE, NB_SCAN, NB_POLISH, NB_ELL };
 
 template <int G>
-__global__ void __launch_bounds__(128, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
+__global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
   static_assert(G == 4 || G == 8, "4 or 8 lanes x 2 trial velocities per model");
   constexpr int P = 2 * G;   // trial velocities per round; point i lives in lane i/2, component i%2
   extern __shared__ float4 smem[];
@@ -1157,7 +1160,7 @@ int launch_phase1(const P1Params& p, cudaStream_t st) {
   q.mstride = p.lpad + 1;  // +1 float4: consecutive groups start 16 B apart mod 128 B (bank spread)
   // 128-thread CTAs (128/G models) for ordinary stacks; deep stacks (up to 1000 layers, 16 KB of layer records
   // per model) shrink the CTA until the records of its models fit in shared memory
-  int threads = 128;
+  int threads = P1_THREADS;
   while (threads > 32 && (size_t)(threads / G) * (q.mstride + 2 * G + 2) * sizeof(float4) > 100 * 1024) threads /= 2;
   const int groups = threads / G;
   size_t smem = (size_t)groups * (q.mstride + 2 * G + 2) * sizeof(float4);   // layer records + sample slots
