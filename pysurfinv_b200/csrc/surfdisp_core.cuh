@@ -468,7 +468,7 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
 // Love secular function for a pair of trial velocities: (displacement, stress) propagated from the half-space
 // up (surfa.f:143-182).  With q = -k d rb (surfa.f:156): y = sin(q)/rb = -sinr, z = rb sin(q) = -rsin (both
 // branches and the rb -> 0 limit of surfa.f:164-166), cos(q) = cs.
-SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec) {
+SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec, V2& ut_out) {
   const V2 csq = vmul(c, c);
   const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
   const V2 ncsq = vneg(csq);
@@ -494,6 +494,7 @@ SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec) {
     ut = eut;
     tt = ett;
   }
+  ut_out = ut;   // surface displacement: has the scale of -tt (used to normalise it)
   return vneg(tt);
 }
 

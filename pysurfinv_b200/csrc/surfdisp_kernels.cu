@@ -158,7 +158,7 @@ __device__ __noinline__ Sec2 secular2(int kind, float2 c, float T, int mm, const
   Sec2 r;
   r.e2 = make_float2(0.f, 0.f); r.e3 = r.e2;
   if (kind == 2) r.d = rayleigh_adjoint2(c, T, mm, rec, ell_only != 0, r.e2, r.e3);
-  else r.d = love_sweep2(c, T, mm, rec);
+  else r.d = love_sweep2(c, T, mm, rec, r.e2);
   return r;
 }
 
@@ -301,8 +301,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   bool has_ends = false;
   SamplePt E0 = {0.f, 0.f, 0.f, 0.f}, E1 = E0;
   // ---- point-by-point path (scan, polish)
-  float cbase = 0.f, cP = 0.f, dP = 0.f, lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, lo0 = 0.f, hi0 = 0.f, dlo0 = 0.f, dhi0 = 0.f;
-  int mjx = 2, mjy = 2, round = 0, pit = 0;
+  float cbase = 0.f, cP = 0.f, dP = 0.f, tP = 0.f, cP2 = 0.f, dP2 = 0.f, tP2 = 0.f, lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, lo0 = 0.f, hi0 = 0.f, dlo0 = 0.f, dhi0 = 0.f;
+  int mjx = 2, mjy = 2, round = 0, pit = 0, stride = 1;
   bool have_prev = false, own_mj = false;
   float bmin = 0.f;   // smallest b below the top layer (this period's records)
   // ---- result of the period
@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     // sign, see below).  The own truncation of a point matters for the stop test c >= b(mmax) + 0.3
     // (calcul.f:166), which cannot fire while c < min b + 0.3: only then is it computed per point.
     float cx = cbase;
-    for (int t = 0; t < 2 * gl; ++t) cx = SD_ADD(cx, p.dc);
-    pc = make_float2(cx, SD_ADD(cx, p.dc));
+    for (int t = 0; t < 2 * gl * stride; ++t) cx = SD_ADD(cx, p.dc);
+    float cy = cx;
+    for (int t = 0; t < stride; ++t) cy = SD_ADD(cy, p.dc);
+    pc = make_float2(cx, cy);
     const float ctop = gshfl<G>(gmask, pc.y, G - 1);
     meval = layer_drop_coop<G>(ctop, T, p.fact, n, rec, gmask, gl);
     own_mj = !(ctop < bmin + 0.3f);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     ell_only = 0;
   };
   auto start_scan = [&]() {
-    cbase = c1; cP = 0.f; dP = 0.f; have_prev = false; round = 0;
+    cbase = c1; cP = 0.f; dP = 0.f; have_prev = false; round = 0; stride = 1;
     stage = ST_SCAN; need = NB_SCAN;
   };
   auto build_polish = [&]() {
@@ -591,37 +593,95 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       else if (signbit(dlast) != signbit(E1.d)) { jb = P + 1; it++; do_interp = true; }
       else start_scan();
     } else if (stage == ST_SCAN) {
-      // ---- point-by-point scan (calcul.f:155-167): first sign change or stop condition in sequence order
+      // ---- scan for the first sign change on the grid c1 + i dc (calcul.f:155-167).  The reference examines
+      // every grid point.  Here only the first round does; after it every 4th grid point is evaluated (stride 4)
+      // and the skipped ones are examined only where they can matter: around a sign change between two coarse
+      // points, and around a coarse point where log|Delta| has a kink -- two roots hidden between two coarse
+      // points multiply the smooth background by (c - r1)(c - r2), whose second difference in log2 at one of the
+      // two neighbouring coarse points is >= 3, while the background's is ~0.01 (Delta is normalised by the other
+      // minors of the same sweep, which removes the scale that changes with the truncation depth).  The fine rounds
+      // follow the reference exactly, so the bracket found is the reference's.  exact_scan keeps stride 1.
+      constexpr int S = 4;
+      constexpr float kKinkThr = 1.0f;
+      // left neighbours in sequence order of the two points of this lane
       float dpx = __shfl_up_sync(gmask, pd.y, 1, G), cpx = __shfl_up_sync(gmask, pc.y, 1, G);
       if (gl == 0) { dpx = dP; cpx = cP; }
       const bool haspx = (gl > 0) || have_prev;
+      const bool nanx = !(pc.x == pc.x) || !(pd.x == pd.x), nany = !(pc.y == pc.y) || !(pd.y == pd.y);
+      const bool stopx = (pc.x < 0.8f * b_top) || (own_mj && !(pc.x < rec[mjx - 1].y + 0.3f)) || nanx;
+      const bool stopy = (pc.y < 0.8f * b_top) || (own_mj && !(pc.y < rec[mjy - 1].y + 0.3f)) || nany;
       const bool chx = haspx && (signbit(dpx) != signbit(pd.x));
-      const bool stx = haspx && !chx && ((pc.x < 0.8f * b_top) || (own_mj && !(pc.x < rec[mjx - 1].y + 0.3f)) || !(pc.x == pc.x));
       const bool chy = (signbit(pd.x) != signbit(pd.y));
-      const bool sty = !chy && ((pc.y < 0.8f * b_top) || (own_mj && !(pc.y < rec[mjy - 1].y + 0.3f)) || !(pc.y == pc.y));
-      const unsigned ev = pair_mask(chx || stx, chy || sty);
-      if (!ev) {
-        cP = gshfl<G>(gmask, pc.y, G - 1);
-        dP = gshfl<G>(gmask, pd.y, G - 1);
-        have_prev = true;
-        cbase = SD_ADD(cP, p.dc);
-        if (++round >= 2048) { flag |= SURFDISP_F_SCAN_LIMIT; flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K; model_done = true; }
-        else need = NB_SCAN;
-      } else {
-        const int j = __ffs(ev) - 1, sl = j >> 1;
-        const bool jy = (j & 1) != 0;
-        const bool found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
-        lo = gshfl<G>(gmask, jy ? pc.x : cpx, sl); hi = gshfl<G>(gmask, jy ? pc.y : pc.x, sl);
-        dlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
-        mm = layer_drop_coop<G>(hi, T, p.fact, n, rec, gmask, gl);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
-        if (found) {
-          // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
-          // (P+1)-section until the bracket is <= 2e-5, then one secant step
-          lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0;
-          stage = ST_POLISH; need = NB_POLISH;
+      if (stride == 1) {
+        const bool stx = haspx && !chx && stopx;
+        const bool sty = !chy && stopy;
+        const unsigned ev = pair_mask(chx || stx, chy || sty);
+        if (!ev) {
+          // nothing in this fine round: go on with coarse rounds, whose left neighbours (at coarse spacing) are the
+          // last point of this round and the point S before it
+          constexpr int i2 = P - 1 - S;
+          cP2 = gshfl<G>(gmask, (i2 & 1) ? pc.y : pc.x, i2 >> 1);
+          dP2 = gshfl<G>(gmask, (i2 & 1) ? pd.y : pd.x, i2 >> 1);
+          tP2 = __log2f(fabsf(dP2) / (fabsf(gshfl<G>(gmask, (i2 & 1) ? pe2.y : pe2.x, i2 >> 1)) + fabsf(gshfl<G>(gmask, (i2 & 1) ? pe3.y : pe3.x, i2 >> 1))));
+          cP = gshfl<G>(gmask, pc.y, G - 1);
+          dP = gshfl<G>(gmask, pd.y, G - 1);
+          tP = __log2f(fabsf(dP) / (fabsf(gshfl<G>(gmask, pe2.y, G - 1)) + fabsf(gshfl<G>(gmask, pe3.y, G - 1))));
+          have_prev = true;
+          if (p.exact_scan) cbase = SD_ADD(cP, p.dc);
+          else {
+            stride = S;
+            cbase = cP;
+            for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, p.dc);
+          }
+          if (++round >= 2048) { flag |= SURFDISP_F_SCAN_LIMIT; flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K; model_done = true; }
+          else need = NB_SCAN;
         } else {
-          flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
-          model_done = true;
+          const int j = __ffs(ev) - 1, sl = j >> 1;
+          const bool jy = (j & 1) != 0;
+          const bool found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
+          lo = gshfl<G>(gmask, jy ? pc.x : cpx, sl); hi = gshfl<G>(gmask, jy ? pc.y : pc.x, sl);
+          dlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
+          mm = layer_drop_coop<G>(hi, T, p.fact, n, rec, gmask, gl);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
+          if (found) {
+            // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
+            // (P+1)-section until the bracket is <= 2e-5, then one secant step
+            lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0;
+            stage = ST_POLISH; need = NB_POLISH;
+          } else {
+            flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
+            model_done = true;
+          }
+        }
+      } else {
+        // coarse round: t = log2 of the normalised |Delta| of every point, second differences along the sequence
+        const float tx = __log2f(fabsf(pd.x) / (fabsf(pe2.x) + fabsf(pe3.x))), ty = __log2f(fabsf(pd.y) / (fabsf(pe2.y) + fabsf(pe3.y)));
+        float tpy = __shfl_up_sync(gmask, ty, 1, G), tpx = __shfl_up_sync(gmask, tx, 1, G);   // t of points 2g-1 and 2g-2
+        float cp2 = __shfl_up_sync(gmask, pc.x, 1, G), dp2 = __shfl_up_sync(gmask, pd.x, 1, G); // point 2g-2
+        if (gl == 0) { tpy = tP; tpx = tP2; cp2 = cP2; dp2 = dP2; }
+        const float qx = tpx - 2.f * tpy + tx;      // kink at point 2g-1 seen from point 2g
+        const float qy = tpy - 2.f * tx + ty;       // kink at point 2g seen from point 2g+1
+        const bool evx = chx || !(fabsf(qx) <= kKinkThr) || stopx;
+        const bool evy = chy || !(fabsf(qy) <= kKinkThr) || stopy;
+        const unsigned ev = pair_mask(evx, evy);
+        if (!ev) {
+          cP2 = gshfl<G>(gmask, pc.x, G - 1); dP2 = gshfl<G>(gmask, pd.x, G - 1); tP2 = gshfl<G>(gmask, tx, G - 1);
+          cP = gshfl<G>(gmask, pc.y, G - 1); dP = gshfl<G>(gmask, pd.y, G - 1); tP = gshfl<G>(gmask, ty, G - 1);
+          cbase = cP;
+          for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, p.dc);
+          if (++round >= 2048) { flag |= SURFDISP_F_SCAN_LIMIT; flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K; model_done = true; }
+          else need = NB_SCAN;
+        } else {
+          // examine the 2 S grid points of the two coarse intervals before the event point like the reference does:
+          // the point two before the event becomes the "previous point" of a fine round
+          const int j = __ffs(ev) - 1, sl = j >> 1;
+          const bool jy = (j & 1) != 0;
+          cP = gshfl<G>(gmask, jy ? cpx : cp2, sl);    // point j-2: for an odd j that is point 2g-1, else point 2g-2
+          dP = gshfl<G>(gmask, jy ? dpx : dp2, sl);
+          have_prev = true;
+          stride = 1;
+          cbase = SD_ADD(cP, p.dc);
+          if (++round >= 2048) { flag |= SURFDISP_F_SCAN_LIMIT; flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K; model_done = true; }
+          else need = NB_SCAN;
         }
       }
     } else if (stage == ST_POLISH) {

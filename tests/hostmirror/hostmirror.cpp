@@ -28,7 +28,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
                const float* qs, int K, const float* per, float dc, float fact, float t_base, int atten,
                int flatten, int stale, int ndiv0, int ndiv_cap, float* c_out, float* u_out, float* ratio_out,
                long long* sweeps, int exact, long long* rounds_out) {
-  long long nrounds = 0, nwin = 0, nwin_ok = 0, ndirect = 0, nslow = 0;
+  long long nrounds = 0, nwin = 0, nwin_ok = 0, ndirect = 0, nslow = 0, ncoarse_ev = 0;
   const int P = 2 * G;
   const int ld = n;
   std::vector<float> cst((size_t)NCONST * ld);
@@ -59,7 +59,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     nsw += 2;
     V2 c = v2(ca, cb), e2 = v2(0.f, 0.f), e3 = v2(0.f, 0.f), dd;
     if (kind == 2) dd = rayleigh_adjoint2(c, T, m, rec.data(), ell_only, e2, e3);
-    else dd = love_sweep2(c, T, m, rec.data());
+    else dd = love_sweep2(c, T, m, rec.data(), e2);
     A = {ca, dd.x, e2.x, e3.x}; B = {cb, dd.y, e2.y, e3.y};
   };
   auto sweep_all = [&](std::vector<Pt>& pt, float T, int m) {
@@ -223,31 +223,75 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       float lo = 0, hi = 0, dlo = 0, dhi = 0;
       int mnew = mm;
       {
-        float cbase = c1, cP = 0, dP = 0;
+        // The reference examines every grid point c1 + i dc (calcul.f:155-167).  Here only the first round does;
+        // after it every 4th grid point is evaluated (stride S = 4) and the skipped ones are examined only where
+        // they can matter: around a sign change between two coarse points, and around a coarse point where
+        // log|Delta| has a kink -- two roots hidden between two coarse points multiply the smooth background by
+        // (c - r1)(c - r2), whose second difference in log2 at the two neighbouring coarse points is >= 3, the
+        // background's is ~0.1.  The fine rounds follow the reference exactly, so the bracket found is the
+        // reference's.
+        const int S = 4;
+        const float QTHR = 1.0f;
+        float cbase = c1;
+        Pt P1 = {0, 0, 0, 0}, P2 = {0, 0, 0, 0};      // the two coarse points before point 0 of the round
         bool have_prev = false, done = false;
+        int stride = 1;
         std::vector<Pt> pt(P);
         std::vector<int> mj(P);
         for (int round = 0; round < 2048 && !done; ++round) {
           nrounds++;
           for (int pi = 0; pi < P; ++pi) {
             float c = cbase;
-            for (int t = 0; t < pi; ++t) c = SD_ADD(c, dc);
+            for (int t = 0; t < pi * stride; ++t) c = SD_ADD(c, dc);
             pt[pi].c = c; mj[pi] = layer_drop(c, T, fact, n, rec.data());
           }
           for (int pi = 0; pi < P; pi += 2) sweep2(pt[pi].c, pt[pi + 1].c, T, std::max(mj[pi], mj[pi + 1]), false, pt[pi], pt[pi + 1]);
-          int jev = -1; bool chg = false;
-          for (int pi = 0; pi < P; ++pi) {
-            const bool hasp = (pi > 0) || have_prev;
-            const float dp = pi ? pt[pi - 1].d : dP;
-            const float c = pt[pi].c;
-            const bool change = hasp && (std::signbit(dp) != std::signbit(pt[pi].d));
-            const bool stop = hasp && !change && ((c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c));
-            if (change || stop) { jev = pi; chg = change; break; }
+          auto stopc = [&](int pi) { const float c = pt[pi].c; return (c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c); };
+          if (stride == 1) {
+            int jev = -1; bool chg = false;
+            for (int pi = 0; pi < P; ++pi) {
+              const bool hasp = (pi > 0) || have_prev;
+              const float dp = pi ? pt[pi - 1].d : P1.d;
+              const bool change = hasp && (std::signbit(dp) != std::signbit(pt[pi].d));
+              const bool stop = hasp && !change && stopc(pi);
+              if (change || stop) { jev = pi; chg = change; break; }
+            }
+            if (jev < 0) {
+              // nothing in this fine round: go on with coarse rounds; left neighbours at coarse spacing
+              P1 = pt[P - 1]; P2 = pt[P - 1 - S]; mnew = mj[P - 1]; have_prev = true;
+              stride = S; cbase = P1.c;
+              for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, dc);
+              continue;
+            }
+            found = chg;
+            lo = jev ? pt[jev - 1].c : P1.c; hi = pt[jev].c; dlo = jev ? pt[jev - 1].d : P1.d; dhi = pt[jev].d; mnew = mj[jev];
+            done = true;
+          } else {
+            int jev = -1;
+            for (int pi = 0; pi < P && jev < 0; ++pi) {
+              const Pt& L1 = pi ? pt[pi - 1] : P1;
+              const Pt& L2 = (pi >= 2) ? pt[pi - 2] : ((pi == 1) ? P1 : P2);
+              const bool change = std::signbit(L1.d) != std::signbit(pt[pi].d);
+              // Delta normalised by the other minors of the same sweep: free of the scale that changes with the
+              // truncation depth
+              auto lg = [](const Pt& p_) { return log2f(fabsf(p_.d) / (fabsf(p_.e2) + fabsf(p_.e3))); };
+              const float q = lg(L2) - 2.f * lg(L1) + lg(pt[pi]);
+              const bool kinked = !(fabsf(q) <= QTHR);
+              if (getenv("HM_Q")) fprintf(stderr, "q k=%d c=%.3f q=%.3f change=%d d=%g\n", k, pt[pi].c, q, (int)change, pt[pi].d);
+              if (change || kinked || stopc(pi)) jev = pi;
+            }
+            if (jev < 0) {
+              P2 = pt[P - 2]; P1 = pt[P - 1]; mnew = mj[P - 1];
+              cbase = P1.c;
+              for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, dc);
+              continue;
+            }
+            // examine the 2 S grid points of the two coarse intervals before the event point like the reference does
+            const Pt L2 = (jev >= 2) ? pt[jev - 2] : ((jev == 1) ? P1 : P2);
+            P1 = L2; have_prev = true;
+            stride = 1; cbase = SD_ADD(L2.c, dc);
+            ncoarse_ev++;
           }
-          if (jev < 0) { cP = pt[P - 1].c; dP = pt[P - 1].d; mnew = mj[P - 1]; have_prev = true; cbase = SD_ADD(cP, dc); continue; }
-          found = chg;
-          lo = jev ? pt[jev - 1].c : cP; hi = pt[jev].c; dlo = jev ? pt[jev - 1].d : dP; dhi = pt[jev].d; mnew = mj[jev];
-          done = true;
         }
       }
       mm = mnew;
@@ -311,7 +355,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
                            : leigen_thread(mv, per[k], c_out[k], fact, ns);
   }
   if (sweeps) *sweeps += nsw;
-  if (rounds_out) { rounds_out[0] += nrounds; rounds_out[1] += nslow; rounds_out[2] += nwin; rounds_out[3] += nwin_ok; rounds_out[4] += ndirect; }
+  if (rounds_out) { rounds_out[0] += nrounds; rounds_out[1] += nslow; rounds_out[2] += nwin; rounds_out[3] += nwin_ok; rounds_out[4] += ndirect; rounds_out[5] += ncoarse_ev; }
   return nfound;
 }
 

@@ -34,9 +34,9 @@ def forward(kind, vp, vs, rho, h, qsinv, periods, G=4, stale=1, ndiv=5, ndiv_cap
     c = np.zeros(K, np.float32); u = np.zeros(K, np.float32); rt = np.zeros(K, np.float32)
     p = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
     sw = C.c_longlong(0)
-    rounds = (C.c_longlong * 5)(0, 0, 0, 0, 0)
+    rounds = (C.c_longlong * 6)(0, 0, 0, 0, 0, 0)
     if ndiv_cap is None:
         ndiv_cap = 99 if kind == 2 else 999
     nf = lib().hm_forward(G, kind, len(b), p(a), p(b), p(r), p(d), p(q), K, p(per), 0.01, 4.0, 1.0, 1, 1, stale,
                           ndiv, ndiv_cap, p(c), p(u), p(rt), C.byref(sw), exact_scan, rounds)
-    return dict(c=c, u=u, ratio=rt, nfound=nf, sweeps=sw.value, rounds=rounds[0], slow_periods=rounds[1], windows=rounds[2], windows_ok=rounds[3], direct=rounds[4])
+    return dict(c=c, u=u, ratio=rt, nfound=nf, sweeps=sw.value, rounds=rounds[0], slow_periods=rounds[1], windows=rounds[2], windows_ok=rounds[3], direct=rounds[4], coarse_events=rounds[5])
