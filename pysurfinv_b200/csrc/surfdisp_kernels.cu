@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   float cbase = 0.f, cP = 0.f, dP = 0.f, tP = 0.f, cP2 = 0.f, dP2 = 0.f, tP2 = 0.f, lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, lo0 = 0.f, hi0 = 0.f, dlo0 = 0.f, dhi0 = 0.f;
   int mjx = 2, mjy = 2, round = 0, pit = 0, stride = 1;
   bool have_prev = false, own_mj = false;
+  bool from_scan = false;   // the interpolation rounds refine a bracket found by the scan (fall-back: uniform-section polish)
   float bmin = 0.f;   // smallest b below the top layer (this period's records)
   // ---- result of the period
   float croot = 0.f, ratio = 0.f;
@@ -354,6 +355,12 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   auto start_scan = [&]() {
     cbase = c1; cP = 0.f; dP = 0.f; have_prev = false; round = 0; stride = 1;
     stage = ST_SCAN; need = NB_SCAN;
+  };
+  // the interpolation rounds gave up: the cluster / window rounds restart as a scan; a bracket that came from
+  // the scan is polished by uniform section instead (mmax is pinned already)
+  auto interp_failed = [&]() {
+    if (from_scan) { from_scan = false; lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0; stage = ST_POLISH; need = NB_POLISH; }
+    else start_scan();
   };
   auto build_polish = [&]() {
     const float st = (hi - lo) / (float)(P + 1);
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
         // around it; 2: window of P grid points moved up or down
         fstage = (k >= 2 && j0 >= 4) ? 0 : 1;
-        w0 = 2; dir = 0; wtry = 0;
+        w0 = 2; dir = 0; wtry = 0; from_scan = false;
         stage = ST_FAST; need = NB_FAST;
       } else start_scan();
     }
@@ -591,7 +598,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       has_ends = true;
       if (ev) { jb = __ffs(ev); it++; do_interp = true; }                                   // point i is list entry i + 1
       else if (signbit(dlast) != signbit(E1.d)) { jb = P + 1; it++; do_interp = true; }
-      else start_scan();
+      else interp_failed();
     } else if (stage == ST_SCAN) {
       // ---- scan for the first sign change on the grid c1 + i dc (calcul.f:155-167).  The reference examines
       // every grid point.  Here only the first round does; after it every 4th grid point is evaluated (stride 4)
@@ -643,10 +650,23 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           dlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
           mm = layer_drop_coop<G>(hi, T, p.fact, n, rec, gmask, gl);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
           if (found) {
-            // ---- polish inside [lo,hi] with mmax pinned, replaces NEVILL (surfa.f:2-83): uniform
-            // (P+1)-section until the bracket is <= 2e-5, then one secant step
-            lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0;
-            stage = ST_POLISH; need = NB_POLISH;
+            // ---- polish inside [lo,hi] (replaces NEVILL, surfa.f:2-83).  The round's points sample one smooth
+            // function around the bracket (same truncation depth), so the interpolation rounds of the fast path
+            // take over: one more round instead of three of uniform section plus the ellipticity sweep.  With
+            // the half-space velocity (kink, possibly several roots in the bracket) nearby, or in exact_scan
+            // mode: uniform (P+1)-section with mmax pinned until the bracket is <= 2e-5, then one
+            // secant step.
+            bool handed = false;
+            if (!p.exact_scan && j >= 1) {
+              const float bh2 = rec[meval - 1].y;
+              nvalid = __popc(pair_mask(pc.x < bh2, pc.y < bh2));
+              const bool kink = (bh2 > lo - 0.011f && bh2 < hi + 0.011f) || nvalid < 6 || j > nvalid - 1;
+              if (!kink) { w0 = 0; has_ends = false; jb = j; it = 0; fstage = 1; mw = meval; from_scan = true; do_interp = true; handed = true; }
+            }
+            if (!handed) {
+              lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0;
+              stage = ST_POLISH; need = NB_POLISH;
+            }
           } else {
             flag |= (k == 0) ? SURFDISP_F_NO_ROOT_FIRST : SURFDISP_F_NO_ROOT_AT_K;
             model_done = true;
@@ -766,12 +786,12 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         if (!(hg > croot)) hg += p.dc;
         const int mnew = layer_drop_coop<G>(hg, T, p.fact, n, rec, gmask, gl);
         const float bh1 = rec[mnew - 1].y;
-        if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) start_scan();   // calcul.f:191 / kink: point-by-point path
+        if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) interp_failed();   // calcul.f:191 / kink: point-by-point path
         else {
           mm = mnew;
           if (p.kind == 2 && mid_liquid) { stage = ST_ELL; need = NB_ELL; } else period_done = true;
         }
-      } else if (it >= 3) start_scan();
+      } else if (it >= 3) interp_failed();
       else {
         // one more round: P points around the estimate, spaced by the disagreement of the two orders
         const float span = (float)(1 << (P / 2 - 1));   // outermost offset of the round, in units of s0

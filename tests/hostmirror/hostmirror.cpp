@@ -80,6 +80,78 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     const float b_top = rec[0].y;
     float croot = 0.f, ratio = 0.f;
     bool found = false, lstop = false, have_ratio = false, fast_done = false;
+    // Interpolation rounds shared by the fast path and by the scan: pt = ordered samples of one smooth function
+    // (same truncation depth mw), list = pt[w0 ..], bracket between list entries jb-1 and jb.  Sets croot / ratio.
+    auto interp_rounds = [&](std::vector<Pt>& pt, int w0, int jb, int nvalid, int mw, bool cluster_stage) -> bool {
+      bool has_ends = false;
+      Pt E0 = {0, 0, 0, 0}, E1 = {0, 0, 0, 0};
+      auto sample = [&](int i) {
+        const int pi = std::min(std::max(has_ends ? i - 1 : i + w0, 0), P - 1);
+        Pt sp = pt[pi];
+        if (has_ends && i == 0) sp = E0;
+        if (has_ends && i == P + 1) sp = E1;
+        return sp;
+      };
+      for (int it = 0; it < 4; ++it) {
+        const int np = has_ends ? P + 2 : nvalid;
+        const int s6 = std::min(std::max(jb - 3, 0), np - 6), s4 = std::min(std::max(jb - 2, 0), np - 4);
+        const Pt B0 = sample(jb - 1), B1 = sample(jb);
+        float x[6], y[6];
+        for (int i = 0; i < 6; ++i) { const Pt sp = sample(s6 + i); x[i] = sp.c - B0.c; y[i] = sp.d; }
+        float e4, e6;
+        inv_interp6(x, y, s4 - s6, e4, e6);
+        const float w = B1.c - B0.c;
+        const bool inside = (e6 > 0.f && e6 < w);
+        const float delta = fabsf(e6 - e4);
+        float e = e6;
+        if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
+        const bool interior = (jb >= 2 && jb <= np - 2);
+        const float tol = (it > 0) ? kInterpTol : ((cluster_stage && w <= 3.0e-3f) ? kClusterTol : -1.f);
+        if ((inside && interior && delta <= tol) || w <= kBracketTol) {
+          croot = B0.c + e;
+          if (getenv("HM_DEBUG2")) fprintf(stderr, "acc k=%d it=%d w=%g delta=%g e4=%g e6=%g inside=%d c=%.7f s6=%d jb=%d np=%d\n", k, it, w, delta, e4, e6, (int)inside, croot, s6, jb, np);
+          if (kind == 2) {
+            float xs[4], f2[4], f3[4], wl[4];
+            for (int i = 0; i < 4; ++i) { const Pt sp = sample(s4 + i); xs[i] = sp.c - B0.c; f2[i] = sp.e2; f3[i] = sp.e3; }
+            lagrange4(xs, e, wl);
+            const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
+            const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
+            ratio = 0.5f * se3 / se2;
+          }
+          ndirect += (it == 0);
+          return true;
+        }
+        if (it == 3) return false;
+        const float span = (float)(1 << (P / 2 - 1));
+        const float s0 = fmaxf(inside ? 0.5f * delta : w / (2.f * span), 1.0e-5f);
+        const bool uni = !(e - span * s0 > 0.f && e + span * s0 < w);
+        E0 = B0; E1 = B1;
+        nrounds++;
+        for (int pi = 0; pi < P; ++pi)
+          pt[pi].c = B0.c + (uni ? (float)(pi + 1) * (w / (float)(P + 1)) : e + geometric_offset(pi, P) * s0);
+        sweep_all(pt, T, mw);
+        has_ends = true;
+        unsigned ev = 0;
+        for (int pi = 0; pi < P; ++pi) {
+          const float dp = pi ? pt[pi - 1].d : E0.d;
+          if (std::signbit(dp) != std::signbit(pt[pi].d)) ev |= 1u << pi;
+        }
+        if (ev) jb = __builtin_ctz(ev) + 1;
+        else if (std::signbit(pt[P - 1].d) != std::signbit(E1.d)) jb = P + 1;
+        else return false;
+      }
+      return false;
+    };
+    // the reference's bracket is the grid interval around the root; its upper end fixes mmax
+    auto settle_mmax = [&]() -> bool {
+      float hg = c1 + (floorf((croot - c1) / dc) + 1.f) * dc;
+      if (!(hg > croot)) hg += dc;
+      const int mnew = layer_drop(hg, T, fact, n, rec.data());
+      const float bh1 = rec[mnew - 1].y;
+      if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) return false;
+      mm = mnew;
+      return true;
+    };
 
     // ---- fast path: cluster / window of trial velocities around the extrapolated root, inverse interpolation
     float c_pred = c_prev;
@@ -137,80 +209,17 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         }
         if (!win_ok && getenv("HM_DEBUG")) fprintf(stderr, "winmiss k=%d T=%g jev=%d dir=%d c_pred=%g c1=%g\n", k, T, jev, dir, c_pred, c1);
         if (win_ok) {
-          bool has_ends = false;
-          Pt E0 = {0, 0, 0, 0}, E1 = {0, 0, 0, 0};
-          auto sample = [&](int i) {
-            const int pi = std::min(std::max(has_ends ? i - 1 : i + w0, 0), P - 1);
-            Pt s = pt[pi];
-            if (has_ends && i == 0) s = E0;
-            if (has_ends && i == P + 1) s = E1;
-            return s;
-          };
           const float bh2 = rec[mw - 1].y;
-          int jb = jev - w0;
-          const float br_lo = sample(jb - 1).c, br_hi = sample(jb).c;
+          const int jb = jev - w0;
+          const float br_lo = pt[jev - 1].c, br_hi = pt[jev].c;
           int nvalid = 0;
           for (int pi = w0; pi < P; ++pi) nvalid += (pt[pi].c < bh2);
           const bool kink = (bh2 > br_lo - 0.011f && bh2 < br_hi + 0.011f) || nvalid < 6 || jb > nvalid - 1;
           if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh2, br_lo, br_hi, nvalid);
           if (!kink) {
             nwin_ok++;
-            for (int it = 0; it < 4; ++it) {
-              const int np = has_ends ? P + 2 : nvalid;
-              const int s6 = std::min(std::max(jb - 3, 0), np - 6), s4 = std::min(std::max(jb - 2, 0), np - 4);
-              const Pt B0 = sample(jb - 1), B1 = sample(jb);
-              float x[6], y[6];
-              for (int i = 0; i < 6; ++i) { const Pt s = sample(s6 + i); x[i] = s.c - B0.c; y[i] = s.d; }
-              float e4, e6;
-              inv_interp6(x, y, s4 - s6, e4, e6);
-              const float w = B1.c - B0.c;
-              const bool inside = (e6 > 0.f && e6 < w);
-              const float delta = fabsf(e6 - e4);
-              float e = e6;
-              if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
-              const bool interior = (jb >= 2 && jb <= np - 2);
-              const float tol = (it > 0) ? kInterpTol : ((stage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
-              if ((inside && interior && delta <= tol) || w <= kBracketTol) {
-                croot = B0.c + e;
-                if (getenv("HM_DEBUG2")) fprintf(stderr, "acc k=%d it=%d w=%g delta=%g e4=%g e6=%g inside=%d c=%.7f s6=%d jb=%d np=%d\n", k, it, w, delta, e4, e6, (int)inside, croot, s6, jb, np);
-                if (kind == 2) {
-                  float xs[4], f2[4], f3[4], wl[4];
-                  for (int i = 0; i < 4; ++i) { const Pt s = sample(s4 + i); xs[i] = s.c - B0.c; f2[i] = s.e2; f3[i] = s.e3; }
-                  lagrange4(xs, e, wl);
-                  const float se2 = wl[0] * f2[0] + wl[1] * f2[1] + wl[2] * f2[2] + wl[3] * f2[3];
-                  const float se3 = wl[0] * f3[0] + wl[1] * f3[1] + wl[2] * f3[2] + wl[3] * f3[3];
-                  ratio = 0.5f * se3 / se2;
-                }
-                fast_done = true;
-                ndirect += (it == 0);
-                break;
-              }
-              if (it == 0 && getenv("HM_DEBUG3")) fprintf(stderr, "noacc k=%d stage=%d inside=%d interior=%d w=%g delta=%g jb=%d np=%d\n", k, stage, (int)inside, (int)interior, w, delta, jb, np);
-              if (it == 3) break;
-              const float s0 = fmaxf(inside ? 0.5f * delta : w * (1.f / 256.f), 1.0e-5f);
-              const bool uni = !(e - 128.f * s0 > 0.f && e + 128.f * s0 < w);
-              E0 = B0; E1 = B1;
-              nrounds++;
-              for (int pi = 0; pi < P; ++pi)
-                pt[pi].c = B0.c + (uni ? (float)(pi + 1) * (w / (float)(P + 1)) : e + geometric_offset(pi, P) * s0);
-              sweep_all(pt, T, mw);
-              has_ends = true;
-              unsigned ev = 0;
-              for (int pi = 0; pi < P; ++pi) {
-                const float dp = pi ? pt[pi - 1].d : E0.d;
-                if (std::signbit(dp) != std::signbit(pt[pi].d)) ev |= 1u << pi;
-              }
-              if (ev) jb = __builtin_ctz(ev) + 1;
-              else if (std::signbit(pt[P - 1].d) != std::signbit(E1.d)) jb = P + 1;
-              else break;
-            }
-            if (fast_done) {
-              float hg = c1 + (floorf((croot - c1) / dc) + 1.f) * dc;
-              if (!(hg > croot)) hg += dc;
-              const int mnew = layer_drop(hg, T, fact, n, rec.data());
-              const float bh1 = rec[mnew - 1].y;
-              if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) fast_done = false;
-              else { mm = mnew; found = true; have_ratio = (kind == 2) && !mid_liquid; }
+            if (interp_rounds(pt, w0, jb, nvalid, mw, stage == 0) && settle_mmax()) {
+              fast_done = true; found = true; have_ratio = (kind == 2) && !mid_liquid;
             }
           }
         }
@@ -222,6 +231,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       // ---- point-by-point scan, P grid points per round
       float lo = 0, hi = 0, dlo = 0, dhi = 0;
       int mnew = mm;
+      bool interp_done = false;
       {
         // The reference examines every grid point c1 + i dc (calcul.f:155-167).  Here only the first round does;
         // after it every 4th grid point is evaluated (stride S = 4) and the skipped ones are examined only where
@@ -245,7 +255,9 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             for (int t = 0; t < pi * stride; ++t) c = SD_ADD(c, dc);
             pt[pi].c = c; mj[pi] = layer_drop(c, T, fact, n, rec.data());
           }
-          for (int pi = 0; pi < P; pi += 2) sweep2(pt[pi].c, pt[pi + 1].c, T, std::max(mj[pi], mj[pi + 1]), false, pt[pi], pt[pi + 1]);
+          // (own truncation per point only for the stop test; the round is evaluated on its deepest one)
+          const int mtop = mj[P - 1];
+          sweep_all(pt, T, mtop);
           auto stopc = [&](int pi) { const float c = pt[pi].c; return (c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c); };
           if (stride == 1) {
             int jev = -1; bool chg = false;
@@ -266,6 +278,19 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             found = chg;
             lo = jev ? pt[jev - 1].c : P1.c; hi = pt[jev].c; dlo = jev ? pt[jev - 1].d : P1.d; dhi = pt[jev].d; mnew = mj[jev];
             done = true;
+            if (found && !exact && jev >= 1) {
+              // the round's points sample one smooth function around the bracket: the interpolation rounds take over
+              const float bh2 = rec[mtop - 1].y;
+              int nvalid = 0;
+              for (int pi = 0; pi < P; ++pi) nvalid += (pt[pi].c < bh2);
+              const bool kink = (bh2 > lo - 0.011f && bh2 < hi + 0.011f) || nvalid < 6 || jev > nvalid - 1;
+              if (!kink) {
+                std::vector<Pt> cp(pt);
+                const int mm_keep = mm;
+                if (interp_rounds(cp, 0, jev, nvalid, mtop, false) && settle_mmax()) { interp_done = true; have_ratio = (kind == 2) && !mid_liquid; }
+                else mm = mm_keep;
+              }
+            }
           } else {
             int jev = -1;
             for (int pi = 0; pi < P && jev < 0; ++pi) {
@@ -294,8 +319,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           }
         }
       }
-      mm = mnew;
-      if (found) {
+      if (!interp_done) mm = mnew;
+      if (found && !interp_done) {
         const float lo0 = lo, hi0 = hi, dlo0 = dlo, dhi0 = dhi;
         bool multi = false;
         std::vector<Pt> pt(P);

@@ -1,5 +1,6 @@
 """CPU tier: the CUDA kernels' per-lane arithmetic (surfdisp_core.cuh compiled with g++) replayed lane by
-lane against the oracle.  This checks the kernel math and the scan / G-section / sequential-polish design
+lane against the oracle.  This checks the kernel math and the round logic (cluster / window / interpolation
+rounds, coarse scan with its kink guard, uniform-section and sequential polish)
 without a GPU; the CUDA build itself is checked in test_gpu_parity.py."""
 import numpy as np
 import pytest
@@ -9,7 +10,7 @@ from pysurfinv_b200 import synth
 from tests.hostmirror import mirror as HM
 
 
-def _run(lay, nl, per, kind, G=8):
+def _run(lay, nl, per, kind, G=4):
     c0, u0, nf0, st0 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
     dc, du = [], []
     for i in range(lay.shape[1]):
@@ -37,7 +38,7 @@ def test_hand_models_unclamped_ndiv(kind):
     assert dc.max() < 1e-4 and du.max() < 1e-4
 
 
-@pytest.mark.parametrize("G", [4, 16, 32])
+@pytest.mark.parametrize("G", [4, 8])   # the two widths the kernel can be instantiated with
 def test_group_width_does_not_change_results(G):
     lay, nl = synth.crustal_models(40, seed=5)
     dc, du = _run(lay, nl, synth.log_periods(12), 2, G=G)
