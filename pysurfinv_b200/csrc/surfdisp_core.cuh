@@ -468,15 +468,17 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
 // Love secular function for a pair of trial velocities: (displacement, stress) propagated from the half-space
 // up (surfa.f:143-182).  With q = -k d rb (surfa.f:156): y = sin(q)/rb = -sinr, z = rb sin(q) = -rsin (both
 // branches and the rb -> 0 limit of surfa.f:164-166), cos(q) = cs.
-SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec, V2& ut_out) {
+SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec, V2& n1_out, V2& n2_out) {
   const V2 csq = vmul(c, c);
   const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
   const V2 ncsq = vneg(csq);
   const int last = mmax - 1;
   V2 ut, tt;
+  float htop;
   {
     const float4 R = rec[last];
     const float h = R.z * R.y * R.y, ib2 = 1.0f / (R.y * R.y);
+    htop = h;
     ut = vs(1.f);
     tt = v2(h * sqrtf(fabsf(csq.x * ib2 - 1.0f)), h * sqrtf(fabsf(csq.y * ib2 - 1.0f)));
   }
@@ -493,8 +495,12 @@ SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec, V2& ut_out) {
     const V2 ett = vfma(cs, tt, vmul(vmul(vs(-h), rsin), ut));
     ut = eut;
     tt = ett;
+    htop = h;
   }
-  ut_out = ut;   // surface displacement: has the scale of -tt (used to normalise it)
+  // (displacement x rigidity x wavenumber, stress) at the surface: together they carry the scale of the sweep and
+  // never vanish together -- the scan normalises -tt by |n1| + |n2|
+  n1_out = vmul(vmul(ut, vs(htop)), wvno);
+  n2_out = tt;
   return vneg(tt);
 }
 

@@ -158,7 +158,7 @@ __device__ __noinline__ Sec2 secular2(int kind, float2 c, float T, int mm, const
   Sec2 r;
   r.e2 = make_float2(0.f, 0.f); r.e3 = r.e2;
   if (kind == 2) r.d = rayleigh_adjoint2(c, T, mm, rec, ell_only != 0, r.e2, r.e3);
-  else r.d = love_sweep2(c, T, mm, rec, r.e2);
+  else r.d = love_sweep2(c, T, mm, rec, r.e2, r.e3);
   return r;
 }
 

@@ -59,7 +59,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     nsw += 2;
     V2 c = v2(ca, cb), e2 = v2(0.f, 0.f), e3 = v2(0.f, 0.f), dd;
     if (kind == 2) dd = rayleigh_adjoint2(c, T, m, rec.data(), ell_only, e2, e3);
-    else dd = love_sweep2(c, T, m, rec.data(), e2);
+    else dd = love_sweep2(c, T, m, rec.data(), e2, e3);
     A = {ca, dd.x, e2.x, e3.x}; B = {cb, dd.y, e2.y, e3.y};
   };
   auto sweep_all = [&](std::vector<Pt>& pt, float T, int m) {
