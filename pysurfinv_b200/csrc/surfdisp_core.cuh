@@ -893,6 +893,23 @@ SD_HD float leigen_thread(const ModelView& mv, float T, float c, float fact, uns
       const float h = rho * b * b;
       const float dz = mv.dsub(j) / 4.f;
       const int ns = (j == dr.jlast) ? dr.nlast : mv.nsub(j);
+      // the propagators to the four interior knots depend on the layer only: formed once per layer, not once
+      // per sub-layer like surfa.f:524-552 does (same operations, same results)
+      float yk[5], zk[5], ck[5];
+#pragma unroll
+      for (int kk = 1; kk < 5; ++kk) {
+        const float q = rb * dz * (float)kk;
+        if (c < b) {
+          const float exqp = expf(q), exqm = 1.f / exqp;
+          yk[kk] = (exqp - exqm) / (2.f * rb); zk[kk] = rb * rb * yk[kk]; ck[kk] = (exqp + exqm) / 2.f;
+        } else if (c == b) {
+          yk[kk] = dz * (float)kk; zk[kk] = 0.f; ck[kk] = 1.f;
+        } else {
+          float sn, cs;
+          sincosf(q, &sn, &cs);
+          yk[kk] = sn / rb; zk[kk] = -rb * sn; ck[kk] = cs;
+        }
+      }
       for (int s = 0; s < ns; ++s) {
         if (fabsf(ut) > 1.e10f) { ut0 = ut0 / 1.e5f; restart = true; break; }  // surfa.f:519-522
         float dmm[5];
@@ -900,20 +917,8 @@ SD_HD float leigen_thread(const ModelView& mv, float T, float c, float fact, uns
         float eut = ut, ett = tq;
 #pragma unroll
         for (int kk = 1; kk < 5; ++kk) {
-          const float q = rb * dz * (float)kk;
-          float y, z, cosq;
-          if (c < b) {
-            const float exqp = expf(q), exqm = 1.f / exqp;
-            y = (exqp - exqm) / (2.f * rb); z = rb * rb * y; cosq = (exqp + exqm) / 2.f;
-          } else if (c == b) {
-            y = dz * (float)kk; z = 0.f; cosq = 1.f;
-          } else {
-            float sn, cs;
-            sincosf(q, &sn, &cs);
-            y = sn / rb; z = -rb * sn; cosq = cs;
-          }
-          eut = cosq * ut - y * tq / h;
-          ett = -h * z * ut + cosq * tq;
+          eut = ck[kk] * ut - yk[kk] * tq / h;
+          ett = -h * zk[kk] * ut + ck[kk] * tq;
           dmm[kk] = eut * eut;
         }
         ut = eut; tq = ett;

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   const float* cst = p.consts;
   float* crow = p.c_out;
   float* rrow = p.ratio_out;
-  float c1 = 1.f, c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f, c_pred = 0.f, b_top = 0.f, T = 1.f;
+  float c1 = 1.f, c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 1.0e-3f, c_pred = 0.f, b_top = 0.f, T = 1.f;
   bool hopped = false, mid_liquid = false;
   // ---- the sweep request of the current iteration (per lane) and its result
   float2 pc = make_float2(1.f, 1.f), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           }
           mm = n;  // reference COMMON mmax carried from period to period
           nfound = 0; flag = 0; k = p.k_begin; hopped = false;
-          c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 2.0e-3f;
+          c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 1.0e-3f;
           stage = ST_PERIOD;
           if (k > 0) {
             // continuing a model whose earlier periods were done by a previous launch

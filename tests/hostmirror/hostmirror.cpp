@@ -51,7 +51,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   for (int i = 1; i < n; ++i) mid_liquid |= !(cst[C_BREF * ld + i] > 0.f);
   int mm = n, nfound = 0;
   bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
-  float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 2.0e-3f;
+  float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 1.0e-3f;
   long long nsw = 0;
   // the kernel evaluates pairs (packed arithmetic); the pair functions are used here too so that the same
   // source is exercised
