@@ -634,7 +634,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           dP = gshfl<G>(gmask, pd.y, G - 1);
           tP = __log2f(fabsf(dP) / (fabsf(gshfl<G>(gmask, pe2.y, G - 1)) + fabsf(gshfl<G>(gmask, pe3.y, G - 1))));
           have_prev = true;
-          if (p.exact_scan) cbase = SD_ADD(cP, p.dc);
+          // (the half-space velocity of the sampled truncation is a kink, not a smooth place: fine rounds there)
+          const bool near_kink = !(cP + 2.f * (float)S * p.dc < rec[meval - 1].y);
+          if (p.exact_scan || near_kink) cbase = SD_ADD(cP, p.dc);
           else {
             stride = S;
             cbase = cP;
@@ -680,8 +682,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         if (gl == 0) { tpy = tP; tpx = tP2; cp2 = cP2; dp2 = dP2; }
         const float qx = tpx - 2.f * tpy + tx;      // kink at point 2g-1 seen from point 2g
         const float qy = tpy - 2.f * tx + ty;       // kink at point 2g seen from point 2g+1
-        const bool evx = chx || !(fabsf(qx) <= kKinkThr) || stopx;
-        const bool evy = chy || !(fabsf(qy) <= kKinkThr) || stopy;
+        const float bhs = rec[meval - 1].y;
+        const bool evx = chx || !(fabsf(qx) <= kKinkThr) || stopx || !(pc.x + (float)S * p.dc < bhs);
+        const bool evy = chy || !(fabsf(qy) <= kKinkThr) || stopy || !(pc.y + (float)S * p.dc < bhs);
         const unsigned ev = pair_mask(evx, evy);
         if (!ev) {
           cP2 = gshfl<G>(gmask, pc.x, G - 1); dP2 = gshfl<G>(gmask, pd.x, G - 1); tP2 = gshfl<G>(gmask, tx, G - 1);

@@ -269,8 +269,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               if (change || stop) { jev = pi; chg = change; break; }
             }
             if (jev < 0) {
-              // nothing in this fine round: go on with coarse rounds; left neighbours at coarse spacing
+              // nothing in this fine round: go on with coarse rounds (left neighbours at coarse spacing) unless the
+              // half-space velocity of the sampled truncation -- a kink, not a smooth place -- is within reach
               P1 = pt[P - 1]; P2 = pt[P - 1 - S]; mnew = mj[P - 1]; have_prev = true;
+              const bool near_kink = !(P1.c + 2.f * (float)S * dc < rec[mtop - 1].y);
+              if (exact || near_kink) { cbase = SD_ADD(P1.c, dc); continue; }
               stride = S; cbase = P1.c;
               for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, dc);
               continue;
@@ -303,7 +306,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               const float q = lg(L2) - 2.f * lg(L1) + lg(pt[pi]);
               const bool kinked = !(fabsf(q) <= QTHR);
               if (getenv("HM_Q")) fprintf(stderr, "q k=%d c=%.3f q=%.3f change=%d d=%g\n", k, pt[pi].c, q, (int)change, pt[pi].d);
-              if (change || kinked || stopc(pi)) jev = pi;
+              const bool near_kink = !(pt[pi].c + (float)S * dc < rec[mtop - 1].y);
+              if (change || kinked || near_kink || stopc(pi)) jev = pi;
             }
             if (jev < 0) {
               P2 = pt[P - 2]; P1 = pt[P - 1]; mnew = mj[P - 1];
