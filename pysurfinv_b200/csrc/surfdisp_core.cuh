@@ -248,38 +248,85 @@ void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float&
 // stack get dispersion-function semantics; for such stacks (e2, e3) must come from a second sweep with
 // ell_only = true, which skips every liquid layer like the reference's ellipticity sweeps do.
 
+// Layer records live in shared memory in the kernel: a 32-bit shared-window address and ld.shared spare the
+// generic-address descriptor set-up that a plain pointer dereference costs on every layer step.
+#if defined(__CUDA_ARCH__) && !defined(SD_REC_GENERIC)
+struct RecLoader {
+  unsigned base;
+  __device__ __forceinline__ explicit RecLoader(const float4* rec) : base((unsigned)__cvta_generic_to_shared(rec)) {}
+  __device__ __forceinline__ float4 operator()(int m) const {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(base + 16u * (unsigned)m));
+    return r;
+  }
+};
+#else
+struct RecLoader {
+  const float4* rec;
+  SD_HD explicit RecLoader(const float4* r) : rec(r) {}
+  SD_HD float4 operator()(int m) const { return rec[m]; }
+};
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // Two trial velocities per lane.  sm_100 has packed FP32 arithmetic (fma/mul/add.rn.f32x2 -> FFMA2 / FMUL2 /
 // FADD2): one issue slot for two lanes' worth of work, and the packed multiply / add also run at twice the
 // scalar rate (tools/microbench/ffma2_bench.cu).  The secular-function loop is issue bound, and everything
 // in it is elementwise in the trial velocity (the layer data are shared), so each lane carries a PAIR of
 // velocities through the sweep.
+// The pair travels as ONE 64-bit value (not a float2): the compiler front end splits a float2 into two scalars at
+// every control-flow join and re-packs it before the next packed instruction, which cost ~40 register moves per
+// layer step (a quarter of the sweep's instructions); a 64-bit carrier keeps the pair in an aligned register pair.
 #if defined(__CUDACC__)
-typedef float2 V2;
-#else
-typedef struct float2 V2;   // the host mirror's plain struct (top of this file)
-#endif
-SD_HD V2 v2(float a, float b) { V2 r; r.x = a; r.y = b; return r; }
+struct V2 { unsigned long long v; };
 #if defined(__CUDA_ARCH__)
-SD_HD V2 vmul(V2 a, V2 b) { return __fmul2_rn(a, b); }
-SD_HD V2 vadd(V2 a, V2 b) { return __fadd2_rn(a, b); }
-SD_HD V2 vfma(V2 a, V2 b, V2 c) { return __ffma2_rn(a, b, c); }
+SD_HD V2 v2(float a, float b) { V2 r; r.v = ((unsigned long long)__float_as_uint(b) << 32) | (unsigned long long)__float_as_uint(a); return r; }
+SD_HD float vx(V2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+SD_HD float vy(V2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
+SD_HD V2 vmul(V2 a, V2 b) { V2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SD_HD V2 vadd(V2 a, V2 b) { V2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SD_HD V2 vfma(V2 a, V2 b, V2 c) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#else   // host pass of nvcc: never executed, only has to compile
+SD_HD V2 v2(float a, float b) { V2 r; unsigned ua, ub; memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); r.v = ((unsigned long long)ub << 32) | ua; return r; }
+SD_HD float vx(V2 a) { const unsigned u = (unsigned)(a.v & 0xffffffffull); float f; memcpy(&f, &u, 4); return f; }
+SD_HD float vy(V2 a) { const unsigned u = (unsigned)(a.v >> 32); float f; memcpy(&f, &u, 4); return f; }
+SD_HD V2 vmul(V2 a, V2 b) { return v2(vx(a) * vx(b), vy(a) * vy(b)); }
+SD_HD V2 vadd(V2 a, V2 b) { return v2(vx(a) + vx(b), vy(a) + vy(b)); }
+SD_HD V2 vfma(V2 a, V2 b, V2 c) { return v2(fmaf(vx(a), vx(b), vx(c)), fmaf(vy(a), vy(b), vy(c))); }
+#endif
 #else
+struct V2 { float x, y; };   // the host mirror's plain pair
+SD_HD V2 v2(float a, float b) { V2 r; r.x = a; r.y = b; return r; }
+SD_HD float vx(V2 a) { return a.x; }
+SD_HD float vy(V2 a) { return a.y; }
 SD_HD V2 vmul(V2 a, V2 b) { return v2(a.x * b.x, a.y * b.y); }
 SD_HD V2 vadd(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
 SD_HD V2 vfma(V2 a, V2 b, V2 c) { return v2(a.x * b.x + c.x, a.y * b.y + c.y); }
 #endif
 SD_HD V2 vs(float s) { return v2(s, s); }
-SD_HD V2 vneg(V2 a) { return v2(-a.x, -a.y); }
+SD_HD V2 vneg(V2 a) { return v2(-vx(a), -vy(a)); }
 SD_HD V2 vsub(V2 a, V2 b) { return vfma(b, vs(-1.f), a); }
 
-// half_terms for a pair.  Two series tiers, taken only if both velocities qualify: |u| < 0.5 (thin layers, the
-// vast majority) and |u| < 3 (thick layers at short periods / low trial velocities, e.g. the whole scan of the
-// first period), where the entire functions S and C need 9 / 10 terms for float32 accuracy; beyond that each
-// velocity goes through the MUFU-based scalar form.
-SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
-  const V2 u = vmul(kd2, arg);
-  const float um = fmaxf(fabsf(u.x), fabsf(u.y));
+// half_terms for a pair, negation-free form (packed FP32 has no operand negation in PTX; an explicit sign flip of a
+// pair costs two scalar instructions).  Inputs either (a, k2s) = (arg, (k d)^2) [NEG = false] or
+// (-arg, -(k d)^2) [NEG = true]: u = k2s * a either way.  Outputs sinr = sin x / r, cs = cos x and p = a * sinr,
+// i.e. r sin x for NEG = true and -r sin x for NEG = false (oscillatory and evanescent alike).  Two series tiers, taken only if both velocities qualify: |u| < 0.5 (thin
+// layers, the vast majority) and |u| < 3 (thick layers at short periods / low trial velocities, e.g. the whole scan
+// of the first period), where the entire functions S and C need 9 / 10 terms for float32 accuracy; beyond that
+// each velocity goes through the MUFU-based scalar form.
+template <bool NEG>
+SD_HD void half_terms2_scalar(V2 a, V2 kd, V2 k2s, V2& p, V2& sinr, V2& cs) {
+  // (temporaries: the out-of-line scalar form takes addresses, which must not pin the pair registers to memory)
+  float r0, s0, c0, r1, s1, c1;
+  half_terms(NEG ? -vx(a) : vx(a), vx(kd), NEG ? -vx(k2s) : vx(k2s), r0, s0, c0);
+  half_terms(NEG ? -vy(a) : vy(a), vy(kd), NEG ? -vy(k2s) : vy(k2s), r1, s1, c1);
+  p = NEG ? v2(r0, r1) : v2(-r0, -r1); sinr = v2(s0, s1); cs = v2(c0, c1);
+}
+
+template <bool NEG>
+SD_HD void half_terms2(V2 narg, V2 kd, V2 nkd2, V2& rsin, V2& sinr, V2& cs) {
+  const V2 u = vmul(nkd2, narg);
+  const float um = fmaxf(fabsf(vx(u)), fabsf(vy(u)));
   if (um < 0.5f) {
     V2 S = vfma(u, vs(2.7557319e-6f), vs(1.9841270e-4f));
     S = vfma(u, S, vs(8.3333333e-3f));
@@ -291,7 +338,7 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
     C = vfma(u, C, vs(0.5f));
     cs = vfma(u, C, vs(1.f));
     sinr = vmul(kd, S);
-    rsin = vmul(vneg(arg), sinr);
+    rsin = vmul(narg, sinr);
     return;
   }
   if (um < 3.0f) {
@@ -315,62 +362,10 @@ SD_HD void half_terms2(V2 arg, V2 kd, V2 kd2, V2& rsin, V2& sinr, V2& cs) {
     C = vfma(u, C, vs(0.5f));
     cs = vfma(u, C, vs(1.f));
     sinr = vmul(kd, S);
-    rsin = vmul(vneg(arg), sinr);
+    rsin = vmul(narg, sinr);
     return;
   }
-  // (temporaries: the out-of-line scalar form takes addresses, which must not pin the pair registers to memory)
-  float r0, s0, c0, r1, s1, c1;
-  half_terms(arg.x, kd.x, kd2.x, r0, s0, c0);
-  half_terms(arg.y, kd.y, kd2.y, r1, s1, c1);
-  rsin = v2(r0, r1); sinr = v2(s0, s1); cs = v2(c0, c1);
-}
-
-// P and SV terms of one Rayleigh layer step together.  When all four arguments are in the thin-layer tier
-// (the common case) the four Horner chains are interleaved in one basic block: no branch between them and four
-// independent dependency chains for the scheduler.
-SD_HD void half_terms2x2(V2 argp, V2 argq, V2 kd, V2 kd2, V2& rsinp, V2& sinpr, V2& cosp, V2& rsinq, V2& sinqr, V2& cosq) {
-  const V2 up = vmul(kd2, argp), uq = vmul(kd2, argq);
-  const float um = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(uq.x), fabsf(uq.y)));
-  if (um < 0.5f) {
-    V2 Sp = vfma(up, vs(2.7557319e-6f), vs(1.9841270e-4f)), Sq = vfma(uq, vs(2.7557319e-6f), vs(1.9841270e-4f));
-    V2 Cp = vfma(up, vs(2.7557319e-7f), vs(2.4801587e-5f)), Cq = vfma(uq, vs(2.7557319e-7f), vs(2.4801587e-5f));
-    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
-    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
-    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
-    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
-    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
-    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
-    cosp = vfma(up, Cp, vs(1.f)); cosq = vfma(uq, Cq, vs(1.f));
-    sinpr = vmul(kd, Sp); sinqr = vmul(kd, Sq);
-    rsinp = vmul(vneg(argp), sinpr); rsinq = vmul(vneg(argq), sinqr);
-    return;
-  }
-  if (um < 3.0f) {
-    // thick-layer tier for both terms at once (one block, four chains): 9 / 10 terms of S and C
-    V2 Sp = vfma(up, vs(8.2206352e-18f), vs(2.8114573e-15f)), Sq = vfma(uq, vs(8.2206352e-18f), vs(2.8114573e-15f));
-    V2 Cp = vfma(up, vs(1.5619207e-16f), vs(4.7794773e-14f)), Cq = vfma(uq, vs(1.5619207e-16f), vs(4.7794773e-14f));
-    Sp = vfma(up, Sp, vs(7.6471637e-13f)); Sq = vfma(uq, Sq, vs(7.6471637e-13f));
-    Cp = vfma(up, Cp, vs(1.1470746e-11f)); Cq = vfma(uq, Cq, vs(1.1470746e-11f));
-    Sp = vfma(up, Sp, vs(1.6059044e-10f)); Sq = vfma(uq, Sq, vs(1.6059044e-10f));
-    Cp = vfma(up, Cp, vs(2.0876757e-9f)); Cq = vfma(uq, Cq, vs(2.0876757e-9f));
-    Sp = vfma(up, Sp, vs(2.5052108e-8f)); Sq = vfma(uq, Sq, vs(2.5052108e-8f));
-    Cp = vfma(up, Cp, vs(2.7557319e-7f)); Cq = vfma(uq, Cq, vs(2.7557319e-7f));
-    Sp = vfma(up, Sp, vs(2.7557319e-6f)); Sq = vfma(uq, Sq, vs(2.7557319e-6f));
-    Cp = vfma(up, Cp, vs(2.4801587e-5f)); Cq = vfma(uq, Cq, vs(2.4801587e-5f));
-    Sp = vfma(up, Sp, vs(1.9841270e-4f)); Sq = vfma(uq, Sq, vs(1.9841270e-4f));
-    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
-    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
-    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
-    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
-    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
-    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
-    cosp = vfma(up, Cp, vs(1.f)); cosq = vfma(uq, Cq, vs(1.f));
-    sinpr = vmul(kd, Sp); sinqr = vmul(kd, Sq);
-    rsinp = vmul(vneg(argp), sinpr); rsinq = vmul(vneg(argq), sinqr);
-    return;
-  }
-  half_terms2(argp, kd, kd2, rsinp, sinpr, cosp);
-  half_terms2(argq, kd, kd2, rsinq, sinqr, cosq);
+  half_terms2_scalar<NEG>(narg, kd, nkd2, rsin, sinr, cs);
 }
 
 // Half-space row of the Rayleigh secular function (surfa.f:341-354) for one velocity; R = (a, b, rho, d)
@@ -396,25 +391,86 @@ SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, flo
   r2 = -SD_FDIV(ih12, g);
 }
 
-// Rayleigh sweep for a pair of trial velocities (same truncation depth mmax, same period)
+// P and SV series of one Rayleigh layer step together (u = nkd2 * narg per term): when all four arguments are in a
+// series tier (the common case) the four Horner chains are interleaved in one basic block -- no branch between them
+// and four independent dependency chains for the scheduler.  Returns false when a term is outside the series range;
+// the caller then takes half_terms2 per term.
+SD_HD bool series2x2(V2 up, V2 uq, V2 kd, V2& Sp_, V2& Cp_, V2& Sq_, V2& Cq_) {
+  const float um = fmaxf(fmaxf(fabsf(vx(up)), fabsf(vy(up))), fmaxf(fabsf(vx(uq)), fabsf(vy(uq))));
+  if (um < 0.5f) {
+    V2 Sp = vfma(up, vs(2.7557319e-6f), vs(1.9841270e-4f)), Sq = vfma(uq, vs(2.7557319e-6f), vs(1.9841270e-4f));
+    V2 Cp = vfma(up, vs(2.7557319e-7f), vs(2.4801587e-5f)), Cq = vfma(uq, vs(2.7557319e-7f), vs(2.4801587e-5f));
+    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
+    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
+    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
+    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
+    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
+    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
+    Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
+    Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
+    return true;
+  }
+  if (um < 3.0f) {
+    // S(u) = sum u^n / (2n+1)!,  C(u) = sum u^n / (2n)!;  |u|^10/21! < 2e-15, |u|^10/20! < 3e-14 relative
+    V2 Sp = vfma(up, vs(8.2206352e-18f), vs(2.8114573e-15f)), Sq = vfma(uq, vs(8.2206352e-18f), vs(2.8114573e-15f));
+    V2 Cp = vfma(up, vs(1.5619207e-16f), vs(4.7794773e-14f)), Cq = vfma(uq, vs(1.5619207e-16f), vs(4.7794773e-14f));
+    Sp = vfma(up, Sp, vs(7.6471637e-13f)); Sq = vfma(uq, Sq, vs(7.6471637e-13f));
+    Cp = vfma(up, Cp, vs(1.1470746e-11f)); Cq = vfma(uq, Cq, vs(1.1470746e-11f));
+    Sp = vfma(up, Sp, vs(1.6059044e-10f)); Sq = vfma(uq, Sq, vs(1.6059044e-10f));
+    Cp = vfma(up, Cp, vs(2.0876757e-9f)); Cq = vfma(uq, Cq, vs(2.0876757e-9f));
+    Sp = vfma(up, Sp, vs(2.5052108e-8f)); Sq = vfma(uq, Sq, vs(2.5052108e-8f));
+    Cp = vfma(up, Cp, vs(2.7557319e-7f)); Cq = vfma(uq, Cq, vs(2.7557319e-7f));
+    Sp = vfma(up, Sp, vs(2.7557319e-6f)); Sq = vfma(uq, Sq, vs(2.7557319e-6f));
+    Cp = vfma(up, Cp, vs(2.4801587e-5f)); Cq = vfma(uq, Cq, vs(2.4801587e-5f));
+    Sp = vfma(up, Sp, vs(1.9841270e-4f)); Sq = vfma(uq, Sq, vs(1.9841270e-4f));
+    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
+    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
+    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
+    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
+    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
+    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
+    Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
+    Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
+    return true;
+  }
+  return false;
+}
+
+#ifndef SD_RAY_UNROLL
+#define SD_RAY_UNROLL 1
+#endif
+constexpr int kRayUnroll = SD_RAY_UNROLL;
+// Rayleigh sweep for a pair of trial velocities (same truncation depth mmax, same period).
+// The row vector is carried as s = (r1, r2, r3, -r4, r5): with that sign convention every entry of the layer matrix
+// enters both of its positions with one sign, and with tp = narg_p sin(x_p)/r_p = r sin x (same for q) no operand
+// ever has to be negated inside the loop.
 SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_only, V2& e2, V2& e3) {
   const V2 csq = vmul(c, c);
-  const V2 icsq = v2(1.0f / csq.x, 1.0f / csq.y);
-  const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
-  const V2 ncsq = vneg(csq);
+  const V2 icsq = v2(1.0f / vx(csq), 1.0f / vy(csq));
+  const V2 nicsq = v2(-vx(icsq), -vy(icsq));
+  const V2 wvno = v2(SD_TWOPI / (vx(c) * T), SD_TWOPI / (vy(c) * T));
+  const V2 nwvno = v2(-vx(wvno), -vy(wvno));
   const int last = mmax - 1;
-  V2 r1, r2, r3, r4, r5;
-  rayleigh_hs_row(csq.x, icsq.x, rec[last], r1.x, r2.x, r3.x, r4.x, r5.x);
-  rayleigh_hs_row(csq.y, icsq.y, rec[last], r1.y, r2.y, r3.y, r4.y, r5.y);
-  const V2 one = vs(1.f), two = vs(2.f);
+  const RecLoader ld(rec);
+  V2 r1, r2, r3, s4, r5;
+  {
+    float x1, x2, x3, x4, x5, y1, y2, y3, y4, y5;
+    const float4 Rh = ld(last);
+    rayleigh_hs_row(vx(csq), vx(icsq), Rh, x1, x2, x3, x4, x5);
+    rayleigh_hs_row(vy(csq), vy(icsq), Rh, y1, y2, y3, y4, y5);
+    r1 = v2(x1, y1); r2 = v2(x2, y2); r3 = v2(x3, y3); s4 = v2(-x4, -y4); r5 = v2(x5, y5);
+  }
+  const V2 one = vs(1.f), two = vs(2.f), mone = vs(-1.f);
+#pragma unroll kRayUnroll
   for (int m = last - 1; m >= 0; --m) {
-    const float4 R = rec[m];
+    const float4 R = ld(m);
     const float ia = sd_rcp(R.x), ia2 = ia * ia;
     const V2 kd = vmul(wvno, vs(R.w));
-    const V2 kd2 = vmul(kd, kd);
-    V2 rsinp, sinpr, cosp;
+    const V2 nkd2 = vmul(kd, vmul(nwvno, vs(R.w)));
+    const V2 nargp = vfma(csq, vs(ia2), mone);
     if (R.y == 0.f) {
-      half_terms2(vfma(ncsq, vs(ia2), one), kd, kd2, rsinp, sinpr, cosp);
+      V2 rsinp, sinpr, cosp;
+      half_terms2<true>(nargp, kd, nkd2, rsinp, sinpr, cosp);
       if (ell_only) continue;
       const V2 a21 = vmul(vmul(vs(R.z), csq), sinpr);
       const V2 n1 = vfma(r1, cosp, vmul(r2, a21));
@@ -422,44 +478,54 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
         e2 = r2; e3 = r3;
         return vneg(n1);
       }
-      const V2 n4 = vneg(vmul(r5, a21)), n5 = vmul(r5, cosp);
-      r1 = n1; r2 = vs(0.f); r3 = vs(0.f); r4 = n4; r5 = n5;
+      const V2 n4 = vmul(r5, a21), n5 = vmul(r5, cosp);   // s4 = -r4 = +r5 a21
+      r1 = n1; r2 = vs(0.f); r3 = vs(0.f); s4 = n4; r5 = n5;
       continue;
     }
     const float ib = sd_rcp(R.y), ib2 = ib * ib, b2 = 2.0f * R.y * R.y, irho = sd_rcp(R.z);
-    V2 rsinq, sinqr, cosq;
-    half_terms2x2(vfma(ncsq, vs(ia2), one), vfma(ncsq, vs(ib2), one), kd, kd2, rsinp, sinpr, cosp, rsinq, sinqr, cosq);
+    const V2 nargq = vfma(csq, vs(ib2), mone);
+    V2 sinpr, cosp, sinqr, cosq, tp, tq;   // tp = r sin x (P), tq = r sin x (SV)
+    if (series2x2(vmul(nkd2, nargp), vmul(nkd2, nargq), kd, sinpr, cosp, sinqr, cosq)) {
+      tp = vmul(nargp, sinpr); tq = vmul(nargq, sinqr);
+    } else {
+      half_terms2<true>(nargp, kd, nkd2, tp, sinpr, cosp);
+      half_terms2<true>(nargq, kd, nkd2, tq, sinqr, cosq);
+    }
     const V2 g = vmul(vs(b2), icsq);
-    const V2 g1 = vadd(g, vs(-1.f));
+    const V2 g1 = vadd(g, mone);
     const V2 rhoc = vmul(vs(R.z), csq);
-    const V2 irhoc = vmul(vs(irho), icsq);
-    const V2 rr = vmul(rsinp, rsinq), ss = vmul(sinpr, sinqr), cc = vmul(cosp, cosq);
-    const V2 rs1 = vmul(rsinp, cosq), rs2 = vmul(sinqr, cosp), rs3 = vmul(sinpr, cosq), rs4 = vmul(rsinq, cosp);
-    const V2 a24 = vmul(sinpr, rsinq), a42 = vmul(rsinp, sinqr);
-    const V2 gm = vadd(g, g1), gs = vmul(g, g), g1s = vmul(g1, g1), gg1 = vmul(g, g1);
-    const V2 ccm = vsub(one, cc);
-    const V2 suu = vfma(gs, rr, vmul(g1s, ss));
-    const V2 w = vfma(vmul(two, gg1), ccm, suu);
-    const V2 a11 = vsub(cc, w);
+    const V2 nirhoc = vmul(vs(irho), nicsq);
+    const V2 rr = vmul(tp, tq), ss = vmul(sinpr, sinqr), cc = vmul(cosp, cosq);
+    const V2 rs1 = vmul(tp, cosq), rs2 = vmul(sinqr, cosp), rs3 = vmul(sinpr, cosq), rs4 = vmul(tq, cosp);
+    const V2 nss = vmul(ss, mone);
+    const V2 m24 = vmul(nargq, nss), m42 = vmul(nargp, nss);   // -a24 = -sinpr tq,  -a42 = -tp sinqr
+    const V2 gs = vmul(g, g), g1s = vmul(g1, g1);
+    const V2 ccm = vfma(cc, mone, one);
+    // The five entries built from (rr, ss, 1 - cc) are  P_n = g^n rr + g1^n ss + (cross term) (1 - cc), n = 0..4.
+    // With A = g rr + g1 ccm, B = g1 ss + g ccm and g - g1 = 1:  P1 = A + B,  P2 = g A + g1 B,
+    // P3 = g^2 A + g1^2 B,  P4 = g^3 A + g1^3 B - g g1 ccm.
+    const V2 A = vfma(g, rr, vmul(g1, ccm)), B = vfma(g1, ss, vmul(g, ccm));
+    const V2 w = vfma(g, A, vmul(g1, B));                                              // P2
+    const V2 tA = vmul(gs, A), tB = vmul(g1s, B);
+    const V2 a11 = vfma(w, mone, cc);
     const V2 a33 = vfma(two, w, one);
-    const V2 nirhoc = vneg(irhoc);
     const V2 a12 = vmul(vadd(rs1, rs2), nirhoc);
-    const V2 a14 = vmul(vadd(rs3, rs4), irhoc);
-    const V2 a13h = vmul(vfma(gm, ccm, vfma(g1, ss, vmul(g, rr))), nirhoc);          // = 0.5 * a13
-    const V2 a15 = vmul(vfma(two, ccm, vadd(rr, ss)), vmul(irhoc, irhoc));
+    const V2 m14 = vmul(vadd(rs3, rs4), nirhoc);                                       // = -a14
+    const V2 a13h = vmul(vadd(A, B), nirhoc);                                          // = 0.5 * a13   (P1)
+    const V2 a15 = vmul(vfma(two, ccm, vadd(rr, ss)), vmul(nirhoc, nirhoc));           // P0
     const V2 a21 = vmul(rhoc, vfma(g1s, rs3, vmul(gs, rs4)));
-    const V2 a41 = vmul(vneg(rhoc), vfma(g1s, rs2, vmul(gs, rs1)));
+    const V2 m41 = vmul(rhoc, vfma(g1s, rs2, vmul(gs, rs1)));                          // = -a41
     const V2 a23h = vfma(g, rs4, vmul(g1, rs3));                                       // = 0.5 * a23
     const V2 a32 = vfma(g1, rs2, vmul(g, rs1));
-    const V2 a31 = vmul(rhoc, vfma(vmul(gg1, gm), ccm, vfma(vmul(g1s, g1), ss, vmul(vmul(gs, g), rr))));
-    const V2 a51 = vmul(vmul(rhoc, rhoc), vfma(vmul(two, vmul(gg1, gg1)), ccm, vfma(vmul(gs, gs), rr, vmul(vmul(g1s, g1s), ss))));
-    // r <- r A (rows of A as in surfa.f:326-330)
-    const V2 n1 = vfma(r1, a11, vfma(r2, a21, vfma(r3, a31, vfma(r4, a41, vmul(r5, a51)))));
-    const V2 n2 = vfma(r1, a12, vfma(r2, cc, vfma(r3, a32, vfma(r4, a42, vmul(vneg(r5), a41)))));
-    const V2 n3 = vfma(two, vfma(r1, a13h, vfma(r2, a23h, vfma(vneg(r4), a32, vmul(r5, a31)))), vmul(r3, a33));
-    const V2 n4 = vfma(r1, a14, vfma(r2, a24, vfma(vneg(r3), a23h, vfma(r4, cc, vmul(vneg(r5), a21)))));
-    const V2 n5 = vfma(r1, a15, vfma(vneg(r2), a14, vfma(r3, a13h, vfma(vneg(r4), a12, vmul(r5, a11)))));
-    r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5;
+    const V2 a31 = vmul(rhoc, vadd(tA, tB));                                           // P3
+    const V2 a51 = vmul(vmul(rhoc, rhoc), vfma(vmul(vmul(g, g1), ccm), mone, vfma(g, tA, vmul(g1, tB))));   // P4
+    // s <- s A' (rows of A as in surfa.f:326-330, signs for s4 = -r4)
+    const V2 n1 = vfma(r1, a11, vfma(r2, a21, vfma(r3, a31, vfma(s4, m41, vmul(r5, a51)))));
+    const V2 n2 = vfma(r1, a12, vfma(r2, cc, vfma(r3, a32, vfma(s4, m42, vmul(r5, m41)))));
+    const V2 n3 = vfma(two, vfma(r1, a13h, vfma(r2, a23h, vfma(s4, a32, vmul(r5, a31)))), vmul(r3, a33));
+    const V2 n4 = vfma(r1, m14, vfma(r2, m24, vfma(r3, a23h, vfma(s4, cc, vmul(r5, a21)))));
+    const V2 n5 = vfma(r1, a15, vfma(r2, m14, vfma(r3, a13h, vfma(s4, a12, vmul(r5, a11)))));
+    r1 = n1; r2 = n2; r3 = n3; s4 = n4; r5 = n5;
   }
   e2 = r2; e3 = r3;
   return vneg(r1);
@@ -470,29 +536,30 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
 // branches and the rb -> 0 limit of surfa.f:164-166), cos(q) = cs.
 SD_HD V2 love_sweep2(V2 c, float T, int mmax, const float4* rec, V2& n1_out, V2& n2_out) {
   const V2 csq = vmul(c, c);
-  const V2 wvno = v2(SD_TWOPI / (c.x * T), SD_TWOPI / (c.y * T));
-  const V2 ncsq = vneg(csq);
+  const V2 wvno = v2(SD_TWOPI / (vx(c) * T), SD_TWOPI / (vy(c) * T));
+  const V2 ncsq = v2(-vx(csq), -vy(csq));
   const int last = mmax - 1;
+  const RecLoader ld(rec);
   V2 ut, tt;
   float htop;
   {
-    const float4 R = rec[last];
+    const float4 R = ld(last);
     const float h = R.z * R.y * R.y, ib2 = 1.0f / (R.y * R.y);
     htop = h;
     ut = vs(1.f);
-    tt = v2(h * sqrtf(fabsf(csq.x * ib2 - 1.0f)), h * sqrtf(fabsf(csq.y * ib2 - 1.0f)));
+    tt = v2(h * sqrtf(fabsf(vx(csq) * ib2 - 1.0f)), h * sqrtf(fabsf(vy(csq) * ib2 - 1.0f)));
   }
   for (int m = last - 1; m >= 0; --m) {
-    const float4 R = rec[m];
+    const float4 R = ld(m);
     if (R.y == 0.f) continue;  // liquid layer skipped (surfa.f:152)
     const float ib = sd_rcp(R.y), ib2 = ib * ib;
     const V2 kd = vmul(wvno, vs(R.w));
-    V2 rsin, sinr, cs;
-    half_terms2(vfma(ncsq, vs(ib2), vs(1.f)), kd, vmul(kd, kd), rsin, sinr, cs);
+    V2 nrsin, sinr, cs;   // nrsin = arg sin x / r = -r sin x
+    half_terms2<false>(vfma(ncsq, vs(ib2), vs(1.f)), kd, vmul(kd, kd), nrsin, sinr, cs);
     const float h = R.z * R.y * R.y;
     const float ih = sd_rcp(R.z) * ib2;
     const V2 eut = vfma(cs, ut, vmul(vmul(sinr, tt), vs(ih)));
-    const V2 ett = vfma(cs, tt, vmul(vmul(vs(-h), rsin), ut));
+    const V2 ett = vfma(cs, tt, vmul(vmul(vs(h), nrsin), ut));
     ut = eut;
     tt = ett;
     htop = h;

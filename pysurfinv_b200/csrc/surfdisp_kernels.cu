@@ -155,10 +155,12 @@ struct P1Params {
 struct Sec2 { float2 d, e2, e3; };
 
 __device__ __noinline__ Sec2 secular2(int kind, float2 c, float T, int mm, const float4* rec, int ell_only) {
+  V2 d, e2 = v2(0.f, 0.f), e3 = e2;
+  const V2 cp = v2(c.x, c.y);
+  if (kind == 2) d = rayleigh_adjoint2(cp, T, mm, rec, ell_only != 0, e2, e3);
+  else d = love_sweep2(cp, T, mm, rec, e2, e3);
   Sec2 r;
-  r.e2 = make_float2(0.f, 0.f); r.e3 = r.e2;
-  if (kind == 2) r.d = rayleigh_adjoint2(c, T, mm, rec, ell_only != 0, r.e2, r.e3);
-  else r.d = love_sweep2(c, T, mm, rec, r.e2, r.e3);
+  r.d = make_float2(vx(d), vy(d)); r.e2 = make_float2(vx(e2), vy(e2)); r.e3 = make_float2(vx(e3), vy(e3));
   return r;
 }
 

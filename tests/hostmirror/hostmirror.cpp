@@ -60,7 +60,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     V2 c = v2(ca, cb), e2 = v2(0.f, 0.f), e3 = v2(0.f, 0.f), dd;
     if (kind == 2) dd = rayleigh_adjoint2(c, T, m, rec.data(), ell_only, e2, e3);
     else dd = love_sweep2(c, T, m, rec.data(), e2, e3);
-    A = {ca, dd.x, e2.x, e3.x}; B = {cb, dd.y, e2.y, e3.y};
+    A = {ca, vx(dd), vx(e2), vx(e3)}; B = {cb, vy(dd), vy(e2), vy(e3)};
   };
   auto sweep_all = [&](std::vector<Pt>& pt, float T, int m) {
     for (int i = 0; i + 1 < (int)pt.size(); i += 2) sweep2(pt[i].c, pt[i + 1].c, T, m, false, pt[i], pt[i + 1]);

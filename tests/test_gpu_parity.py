@@ -227,6 +227,26 @@ def test_exact_scan_mode_gives_same_roots():
         assert float(du.median()) < 2e-6 and float((du > 1e-4).float().mean()) < 1e-3
 
 
+def test_love_roots_just_below_half_space_velocity(solver):
+    """Long periods: the Love root sits ~1e-4 km/s below the flattened half-space velocity, where the secular
+    function has a square-root cusp (surfa.f:407-416 switches to the evanescent branch).  The coarse scan must
+    fall back to point-by-point there; root counts against the oracle and against exact_scan=1."""
+    import torch
+    from pysurfinv_b200 import api
+    lay, nl = synth.crustal_models(4096, seed=303)
+    per = synth.log_periods(100, 5.0, 120.0)
+    dl, dn = torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda()
+    a = solver.forward(dl, dn, per, kind=1)
+    b = api.DispersionSolver("cuda:0", opts=api.default_opts(exact_scan=1)).forward(dl, dn, per, kind=1)
+    assert torch.equal(a["nfound"], b["nfound"])
+    partial = np.nonzero((a["nfound"] < len(per)).cpu().numpy())[0]
+    assert len(partial) > 100            # the family does exercise the cut-off
+    idx = partial[:256]
+    c0, u0, nf0, st0 = O.forward_batch(1, lay[:, idx], nl[idx], per, opts=O.make_opts(precision=0), nthreads=8)
+    assert np.array_equal(a["nfound"].cpu().numpy()[idx], nf0)
+    assert np.abs(a["c"].cpu().numpy()[idx] - c0).max() <= TOL
+
+
 def test_config4_deep_stacks_ndiv_zero(solver):
     """BASELINE config 4 shape: ~150 fine layers, Rayleigh 10-150 s.  n >= 101 clamps ndiv to 99/(n-1) = 0
     (no sub-division, surfa.f:783-787)."""
