@@ -737,41 +737,40 @@ SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, b
 // A couples p = (ur, tz) with q = (uz, tr) only (p' = B q, q' = C p), which makes P cheap to build from
 // 2x2 blocks once per layer; each step is then 16 FMAs per solution instead of 64.
 struct RkCoef { double a12, a13, a21, a24, a31, a34, a42, a43; double h; };
-struct StepMat { double pp00, pp01, pp10, pp11, pq00, pq01, pq10, pq11, qp00, qp01, qp10, qp11, qq00, qq01, qq10, qq11; };
+// B and C are trace-free (a24 = -a31, a42 = -a13), so adj(B) = -B, adj(C) = -C and CB = adj(BC): with X = BC,
+// t = tr X, d = det X (X^2 = t X - d I) the blocks are
+//   pp = (1 - h^4/24 d) I + (h^2/2 + h^4/24 t) X,   qq = adj(pp),
+//   pq = h F B,  qp = h adj(F) C   with  F = I + h^2/6 X
+// -- 12 stored entries and about half the arithmetic of forming the four blocks separately.
+struct StepMat { double pp00, pp01, pp10, pp11, pq00, pq01, pq10, pq11, qp00, qp01, qp10, qp11; };
 
 SD_HD StepMat make_stepmat(const RkCoef& k) {
   // B = [[a31, a34], [a21, a24]] : (uz, tr) -> (ur', tz');  C = [[a13, a12], [a43, a42]] : (ur, tz) -> (uz', tr')
-  const double b00 = k.a31, b01 = k.a34, b10 = k.a21, b11 = k.a24;
-  const double c00 = k.a13, c01 = k.a12, c10 = k.a43, c11 = k.a42;
+  const double b00 = k.a31, b01 = k.a34, b10 = k.a21;     // b11 = -b00
+  const double c00 = k.a13, c01 = k.a12, c10 = k.a43;     // c11 = -c00
   const double h = k.h, h2 = h * h;
-  const double bc00 = b00 * c00 + b01 * c10, bc01 = b00 * c01 + b01 * c11, bc10 = b10 * c00 + b11 * c10, bc11 = b10 * c01 + b11 * c11;
-  const double cb00 = c00 * b00 + c01 * b10, cb01 = c00 * b01 + c01 * b11, cb10 = c10 * b00 + c11 * b10, cb11 = c10 * b01 + c11 * b11;
+  const double x00 = b00 * c00 + b01 * c10, x01 = b00 * c01 - b01 * c00, x10 = b10 * c00 - b00 * c10, x11 = b10 * c01 + b00 * c00;
   const double e2 = h2 * 0.5, e4 = h2 * h2 * (1.0 / 24.0), e3 = h2 * (1.0 / 6.0);
+  const double t = x00 + x11, d = x00 * x11 - x01 * x10;
+  const double al = 1.0 - e4 * d, be = e2 + e4 * t;
   StepMat m;
-  // diagonal blocks: I + h^2/2 X + h^4/24 X^2
-  m.pp00 = 1.0 + e2 * bc00 + e4 * (bc00 * bc00 + bc01 * bc10);
-  m.pp01 = e2 * bc01 + e4 * (bc00 * bc01 + bc01 * bc11);
-  m.pp10 = e2 * bc10 + e4 * (bc10 * bc00 + bc11 * bc10);
-  m.pp11 = 1.0 + e2 * bc11 + e4 * (bc10 * bc01 + bc11 * bc11);
-  m.qq00 = 1.0 + e2 * cb00 + e4 * (cb00 * cb00 + cb01 * cb10);
-  m.qq01 = e2 * cb01 + e4 * (cb00 * cb01 + cb01 * cb11);
-  m.qq10 = e2 * cb10 + e4 * (cb10 * cb00 + cb11 * cb10);
-  m.qq11 = 1.0 + e2 * cb11 + e4 * (cb10 * cb01 + cb11 * cb11);
-  // off-diagonal blocks: h (I + h^2/6 BC) B  and  h (I + h^2/6 CB) C
-  const double f00 = 1.0 + e3 * bc00, f01 = e3 * bc01, f10 = e3 * bc10, f11 = 1.0 + e3 * bc11;
-  m.pq00 = h * (f00 * b00 + f01 * b10); m.pq01 = h * (f00 * b01 + f01 * b11);
-  m.pq10 = h * (f10 * b00 + f11 * b10); m.pq11 = h * (f10 * b01 + f11 * b11);
-  const double g00 = 1.0 + e3 * cb00, g01 = e3 * cb01, g10 = e3 * cb10, g11 = 1.0 + e3 * cb11;
-  m.qp00 = h * (g00 * c00 + g01 * c10); m.qp01 = h * (g00 * c01 + g01 * c11);
-  m.qp10 = h * (g10 * c00 + g11 * c10); m.qp11 = h * (g10 * c01 + g11 * c11);
+  m.pp00 = al + be * x00; m.pp01 = be * x01; m.pp10 = be * x10; m.pp11 = al + be * x11;
+  const double f00 = 1.0 + e3 * x00, f01 = e3 * x01, f10 = e3 * x10, f11 = 1.0 + e3 * x11;
+  const double hb00 = h * b00, hb01 = h * b01, hb10 = h * b10;    // h B, (1,1) entry = -hb00
+  m.pq00 = f00 * hb00 + f01 * hb10; m.pq01 = f00 * hb01 - f01 * hb00;
+  m.pq10 = f10 * hb00 + f11 * hb10; m.pq11 = f10 * hb01 - f11 * hb00;
+  const double hc00 = h * c00, hc01 = h * c01, hc10 = h * c10;    // h C, (1,1) entry = -hc00
+  // adj(F) = [[f11, -f01], [-f10, f00]]
+  m.qp00 = f11 * hc00 - f01 * hc10; m.qp01 = f11 * hc01 + f01 * hc00;
+  m.qp10 = f00 * hc10 - f10 * hc00; m.qp11 = -(f10 * hc01 + f00 * hc00);
   return m;
 }
 
 SD_HD void rk4_step(const StepMat& m, double& ur, double& uz, double& tz, double& tr) {
   const double nur = m.pp00 * ur + m.pp01 * tz + m.pq00 * uz + m.pq01 * tr;
   const double ntz = m.pp10 * ur + m.pp11 * tz + m.pq10 * uz + m.pq11 * tr;
-  const double nuz = m.qp00 * ur + m.qp01 * tz + m.qq00 * uz + m.qq01 * tr;
-  const double ntr = m.qp10 * ur + m.qp11 * tz + m.qq10 * uz + m.qq11 * tr;
+  const double nuz = m.qp00 * ur + m.qp01 * tz + m.pp11 * uz - m.pp01 * tr;   // qq = adj(pp)
+  const double ntr = m.qp10 * ur + m.qp11 * tz - m.pp10 * uz + m.pp00 * tr;
   ur = nur; uz = nuz; tz = ntz; tr = ntr;
 }
 

@@ -854,7 +854,7 @@ struct P2Params {
 
 #ifndef P2_THREADS
 #define P2_THREADS 128
-#define P2_MINBLK 3
+#define P2_MINBLK 4
 #endif
 __global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __grid_constant__ P2Params p) {
   extern __shared__ float4 smem[];
