@@ -198,6 +198,14 @@ SD_HD void sd_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
 // For |u| < 0.5 (thin layers / long periods: the vast majority of layer steps) the series are used: no
 // square root, no MUFU, no branch on the sign of arg, and none of the cancellation that
 // (exp(x)-exp(-x))/2 suffers for small x (the reference's float32 form loses ~x^-1 ulps there).
+// Thin tier: degree-3 / degree-4 minimax polynomials on |u| <= 0.5 (constant term exact); their float32 evaluation
+// error (9e-8) is the rounding floor of the Horner scheme itself -- the Taylor polynomials need one more term each.
+#define SD_S1 1.66666666e-1f
+#define SD_S2 8.33389324e-3f
+#define SD_S3 1.98420544e-4f
+#define SD_C2 4.16666670e-2f
+#define SD_C3 1.38898493e-3f
+#define SD_C4 2.48008682e-5f
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
@@ -206,8 +214,8 @@ inline
 void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float& cs) {
   const float u = kd2 * arg;
   if (fabsf(u) < 0.5f) {
-    const float S = 1.f + u * (1.6666667e-1f + u * (8.3333333e-3f + u * (1.9841270e-4f + u * 2.7557319e-6f)));
-    cs = 1.f + u * (0.5f + u * (4.1666667e-2f + u * (1.3888889e-3f + u * (2.4801587e-5f + u * 2.7557319e-7f))));
+    const float S = 1.f + u * (SD_S1 + u * (SD_S2 + u * SD_S3));
+    cs = 1.f + u * (0.5f + u * (SD_C2 + u * (SD_C3 + u * SD_C4)));
     sinr = kd * S;
     rsin = -arg * sinr;
     return;
@@ -328,13 +336,11 @@ SD_HD void half_terms2(V2 narg, V2 kd, V2 nkd2, V2& rsin, V2& sinr, V2& cs) {
   const V2 u = vmul(nkd2, narg);
   const float um = fmaxf(fabsf(vx(u)), fabsf(vy(u)));
   if (um < 0.5f) {
-    V2 S = vfma(u, vs(2.7557319e-6f), vs(1.9841270e-4f));
-    S = vfma(u, S, vs(8.3333333e-3f));
-    S = vfma(u, S, vs(1.6666667e-1f));
+    V2 S = vfma(u, vs(SD_S3), vs(SD_S2));
+    S = vfma(u, S, vs(SD_S1));
     S = vfma(u, S, vs(1.f));
-    V2 C = vfma(u, vs(2.7557319e-7f), vs(2.4801587e-5f));
-    C = vfma(u, C, vs(1.3888889e-3f));
-    C = vfma(u, C, vs(4.1666667e-2f));
+    V2 C = vfma(u, vs(SD_C4), vs(SD_C3));
+    C = vfma(u, C, vs(SD_C2));
     C = vfma(u, C, vs(0.5f));
     cs = vfma(u, C, vs(1.f));
     sinr = vmul(kd, S);
@@ -398,12 +404,10 @@ SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, flo
 SD_HD bool series2x2(V2 up, V2 uq, V2 kd, V2& Sp_, V2& Cp_, V2& Sq_, V2& Cq_) {
   const float um = fmaxf(fmaxf(fabsf(vx(up)), fabsf(vy(up))), fmaxf(fabsf(vx(uq)), fabsf(vy(uq))));
   if (um < 0.5f) {
-    V2 Sp = vfma(up, vs(2.7557319e-6f), vs(1.9841270e-4f)), Sq = vfma(uq, vs(2.7557319e-6f), vs(1.9841270e-4f));
-    V2 Cp = vfma(up, vs(2.7557319e-7f), vs(2.4801587e-5f)), Cq = vfma(uq, vs(2.7557319e-7f), vs(2.4801587e-5f));
-    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
-    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
-    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
-    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
+    V2 Sp = vfma(up, vs(SD_S3), vs(SD_S2)), Sq = vfma(uq, vs(SD_S3), vs(SD_S2));
+    V2 Cp = vfma(up, vs(SD_C4), vs(SD_C3)), Cq = vfma(uq, vs(SD_C4), vs(SD_C3));
+    Sp = vfma(up, Sp, vs(SD_S1)); Sq = vfma(uq, Sq, vs(SD_S1));
+    Cp = vfma(up, Cp, vs(SD_C2)); Cq = vfma(uq, Cq, vs(SD_C2));
     Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
     Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
     Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
