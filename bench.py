@@ -26,6 +26,10 @@ UNIT = "evals/s"
 # FLOP-equivalents per unit of work, SURVEY.md 8(d): Rayleigh layer-step 150 FLOP + 4 transcendentals
 # (10 FLOP each), REIGEN sub-layer 1800 FLOP (fp64), flattening 12 FLOP + 3 transcendentals per layer.
 F_R, F_U, F_FLAT = 190.0, 1800.0, 42.0
+# FP64 FLOP the group-velocity kernel actually executes per sub-layer (per-layer step matrix + quadratic-form
+# accumulation instead of the reference's stage-by-stage RK4): 2 x DFMA + DMUL + DADD of the ncu capture
+# profiles/r1_ncu_prep_phase2_final.txt divided by the sub-layers counted on the device.
+F_U_EXEC = 520.0
 
 
 def parse():
@@ -275,7 +279,10 @@ def main():
                 "layer_steps_per_eval": steps_ctr / (M * K), "sweeps_per_eval": sweeps_ctr / (M * K),
                 "u_sublayers_per_eval": subu_ctr / (M * K),
                 "phase2": {"bound": "fp64", "achieved": subu_ctr * F_U / (kms[2] * 1e-3) * 1e-12, "peak": peaks[1],
-                           "unit": "TFLOP/s"},
+                           "unit": "TFLOP/s", "executed": subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12,
+                           "frac_executed": (subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12 / peaks[1]) if peaks[1] else None,
+                           "note": "achieved = reference-equivalent work (SURVEY 8d, %.0f FLOP per sub-layer); executed = "
+                                   "FP64 FLOP of this kernel's formulation (%.0f per sub-layer)" % (F_U, F_U_EXEC)},
                 "mufu_peak_Tops": peaks[2]}
         cpu = None
         if not args.no_cpu:

@@ -188,6 +188,9 @@ SD_HD float sd_ex2(float x) { return exp2f(x); }
 SD_HD void sd_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
 #endif
 #define SD_LOG2E 1.4426950408889634f
+// block-placement hints: the common path of the sweep loop (solid layer, thin-tier series) should fall through
+#define SD_LIKELY(x) __builtin_expect(!!(x), 1)
+#define SD_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 // One "half" of a layer propagator: for r = sqrt(|arg|) and x = kd*r returns
 //   (r sin x, sin x / r, cos x)  when arg < 0 (oscillatory, c above the layer velocity)
@@ -335,7 +338,7 @@ template <bool NEG>
 SD_HD void half_terms2(V2 narg, V2 kd, V2 nkd2, V2& rsin, V2& sinr, V2& cs) {
   const V2 u = vmul(nkd2, narg);
   const float um = fmaxf(fabsf(vx(u)), fabsf(vy(u)));
-  if (um < 0.5f) {
+  if (SD_LIKELY(um < 0.5f)) {
     V2 S = vfma(u, vs(SD_S3), vs(SD_S2));
     S = vfma(u, S, vs(SD_S1));
     S = vfma(u, S, vs(1.f));
@@ -397,47 +400,41 @@ SD_HD void rayleigh_hs_row(float csq, float icsq, const float4 R, float& r1, flo
   r2 = -SD_FDIV(ih12, g);
 }
 
-// P and SV series of one Rayleigh layer step together (u = nkd2 * narg per term): when all four arguments are in a
-// series tier (the common case) the four Horner chains are interleaved in one basic block -- no branch between them
-// and four independent dependency chains for the scheduler.  Returns false when a term is outside the series range;
-// the caller then takes half_terms2 per term.
-SD_HD bool series2x2(V2 up, V2 uq, V2 kd, V2& Sp_, V2& Cp_, V2& Sq_, V2& Cq_) {
-  const float um = fmaxf(fmaxf(fabsf(vx(up)), fabsf(vy(up))), fmaxf(fabsf(vx(uq)), fabsf(vy(uq))));
-  if (um < 0.5f) {
-    V2 Sp = vfma(up, vs(SD_S3), vs(SD_S2)), Sq = vfma(uq, vs(SD_S3), vs(SD_S2));
-    V2 Cp = vfma(up, vs(SD_C4), vs(SD_C3)), Cq = vfma(uq, vs(SD_C4), vs(SD_C3));
-    Sp = vfma(up, Sp, vs(SD_S1)); Sq = vfma(uq, Sq, vs(SD_S1));
-    Cp = vfma(up, Cp, vs(SD_C2)); Cq = vfma(uq, Cq, vs(SD_C2));
-    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
-    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
-    Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
-    Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
-    return true;
-  }
-  if (um < 3.0f) {
-    // S(u) = sum u^n / (2n+1)!,  C(u) = sum u^n / (2n)!;  |u|^10/21! < 2e-15, |u|^10/20! < 3e-14 relative
-    V2 Sp = vfma(up, vs(8.2206352e-18f), vs(2.8114573e-15f)), Sq = vfma(uq, vs(8.2206352e-18f), vs(2.8114573e-15f));
-    V2 Cp = vfma(up, vs(1.5619207e-16f), vs(4.7794773e-14f)), Cq = vfma(uq, vs(1.5619207e-16f), vs(4.7794773e-14f));
-    Sp = vfma(up, Sp, vs(7.6471637e-13f)); Sq = vfma(uq, Sq, vs(7.6471637e-13f));
-    Cp = vfma(up, Cp, vs(1.1470746e-11f)); Cq = vfma(uq, Cq, vs(1.1470746e-11f));
-    Sp = vfma(up, Sp, vs(1.6059044e-10f)); Sq = vfma(uq, Sq, vs(1.6059044e-10f));
-    Cp = vfma(up, Cp, vs(2.0876757e-9f)); Cq = vfma(uq, Cq, vs(2.0876757e-9f));
-    Sp = vfma(up, Sp, vs(2.5052108e-8f)); Sq = vfma(uq, Sq, vs(2.5052108e-8f));
-    Cp = vfma(up, Cp, vs(2.7557319e-7f)); Cq = vfma(uq, Cq, vs(2.7557319e-7f));
-    Sp = vfma(up, Sp, vs(2.7557319e-6f)); Sq = vfma(uq, Sq, vs(2.7557319e-6f));
-    Cp = vfma(up, Cp, vs(2.4801587e-5f)); Cq = vfma(uq, Cq, vs(2.4801587e-5f));
-    Sp = vfma(up, Sp, vs(1.9841270e-4f)); Sq = vfma(uq, Sq, vs(1.9841270e-4f));
-    Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
-    Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
-    Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
-    Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
-    Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
-    Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
-    Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
-    Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
-    return true;
-  }
-  return false;
+// P and SV series of one Rayleigh layer step together (u = nkd2 * narg per term): the four Horner chains are
+// interleaved in one basic block -- no branch between them and four independent dependency chains for the
+// scheduler.  thin: all four |u| < 0.5;  thick: all four |u| < 3.
+SD_HD void series_thin2x2(V2 up, V2 uq, V2 kd, V2& Sp_, V2& Cp_, V2& Sq_, V2& Cq_) {
+  V2 Sp = vfma(up, vs(SD_S3), vs(SD_S2)), Sq = vfma(uq, vs(SD_S3), vs(SD_S2));
+  V2 Cp = vfma(up, vs(SD_C4), vs(SD_C3)), Cq = vfma(uq, vs(SD_C4), vs(SD_C3));
+  Sp = vfma(up, Sp, vs(SD_S1)); Sq = vfma(uq, Sq, vs(SD_S1));
+  Cp = vfma(up, Cp, vs(SD_C2)); Cq = vfma(uq, Cq, vs(SD_C2));
+  Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
+  Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
+  Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
+  Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
+}
+
+SD_HD void series_thick2x2(V2 up, V2 uq, V2 kd, V2& Sp_, V2& Cp_, V2& Sq_, V2& Cq_) {
+  // S(u) = sum u^n / (2n+1)!,  C(u) = sum u^n / (2n)!;  |u|^10/21! < 2e-15, |u|^10/20! < 3e-14 relative
+  V2 Sp = vfma(up, vs(8.2206352e-18f), vs(2.8114573e-15f)), Sq = vfma(uq, vs(8.2206352e-18f), vs(2.8114573e-15f));
+  V2 Cp = vfma(up, vs(1.5619207e-16f), vs(4.7794773e-14f)), Cq = vfma(uq, vs(1.5619207e-16f), vs(4.7794773e-14f));
+  Sp = vfma(up, Sp, vs(7.6471637e-13f)); Sq = vfma(uq, Sq, vs(7.6471637e-13f));
+  Cp = vfma(up, Cp, vs(1.1470746e-11f)); Cq = vfma(uq, Cq, vs(1.1470746e-11f));
+  Sp = vfma(up, Sp, vs(1.6059044e-10f)); Sq = vfma(uq, Sq, vs(1.6059044e-10f));
+  Cp = vfma(up, Cp, vs(2.0876757e-9f)); Cq = vfma(uq, Cq, vs(2.0876757e-9f));
+  Sp = vfma(up, Sp, vs(2.5052108e-8f)); Sq = vfma(uq, Sq, vs(2.5052108e-8f));
+  Cp = vfma(up, Cp, vs(2.7557319e-7f)); Cq = vfma(uq, Cq, vs(2.7557319e-7f));
+  Sp = vfma(up, Sp, vs(2.7557319e-6f)); Sq = vfma(uq, Sq, vs(2.7557319e-6f));
+  Cp = vfma(up, Cp, vs(2.4801587e-5f)); Cq = vfma(uq, Cq, vs(2.4801587e-5f));
+  Sp = vfma(up, Sp, vs(1.9841270e-4f)); Sq = vfma(uq, Sq, vs(1.9841270e-4f));
+  Cp = vfma(up, Cp, vs(1.3888889e-3f)); Cq = vfma(uq, Cq, vs(1.3888889e-3f));
+  Sp = vfma(up, Sp, vs(8.3333333e-3f)); Sq = vfma(uq, Sq, vs(8.3333333e-3f));
+  Cp = vfma(up, Cp, vs(4.1666667e-2f)); Cq = vfma(uq, Cq, vs(4.1666667e-2f));
+  Sp = vfma(up, Sp, vs(1.6666667e-1f)); Sq = vfma(uq, Sq, vs(1.6666667e-1f));
+  Cp = vfma(up, Cp, vs(0.5f)); Cq = vfma(uq, Cq, vs(0.5f));
+  Sp = vfma(up, Sp, vs(1.f)); Sq = vfma(uq, Sq, vs(1.f));
+  Cp_ = vfma(up, Cp, vs(1.f)); Cq_ = vfma(uq, Cq, vs(1.f));
+  Sp_ = vmul(kd, Sp); Sq_ = vmul(kd, Sq);
 }
 
 #ifndef SD_RAY_UNROLL
@@ -465,15 +462,77 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
     r1 = v2(x1, y1); r2 = v2(x2, y2); r3 = v2(x3, y3); s4 = v2(-x4, -y4); r5 = v2(x5, y5);
   }
   const V2 one = vs(1.f), two = vs(2.f), mone = vs(-1.f);
-#pragma unroll kRayUnroll
+  // The loop body is laid out by hand (labels): the common path -- solid layer, thin-tier series -- runs straight
+  // through; the thick-tier / MUFU terms and the liquid layer sit behind it.  (Taken branches cost instruction-fetch
+  // bubbles: with them on the common path the kernel stalled on "no instruction" as often as on arithmetic.)
   for (int m = last - 1; m >= 0; --m) {
-    const float4 R = ld(m);
-    const float ia = sd_rcp(R.x), ia2 = ia * ia;
-    const V2 kd = vmul(wvno, vs(R.w));
-    const V2 nkd2 = vmul(kd, vmul(nwvno, vs(R.w)));
-    const V2 nargp = vfma(csq, vs(ia2), mone);
-    if (R.y == 0.f) {
-      V2 rsinp, sinpr, cosp;
+    float4 R;
+    float ia2, ib2, b2, irho, um;
+    V2 kd, nkd2, nargp, nargq, up, uq, sinpr, cosp, sinqr, cosq, tp, tq;   // tp = r sin x (P), tq = r sin x (SV)
+    R = ld(m);
+    { const float ia = sd_rcp(R.x); ia2 = ia * ia; }
+    kd = vmul(wvno, vs(R.w));
+    nkd2 = vmul(kd, vmul(nwvno, vs(R.w)));
+    nargp = vfma(csq, vs(ia2), mone);
+    if (R.y == 0.f) goto liquid_layer;
+    { const float ib = sd_rcp(R.y); ib2 = ib * ib; b2 = 2.0f * R.y * R.y; irho = sd_rcp(R.z); }
+    nargq = vfma(csq, vs(ib2), mone);
+    up = vmul(nkd2, nargp); uq = vmul(nkd2, nargq);
+    um = fmaxf(fmaxf(fabsf(vx(up)), fabsf(vy(up))), fmaxf(fabsf(vx(uq)), fabsf(vy(uq))));
+    if (!(um < 0.5f)) goto slow_terms;
+    series_thin2x2(up, uq, kd, sinpr, cosp, sinqr, cosq);
+    tp = vmul(nargp, sinpr); tq = vmul(nargq, sinqr);
+  have_terms:
+    {
+      const V2 g = vmul(vs(b2), icsq);
+      const V2 g1 = vadd(g, mone);
+      const V2 rhoc = vmul(vs(R.z), csq);
+      const V2 nirhoc = vmul(vs(irho), nicsq);
+      const V2 rr = vmul(tp, tq), ss = vmul(sinpr, sinqr), cc = vmul(cosp, cosq);
+      const V2 rs1 = vmul(tp, cosq), rs2 = vmul(sinqr, cosp), rs3 = vmul(sinpr, cosq), rs4 = vmul(tq, cosp);
+      const V2 nss = vmul(ss, mone);
+      const V2 m24 = vmul(nargq, nss), m42 = vmul(nargp, nss);   // -a24 = -sinpr tq,  -a42 = -tp sinqr
+      const V2 gs = vmul(g, g), g1s = vmul(g1, g1);
+      const V2 ccm = vfma(cc, mone, one);
+      // The five entries built from (rr, ss, 1 - cc) are  P_n = g^n rr + g1^n ss + (cross term) (1 - cc), n = 0..4.
+      // With A = g rr + g1 ccm, B = g1 ss + g ccm and g - g1 = 1:  P1 = A + B,  P2 = g A + g1 B,
+      // P3 = g^2 A + g1^2 B,  P4 = g^3 A + g1^3 B - g g1 ccm.
+      const V2 A = vfma(g, rr, vmul(g1, ccm)), B = vfma(g1, ss, vmul(g, ccm));
+      const V2 w = vfma(g, A, vmul(g1, B));                                              // P2
+      const V2 tA = vmul(gs, A), tB = vmul(g1s, B);
+      const V2 a11 = vfma(w, mone, cc);
+      const V2 a33 = vfma(two, w, one);
+      const V2 a12 = vmul(vadd(rs1, rs2), nirhoc);
+      const V2 m14 = vmul(vadd(rs3, rs4), nirhoc);                                       // = -a14
+      const V2 a13h = vmul(vadd(A, B), nirhoc);                                          // = 0.5 * a13   (P1)
+      const V2 a15 = vmul(vfma(two, ccm, vadd(rr, ss)), vmul(nirhoc, nirhoc));           // P0
+      const V2 a21 = vmul(rhoc, vfma(g1s, rs3, vmul(gs, rs4)));
+      const V2 m41 = vmul(rhoc, vfma(g1s, rs2, vmul(gs, rs1)));                          // = -a41
+      const V2 a23h = vfma(g, rs4, vmul(g1, rs3));                                       // = 0.5 * a23
+      const V2 a32 = vfma(g1, rs2, vmul(g, rs1));
+      const V2 a31 = vmul(rhoc, vadd(tA, tB));                                           // P3
+      const V2 a51 = vmul(vmul(rhoc, rhoc), vfma(vmul(vmul(g, g1), ccm), mone, vfma(g, tA, vmul(g1, tB))));   // P4
+      // s <- s A' (rows of A as in surfa.f:326-330, signs for s4 = -r4)
+      const V2 n1 = vfma(r1, a11, vfma(r2, a21, vfma(r3, a31, vfma(s4, m41, vmul(r5, a51)))));
+      const V2 n2 = vfma(r1, a12, vfma(r2, cc, vfma(r3, a32, vfma(s4, m42, vmul(r5, m41)))));
+      const V2 n3 = vfma(two, vfma(r1, a13h, vfma(r2, a23h, vfma(s4, a32, vmul(r5, a31)))), vmul(r3, a33));
+      const V2 n4 = vfma(r1, m14, vfma(r2, m24, vfma(r3, a23h, vfma(s4, cc, vmul(r5, a21)))));
+      const V2 n5 = vfma(r1, a15, vfma(r2, m14, vfma(r3, a13h, vfma(s4, a12, vmul(r5, a11)))));
+      r1 = n1; r2 = n2; r3 = n3; s4 = n4; r5 = n5;
+    }
+    continue;
+  slow_terms:
+    if (um < 3.0f) {
+      series_thick2x2(up, uq, kd, sinpr, cosp, sinqr, cosq);
+      tp = vmul(nargp, sinpr); tq = vmul(nargq, sinqr);
+    } else {
+      half_terms2<true>(nargp, kd, nkd2, tp, sinpr, cosp);
+      half_terms2<true>(nargq, kd, nkd2, tq, sinqr, cosq);
+    }
+    goto have_terms;
+  liquid_layer:
+    {
+      V2 rsinp;
       half_terms2<true>(nargp, kd, nkd2, rsinp, sinpr, cosp);
       if (ell_only) continue;
       const V2 a21 = vmul(vmul(vs(R.z), csq), sinpr);
@@ -484,52 +543,7 @@ SD_HD V2 rayleigh_adjoint2(V2 c, float T, int mmax, const float4* rec, bool ell_
       }
       const V2 n4 = vmul(r5, a21), n5 = vmul(r5, cosp);   // s4 = -r4 = +r5 a21
       r1 = n1; r2 = vs(0.f); r3 = vs(0.f); s4 = n4; r5 = n5;
-      continue;
     }
-    const float ib = sd_rcp(R.y), ib2 = ib * ib, b2 = 2.0f * R.y * R.y, irho = sd_rcp(R.z);
-    const V2 nargq = vfma(csq, vs(ib2), mone);
-    V2 sinpr, cosp, sinqr, cosq, tp, tq;   // tp = r sin x (P), tq = r sin x (SV)
-    if (series2x2(vmul(nkd2, nargp), vmul(nkd2, nargq), kd, sinpr, cosp, sinqr, cosq)) {
-      tp = vmul(nargp, sinpr); tq = vmul(nargq, sinqr);
-    } else {
-      half_terms2<true>(nargp, kd, nkd2, tp, sinpr, cosp);
-      half_terms2<true>(nargq, kd, nkd2, tq, sinqr, cosq);
-    }
-    const V2 g = vmul(vs(b2), icsq);
-    const V2 g1 = vadd(g, mone);
-    const V2 rhoc = vmul(vs(R.z), csq);
-    const V2 nirhoc = vmul(vs(irho), nicsq);
-    const V2 rr = vmul(tp, tq), ss = vmul(sinpr, sinqr), cc = vmul(cosp, cosq);
-    const V2 rs1 = vmul(tp, cosq), rs2 = vmul(sinqr, cosp), rs3 = vmul(sinpr, cosq), rs4 = vmul(tq, cosp);
-    const V2 nss = vmul(ss, mone);
-    const V2 m24 = vmul(nargq, nss), m42 = vmul(nargp, nss);   // -a24 = -sinpr tq,  -a42 = -tp sinqr
-    const V2 gs = vmul(g, g), g1s = vmul(g1, g1);
-    const V2 ccm = vfma(cc, mone, one);
-    // The five entries built from (rr, ss, 1 - cc) are  P_n = g^n rr + g1^n ss + (cross term) (1 - cc), n = 0..4.
-    // With A = g rr + g1 ccm, B = g1 ss + g ccm and g - g1 = 1:  P1 = A + B,  P2 = g A + g1 B,
-    // P3 = g^2 A + g1^2 B,  P4 = g^3 A + g1^3 B - g g1 ccm.
-    const V2 A = vfma(g, rr, vmul(g1, ccm)), B = vfma(g1, ss, vmul(g, ccm));
-    const V2 w = vfma(g, A, vmul(g1, B));                                              // P2
-    const V2 tA = vmul(gs, A), tB = vmul(g1s, B);
-    const V2 a11 = vfma(w, mone, cc);
-    const V2 a33 = vfma(two, w, one);
-    const V2 a12 = vmul(vadd(rs1, rs2), nirhoc);
-    const V2 m14 = vmul(vadd(rs3, rs4), nirhoc);                                       // = -a14
-    const V2 a13h = vmul(vadd(A, B), nirhoc);                                          // = 0.5 * a13   (P1)
-    const V2 a15 = vmul(vfma(two, ccm, vadd(rr, ss)), vmul(nirhoc, nirhoc));           // P0
-    const V2 a21 = vmul(rhoc, vfma(g1s, rs3, vmul(gs, rs4)));
-    const V2 m41 = vmul(rhoc, vfma(g1s, rs2, vmul(gs, rs1)));                          // = -a41
-    const V2 a23h = vfma(g, rs4, vmul(g1, rs3));                                       // = 0.5 * a23
-    const V2 a32 = vfma(g1, rs2, vmul(g, rs1));
-    const V2 a31 = vmul(rhoc, vadd(tA, tB));                                           // P3
-    const V2 a51 = vmul(vmul(rhoc, rhoc), vfma(vmul(vmul(g, g1), ccm), mone, vfma(g, tA, vmul(g1, tB))));   // P4
-    // s <- s A' (rows of A as in surfa.f:326-330, signs for s4 = -r4)
-    const V2 n1 = vfma(r1, a11, vfma(r2, a21, vfma(r3, a31, vfma(s4, m41, vmul(r5, a51)))));
-    const V2 n2 = vfma(r1, a12, vfma(r2, cc, vfma(r3, a32, vfma(s4, m42, vmul(r5, m41)))));
-    const V2 n3 = vfma(two, vfma(r1, a13h, vfma(r2, a23h, vfma(s4, a32, vmul(r5, a31)))), vmul(r3, a33));
-    const V2 n4 = vfma(r1, m14, vfma(r2, m24, vfma(r3, a23h, vfma(s4, cc, vmul(r5, a21)))));
-    const V2 n5 = vfma(r1, a15, vfma(r2, m14, vfma(r3, a13h, vfma(s4, a12, vmul(r5, a11)))));
-    r1 = n1; r2 = n2; r3 = n3; s4 = n4; r5 = n5;
   }
   e2 = r2; e3 = r3;
   return vneg(r1);

@@ -186,21 +186,28 @@ __device__ __forceinline__ unsigned interleave(unsigned a, unsigned b) {
   return r;
 }
 
-// Layer dropping (surfa.f:92-106) for ONE trial velocity, computed by the G lanes of a group together: each lane
-// sums the thicknesses of its contiguous chunk of layers (those with c < b), the chunk sums are prefixed across
-// the lanes, and the lane whose chunk crosses dmax = fact c T walks it again to find the layer.  The additions
-// inside a chunk are in the reference's order; the chunked total rounds differently from the reference's
-// single running sum only in the last ulp, i.e. the result can differ by one layer on an exact tie (1e-10 in c).
+// Layer dropping (surfa.f:92-106) for ONE trial velocity, computed by the G lanes of a group together.  Each lane
+// owns a contiguous chunk of layers, cut into four sub-chunks whose thickness sums (layers with c < b only) are
+// accumulated side by side -- four independent loads and additions per step instead of one dependent chain.  The
+// chunk sums are prefixed across the lanes; the lane whose chunk crosses dmax = fact c T picks the sub-chunk from its
+// partial sums and walks only that one, in the reference's order, to find the layer.  The additions inside a
+// sub-chunk are in the reference's order; the total rounds differently from the reference's single running sum
+// only in the last ulp, i.e. the result can differ by one layer on an exact tie (1e-5 per call).
 template <int G>
 __device__ __noinline__ int layer_drop_coop(float c, float T, float fact, int nmax, const float4* rec, unsigned gmask, int gl) {
   const float dmax = SD_MUL(SD_MUL(fact, c), T);
-  const int L = (nmax + G - 1) / G;
-  const int i0 = gl * L, i1 = min(i0 + L, nmax);
-  float s = 0.f;
-  for (int i = i0; i < i1; ++i) {
-    const float4 e = rec[i];
-    if (c < e.y) s = SD_ADD(s, e.w);
+  const int Q = (nmax + 4 * G - 1) / (4 * G);      // layers per sub-chunk
+  const int i0 = gl * 4 * Q;
+  float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+  for (int t = 0; t < Q; ++t) {
+    const int j0 = i0 + t, j1 = j0 + Q, j2 = j1 + Q, j3 = j2 + Q;
+    const float4 e0 = rec[min(j0, nmax - 1)], e1 = rec[min(j1, nmax - 1)], e2 = rec[min(j2, nmax - 1)], e3 = rec[min(j3, nmax - 1)];
+    if (j0 < nmax && c < e0.y) u0 = SD_ADD(u0, e0.w);
+    if (j1 < nmax && c < e1.y) u1 = SD_ADD(u1, e1.w);
+    if (j2 < nmax && c < e2.y) u2 = SD_ADD(u2, e2.w);
+    if (j3 < nmax && c < e3.y) u3 = SD_ADD(u3, e3.w);
   }
+  const float p1 = SD_ADD(u0, u1), p2 = SD_ADD(p1, u2), s = SD_ADD(p2, u3);
   // exclusive prefix over the lanes of the group
   float base = 0.f;
 #pragma unroll
@@ -210,8 +217,14 @@ __device__ __noinline__ int layer_drop_coop(float c, float T, float fact, int nm
   }
   int found = nmax;
   if (!(base > dmax) && SD_ADD(base, s) > dmax) {
-    float sum = base;
-    for (int i = i0; i < i1; ++i) {
+    // first sub-chunk whose end is beyond dmax
+    int q = 3; float sum = SD_ADD(base, p2);
+    if (SD_ADD(base, u0) > dmax) { q = 0; sum = base; }
+    else if (SD_ADD(base, p1) > dmax) { q = 1; sum = SD_ADD(base, u0); }
+    else if (SD_ADD(base, p2) > dmax) { q = 2; sum = SD_ADD(base, p1); }
+    const int b0 = i0 + q * Q, b1 = min(b0 + Q, nmax);
+    found = b1;      // (rounding of the split sums: the crossing is at the end of the sub-chunk at the latest)
+    for (int i = b0; i < b1; ++i) {
       const float4 e = rec[i];
       if (c < e.y) { sum = SD_ADD(sum, e.w); if (sum > dmax) { found = i + 1; break; } }
     }

@@ -1,0 +1,28 @@
+#!/bin/bash
+# GPU box: the round's evidence.  usage: bash tools/profile_round.sh <tag> <stage>
+#   stage bench    : plain bench (the numbers) + reference arm
+#   stage launches : ncu launch list of the short command (after it exited 0 without ncu)
+#   stage phase1   : ncu --set full of the two root-search launches
+#   stage other    : ncu --set full of prep + phase 2
+# Nothing printed under ncu is a bench value.
+TAG=${1:-r1}; STAGE=${2:-bench}
+mkdir -p gpurun_out
+CMD="python bench.py --models 524288 --steps 1 --warmup 3 --no-cpu --no-e2e"
+case $STAGE in
+bench)
+  python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || exit 1
+  python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
+  cut -c 1-600 gpurun_out/bench_$TAG.json; cut -c 1-300 gpurun_out/bench_ref_$TAG.json ;;
+launches)
+  $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 2
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 8 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > /dev/null 2>&1
+  tail -9 gpurun_out/launches_$TAG.csv | cut -c 1-200 ;;
+phase1)
+  $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 2
+  ncu --set full --clock-control none --import-source on -k regex:phase1 -s 6 -c 2 -o gpurun_out/prof_phase1_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
+  tail -2 gpurun_out/ncu_$TAG.log ;;
+other)
+  $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 2
+  ncu --set full --clock-control none --import-source on -k regex:"prep|phase2" -s 6 -c 2 -o gpurun_out/prof_other_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
+  tail -2 gpurun_out/ncu_$TAG.log ;;
+esac
