@@ -100,12 +100,25 @@ int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_
                           const float* obs, const float* sigma, const unsigned char* mask,
                           const float* periods, float* out, void* stream);
 
-/* Host-buffer wrapper: copies inputs to the device, runs surfdisp_batch, copies results back and
- * synchronises.  All pointers are HOST memory (pinned memory makes the copies asynchronous).
- * device = CUDA device ordinal. */
+/* Host-buffer wrapper: allocates device memory, copies inputs to the device, solves, copies results back and
+ * synchronises (through surfdisp_host_batch_pipelined, 8 chunks from 65536 models on).  All pointers are HOST
+ * memory (pinned memory makes the copies asynchronous).  device = CUDA device ordinal. */
 int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_models, int n_layers_max,
                         const int* n_layers, const float* layers, int n_periods, const float* periods,
                         float* c_out, float* u_out, int* nfound, int* flags);
+
+/* The same with caller-owned device memory and streams, as a pipeline: the batch is cut into n_chunks chunks;
+ * chunk i is copied host->device on copy_stream while chunk i-1 is prepared and its first period searched on
+ * compute_stream; the later periods run as one launch over the whole batch; the group velocities are computed
+ * chunk by chunk, each chunk copied device->host under the next one.  Host pointers should be pinned (pageable
+ * memory works but serialises the copies).  device_buffer: surfdisp_pipelined_bytes() bytes of device memory.
+ * Synchronises both streams: the host outputs are valid on return.  Replaces the per-model host round trip of
+ * models.py:27 (one f2py call per model) for a batch. */
+size_t surfdisp_pipelined_bytes(int n_models, int n_layers_max, int n_periods);
+int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
+                                  const int* n_layers, const float* layers, int n_periods, const float* periods,
+                                  float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                                  size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream);
 
 /* ABI-level replacement of the gfortran symbol FAST_SURF (fast_surf.f:2-5): one model, all arguments
  * by reference, host memory.  cvper has 200 entries of which the first *ncvper are used (init.f:62-72).

@@ -56,6 +56,11 @@ def load_library():
     L.surfdisp_host_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, C.c_int, ip, fp,
                                       C.c_int, fp, fp, fp, ip, ip]
     L.surfdisp_host_batch.restype = C.c_int
+    L.surfdisp_pipelined_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.surfdisp_pipelined_bytes.restype = C.c_size_t
+    L.surfdisp_host_batch_pipelined.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, ip, fp, C.c_int, fp,
+                                                fp, fp, ip, ip, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    L.surfdisp_host_batch_pipelined.restype = C.c_int
     L.fast_surf_.argtypes = [ip, ip, fp, fp, fp, fp, fp, fp, ip, fp, fp, fp, fp]
     L.fast_surf_.restype = None
     L.surfdisp_read_counters.argtypes = [vp, C.POINTER(C.c_ulonglong), vp]
@@ -289,76 +294,56 @@ class DispersionSolver:
         return self.forward_pinned(hl, hn, periods, kind, group, chunks)
 
     def forward_pinned(self, hl, hn, periods, kind=KIND_RAYLEIGH, group=True, chunks=None):
-        """Same as forward_host but the caller already holds pinned host tensors.  With chunks > 1 the batch is cut
-        into chunks whose host->device / device->host copies run on a copy stream while the neighbouring chunk is
-        being solved.  Measured on B200 (tools/e2e_chunks.py, 2^20 models x 40 periods): the copies are 35 ms of a
-        400 ms step (55 GB/s), while every extra launch of the persistent kernels costs ~10 ms of tail, so one
-        chunk is fastest; chunking is the default only for batches that would not fit device memory at once."""
+        """Same as forward_host but the caller already holds pinned host tensors (hl float32 [5][M][L], hn int32 [M]).
+        One call of surfdisp_host_batch_pipelined: the batch is cut into `chunks` chunks (default 8 from 65536
+        models on); a chunk is copied host->device while the previous one is prepared and its first period
+        searched, the later periods run as one launch over the whole batch, the group velocities are computed
+        chunk by chunk and copied out under the next chunk.  Batches above 2^21 models go through the same call
+        in pieces of 2^21 (bounded device memory)."""
         torch = self.torch
         M, lmax = int(hl.shape[1]), int(hl.shape[2])
-        K = int(np.asarray(periods).size)
-        if chunks is None:
-            chunks = 1 if M <= (1 << 21) else (M + (1 << 20) - 1) >> 20
-        chunks = max(1, min(int(chunks), M if M > 0 else 1))
+        per = np.ascontiguousarray(periods, dtype=np.float32)
+        K = int(per.size)
         hc = self._pin("c", (M, K), torch.float32)
         hf = self._pin("nf", (M,), torch.int32)
         hg = self._pin("fl", (M,), torch.int32)
         hu = self._pin("u", (M, K), torch.float32) if group else None
         if M == 0:
             return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+        piece = 1 << 21
         compute = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         copy = self._copy_stream
-        bounds = [(i * M) // chunks for i in range(chunks + 1)]
-        mc = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
-        key = (mc, lmax, K, bool(group))
-        if getattr(self, "_chunk_key", None) != key:
-            # double-buffered device staging for inputs and outputs
-            self._chunk_buf = [dict(lay=torch.empty((5, mc, lmax), dtype=torch.float32, device=self.device),
-                                    nl=torch.empty(mc, dtype=torch.int32, device=self.device),
-                                    c=torch.empty((mc, K), dtype=torch.float32, device=self.device),
-                                    u=torch.empty((mc, K), dtype=torch.float32, device=self.device) if group else None,
-                                    nfound=torch.empty(mc, dtype=torch.int32, device=self.device),
-                                    flags=torch.empty(mc, dtype=torch.int32, device=self.device)) for _ in range(2)]
-            self._chunk_key = key
-        copy.wait_stream(compute)
-        h2d_done, solved, d2h_done = [None] * chunks, [None] * chunks, [None] * chunks
+        ip = C.POINTER(C.c_int)
 
-        def upload(i):
-            a, b = bounds[i], bounds[i + 1]
-            buf = self._chunk_buf[i % 2]
-            with torch.cuda.stream(copy):
-                if i >= 2:
-                    copy.wait_event(d2h_done[i - 2])     # the buffer's previous results have left
-                for comp in range(5):
-                    buf["lay"][comp, :b - a].copy_(hl[comp, a:b], non_blocking=True)
-                buf["nl"][:b - a].copy_(hn[a:b], non_blocking=True)
-                h2d_done[i] = torch.cuda.Event(); h2d_done[i].record(copy)
+        def run(lay_t, nl_t, a, b):
+            m = b - a
+            nch = chunks if chunks is not None else (8 if m >= (1 << 16) else 1)
+            nch = max(1, min(int(nch), m))
+            need = int(self.lib.surfdisp_pipelined_bytes(m, lmax, K))
+            if getattr(self, "_pipe_buf", None) is None or self._pipe_buf.numel() < need:
+                self._pipe_buf = None
+                self._pipe_buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self.lib.surfdisp_host_batch_pipelined(
+                    C.byref(self.opts), int(kind), m, lmax, C.cast(C.c_void_p(nl_t.data_ptr()), ip),
+                    C.cast(C.c_void_p(lay_t.data_ptr()), C.POINTER(C.c_float)), K, _fptr(per),
+                    C.cast(C.c_void_p(hc[a:b].data_ptr()), C.POINTER(C.c_float)),
+                    C.cast(C.c_void_p(hu[a:b].data_ptr()), C.POINTER(C.c_float)) if group else None,
+                    C.cast(C.c_void_p(hf[a:b].data_ptr()), ip), C.cast(C.c_void_p(hg[a:b].data_ptr()), ip),
+                    C.c_void_p(self._pipe_buf.data_ptr()), C.c_size_t(self._pipe_buf.numel()), nch,
+                    C.c_void_p(compute.cuda_stream), C.c_void_p(copy.cuda_stream))
+            _check(rc, "surfdisp_host_batch_pipelined")
 
-        upload(0)
-        for i in range(chunks):
-            a, b = bounds[i], bounds[i + 1]
-            n = b - a
-            buf = self._chunk_buf[i % 2]
-            if i + 1 < chunks:
-                upload(i + 1)
-            compute.wait_event(h2d_done[i])
-            lay = buf["lay"] if n == mc else buf["lay"][:, :n].contiguous()
-            out = dict(c=buf["c"][:n], u=None if buf["u"] is None else buf["u"][:n], nfound=buf["nfound"][:n],
-                       flags=buf["flags"][:n])
-            self.forward(lay, buf["nl"][:n], periods, kind, group, out=out)
-            solved[i] = torch.cuda.Event(); solved[i].record(compute)
-            with torch.cuda.stream(copy):
-                copy.wait_event(solved[i])
-                hc[a:b].copy_(out["c"], non_blocking=True)
-                hf[a:b].copy_(out["nfound"], non_blocking=True)
-                hg[a:b].copy_(out["flags"], non_blocking=True)
-                if group:
-                    hu[a:b].copy_(out["u"], non_blocking=True)
-                d2h_done[i] = torch.cuda.Event(); d2h_done[i].record(copy)
-        compute.wait_stream(copy)
-        compute.synchronize()
+        if M <= piece:
+            run(hl, hn, 0, M)
+        else:
+            for a in range(0, M, piece):
+                b = min(M, a + piece)
+                st = self._pin("lay_piece", (5, b - a, lmax), torch.float32)
+                st.copy_(hl[:, a:b])
+                run(st, hn[a:b], a, b)
         return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
 
 

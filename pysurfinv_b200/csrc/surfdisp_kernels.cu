@@ -68,13 +68,14 @@ int cuda_fail(cudaError_t e, const char* where) {
 // done here with a 32-step shuffle loop per chunk of 32 layers.
 __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, int kind, int flatten,
                                                    const int* __restrict__ nlay,
-                                                   const float* __restrict__ layers, float* __restrict__ consts) {
+                                                   const float* __restrict__ layers, size_t comp_stride,
+                                                   float* __restrict__ consts) {
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
   const int n = nlay[m];
   if (n < 2 || n > lmax) return;
-  const size_t pl = (size_t)M * lmax;
+  const size_t pl = comp_stride;   // distance between the five input rows (the whole batch, not the launched range)
   const float* a = layers + 0 * pl + (size_t)m * lmax;
   const float* b = layers + 1 * pl + (size_t)m * lmax;
   const float* rho = layers + 2 * pl + (size_t)m * lmax;
@@ -1293,79 +1294,219 @@ size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods) {
   return ws_layout(n_models, n_layers_max, n_periods).total;
 }
 
-int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
-                   const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
-                   int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+// ---- the batch as a plan plus stages over a range of models [a, b): surfdisp_batch runs every stage on the whole
+// batch, the host path runs the first stages chunk by chunk under the host->device copies
+struct Plan {
   SurfdispOpts o;
-  if (opts) o = *opts; else surfdisp_default_opts(&o);
+  int kind, M, lmax, K;
+  WsLayout w;
+  const int* nlay; const float* layers;
+  float *c_out, *u_out, *consts, *ratio;
+  int *nfound, *flags, *mm_state;
+  unsigned long long* counters;
+  unsigned int* queue;
+  PeriodTab tab;
+};
+
+static int make_plan(Plan& pl, const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                     const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
+                     int* nfound, int* flags, void* workspace, size_t workspace_bytes) {
+  if (opts) pl.o = *opts; else surfdisp_default_opts(&pl.o);
   if ((kind != 1 && kind != 2) || n_models < 0 || n_layers_max < 2 || n_layers_max > SURFDISP_MAX_LAYERS ||
-      n_periods < 1 || n_periods > kMaxPer || !periods || !(o.dc > 0.f))
+      n_periods < 1 || n_periods > kMaxPer || !periods || !(pl.o.dc > 0.f))
     return SURFDISP_EINVAL;
   if (n_models == 0) return 0;
   if (!n_layers || !layers || !c_out || !nfound || !workspace) return SURFDISP_EINVAL;
-  const WsLayout w = ws_layout(n_models, n_layers_max, n_periods);
-  if (workspace_bytes < w.total) return SURFDISP_ENOMEM;
-  cudaStream_t st = (cudaStream_t)stream;
+  pl.w = ws_layout(n_models, n_layers_max, n_periods);
+  if (workspace_bytes < pl.w.total) return SURFDISP_ENOMEM;
   char* ws = (char*)workspace;
-  unsigned long long* counters = (unsigned long long*)ws;
-  unsigned int* queue = (unsigned int*)(ws + 64);
-  float* consts = (float*)(ws + w.consts_off);
-  float* ratio = (float*)(ws + w.ratio_off);
+  pl.kind = kind; pl.M = n_models; pl.lmax = n_layers_max; pl.K = n_periods;
+  pl.nlay = n_layers; pl.layers = layers; pl.c_out = c_out; pl.u_out = u_out; pl.nfound = nfound; pl.flags = flags;
+  pl.counters = (unsigned long long*)ws;
+  pl.queue = (unsigned int*)(ws + 64);
+  pl.consts = (float*)(ws + pl.w.consts_off);
+  pl.ratio = (float*)(ws + pl.w.ratio_off);
+  pl.mm_state = (int*)(ws + pl.w.mm_off);
+  return fill_tab(pl.tab, n_periods, periods, pl.o.t_base);
+}
+
+// the first launch of the root search covers the periods [0, k_split)
+static int k_split(const Plan& pl) { return (pl.K > 1 && !pl.o.exact_scan) ? 1 : pl.K; }
+
+static int stage_prep(const Plan& pl, int a, int b, cudaStream_t st) {
+  const int m = b - a;
+  if (m <= 0) return 0;
+  prep_kernel<<<(unsigned)(((size_t)m * 32 + 127) / 128), 128, 0, st>>>(
+      m, pl.lmax, pl.w.lpad, pl.kind, pl.o.flatten, pl.nlay + a, pl.layers + (size_t)a * pl.lmax, (size_t)pl.M * pl.lmax,
+      pl.consts + (size_t)a * NCONST * pl.w.lpad);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// root search of the periods [k_begin, k_end) for the models [a, b)
+static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaStream_t st) {
+  if (b <= a || k_end <= k_begin) return 0;
   P1Params p1;
   memset(&p1, 0, sizeof(p1));
-  p1.kind = kind; p1.M = n_models; p1.lpad = w.lpad; p1.K = n_periods; p1.nlay = n_layers; p1.consts = consts;
-  p1.c_out = c_out; p1.ratio_out = ratio; p1.nfound = nfound; p1.flags = flags; p1.counters = counters;
-  p1.queue = queue; p1.dc = o.dc; p1.fact = o.fact; p1.atten = o.atten; p1.stale = o.stale_mmax; p1.exact_scan = o.exact_scan;
-  int rc = fill_tab(p1.tab, n_periods, periods, o.t_base);
-  if (rc) return rc;
-  CK(cudaMemsetAsync(ws, 0, kHdrBytes, st));
-  if (g_prof_events) CK(cudaEventRecord(g_prof_events[0], st));
+  p1.kind = pl.kind; p1.M = b - a; p1.lpad = pl.w.lpad; p1.K = pl.K; p1.nlay = pl.nlay + a;
+  p1.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
+  p1.c_out = pl.c_out + (size_t)a * pl.K; p1.ratio_out = pl.ratio + (size_t)a * pl.K; p1.nfound = pl.nfound + a;
+  p1.flags = pl.flags ? pl.flags + a : nullptr; p1.counters = pl.counters; p1.queue = pl.queue;
+  p1.dc = pl.o.dc; p1.fact = pl.o.fact; p1.atten = pl.o.atten; p1.stale = pl.o.stale_mmax; p1.exact_scan = pl.o.exact_scan;
+  p1.tab = pl.tab;
+  p1.mm_state = pl.mm_state + a;
+  p1.k_begin = k_begin; p1.k_end = k_end;
+  CK(cudaMemsetAsync(pl.queue, 0, sizeof(unsigned int), st));
+  return launch_phase1<P1_G>(p1, st);
+}
 
-  prep_kernel<<<(unsigned)(((size_t)n_models * 32 + 127) / 128), 128, 0, st>>>(n_models, n_layers_max, w.lpad, kind, o.flatten,
-                                                                               n_layers, layers, consts);
+static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
+  const int m = b - a;
+  if (m <= 0 || !pl.u_out) return 0;
+  if (!pl.o.compute_group) {
+    CK(cudaMemsetAsync(pl.u_out + (size_t)a * pl.K, 0, (size_t)m * pl.K * sizeof(float), st));
+    return 0;
+  }
+  P2Params p2;
+  memset(&p2, 0, sizeof(p2));
+  p2.kind = pl.kind; p2.M = m; p2.lpad = pl.w.lpad; p2.K = pl.K; p2.nlay = pl.nlay + a;
+  p2.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
+  p2.c_in = pl.c_out + (size_t)a * pl.K; p2.ratio_in = pl.ratio + (size_t)a * pl.K; p2.nfound = pl.nfound + a;
+  p2.u_out = pl.u_out + (size_t)a * pl.K; p2.counters = pl.counters;
+  p2.fact = pl.o.fact; p2.atten = pl.o.atten; p2.ndiv = pl.o.ndiv;
+  p2.ndiv_cap = (pl.kind == 2) ? pl.o.ndiv_cap_rayleigh : pl.o.ndiv_cap_love;
+  p2.tab = pl.tab;
+  const size_t per_model = (size_t)NCONST * pl.w.lpad * sizeof(float);
+  int mpb = P2_THREADS / pl.K;
+  if (mpb < 1) mpb = 1;
+  while (mpb > 1 && mpb * per_model > 96 * 1024) --mpb;
+  if (mpb * per_model > 200 * 1024) return SURFDISP_EINVAL;
+  p2.mpb = mpb;
+  int threads = round_up(mpb * pl.K, 32);
+  if (threads > P2_THREADS) threads = P2_THREADS;
+  const size_t smem = mpb * per_model;
+  CK(cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (m + mpb - 1) / mpb;
+  phase2_kernel<<<grid, threads, smem, st>>>(p2);
   CK(cudaGetLastError());
+  return 0;
+}
 
+int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                   const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
+                   int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(pl, opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out, u_out, nfound,
+                     flags, workspace, workspace_bytes);
+  if (rc || n_models == 0) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(workspace, 0, kHdrBytes, st));
+  if (g_prof_events) CK(cudaEventRecord(g_prof_events[0], st));
+  if ((rc = stage_prep(pl, 0, n_models, st))) return rc;
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[1], st));
   // The scan of the first period (calcul.f:155-167 from 0.9 b(1)) consists of many shallow sweeps, the later
   // periods of one or two deep ones each: run as separate launches, the groups of a warp never mix the two.
-  p1.mm_state = (int*)(ws + w.mm_off);
-  p1.k_begin = 0; p1.k_end = (n_periods > 1 && !o.exact_scan) ? 1 : n_periods;
-  rc = launch_phase1<P1_G>(p1, st);
-  if (rc) return rc;
-  if (p1.k_end < n_periods) {
-    CK(cudaMemsetAsync(p1.queue, 0, sizeof(unsigned int), st));
-    p1.k_begin = p1.k_end; p1.k_end = n_periods;
-    rc = launch_phase1<P1_G>(p1, st);
-    if (rc) return rc;
-  }
+  const int ks = k_split(pl);
+  if ((rc = stage_p1(pl, 0, n_models, 0, ks, st))) return rc;
+  if ((rc = stage_p1(pl, 0, n_models, ks, n_periods, st))) return rc;
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[2], st));
-
-  if (u_out && o.compute_group) {
-    P2Params p2;
-    memset(&p2, 0, sizeof(p2));
-    p2.kind = kind; p2.M = n_models; p2.lpad = w.lpad; p2.K = n_periods; p2.nlay = n_layers; p2.consts = consts;
-    p2.c_in = c_out; p2.ratio_in = ratio; p2.nfound = nfound; p2.u_out = u_out; p2.counters = counters;
-    p2.fact = o.fact; p2.atten = o.atten; p2.ndiv = o.ndiv;
-    p2.ndiv_cap = (kind == 2) ? o.ndiv_cap_rayleigh : o.ndiv_cap_love;
-    p2.tab = p1.tab;
-    const size_t per_model = (size_t)NCONST * w.lpad * sizeof(float);
-    int mpb = P2_THREADS / n_periods;
-    if (mpb < 1) mpb = 1;
-    while (mpb > 1 && mpb * per_model > 96 * 1024) --mpb;
-    if (mpb * per_model > 200 * 1024) return SURFDISP_EINVAL;
-    p2.mpb = mpb;
-    int threads = round_up(mpb * n_periods, 32);
-    if (threads > P2_THREADS) threads = P2_THREADS;
-    size_t smem = mpb * per_model;
-    CK(cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (n_models + mpb - 1) / mpb;
-    phase2_kernel<<<grid, threads, smem, st>>>(p2);
-    CK(cudaGetLastError());
-  } else if (u_out) {
-    CK(cudaMemsetAsync(u_out, 0, (size_t)n_models * n_periods * sizeof(float), st));
-  }
+  if ((rc = stage_p2(pl, 0, n_models, st))) return rc;
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[3], st));
   return 0;
+}
+
+size_t surfdisp_pipelined_bytes(int n_models, int n_layers_max, int n_periods) {
+  if (n_models < 0 || n_layers_max < 2 || n_periods < 1) return 0;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t nl = (size_t)5 * n_models * n_layers_max * sizeof(float), no = (size_t)n_models * n_periods * sizeof(float);
+  return al(nl) + 3 * al((size_t)n_models * sizeof(int)) + 2 * al(no) + surfdisp_workspace_bytes(n_models, n_layers_max, n_periods);
+}
+
+int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
+                                  const int* n_layers, const float* layers, int n_periods, const float* periods,
+                                  float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                                  size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream) {
+  if (n_models < 0 || n_layers_max < 2 || n_periods < 1 || n_periods > kMaxPer) return SURFDISP_EINVAL;
+  if (n_models == 0) return 0;
+  if (!n_layers || !layers || !c_out || !nfound || !periods || !device_buffer) return SURFDISP_EINVAL;
+  if (device_bytes < surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods)) return SURFDISP_ENOMEM;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 64) n_chunks = 64;
+  if (n_chunks > n_models) n_chunks = n_models;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t M = (size_t)n_models, L = (size_t)n_layers_max, K = (size_t)n_periods;
+  const size_t nl = 5 * M * L * sizeof(float), no = M * K * sizeof(float), ni = M * sizeof(int);
+  char* dev = (char*)device_buffer;
+  const size_t o_lay = 0, o_n = o_lay + al(nl), o_c = o_n + al(ni), o_u = o_c + al(no), o_nf = o_u + al(no),
+               o_fl = o_nf + al(ni), o_ws = o_fl + al(ni);
+  float* d_lay = (float*)(dev + o_lay);
+  int* d_n = (int*)(dev + o_n);
+  float *d_c = (float*)(dev + o_c), *d_u = u_out ? (float*)(dev + o_u) : nullptr;
+  int *d_nf = (int*)(dev + o_nf), *d_fl = (int*)(dev + o_fl);
+  Plan pl;
+  int rc = make_plan(pl, opts, kind, n_models, n_layers_max, d_n, d_lay, n_periods, periods, d_c, d_u, d_nf, d_fl,
+                     dev + o_ws, device_bytes - o_ws);
+  if (rc) return rc;
+  cudaStream_t cs = (cudaStream_t)compute_stream, xs = (cudaStream_t)copy_stream;
+  cudaEvent_t ev[2 * 64 + 2];
+  int nev = 0;
+  auto new_event = [&](cudaEvent_t& e) -> cudaError_t { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r == cudaSuccess) ev[nev++] = e; return r; };
+  cudaError_t e = cudaSuccess;
+#define PCK(call, what) if ((e = (call)) != cudaSuccess) { rc = cuda_fail(e, what); break; }
+  do {
+    cudaEvent_t start, roots;
+    PCK(new_event(start), "event");
+    PCK(cudaMemsetAsync(dev + o_ws, 0, kHdrBytes, cs), "memset");
+    PCK(cudaEventRecord(start, cs), "record");         // earlier work on the compute stream may still read the buffers
+    PCK(cudaStreamWaitEvent(xs, start, 0), "wait");
+    const int ks = k_split(pl);
+    // stage 1: host->device copy of chunk i under preparation + first-period root search of chunk i-1
+    for (int i = 0; i < n_chunks && rc == 0; ++i) {
+      const int a = (int)((long long)n_models * i / n_chunks), b = (int)((long long)n_models * (i + 1) / n_chunks);
+      const size_t cnt = (size_t)(b - a);
+      for (int comp = 0; comp < 5 && e == cudaSuccess; ++comp)
+        e = cudaMemcpyAsync(d_lay + comp * M * L + (size_t)a * L, layers + comp * M * L + (size_t)a * L, cnt * L * sizeof(float),
+                            cudaMemcpyHostToDevice, xs);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "H2D layers"); break; }
+      PCK(cudaMemcpyAsync(d_n + a, n_layers + a, cnt * sizeof(int), cudaMemcpyHostToDevice, xs), "H2D nlay");
+      cudaEvent_t up;
+      PCK(new_event(up), "event");
+      PCK(cudaEventRecord(up, xs), "record");
+      PCK(cudaStreamWaitEvent(cs, up, 0), "wait");
+      if ((rc = stage_prep(pl, a, b, cs))) break;
+      if ((rc = stage_p1(pl, a, b, 0, ks, cs))) break;
+    }
+    if (rc) break;
+    // stage 2: the later periods on the whole batch (one persistent launch: its tail is paid once)
+    if ((rc = stage_p1(pl, 0, n_models, ks, n_periods, cs))) break;
+    PCK(new_event(roots), "event");
+    PCK(cudaEventRecord(roots, cs), "record");
+    PCK(cudaStreamWaitEvent(xs, roots, 0), "wait");
+    PCK(cudaMemcpyAsync(nfound, d_nf, ni, cudaMemcpyDeviceToHost, xs), "D2H nfound");
+    if (flags) PCK(cudaMemcpyAsync(flags, d_fl, ni, cudaMemcpyDeviceToHost, xs), "D2H flags");
+    PCK(cudaMemcpyAsync(c_out, d_c, no, cudaMemcpyDeviceToHost, xs), "D2H c");
+    // stage 3: group velocities chunk by chunk, each chunk copied out under the next one
+    if (u_out) {
+      for (int i = 0; i < n_chunks && rc == 0; ++i) {
+        const int a = (int)((long long)n_models * i / n_chunks), b = (int)((long long)n_models * (i + 1) / n_chunks);
+        if ((rc = stage_p2(pl, a, b, cs))) break;
+        cudaEvent_t done;
+        PCK(new_event(done), "event");
+        PCK(cudaEventRecord(done, cs), "record");
+        PCK(cudaStreamWaitEvent(xs, done, 0), "wait");
+        PCK(cudaMemcpyAsync(u_out + (size_t)a * K, d_u + (size_t)a * K, (size_t)(b - a) * K * sizeof(float), cudaMemcpyDeviceToHost, xs),
+            "D2H u");
+      }
+      if (rc) break;
+    }
+  } while (0);
+#undef PCK
+  // results are valid on return
+  cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(xs);
+  for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  if (rc == 0 && e1 != cudaSuccess) rc = cuda_fail(e1, "sync compute");
+  if (rc == 0 && e2 != cudaSuccess) rc = cuda_fail(e2, "sync copy");
+  return rc;
 }
 
 int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_pred, const int* nfound,
@@ -1402,33 +1543,18 @@ int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_mo
   if (n_models == 0) return 0;
   if (!n_layers || !layers || !c_out || !nfound || !periods) return SURFDISP_EINVAL;
   CK(cudaSetDevice(device));
-  const size_t nl = (size_t)5 * n_models * n_layers_max * sizeof(float);
-  const size_t no = (size_t)n_models * n_periods * sizeof(float);
-  const size_t wsb = surfdisp_workspace_bytes(n_models, n_layers_max, n_periods);
+  const size_t total = surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods);
   char* dev = nullptr;
-  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t o_lay = 0, o_n = o_lay + al(nl), o_c = o_n + al(n_models * sizeof(int)), o_u = o_c + al(no),
-               o_nf = o_u + al(no), o_fl = o_nf + al(n_models * sizeof(int)), o_ws = o_fl + al(n_models * sizeof(int)),
-               total = o_ws + wsb;
   CK(cudaMalloc(&dev, total));
-  cudaStream_t st;
+  cudaStream_t st = nullptr, xs = nullptr;
   cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { cudaFree(dev); return cuda_fail(e, "cudaStreamCreate"); }
-  int rc = 0;
-  do {
-    if ((e = cudaMemcpyAsync(dev + o_lay, layers, nl, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D layers"); break; }
-    if ((e = cudaMemcpyAsync(dev + o_n, n_layers, n_models * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D nlay"); break; }
-    rc = surfdisp_batch(opts, kind, n_models, n_layers_max, (const int*)(dev + o_n), (const float*)(dev + o_lay),
-                        n_periods, periods, (float*)(dev + o_c), u_out ? (float*)(dev + o_u) : nullptr,
-                        (int*)(dev + o_nf), (int*)(dev + o_fl), dev + o_ws, wsb, st);
-    if (rc) break;
-    if ((e = cudaMemcpyAsync(c_out, dev + o_c, no, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H c"); break; }
-    if (u_out && (e = cudaMemcpyAsync(u_out, dev + o_u, no, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H u"); break; }
-    if ((e = cudaMemcpyAsync(nfound, dev + o_nf, n_models * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H nfound"); break; }
-    if (flags && (e = cudaMemcpyAsync(flags, dev + o_fl, n_models * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H flags"); break; }
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "sync"); break; }
-  } while (0);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { if (st) cudaStreamDestroy(st); cudaFree(dev); return cuda_fail(e, "cudaStreamCreate"); }
+  const int chunks = n_models >= (1 << 16) ? 8 : 1;
+  const int rc = surfdisp_host_batch_pipelined(opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out,
+                                               u_out, nfound, flags, dev, total, chunks, st, xs);
   cudaStreamDestroy(st);
+  cudaStreamDestroy(xs);
   cudaFree(dev);
   return rc;
 }
