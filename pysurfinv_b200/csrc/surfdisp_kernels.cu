@@ -886,7 +886,9 @@ __global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __g
   __syncthreads();
   unsigned long long nsub = 0;
   for (int t = threadIdx.x; t < nmod * K; t += blockDim.x) {
-    const int ml = t / K, k = t - ml * K;
+    // period-major inside the block: the 32 work items of a warp are neighbouring periods of the block's models,
+    // i.e. integrations of similar depth (the depth grows with the period)
+    const int k = t / nmod, ml = t - k * nmod;
     const int model = model0 + ml;
     float* urow = p.u_out + (size_t)model * K;
     const int n = p.nlay[model];
