@@ -153,6 +153,26 @@ def test_host_batch_matches_device_path(solver):
     assert np.array_equal(p["c"], g["c"]) and np.array_equal(p["u"], g["u"])
 
 
+def test_pipelined_host_batch_large(solver):
+    """surfdisp_host_batch above 65536 models runs as an 8-chunk pipeline (copies under the kernels, first period per
+    chunk, later periods in one launch, group velocities per chunk): identical to the device-resident call, Rayleigh
+    and Love, pageable host memory through the pure C ABI and pinned memory through the solver."""
+    from pysurfinv_b200 import api
+    lay, nl = synth.ragged_models(70001, seed=33)
+    per = np.array([10, 14, 20, 28, 40, 60], np.float32)
+    for kind in (2, 1):
+        g = _gpu(solver, lay, nl, per, kind)
+        h = api.host_batch(lay, nl, per, kind)
+        for key in ("c", "u", "nfound", "flags"):
+            assert np.array_equal(h[key], g[key]), key
+        p = solver.forward_host(lay, nl, per, kind)
+        for key in ("c", "u", "nfound", "flags"):
+            assert np.array_equal(p[key], g[key]), key
+    # phase velocities only
+    p = solver.forward_host(lay, nl, per, 2, group=False)
+    assert np.array_equal(p["c"], _gpu(solver, lay, nl, per, 2)["c"]) and p["u"] is None
+
+
 def test_misfit_kernel(solver):
     import torch
     from pysurfinv_b200.forward import misfit as host_misfit
