@@ -174,7 +174,9 @@ __device__ __forceinline__ int gshfl(unsigned mask, int v, int src) { return __s
 struct SamplePt { float c, d, e2, e3; };
 
 constexpr float kInterpTol = 1.0e-5f;   // agreement of the 4- and 6-point root estimates that ends the refinement
-constexpr float kClusterTol = 2.0e-6f;  // same, for the first round (cluster around the predicted root, bracket <= 3e-3 km/s)
+constexpr float kClusterTol = 2.0e-6f;  // same, for the first round (cluster around the predicted root)
+constexpr float kClusterWmax = 6.0e-3f; // widest bracket of a first-round cluster that may be accepted (the cluster's spacing never exceeds it;
+                                        // window rounds on the 0.01 grid never are)
 constexpr float kBracketTol = 2.0e-5f;  // bracket width below which a secant step is final
 constexpr float kClusterH0 = 2.5e-4f;   // smallest innermost spacing of the first-round cluster
 
@@ -251,6 +253,9 @@ __device__ __noinline__ bool nevill_out_of_line(const SecFn& f, float c1, float 
 #ifndef P1_G
 #define P1_G 4
 #endif
+#ifndef P1_SOFT_SYNC
+#define P1_SOFT_SYNC 4     // 0 = every group pulls its next model as soon as it is done
+#endif
 #ifndef P1_MINBLK
 #define P1_MINBLK 4
 #endif
@@ -308,7 +313,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   float* crow = p.c_out;
   float* rrow = p.ratio_out;
   float c1 = 1.f, c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 1.0e-3f, c_pred = 0.f, b_top = 0.f, T = 1.f;
-  bool hopped = false, mid_liquid = false;
+  int hopped = 0;            // > 0: the root left the extrapolation of its branch; periods of good predictions still required
+  bool mid_liquid = false;
   // ---- the sweep request of the current iteration (per lane) and its result
   float2 pc = make_float2(1.f, 1.f), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
   int meval = 2, ell_only = 0;
@@ -439,6 +445,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     // warp whose groups sit at very different periods would run every sweep to the depth of the deepest one).
 #ifdef P1_SYNC_MODELS
     const bool warp_fetch = __all_sync(0xffffffffu, stage == ST_FETCH || stage == ST_DONE);
+#elif P1_SOFT_SYNC > 0
+    // soft re-alignment at model boundaries: a group that is done waits for the groups of its warp that are
+    // within P1_SOFT_SYNC periods of finishing (not for stragglers, not for models that are being scanned every
+    // period), so that the next models start together again
+    const bool near_end = (stage != ST_FETCH && stage != ST_DONE) && !hopped && (p.k_end - p.k_begin > 8) &&
+                          (p.k_end - k <= P1_SOFT_SYNC);
+    const bool warp_fetch = __ballot_sync(0xffffffffu, near_end) == 0u;
 #else
     const bool warp_fetch = true;
 #endif
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
             if (b0 < 0.1f) c1 = 0.5f;
           }
           mm = n;  // reference COMMON mmax carried from period to period
-          nfound = 0; flag = 0; k = p.k_begin; hopped = false;
+          nfound = 0; flag = 0; k = p.k_begin; hopped = 0;
           c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 1.0e-3f;
           stage = ST_PERIOD;
           if (k > 0) {
@@ -788,7 +801,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       // accepted when the two orders agree AND the bracket has two samples on either side (one-sided
       // estimates agree with each other without being right); never on the 0.01 km/s grid of a window
       const bool interior = (jb >= 2 && jb <= np - 2);
-      const float tol = (it > 0) ? kInterpTol : ((fstage == 0 && w <= 3.0e-3f) ? kClusterTol : -1.f);
+      const float tol = (it > 0) ? kInterpTol : ((fstage == 0 && w <= kClusterWmax) ? kClusterTol : -1.f);
       if ((inside && interior && delta <= tol) || w <= kBracketTol) {
         croot = B0.c + e;
         if (p.kind == 2) {
@@ -826,7 +839,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 
     if (period_done) {
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
-      if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
+      if (k >= 2) {
+        // A root more than 0.1 km/s off the extrapolation: mode hopping, or a branch that bends too fast to be
+        // extrapolated (thick slow sediments at the short-period end).  Scan from c1 like the reference until
+        // two periods in a row were predictable again.
+        pred_err = fabsf(croot - c_pred);
+        if (pred_err > 0.1f) hopped = 2;
+        else if (hopped > 0) hopped = (pred_err < 0.01f) ? hopped - 1 : 2;
+      }
       c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot;
       nfound = ++k;
       if (k == p.k_end) model_done = true; else stage = ST_PERIOD;

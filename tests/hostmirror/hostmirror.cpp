@@ -50,7 +50,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   bool mid_liquid = false;
   for (int i = 1; i < n; ++i) mid_liquid |= !(cst[C_BREF * ld + i] > 0.f);
   int mm = n, nfound = 0;
-  bool hopped = false;   // the root left the extrapolation of its branch once: scan this model point by point
+  int hopped = 0;   // > 0: the root left the extrapolation of its branch: scan until two periods in a row were predictable again
   float c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 1.0e-3f;
   long long nsw = 0;
   // the kernel evaluates pairs (packed arithmetic); the pair functions are used here too so that the same
@@ -106,7 +106,10 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         float e = e6;
         if (!inside) { const float den = B1.d - B0.d; e = (den != 0.f) ? -B0.d * w / den : 0.5f * w; }
         const bool interior = (jb >= 2 && jb <= np - 2);
-        const float tol = (it > 0) ? kInterpTol : ((cluster_stage && w <= 3.0e-3f) ? kClusterTol : -1.f);
+        // (test instrumentation: HM_CTOL / HM_WMAX override the first-round acceptance, see tools/cluster_tolerance.py)
+        static const float ctol = getenv("HM_CTOL") ? (float)atof(getenv("HM_CTOL")) : kClusterTol;
+        static const float wmax = getenv("HM_WMAX") ? (float)atof(getenv("HM_WMAX")) : 6.0e-3f;
+        const float tol = (it > 0) ? kInterpTol : ((cluster_stage && w <= wmax) ? ctol : -1.f);
         if ((inside && interior && delta <= tol) || w <= kBracketTol) {
           croot = B0.c + e;
           if (getenv("HM_DEBUG2")) fprintf(stderr, "acc k=%d it=%d w=%g delta=%g e4=%g e6=%g inside=%d c=%.7f s6=%d jb=%d np=%d\n", k, it, w, delta, e4, e6, (int)inside, croot, s6, jb, np);
@@ -218,9 +221,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           if (kink && getenv("HM_DEBUG")) fprintf(stderr, "kink k=%d T=%g bh2=%g br=%g..%g nvalid=%d\n", k, T, bh2, br_lo, br_hi, nvalid);
           if (!kink) {
             nwin_ok++;
-            if (interp_rounds(pt, w0, jb, nvalid, mw, stage == 0) && settle_mmax()) {
+            const bool ir = interp_rounds(pt, w0, jb, nvalid, mw, stage == 0);
+            const bool sm = ir && settle_mmax();
+            if (sm) {
               fast_done = true; found = true; have_ratio = (kind == 2) && !mid_liquid;
-            }
+            } else if (getenv("HM_DEBUG")) fprintf(stderr, "%s k=%d T=%g croot=%g\n", ir ? "settlefail" : "interpfail", k, T, croot);
           }
         }
       }
@@ -228,6 +233,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
 
     if (!fast_done) {
       nslow++;
+      if (getenv("HM_DEBUG") && k > 0) fprintf(stderr, "slow k=%d hopped=%d\n", k, (int)hopped);
       // ---- point-by-point scan, P grid points per round
       float lo = 0, hi = 0, dlo = 0, dhi = 0;
       int mnew = mm;
@@ -367,7 +373,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
       ratio = 0.5f * A.e3 / A.e2;
     }
     if (getenv("HM_PRED") && k >= 1) fprintf(stderr, "pred %d %g %g\n", k, croot - c_pred, (croot - c1) / dc);
-    if (k >= 2) { pred_err = fabsf(croot - c_pred); if (pred_err > 0.1f) hopped = true; }
+    if (k >= 2) {
+      pred_err = fabsf(croot - c_pred);
+      if (pred_err > 0.1f) hopped = 2;
+      else if (hopped > 0) hopped = (pred_err < 0.01f) ? hopped - 1 : 2;
+    }
     c_out[k] = croot; ratio_out[k] = ratio; c_prev3 = c_prev2; c_prev2 = c_prev; c_prev = croot; nfound = k + 1;
   }
   // phase 2
