@@ -749,6 +749,14 @@ SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, b
   return r;
 }
 
+// (test instrumentation of the host mirror: how often the reference's second REIGEN iteration is taken)
+#if !defined(__CUDACC__) && defined(SD_HOST_COUNTERS)
+static long sd_second_pass_count = 0;
+#define SD_COUNT_SECOND_PASS() (++sd_second_pass_count)
+#else
+#define SD_COUNT_SECOND_PASS() ((void)0)
+#endif
+
 // The reference integrates the 4x4 stress-displacement system  v' = A v,  v = (ur, uz, tz, tr), with
 // classical RK4, 4 sub-steps per sub-layer (surfa.f:945-978).  A is constant inside a layer, so one RK4
 // step is exactly the matrix polynomial  P = I + hA + (hA)^2/2 + (hA)^3/6 + (hA)^4/24  applied to v.
@@ -920,6 +928,7 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
       const float xtest = fabsf(ampur / ratio - 1.f);
       if (!(xtest >= 0.00001f)) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
       // second iteration of the reference (surfa.f:986-998): solution 2 restarted from z + xnorm*y
+      SD_COUNT_SECOND_PASS();
       zs_ur = 0.0 + xnorm * 1.0; zs_uz = 1.0 + xnorm * 0.0; zs_tz = z0tz + xnorm * y0tz; zs_tr = z0tr + xnorm * y0tr;
     }
   }

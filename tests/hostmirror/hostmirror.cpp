@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <algorithm>
+#define SD_HOST_COUNTERS 1
 #include "../../pysurfinv_b200/csrc/surfdisp_core.cuh"
 
 using namespace sd;
@@ -22,6 +23,8 @@ constexpr float kClusterH0 = 2.5e-4f;
 }
 
 extern "C" {
+
+long hm_second_pass_count() { return sd::sd_second_pass_count; }
 
 // one model, shared periods; returns nfound.  `exact` = SurfdispOpts.exact_scan.  G lanes x 2 trial velocities.
 int hm_forward(int G, int kind, int n, const float* a, const float* b, const float* rho, const float* d,
