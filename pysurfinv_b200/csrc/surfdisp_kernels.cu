@@ -887,8 +887,8 @@ struct P2Params {
 };
 
 #ifndef P2_THREADS
-#define P2_THREADS 128
-#define P2_MINBLK 4
+#define P2_THREADS 256     // upper bound of a block; the launch uses the multiple of 32 that the work items fill
+#define P2_MINBLK 2        // = 128 registers per thread
 #endif
 __global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __grid_constant__ P2Params p) {
   extern __shared__ float4 smem[];
@@ -1399,9 +1399,19 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   p2.ndiv_cap = (pl.kind == 2) ? pl.o.ndiv_cap_rayleigh : pl.o.ndiv_cap_love;
   p2.tab = pl.tab;
   const size_t per_model = (size_t)NCONST * pl.w.lpad * sizeof(float);
-  int mpb = P2_THREADS / pl.K;
-  if (mpb < 1) mpb = 1;
-  while (mpb > 1 && mpb * per_model > 96 * 1024) --mpb;
+  // models per block: the one whose (models x periods) work items fill whole warps best (40 periods: 4 models =
+  // 160 threads, no idle lane; 3 models in 128 threads leave 8 of 128 lanes idle in every FP64 instruction)
+  int mpb = 1;
+  {
+    const int mmax_blk = P2_THREADS / pl.K < 1 ? 1 : P2_THREADS / pl.K;
+    double best = -1.0;
+    for (int m2 = 1; m2 <= mmax_blk; ++m2) {
+      if (m2 > 1 && m2 * per_model > 96 * 1024) break;
+      const int items = m2 * pl.K, thr = round_up(items, 32) > P2_THREADS ? P2_THREADS : round_up(items, 32);
+      const double eff = (double)items / ((double)thr * ((items + thr - 1) / thr));
+      if (eff > best + 1e-9) { best = eff; mpb = m2; }
+    }
+  }
   if (mpb * per_model > 200 * 1024) return SURFDISP_EINVAL;
   p2.mpb = mpb;
   int threads = round_up(mpb * pl.K, 32);
