@@ -451,7 +451,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     // period), so that the next models start together again
     const bool near_end = (stage != ST_FETCH && stage != ST_DONE) && !hopped && (p.k_end - p.k_begin > 8) &&
                           (p.k_end - k <= P1_SOFT_SYNC);
-    const bool warp_fetch = __ballot_sync(0xffffffffu, near_end) == 0u;
+    // (a launch of one period per model -- the first-period launch -- hands out models to the whole warp at once:
+    // the eight scans then pass through their stages together, 26 -> 23 ms)
+    const bool first_wait = (p.k_end - p.k_begin == 1) && (stage != ST_FETCH && stage != ST_DONE);
+    const bool warp_fetch = __ballot_sync(0xffffffffu, near_end || first_wait) == 0u;
 #else
     const bool warp_fetch = true;
 #endif
