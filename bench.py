@@ -303,7 +303,7 @@ def main():
                            "l2_policy": "inputs (%.2f GB layers + %.2f GB workspace per step) exceed the 126 MB L2"
                                         % (lay.nbytes / 1e9, solver._ws.numel() / 1e9),
                            "roots_found_frac": nfound_ok / M},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * args.steps, "roofline": roof, "cpu_baseline": cpu,
                 "love": love}
         emit(line)
     if world > 1:

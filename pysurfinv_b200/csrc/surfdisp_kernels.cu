@@ -34,9 +34,10 @@ struct PeriodTab {
 };
 
 struct WsLayout {
-  size_t consts_off, ratio_off, mm_off, total;
+  size_t consts_off, ratio_off, mm_off, order_off, bucket_off, total;
   int lpad;
 };
+constexpr int kOrderBuckets = 1024;   // models are handed out in the order of their top shear velocity (bucket sort)
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -48,7 +49,9 @@ WsLayout ws_layout(int M, int lmax, int K) {
   w.ratio_off = w.consts_off + ((consts + 255) / 256) * 256;
   size_t ratio = (size_t)M * K * sizeof(float);
   w.mm_off = w.ratio_off + ((ratio + 255) / 256) * 256;
-  w.total = w.mm_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.order_off = w.mm_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.bucket_off = w.order_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.total = w.bucket_off + 2 * kOrderBuckets * sizeof(int);
   return w;
 }
 
@@ -144,6 +147,8 @@ struct P1Params {
   int atten, stale, exact_scan;
   int k_begin, k_end;   // periods [k_begin, k_end) are done by this launch (the first period runs as a launch of its own)
   int* mm_state;        // layer-dropping depth carried from launch to launch
+  const int* order;     // order[i] - order_base = i-th model to hand out (nullptr: index order)
+  int order_base;
   int mstride;  // float4 units between consecutive groups' shared-memory records
   PeriodTab tab;
 };
@@ -459,7 +464,10 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     const bool warp_fetch = true;
 #endif
     if (stage == ST_FETCH && warp_fetch) {
-      if (gl == 0) model = (int)atomicAdd(p.queue, 1u);
+      if (gl == 0) {
+        model = (int)atomicAdd(p.queue, 1u);
+        if (model < p.M && p.order) model = p.order[model] - p.order_base;
+      }
       model = gshfl<G>(gmask, model, 0);
       if (model >= p.M) stage = ST_DONE;
       else {
@@ -1319,6 +1327,43 @@ size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods) {
   return ws_layout(n_models, n_layers_max, n_periods).total;
 }
 
+// ---- order in which the models are handed out: by the shear velocity of the top solid layer (1024 buckets).  The
+// first-period scan starts at 0.9 of that velocity (fast_surf.f:157-171), so models with similar keys scan for
+// similarly long, and a warp's eight models pass through their periods at a similar pace (first-period launch and
+// later periods together: -5 %).  The order inside a bucket is whatever the atomics give; results do not depend on it.
+__device__ __forceinline__ int order_bucket(const float* __restrict__ layers, size_t comp_stride, int lmax, const int* nlay, int m) {
+  const int n = nlay[m];
+  if (n < 2 || n > lmax) return 0;
+  const float* vs = layers + comp_stride + (size_t)m * lmax;
+  const float b = (vs[0] < 0.1f) ? vs[1] : vs[0];
+  int k = (int)(b * 200.0f);
+  return k < 0 ? 0 : (k >= kOrderBuckets ? kOrderBuckets - 1 : k);
+}
+__global__ void order_count_kernel(int M, int lmax, const int* __restrict__ nlay, const float* __restrict__ layers,
+                                   size_t comp_stride, int* __restrict__ count) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) atomicAdd(&count[order_bucket(layers, comp_stride, lmax, nlay, m)], 1);
+}
+__global__ void order_scan_kernel(const int* __restrict__ count, int* __restrict__ offset) {
+  // one block of kOrderBuckets threads: exclusive prefix sum
+  __shared__ int sh[kOrderBuckets];
+  const int t = threadIdx.x;
+  sh[t] = count[t];
+  __syncthreads();
+  for (int o = 1; o < kOrderBuckets; o <<= 1) {
+    const int v = (t >= o) ? sh[t - o] : 0;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  offset[t] = sh[t] - count[t];
+}
+__global__ void order_scatter_kernel(int M, int lmax, const int* __restrict__ nlay, const float* __restrict__ layers,
+                                     size_t comp_stride, int* __restrict__ offset, int* __restrict__ order, int base) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) order[atomicAdd(&offset[order_bucket(layers, comp_stride, lmax, nlay, m)], 1)] = base + m;
+}
+
 // ---- the batch as a plan plus stages over a range of models [a, b): surfdisp_batch runs every stage on the whole
 // batch, the host path runs the first stages chunk by chunk under the host->device copies
 struct Plan {
@@ -1327,7 +1372,7 @@ struct Plan {
   WsLayout w;
   const int* nlay; const float* layers;
   float *c_out, *u_out, *consts, *ratio;
-  int *nfound, *flags, *mm_state;
+  int *nfound, *flags, *mm_state, *order, *buckets;
   unsigned long long* counters;
   unsigned int* queue;
   PeriodTab tab;
@@ -1352,6 +1397,8 @@ static int make_plan(Plan& pl, const SurfdispOpts* opts, int kind, int n_models,
   pl.consts = (float*)(ws + pl.w.consts_off);
   pl.ratio = (float*)(ws + pl.w.ratio_off);
   pl.mm_state = (int*)(ws + pl.w.mm_off);
+  pl.order = (int*)(ws + pl.w.order_off);
+  pl.buckets = (int*)(ws + pl.w.bucket_off);
   return fill_tab(pl.tab, n_periods, periods, pl.o.t_base);
 }
 
@@ -1364,6 +1411,14 @@ static int stage_prep(const Plan& pl, int a, int b, cudaStream_t st) {
   prep_kernel<<<(unsigned)(((size_t)m * 32 + 127) / 128), 128, 0, st>>>(
       m, pl.lmax, pl.w.lpad, pl.kind, pl.o.flatten, pl.nlay + a, pl.layers + (size_t)a * pl.lmax, (size_t)pl.M * pl.lmax,
       pl.consts + (size_t)a * NCONST * pl.w.lpad);
+  CK(cudaGetLastError());
+  // hand-out order of this range: order[a .. b) = the models a .. b-1 sorted by bucket
+  CK(cudaMemsetAsync(pl.buckets, 0, 2 * kOrderBuckets * sizeof(int), st));
+  const float* lay = pl.layers + (size_t)a * pl.lmax;
+  const size_t cs = (size_t)pl.M * pl.lmax;
+  order_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, pl.lmax, pl.nlay + a, lay, cs, pl.buckets);
+  order_scan_kernel<<<1, kOrderBuckets, 0, st>>>(pl.buckets, pl.buckets + kOrderBuckets);
+  order_scatter_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, pl.lmax, pl.nlay + a, lay, cs, pl.buckets + kOrderBuckets, pl.order + a, a);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1380,6 +1435,7 @@ static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaSt
   p1.dc = pl.o.dc; p1.fact = pl.o.fact; p1.atten = pl.o.atten; p1.stale = pl.o.stale_mmax; p1.exact_scan = pl.o.exact_scan;
   p1.tab = pl.tab;
   p1.mm_state = pl.mm_state + a;
+  p1.order = pl.order + a; p1.order_base = a;
   p1.k_begin = k_begin; p1.k_end = k_end;
   CK(cudaMemsetAsync(pl.queue, 0, sizeof(unsigned int), st));
   return launch_phase1<P1_G>(p1, st);
