@@ -901,7 +901,13 @@ struct P2Params {
 #define P2_THREADS 256     // upper bound of a block; the launch uses the multiple of 32 that the work items fill
 #define P2_MINBLK 2        // = 128 registers per thread
 #endif
-__global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __grid_constant__ P2Params p) {
+#ifndef P2_MINBLK_LOVE
+#define P2_MINBLK_LOVE 3   // 65536 / (3 x 256) = 85 registers per thread
+#endif
+// One instantiation per wave type: the Rayleigh one (FP64 ODE) needs 128 registers, the Love one (float32 analytic
+// propagation) is latency bound and runs with 96 registers and a third more resident warps.
+template <int KIND>
+__global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_LOVE) phase2_kernel(const __grid_constant__ P2Params p) {
   extern __shared__ float4 smem[];
   float* sc = reinterpret_cast<float*>(smem);
   const int K = p.K;
@@ -937,7 +943,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) phase2_kernel(const __g
       const float T = p.tab.per[k];
       const float c = p.c_in[(size_t)model * K + k];
       float u;
-      if (p.kind == 2) u = reigen_thread(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
+      if (KIND == 2) u = reigen_thread(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
       else u = leigen_thread(mv, T, c, p.fact, nsub);
       urow[k] = u;
     }
@@ -1476,9 +1482,14 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   int threads = round_up(mpb * pl.K, 32);
   if (threads > P2_THREADS) threads = P2_THREADS;
   const size_t smem = mpb * per_model;
-  CK(cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (m + mpb - 1) / mpb;
-  phase2_kernel<<<grid, threads, smem, st>>>(p2);
+  if (pl.kind == 2) {
+    CK(cudaFuncSetAttribute(phase2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    phase2_kernel<2><<<grid, threads, smem, st>>>(p2);
+  } else {
+    CK(cudaFuncSetAttribute(phase2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    phase2_kernel<1><<<grid, threads, smem, st>>>(p2);
+  }
   CK(cudaGetLastError());
   return 0;
 }
