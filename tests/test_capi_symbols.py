@@ -40,6 +40,13 @@ def test_argument_validation_without_gpu():
     assert L.surfdisp_batch(None, 2, 1, 8, None, None, 0, per, None, None, None, None, None, 0, None) == -1
     assert L.surfdisp_batch(None, 2, 0, 8, None, None, 4, per, None, None, None, None, None, 0, None) == 0  # empty batch
     assert L.surfdisp_misfit_batch(5, 1, 4, None, None, per, per, None, None, None, None) == -1
+    # pipelined host path: device block = inputs + outputs + workspace; argument checks before any CUDA call
+    ws = L.surfdisp_workspace_bytes(1000, 77, 40)
+    pb = L.surfdisp_pipelined_bytes(1000, 77, 40)
+    assert pb >= ws + 5 * 1000 * 77 * 4 + 2 * 1000 * 40 * 4 + 3 * 1000 * 4
+    assert L.surfdisp_pipelined_bytes(0, 1, 1) == 0
+    assert L.surfdisp_host_batch_pipelined(None, 2, 1, 8, None, None, 4, per, None, None, None, None, None, 0, 4, None, None) == -1
+    assert L.surfdisp_host_batch_pipelined(None, 2, 0, 8, None, None, 4, per, None, None, None, None, None, 0, 4, None, None) == 0
 
 
 def test_product_fails_loudly_without_gpu():
