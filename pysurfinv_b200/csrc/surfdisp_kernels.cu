@@ -751,9 +751,12 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       const unsigned ev = change_mask(pd, dlo);
       const float dlast = gshfl<G>(gmask, pd.y, G - 1);
       bool have_root = false, lstop = false;
-      if (pit == 0 && __popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1) {
-        // several roots inside the scan bracket (kink at the half-space velocity): follow the reference's own
-        // sequential bisection/Neville sequence so that the same one is picked (all lanes run it redundantly)
+      const float bhk = rec[mm - 1].y;
+      if (pit == 0 && (__popc(ev) + (int)(signbit(dlast) != signbit(dhi)) > 1 || (bhk > lo0 && bhk < hi0))) {
+        // several roots inside the scan bracket -- or the half-space velocity of the truncation inside it: beyond
+        // that kink the function can turn back within 1e-4 km/s of a root just below it, which a uniform section
+        // steps over --: follow the reference's own sequential bisection/Neville sequence so that the same root is
+        // picked (all lanes run it redundantly)
         int ev_n = 0;
         SecFn f; f.kind = p.kind; f.T = T; f.mm = mm; f.rec = rec;
         const bool okp = nevill_out_of_line(f, lo0, hi0, dlo0, dhi0, &croot, &ev_n);

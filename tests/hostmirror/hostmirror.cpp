@@ -251,6 +251,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         // reference's.
         const int S = 4;
         const float QTHR = 1.0f;
+        static const bool no_near_kink = getenv("HM_NO_NEAR_KINK") != nullptr;   // (test instrumentation: the rule switched off)
         float cbase = c1;
         Pt P1 = {0, 0, 0, 0}, P2 = {0, 0, 0, 0};      // the two coarse points before point 0 of the round
         bool have_prev = false, done = false;
@@ -269,6 +270,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           sweep_all(pt, T, mtop);
           auto stopc = [&](int pi) { const float c = pt[pi].c; return (c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c); };
           if (stride == 1) {
+            if (getenv("HM_TRACE_K") && atoi(getenv("HM_TRACE_K")) == k)
+              for (int pi = 0; pi < P; ++pi) fprintf(stderr, "fine k=%d c=%.6f d=%g mj=%d mtop=%d bhs(mj)=%.6f stop=%d\n", k, pt[pi].c, pt[pi].d, mj[pi], mtop, rec[mj[pi] - 1].y, (int)stopc(pi));
             int jev = -1; bool chg = false;
             for (int pi = 0; pi < P; ++pi) {
               const bool hasp = (pi > 0) || have_prev;
@@ -281,7 +284,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               // nothing in this fine round: go on with coarse rounds (left neighbours at coarse spacing) unless the
               // half-space velocity of the sampled truncation -- a kink, not a smooth place -- is within reach
               P1 = pt[P - 1]; P2 = pt[P - 1 - S]; mnew = mj[P - 1]; have_prev = true;
-              const bool near_kink = !(P1.c + 2.f * (float)S * dc < rec[mtop - 1].y);
+              const bool near_kink = !no_near_kink && !(P1.c + 2.f * (float)S * dc < rec[mtop - 1].y);
               if (exact || near_kink) { cbase = SD_ADD(P1.c, dc); continue; }
               stride = S; cbase = P1.c;
               for (int t = 0; t < S; ++t) cbase = SD_ADD(cbase, dc);
@@ -315,7 +318,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
               const float q = lg(L2) - 2.f * lg(L1) + lg(pt[pi]);
               const bool kinked = !(fabsf(q) <= QTHR);
               if (getenv("HM_Q")) fprintf(stderr, "q k=%d c=%.3f q=%.3f change=%d d=%g\n", k, pt[pi].c, q, (int)change, pt[pi].d);
-              const bool near_kink = !(pt[pi].c + (float)S * dc < rec[mtop - 1].y);
+              const bool near_kink = !no_near_kink && !(pt[pi].c + (float)S * dc < rec[mtop - 1].y);
               if (change || kinked || near_kink || stopc(pi)) jev = pi;
             }
             if (jev < 0) {
@@ -348,7 +351,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             if (std::signbit(dp) != std::signbit(pt[pi].d)) { if (j < 0) j = pi; nchg++; }
           }
           if (std::signbit(pt[P - 1].d) != std::signbit(dhi)) nchg++;
-          if (it == 0 && nchg > 1) { multi = true; break; }
+          // several sign changes -- or the half-space velocity of the truncation inside the bracket: beyond that kink
+          // the function can turn back within 1e-4 km/s of a root just below it, which a uniform section steps
+          // over -- : the reference's own sequence decides which root it is
+          const float bhk = rec[mm - 1].y;
+          if (it == 0 && (nchg > 1 || (bhk > lo0 && bhk < hi0))) { multi = true; break; }
           if (j >= 0) {
             const float nlo = j ? pt[j - 1].c : lo, ndlo = j ? pt[j - 1].d : dlo;
             hi = pt[j].c; dhi = pt[j].d; lo = nlo; dlo = ndlo;
@@ -364,6 +371,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           auto f = [&](float cc) { Pt A, B; sweep2(cc, cc, T, mm, false, A, B); return A.d; };
           if (!nevill_seq(f, lo0, hi0, dlo0, dhi0, croot, ev_n)) { found = false; lstop = true; }
         }
+        if (getenv("HM_TRACE_K") && atoi(getenv("HM_TRACE_K")) == k)
+          fprintf(stderr, "polish k=%d multi=%d lo0=%.6f hi0=%.6f croot=%.7f found=%d bhs=%.7f mm=%d\n", k, (int)multi, lo0, hi0, croot, (int)found, rec[mm - 1].y, mm);
         if (found && croot > rec[mm - 1].y) found = false;
       }
     }

@@ -265,6 +265,14 @@ def test_love_roots_just_below_half_space_velocity(solver):
     c0, u0, nf0, st0 = O.forward_batch(1, lay[:, idx], nl[idx], per, opts=O.make_opts(precision=0), nthreads=8)
     assert np.array_equal(a["nfound"].cpu().numpy()[idx], nf0)
     assert np.abs(a["c"].cpu().numpy()[idx] - c0).max() <= TOL
+    # a bracket that contains the cusp: the function turns back 9e-5 km/s above the root of model 104 / period 58; only
+    # the reference's own bisection/Neville sequence ends on the root the reference finds (tests/test_hostmirror.py)
+    lay, nl = synth.crustal_models(400, seed=303)
+    g = _gpu(solver, lay, nl, per, 1)
+    c0, u0, nf0, st0 = O.forward_batch(1, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+    ok = st0 != 3
+    assert np.array_equal(g["nfound"][ok], nf0[ok]) and nf0[104] == 59
+    assert np.abs(g["c"] - c0)[ok].max() <= TOL
 
 
 def test_config4_deep_stacks_ndiv_zero(solver):

@@ -51,3 +51,17 @@ def test_water_layer_and_ragged():
     for kind in (2, 1):
         dc, du = _run(lay, nl, per, kind)
         assert dc.max() < 1e-4 and (du > 1e-4).mean() < 5e-3
+
+
+def test_love_roots_just_below_half_space_velocity():
+    """Long periods: the Love root sits ~1e-4 km/s below the flattened half-space velocity (a square-root cusp of
+    the secular function).  The coarse scan has to fall back to the point-by-point one there (15 of these 400
+    models lose their last root without that rule), and a bracket that contains the cusp has to be polished with
+    the reference's own bisection/Neville sequence (model 104: the function turns back 9e-5 km/s above the root,
+    a uniform section steps over both sign changes and ends on a third one above the half-space velocity)."""
+    lay, nl = synth.crustal_models(400, seed=303)
+    per = synth.log_periods(100, 5.0, 120.0)
+    c0, u0, nf0, st0 = O.forward_batch(1, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+    assert (nf0 < len(per)).sum() >= 50       # the family does exercise the cut-off
+    dc, du = _run(lay, nl, per, 1)
+    assert dc.max() < 1e-4
