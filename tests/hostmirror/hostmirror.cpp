@@ -267,6 +267,15 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           }
           // (own truncation per point only for the stop test; the round is evaluated on its deepest one)
           const int mtop = mj[P - 1];
+          // (prototype of the fix for the known deviation of DESIGN.md 2, case 3 -- HM_OWN_TRUNC=1, not in the kernel yet:
+          // when the round's top point is not below the half-space velocity of the deepest truncation, points whose own
+          // truncation is shallower do not have the same sign there; evaluate every point on its own truncation)
+          static const bool own_trunc = getenv("HM_OWN_TRUNC") != nullptr;
+          bool mixed = false;
+          for (int pi = 0; pi < P; ++pi) mixed |= (mj[pi] != mtop);
+          if (own_trunc && mixed && !(pt[P - 1].c < rec[mtop - 1].y)) {
+            for (int pi = 0; pi < P; ++pi) { Pt A, B; sweep2(pt[pi].c, pt[pi].c, T, mj[pi], false, A, B); pt[pi] = A; }
+          } else
           sweep_all(pt, T, mtop);
           auto stopc = [&](int pi) { const float c = pt[pi].c; return (c < 0.8f * b_top) || !(c < rec[mj[pi] - 1].y + 0.3f) || !(c == c); };
           if (stride == 1) {
