@@ -184,6 +184,7 @@ constexpr float kClusterWmax = 6.0e-3f; // widest bracket of a first-round clust
                                         // window rounds on the 0.01 grid never are)
 constexpr float kBracketTol = 2.0e-5f;  // bracket width below which a secant step is final
 constexpr float kClusterH0 = 2.5e-4f;   // smallest innermost spacing of the first-round cluster
+constexpr float kMaxPredStep = 0.15f;   // largest change of the root from one period to the next that the extrapolation is trusted with
 
 // bit i of the result = bit i/2 of a (i even) or of b (i odd)
 template <int G>
@@ -558,7 +559,11 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       }
       j0 = (int)floorf((c_pred - c1) / p.dc) - (P - 4) / 2;
       if (j0 < 2) j0 = 2;
-      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000) {
+      // (an extrapolation that moves the root by more than 0.15 km/s is not trusted: where the branch is that steep --
+      // thick slow sediments, coarse period lists -- the cluster can land on a higher mode with an even number of roots
+      // between c1 and it, which the sign guard cannot see; scan from c1 like the reference)
+      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000 &&
+          fabsf(c_pred - c_prev) <= kMaxPredStep) {
         // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
         // around it; 2: window of P grid points moved up or down
         fstage = (k >= 2 && j0 >= 4) ? 0 : 1;

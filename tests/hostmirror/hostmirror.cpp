@@ -171,7 +171,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
         c_pred += (d01 - d12) / (x0 - x2) * (x - x0) * (x - x1);
       }
     }
-    if (P >= 8 && !exact && k >= 1 && !hopped && !(SD_ADD(c1, dc) < 0.8f * b_top)) {
+    // (an extrapolation that moves the root by more than kMaxPredStep is not trusted: where the branch is that steep
+    // -- thick slow sediments, coarse period lists -- the cluster can land on a higher mode with an even number of
+    // roots between c1 and it, which the sign guard cannot see; scan from c1 like the reference)
+    static const float kMaxPredStep = getenv("HM_MAXSTEP") ? (float)atof(getenv("HM_MAXSTEP")) : 0.15f;
+    if (P >= 8 && !exact && k >= 1 && !hopped && !(SD_ADD(c1, dc) < 0.8f * b_top) && fabsf(c_pred - c_prev) <= kMaxPredStep) {
       int j0 = (int)floorf((c_pred - c1) / dc) - (P - 4) / 2;
       if (j0 < 2) j0 = 2;
       if (j0 < 1000) {

@@ -285,6 +285,19 @@ def test_config4_deep_stacks_ndiv_zero(solver):
     _check(g, lay, nl, per, 2, max_noisy_frac=0.02)
 
 
+def test_config4_love_steep_branch_coarse_periods(solver):
+    """Config-4 stacks, Love, 10 s period steps: the curve jumps by 1.7 km/s between the first two periods; the third
+    period must not be extrapolated onto a higher mode (tests/test_hostmirror.py, same models)."""
+    per = np.arange(10.0, 151.0, 10.0, dtype=np.float32)
+    for seed in (3005, 3009):
+        lay, nl = synth.crustal_models(100, seed=seed, n_crust=15, n_mantle=130, zmax=400.0)
+        g = _gpu(solver, lay, nl, per, 1)
+        c0, u0, nf0, st0 = O.forward_batch(1, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+        ok = st0 != 3
+        assert np.array_equal(g["nfound"][ok], nf0[ok])
+        assert np.abs(g["c"] - c0)[ok].max() <= TOL
+
+
 def test_very_deep_stack_and_many_periods(solver):
     """Shared-memory sizing path: 500-layer stacks (CTA shrinks) and the maximum of 200 periods."""
     lay, nl = synth.crustal_models(24, seed=72, n_crust=60, n_mantle=438, zmax=600.0)

@@ -65,3 +65,15 @@ def test_love_roots_just_below_half_space_velocity():
     assert (nf0 < len(per)).sum() >= 50       # the family does exercise the cut-off
     dc, du = _run(lay, nl, per, 1)
     assert dc.max() < 1e-4
+
+
+def test_steep_branch_on_a_coarse_period_list_is_not_extrapolated():
+    """Deep stacks, Love, periods 10..150 s in 10 s steps: the curve jumps by 1.7 km/s between the first two periods
+    (thick slow sediments); a linear extrapolation to the third period lands on a higher mode with an even number of
+    roots between c1 and the cluster (wrong by 0.7 km/s, same root count).  Extrapolations that move the root by more
+    than 0.15 km/s are not trusted."""
+    per = np.arange(10.0, 151.0, 10.0, dtype=np.float32)
+    for seed in (3005, 3009):
+        lay, nl = synth.crustal_models(100, seed=seed, n_crust=15, n_mantle=130, zmax=400.0)
+        dc, du = _run(lay, nl, per, 1)
+        assert dc.max() < 1e-4
