@@ -283,7 +283,8 @@ class DispersionSolver:
 
     def forward_host(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, chunks=None):
         """numpy in, numpy out.  Inputs are staged through pinned memory, copied to the GPU, solved and
-        copied back; returns dict(c, u, nfound, flags) of numpy arrays."""
+        copied back; returns dict(c, u, nfound, flags) of numpy arrays the caller owns (copies of the pinned
+        staging buffers: a later call does not change them)."""
         torch = self.torch
         lay = np.ascontiguousarray(layers, dtype=np.float32)
         nl = np.ascontiguousarray(nlay, dtype=np.int32)
@@ -291,7 +292,8 @@ class DispersionSolver:
         hn = self._pin("nl", nl.shape, torch.int32)
         hl.numpy()[...] = lay
         hn.numpy()[...] = nl
-        return self.forward_pinned(hl, hn, periods, kind, group, chunks)
+        r = self.forward_pinned(hl, hn, periods, kind, group, chunks)
+        return {k: (None if v is None else v.copy()) for k, v in r.items()}
 
     def forward_pinned(self, hl, hn, periods, kind=KIND_RAYLEIGH, group=True, chunks=None):
         """Same as forward_host but the caller already holds pinned host tensors (hl float32 [5][M][L], hn int32 [M]).
@@ -299,7 +301,11 @@ class DispersionSolver:
         models on); a chunk is copied host->device while the previous one is prepared and its first period
         searched, the later periods run as one launch over the whole batch, the group velocities are computed
         chunk by chunk and copied out under the next chunk.  Batches above 2^21 models go through the same call
-        in pieces of 2^21 (bounded device memory)."""
+        in pieces of 2^21 (bounded device memory).
+
+        The returned arrays are VIEWS of pinned result buffers that this solver keeps and reuses: the next
+        forward_pinned / forward_host call with the same shapes overwrites them (zero-copy hand-over for callers
+        that consume a result before asking for the next one; forward_host returns copies)."""
         torch = self.torch
         M, lmax = int(hl.shape[1]), int(hl.shape[2])
         per = np.ascontiguousarray(periods, dtype=np.float32)

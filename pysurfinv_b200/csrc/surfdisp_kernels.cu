@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, in
 
 // ------------------------------------------------------------------------------------ phase 1
 struct P1Params {
-  int kind, M, lpad, K;
+  int kind, M, lpad, K, lmax;
   const int* nlay;
   const float* consts;
   float* c_out;
@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   float cbase = 0.f, cP = 0.f, dP = 0.f, tP = 0.f, cP2 = 0.f, dP2 = 0.f, tP2 = 0.f, lo = 0.f, hi = 0.f, dlo = 0.f, dhi = 0.f, lo0 = 0.f, hi0 = 0.f, dlo0 = 0.f, dhi0 = 0.f;
   int mjx = 2, mjy = 2, round = 0, pit = 0, stride = 1;
   bool have_prev = false, own_mj = false;
+  bool own_eval = false;    // this scan round evaluates every point on its own truncation (see build_scan)
   bool from_scan = false;   // the interpolation rounds refine a bracket found by the scan (fall-back: uniform-section polish)
   float bmin = 0.f;   // smallest b below the top layer (this period's records)
   // ---- result of the period
@@ -366,9 +367,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   };
   auto build_scan = [&]() {
     // 2G consecutive grid points, accumulated like the reference does (calcul.f:157).  The reference gives each
-    // point its own layer dropping; here the whole round is evaluated on the deepest of them (same
-    // sign, see below).  The own truncation of a point matters for the stop test c >= b(mmax) + 0.3
-    // (calcul.f:166), which cannot fire while c < min b + 0.3: only then is it computed per point.
+    // point its own layer dropping (calcul.f:155-159, surfa.f:92-106).  As long as the round's top
+    // point is below the half-space velocity of the deepest truncation, all truncations have the same sign there
+    // and the whole round is evaluated on the deepest one.  When it is not -- the walk ran through the whole stack
+    // and the true half-space is slower than the trial velocities (velocity inversion at depth) -- points whose own
+    // truncation is shallower do not have the same sign: every point is then evaluated on its own truncation, like
+    // the reference does (two sweeps for the lane; exact_scan: whenever the truncations of a round differ).
+    // The own truncation of a point also matters for the stop test c >= b(mmax) + 0.3 (calcul.f:166), which
+    // cannot fire while c < min b + 0.3.
     float cx = cbase;
     for (int t = 0; t < 2 * gl * stride; ++t) cx = SD_ADD(cx, p.dc);
     float cy = cx;
@@ -377,7 +383,15 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     const float ctop = gshfl<G>(gmask, pc.y, G - 1);
     meval = layer_drop_coop<G>(ctop, T, p.fact, n, rec, gmask, gl);
     own_mj = !(ctop < bmin + 0.3f);
-    if (own_mj) { mjx = layer_drop(pc.x, T, p.fact, n, rec); mjy = layer_drop(pc.y, T, p.fact, n, rec); }
+    const bool above_hs = !(ctop < rec[meval - 1].y) || p.exact_scan;
+    if (own_mj || above_hs) {
+      mjx = layer_drop(pc.x, T, p.fact, n, rec); mjy = layer_drop(pc.y, T, p.fact, n, rec);
+      own_mj = true;
+      if (above_hs) {
+        const int mtop = gshfl<G>(gmask, mjy, G - 1);
+        own_eval = (__ballot_sync(gmask, mjx != mtop || mjy != mtop) & gmask) != 0u;
+      }
+    }
     ell_only = 0;
   };
   auto start_scan = [&]() {
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         n = p.nlay[model];
         crow = p.c_out + (size_t)model * K;
         rrow = p.ratio_out + (size_t)model * K;
-        if (n < 2 || n > p.lpad) {
+        if (n < 2 || n > p.lmax) {
           for (int kk = gl; kk < K; kk += G) { crow[kk] = 0.f; rrow[kk] = 0.f; }
           if (gl == 0) { p.nfound[model] = 0; if (p.flags) p.flags[model] = SURFDISP_F_NO_ROOT_FIRST; }
           n = 2;  // stays in ST_FETCH: sits this iteration's sweep out and pulls another model next time
@@ -573,6 +587,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     }
     if (__all_sync(0xffffffffu, stage == ST_DONE)) break;
     // ---- trial velocities of this iteration's sweep
+    own_eval = false;
     if (need == NB_FAST) build_fast();
     else if (need == NB_REFINE) build_refine();
     else if (need == NB_SCAN) build_scan();
@@ -583,9 +598,17 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     // =========================================================== the sweep (the only call site)
     const bool active = (stage >= ST_FAST && stage <= ST_ELL);
     if (active) {
-      const Sec2 sv = secular2(p.kind, pc, T, meval, rec, ell_only);
-      my_steps += 2u * (unsigned)(meval - 1); my_sweeps += 2;
-      pd = sv.d; pe2 = sv.e2; pe3 = sv.e3;
+      // (one pass; two for a scan round on own truncations: first the lane's lower point, then the upper one)
+      for (int ps = 0; ps < (own_eval ? 2 : 1); ++ps) {
+        float2 cc = pc;
+        int me = meval;
+        if (own_eval) { cc = ps ? make_float2(pc.y, pc.y) : make_float2(pc.x, pc.x); me = ps ? mjy : mjx; }
+        const Sec2 sv = secular2(p.kind, cc, T, me, rec, ell_only);
+        my_steps += 2u * (unsigned)(me - 1); my_sweeps += 2;
+        if (!own_eval) { pd = sv.d; pe2 = sv.e2; pe3 = sv.e3; }
+        else if (ps == 0) { pd.x = sv.d.x; pe2.x = sv.e2.x; pe3.x = sv.e3.x; }
+        else { pd.y = sv.d.x; pe2.y = sv.e2.x; pe3.y = sv.e3.x; }
+      }
     }
 
 #ifdef P1_DEBUG
@@ -704,7 +727,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
             // mode: uniform (P+1)-section with mmax pinned until the bracket is <= 2e-5, then one
             // secant step.
             bool handed = false;
-            if (!p.exact_scan && j >= 1) {
+            if (!p.exact_scan && !own_eval && j >= 1) {
               const float bh2 = rec[meval - 1].y;
               nvalid = __popc(pair_mask(pc.x < bh2, pc.y < bh2));
               const bool kink = (bh2 > lo - 0.011f && bh2 < hi + 0.011f) || nvalid < 6 || j > nvalid - 1;
@@ -892,7 +915,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 
 // ------------------------------------------------------------------------------------ phase 2
 struct P2Params {
-  int kind, M, lpad, K, mpb;
+  int kind, M, lpad, K, mpb, lmax;
   const int* nlay;
   const float* consts;
   const float* c_in;
@@ -937,7 +960,7 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
     const int model = model0 + ml;
     float* urow = p.u_out + (size_t)model * K;
     const int n = p.nlay[model];
-    if (k >= p.nfound[model] || n < 2 || n > p.lpad) {
+    if (k >= p.nfound[model] || n < 2 || n > p.lmax) {
       urow[k] = 0.f;
     } else {
       ModelView mv;
@@ -1442,7 +1465,7 @@ static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaSt
   if (b <= a || k_end <= k_begin) return 0;
   P1Params p1;
   memset(&p1, 0, sizeof(p1));
-  p1.kind = pl.kind; p1.M = b - a; p1.lpad = pl.w.lpad; p1.K = pl.K; p1.nlay = pl.nlay + a;
+  p1.kind = pl.kind; p1.M = b - a; p1.lpad = pl.w.lpad; p1.lmax = pl.lmax; p1.K = pl.K; p1.nlay = pl.nlay + a;
   p1.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
   p1.c_out = pl.c_out + (size_t)a * pl.K; p1.ratio_out = pl.ratio + (size_t)a * pl.K; p1.nfound = pl.nfound + a;
   p1.flags = pl.flags ? pl.flags + a : nullptr; p1.counters = pl.counters; p1.queue = pl.queue;
@@ -1464,7 +1487,7 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   }
   P2Params p2;
   memset(&p2, 0, sizeof(p2));
-  p2.kind = pl.kind; p2.M = m; p2.lpad = pl.w.lpad; p2.K = pl.K; p2.nlay = pl.nlay + a;
+  p2.kind = pl.kind; p2.M = m; p2.lpad = pl.w.lpad; p2.lmax = pl.lmax; p2.K = pl.K; p2.nlay = pl.nlay + a;
   p2.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
   p2.c_in = pl.c_out + (size_t)a * pl.K; p2.ratio_in = pl.ratio + (size_t)a * pl.K; p2.nfound = pl.nfound + a;
   p2.u_out = pl.u_out + (size_t)a * pl.K; p2.counters = pl.counters;

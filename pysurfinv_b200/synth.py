@@ -59,14 +59,21 @@ def _rho_quartic(vs):
     return 1.22679 + 1.53201 * vs - 0.83668 * vs * vs + 0.20673 * vs ** 3 - 0.01656 * vs ** 4
 
 
-def crustal_models(M, seed=DEFAULT_SEED, n_crust=15, n_mantle=60, zmax=200.0, water=False):
-    """Config-2 workload: M random sediment + crust + mantle stacks (n = 77, or 78 with a water layer)."""
+def crustal_models(M, seed=DEFAULT_SEED, n_crust=15, n_mantle=60, zmax=200.0, water=False, lvz=False):
+    """Config-2 workload: M random sediment + crust + mantle stacks (n = 77, or 78 with a water layer).
+    lvz=True: the crustal coefficients are NOT sorted (low-velocity zones inside the crust, which the prior of
+    the reference's model classes forbids but fast_surf itself accepts) and the mantle range is wider (stronger
+    inversions, half-spaces slower than the layers above them)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     Hsed = rng.uniform(0.5, 4.0, M)
     Vsed = rng.uniform(1.0, 2.5, M)
     Hcr = rng.uniform(20.0, 45.0, M)
-    ccr = np.sort(rng.uniform(3.2, 4.0, (M, 4)), axis=1)          # monotone increasing crust
-    cma = rng.uniform(4.1, 4.7, (M, 5))
+    if lvz:
+        ccr = rng.uniform(3.0, 4.1, (M, 4))
+        cma = rng.uniform(3.9, 4.8, (M, 5))
+    else:
+        ccr = np.sort(rng.uniform(3.2, 4.0, (M, 4)), axis=1)          # monotone increasing crust
+        cma = rng.uniform(4.1, 4.7, (M, 5))
     Hw = rng.uniform(0.5, 4.0, M) if water else None
 
     Bc = bspline_basis(np.linspace(0, 1, n_crust + 1), 4)          # [4, 16]

@@ -271,13 +271,16 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
           }
           // (own truncation per point only for the stop test; the round is evaluated on its deepest one)
           const int mtop = mj[P - 1];
-          // (prototype of the fix for the known deviation of DESIGN.md 2, case 3 -- HM_OWN_TRUNC=1, not in the kernel yet:
-          // when the round's top point is not below the half-space velocity of the deepest truncation, points whose own
-          // truncation is shallower do not have the same sign there; evaluate every point on its own truncation)
-          static const bool own_trunc = getenv("HM_OWN_TRUNC") != nullptr;
+          // Own-truncation rounds (calcul.f:155-159 gives every scan point its own layer dropping, surfa.f:92-106):
+          // as long as the round's top point is below the half-space velocity of the deepest truncation all
+          // truncations have the same sign and the round is evaluated on the deepest one; when it is not (the
+          // walk ran through the whole stack and the true half-space is slower than the trial velocities --
+          // velocity inversion at depth), points whose own truncation is shallower do not have the same sign
+          // there: every point is evaluated on its own truncation like the reference does.  exact: always.
           bool mixed = false;
           for (int pi = 0; pi < P; ++pi) mixed |= (mj[pi] != mtop);
-          if (own_trunc && mixed && !(pt[P - 1].c < rec[mtop - 1].y)) {
+          const bool own_eval = mixed && (exact || !(pt[P - 1].c < rec[mtop - 1].y));
+          if (own_eval) {
             for (int pi = 0; pi < P; ++pi) { Pt A, B; sweep2(pt[pi].c, pt[pi].c, T, mj[pi], false, A, B); pt[pi] = A; }
           } else
           sweep_all(pt, T, mtop);
@@ -306,7 +309,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
             found = chg;
             lo = jev ? pt[jev - 1].c : P1.c; hi = pt[jev].c; dlo = jev ? pt[jev - 1].d : P1.d; dhi = pt[jev].d; mnew = mj[jev];
             done = true;
-            if (found && !exact && jev >= 1) {
+            if (found && !exact && !own_eval && jev >= 1) {
               // the round's points sample one smooth function around the bracket: the interpolation rounds take over
               const float bh2 = rec[mtop - 1].y;
               int nvalid = 0;

@@ -1,0 +1,37 @@
+"""GPU hunt (tools/gpu_hunt.py): the CUDA path through the C ABI against the float32 oracle on many random curves
+per model family and wave type.  Bar (BASELINE.json north_star): identical root counts outside the reference's own
+LSTOP aborts, |dc| <= 1e-4 km/s everywhere; U: at most 3x the reference's own noisy fraction + 1e-4.
+
+SURFDISP_HUNT_CURVES sets the number of curves per (family, wave type); the default keeps the whole module at a
+few minutes of host time for the oracle on the GPU box.  The committed profiles/r2_parity_report.json is the same
+hunt at 100000 curves per (family, wave type)."""
+import os
+
+import pytest
+
+from tools import gpu_hunt as H
+
+pytestmark = pytest.mark.gpu
+
+CURVES = int(os.environ.get("SURFDISP_HUNT_CURVES", "20000"))
+
+
+@pytest.fixture(scope="module")
+def solver():
+    import torch
+    from pysurfinv_b200 import api
+    assert torch.cuda.is_available()
+    return api.DispersionSolver("cuda:0")
+
+
+@pytest.mark.parametrize("kind", [2, 1])
+@pytest.mark.parametrize("family", list(H.FAMILIES))
+def test_hunt(solver, family, kind):
+    n = CURVES if H.FAMILIES[family][1].size <= 40 else max(CURVES // 2, 1)
+    r = H.hunt(solver, family, kind, n)
+    assert r["curves"] >= 0.98 * n
+    assert r["nfound_mismatch"] == 0, r["mismatches"]
+    assert r["dc_max"] <= 1e-4 and r["dc_gt_1e4"] == 0
+    assert r["dc_median"] < 2e-6
+    assert r["du_frac_gt_1e4"] <= 3.0 * r["noise_du_frac_gt_1e4"] + 1e-4, (r["du_frac_gt_1e4"], r["noise_du_frac_gt_1e4"])
+    assert r["du_median"] < 5e-6

@@ -32,7 +32,7 @@ def _gpu(solver, lay, nl, per, kind):
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def _check(g, lay, nl, per, kind, max_noisy_frac=0.01):
+def _check(g, lay, nl, per, kind):
     c0, u0, nf0, st0 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
     c1, u1, nf1, st1 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=1), nthreads=8)
     ok = st0 != 3  # LSTOP aborts of the reference are excluded and counted
@@ -43,14 +43,14 @@ def _check(g, lay, nl, per, kind, max_noisy_frac=0.01):
     noise_u = np.abs(u0 - u1)[ok]
     assert dc.max() <= TOL, "phase velocity off by %g" % dc.max()
     assert np.median(dc) < 2e-6
-    # group velocity: the reference's U is ill-conditioned at a few (model, period) points (its own
-    # float32-vs-float64-solver spread reaches 1e-3..1e-2 there), so the bar is distributional: the CUDA
-    # path must not be noisier than the reference is against itself.
+    # group velocity: |dU| <= 1e-4 except where the reference's own U is ill-conditioned (its float32-vs-float64-solver
+    # spread on the same float32 model reaches 1e-3..1e-2 at ~1e-4 of the points: short periods on slow sediments).
+    # The bar is the reference's own noise, measured on the same models: at most 3x its noisy fraction (+1e-4 for the
+    # sampling error of a rare event), the same for the 99.9 % quantile and the maximum.
     frac_bad = (du > TOL).mean()
-    assert frac_bad <= max(3.0 * (noise_u > TOL).mean(), 5e-4, 0.0 if max_noisy_frac is None else 0.0), frac_bad
-    assert frac_bad <= max_noisy_frac
+    assert frac_bad <= 3.0 * (noise_u > TOL).mean() + 1e-4, (frac_bad, (noise_u > TOL).mean())
     assert np.quantile(du, 0.999) <= 3.0 * max(np.quantile(noise_u, 0.999), 1e-5)
-    assert du.max() <= max(10.0 * noise_u.max(), 5e-3), du.max()
+    assert du.max() <= max(3.0 * noise_u.max(), TOL), (du.max(), noise_u.max())
     assert np.median(du) < 5e-6
     # beyond nfound everything is zero
     K = len(per)
@@ -80,7 +80,7 @@ def test_ragged_with_water(solver, kind):
     lay, nl = synth.ragged_models(800, seed=13)
     per = np.array([10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)  # point.py:400
     g = _gpu(solver, lay, nl, per, kind)
-    _check(g, lay, nl, per, kind, max_noisy_frac=0.03)
+    _check(g, lay, nl, per, kind)
 
 
 def test_golden_test1_model(solver, golden_test1):
@@ -275,6 +275,31 @@ def test_love_roots_just_below_half_space_velocity(solver):
     assert np.abs(g["c"] - c0)[ok].max() <= TOL
 
 
+def test_velocity_inversion_scan_rounds_on_own_truncations(solver):
+    """A stack whose half-space is slower than the mantle above it (crustal_models(400, seed=2089)[324], Rayleigh,
+    T = 8.4 s): the scan passes the half-space velocity of the whole stack, where the truncations of the lower points
+    of a round (calcul.f:155-159: own layer dropping per point, surfa.f:92-106) do not have the sign of the deepest
+    one.  Round 1 reported 17 roots there, the reference 16.  Default and exact_scan modes, plus the LVZ family."""
+    from pysurfinv_b200 import api
+    lay, nl = synth.crustal_models(400, seed=2089)
+    per = synth.log_periods(100, 5.0, 120.0)
+    c0, u0, nf0, st0 = O.forward_batch(2, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+    assert nf0[324] == 16
+    ok = st0 != 3
+    for sv in (solver, api.DispersionSolver("cuda:0", opts=api.default_opts(exact_scan=1))):
+        g = _gpu(sv, lay, nl, per, 2)
+        assert g["nfound"][324] == 16
+        assert np.array_equal(g["nfound"][ok], nf0[ok])
+        assert np.abs(g["c"] - c0)[ok].max() <= TOL
+    for kind in (2, 1):
+        lay, nl = synth.crustal_models(1500, seed=2090, lvz=True)
+        g = _gpu(solver, lay, nl, per, kind)
+        c0, u0, nf0, st0 = O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=8)
+        ok = st0 != 3
+        assert np.array_equal(g["nfound"][ok], nf0[ok])
+        assert np.abs(g["c"] - c0)[ok].max() <= TOL
+
+
 def test_config4_deep_stacks_ndiv_zero(solver):
     """BASELINE config 4 shape: ~150 fine layers, Rayleigh 10-150 s.  n >= 101 clamps ndiv to 99/(n-1) = 0
     (no sub-division, surfa.f:783-787)."""
@@ -282,7 +307,7 @@ def test_config4_deep_stacks_ndiv_zero(solver):
     assert lay.shape[2] == 147
     per = np.arange(10.0, 151.0, 10.0, dtype=np.float32)
     g = _gpu(solver, lay, nl, per, 2)
-    _check(g, lay, nl, per, 2, max_noisy_frac=0.02)
+    _check(g, lay, nl, per, 2)
 
 
 def test_config4_love_steep_branch_coarse_periods(solver):
