@@ -100,12 +100,17 @@ int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_
                           const float* obs, const float* sigma, const unsigned char* mask,
                           const float* periods, float* out, void* stream);
 
-/* Host-buffer wrapper: allocates device memory, copies inputs to the device, solves, copies results back and
- * synchronises (through surfdisp_host_batch_pipelined, 8 chunks from 65536 models on).  All pointers are HOST
- * memory (pinned memory makes the copies asynchronous).  device = CUDA device ordinal. */
+/* Host-buffer wrapper: copies inputs to the device, solves, copies results back and synchronises (through
+ * surfdisp_host_batch_pipelined, 8 chunks from 65536 models on).  All pointers are HOST memory (pinned memory
+ * makes the copies asynchronous).  device = CUDA device ordinal.  The device block and the two streams belong
+ * to a per-host-thread context that is kept between calls (the block only grows, up to 1 GiB kept): a caller
+ * that loops over single models like models.py:27 does not pay cudaMalloc / cudaStreamCreate per call.
+ * Re-entrant: nothing is shared between host threads.  surfdisp_host_release() frees the calling thread's
+ * context (optional; it is also freed at thread exit). */
 int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_models, int n_layers_max,
                         const int* n_layers, const float* layers, int n_periods, const float* periods,
                         float* c_out, float* u_out, int* nfound, int* flags);
+void surfdisp_host_release(void);
 
 /* The same with caller-owned device memory and streams, as a pipeline: the batch is cut into n_chunks chunks;
  * chunk i is copied host->device on copy_stream while chunk i-1 is prepared and its first period searched on

@@ -926,7 +926,16 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
     if (pass == 0) {
       const float ampur = (float)((xnorm * yur + zur) / bb);
       const float xtest = fabsf(ampur / ratio - 1.f);
-      if (!(xtest >= 0.00001f)) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
+      // The reference forms the eigenfunction knot by knot (xnorm y + z, surfa.f:1076-1086) and squares it; the
+      // quadratic forms used here square the dynamic range of the cancellation instead: where y and z have grown
+      // nearly parallel (short periods, c above the crustal velocities: the P part grows by e^18 over the depth
+      // range) x^2 Qyy + x Qyz + Qzz loses every digit although the reference's first iteration is still fine.
+      // The conditioning of the two positive integrals is checked; below 1e-7 the second iteration is taken too
+      // (solution 2 restarted from the eigenfunction itself: no cancellation left in the sums).
+      const double a0 = xnorm * xnorm * Q.i0yy, b0 = xnorm * Q.i0yz, a1 = xnorm * xnorm * Q.i1yy, b1 = xnorm * Q.i1yz;
+      const bool lost = fabs(a0 + b0 + Q.i0zz) < 1.0e-7 * (fabs(a0) + fabs(b0) + fabs(Q.i0zz)) ||
+                        fabs(a1 + b1 + Q.i1zz) < 1.0e-7 * (fabs(a1) + fabs(b1) + fabs(Q.i1zz));
+      if (!(xtest >= 0.00001f) && !lost) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
       // second iteration of the reference (surfa.f:986-998): solution 2 restarted from z + xnorm*y
       SD_COUNT_SECOND_PASS();
       zs_ur = 0.0 + xnorm * 1.0; zs_uz = 1.0 + xnorm * 0.0; zs_tz = z0tz + xnorm * y0tz; zs_tr = z0tr + xnorm * y0tr;
@@ -955,6 +964,286 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
     s2 += xmu * dzsr - xlamb * drsz;
   }
   (void)n;
+  return (float)(((double)wvno * s1 + s2) / ((double)omega * s0));  // surfa.f:1186
+}
+
+// ----------------------------------------------------------------------------------------------
+// REIGEN, second formulation (the one the kernel runs; reigen_thread above is kept as the plain statement of the
+// same algorithm and is what tests/hostmirror compares it with).  Same integration -- RK4 step matrix per layer,
+// Boole sums as quadratic forms in the two half-space solutions -- with the per-layer arithmetic trimmed:
+//  * the float32 coefficient set-up uses MUFU reciprocals (1 ulp) instead of IEEE divisions with their slow-path
+//    calls: the coefficients are layer constants of an ODE, an ulp of them is 1e-7 of U;
+//  * the step matrix is formed from hB and hC (X' = (hB)(hC) = h^2 BC makes the RK4 coefficients constants):
+//    37 FP64 operations instead of 48;
+//  * Boole weights divided by 32: the two interior knots of weight 32 need no multiply; every sum is a chain of
+//    FMAs (the cross sums take two FMAs per knot instead of multiply + FMA + add); the first knot initialises
+//    the sums (no zeroing): 210 FP64 operations per sub-layer instead of 228;
+//  * closing of a layer: the integrands' layer constants are folded once (mu uz ur' - lambda ur uz' =
+//    mu f34 uz tr - mu k uz^2 - lambda f12 ur tz - lambda^2 f12 k ur^2): 35 operations instead of 42;
+//  * the float32 set-up of the NEXT layer is issued before the FP64 work of the current one, so that its latency
+//    (a dependent chain of ~25 float operations and 6 conversions) hides under the FP64 stream.
+struct LayerF {
+  float hb00, hb01, hb10, hc00, hc01, hc10;   // h B, h C (float32 products; B = [[-k, f34], [f21, k]], C = [[f13, f12], [f43, -f13]])
+  float qw, rho, mu, lam, f12, f34;           // closing constants
+  int ns;                                     // sub-layers to integrate (0: liquid layer, skipped)
+};
+
+SD_HD LayerF reigen_layer_setup(const ModelView& mv, int j, int ns, float wvno, float wvnosq, float omegsq) {
+  LayerF L;
+  float a, b;
+  mv.ab(j, a, b);
+  const float rho = mv.rho(j);
+  const float b2 = b * b;
+  const float xmu = rho * b2;
+  const float xlamb = rho * (a * a - 2.f * b2);
+  const float ds = mv.cst[C_DFL * mv.ld + j] * ((mv.ndiv > 1 && j >= mv.jj0) ? sd_rcp((float)mv.ndiv) : 1.0f);   // surfa.f:800-815
+  const float h = -0.25f * ds;
+  const float l2m = xlamb + 2.f * xmu;
+  const float f12 = sd_rcp(l2m);
+  const float f13 = wvno * xlamb * f12;
+  const float f21 = -omegsq * rho;
+  const float f34 = sd_rcp(xmu);
+  const float f43 = f21 + 4.f * wvnosq * xmu * (xlamb + xmu) * f12;
+  L.hb00 = -h * wvno; L.hb01 = h * f34; L.hb10 = h * f21;
+  L.hc00 = h * f13; L.hc01 = h * f12; L.hc10 = h * f43;
+  L.qw = ds * (0.25f * 32.f / 22.5f);     // Boole: dz / 22.5 with the weights carried as w / 32
+  L.rho = rho; L.mu = xmu; L.lam = xlamb; L.f12 = f12; L.f34 = f34;
+  L.ns = (b > 0.f) ? ns : 0;
+  return L;
+}
+
+struct StepMat2 { double pp00, pp01, pp10, pp11, pq00, pq01, pq10, pq11, qp00, qp01, qp10, qp11; };
+
+SD_HD StepMat2 make_stepmat2(const LayerF& L) {
+  const double hb00 = L.hb00, hb01 = L.hb01, hb10 = L.hb10, hc00 = L.hc00, hc01 = L.hc01, hc10 = L.hc10;
+  // X' = (hB)(hC), B = [[b00, b01], [b10, -b00]], C = [[c00, c01], [c10, -c00]]
+  const double x00 = hb00 * hc00 + hb01 * hc10, x01 = hb00 * hc01 - hb01 * hc00;
+  const double x10 = hb10 * hc00 - hb00 * hc10, x11 = hb10 * hc01 + hb00 * hc00;
+  const double t = x00 + x11, d = x00 * x11 - x01 * x10;
+  const double al = 1.0 - d * (1.0 / 24.0), be = 0.5 + t * (1.0 / 24.0);
+  StepMat2 m;
+  m.pp00 = al + be * x00; m.pp01 = be * x01; m.pp10 = be * x10; m.pp11 = al + be * x11;
+  const double f00 = 1.0 + x00 * (1.0 / 6.0), f01 = x01 * (1.0 / 6.0), f10 = x10 * (1.0 / 6.0), f11 = 1.0 + x11 * (1.0 / 6.0);
+  m.pq00 = f00 * hb00 + f01 * hb10; m.pq01 = f00 * hb01 - f01 * hb00;
+  m.pq10 = f10 * hb00 + f11 * hb10; m.pq11 = f10 * hb01 - f11 * hb00;
+  m.qp00 = f11 * hc00 - f01 * hc10; m.qp01 = f11 * hc01 + f01 * hc00;
+  m.qp10 = f00 * hc10 - f10 * hc00; m.qp11 = -f10 * hc01 - f00 * hc00;
+  return m;
+}
+
+SD_HD void rk4_step2(const StepMat2& m, double& ur, double& uz, double& tz, double& tr) {
+  const double nur = m.pp00 * ur + m.pp01 * tz + m.pq00 * uz + m.pq01 * tr;
+  const double ntz = m.pp10 * ur + m.pp11 * tz + m.pq10 * uz + m.pq11 * tr;
+  const double nuz = m.qp00 * ur + m.qp01 * tz + m.pp11 * uz - m.pp01 * tr;   // qq = adj(pp)
+  const double ntr = m.qp10 * ur + m.qp11 * tz - m.pp10 * uz + m.pp00 * tr;
+  ur = nur; uz = nuz; tz = ntz; tr = ntr;
+}
+
+// the twelve Boole sums of a layer: (ur^2, uz^2, uz tr, ur tz) x (yy, yz, zz)
+struct Raw12 { double r0, r1, r2, r3, r4, r5, q6, q7, q8, q9, q10, q11; };
+
+template <bool FIRST>
+SD_HD void boole_knot(Raw12& R, double w, bool unit, double yur, double yuz, double ytz, double ytr, double zur, double zuz,
+                      double ztz, double ztr) {
+  const double ay = unit ? yur : w * yur, by = unit ? yuz : w * yuz, az = unit ? zur : w * zur, bz = unit ? zuz : w * zuz;
+  if (FIRST) {
+    R.r0 = ay * yur; R.r1 = ay * zur; R.r2 = az * zur;
+    R.r3 = by * yuz; R.r4 = by * zuz; R.r5 = bz * zuz;
+    R.q6 = by * ytr; R.q7 = by * ztr; R.q8 = bz * ztr;
+    R.q9 = ay * ytz; R.q10 = ay * ztz; R.q11 = az * ztz;
+  } else {
+    R.r0 = fma(ay, yur, R.r0); R.r1 = fma(ay, zur, R.r1); R.r2 = fma(az, zur, R.r2);
+    R.r3 = fma(by, yuz, R.r3); R.r4 = fma(by, zuz, R.r4); R.r5 = fma(bz, zuz, R.r5);
+    R.q6 = fma(by, ytr, R.q6); R.q7 = fma(by, ztr, R.q7); R.q8 = fma(bz, ztr, R.q8);
+    R.q9 = fma(ay, ytz, R.q9); R.q10 = fma(ay, ztz, R.q10); R.q11 = fma(az, ztz, R.q11);
+  }
+  R.q7 = fma(bz, ytr, R.q7); R.q10 = fma(az, ytz, R.q10);
+}
+
+SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, float fact,
+                           unsigned long long& nsubsteps) {
+  const DropResult dr = eigen_drop(mv, c, T, fact, true);
+  const float wvno = SD_DIV(SD_TWOPI, SD_MUL(c, T));
+  const float wvnosq = SD_MUL(wvno, wvno);
+  const float omega = SD_DIV(SD_TWOPI, T);
+  const float omegsq = SD_MUL(omega, omega);
+  const bool water = !(mv.cst[C_BREF * mv.ld + 0] > 0.f);
+  // water layer integrals (surfa.f:879-910)
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if (water) {
+    float a1, b1;
+    mv.ab(0, a1, b1);
+    const float rho1 = mv.rho(0), d1 = mv.dsub(0);
+    const float xl1 = rho1 * (a1 * a1 - 2.f * b1 * b1);
+    const float ra = c / a1;
+    const float x = ra * ra - 1.f;
+    const float mag = wvno * sqrtf(fabsf(x));
+    if (mag <= 1.0e-35f) { w0 = rho1 * d1; }
+    else {
+      float sin2ra, cosra, rab1;
+      if (x >= 0.f) {
+        sin2ra = sinf(2.f * mag * d1) / (4.f * mag); cosra = cosf(mag * d1); rab1 = mag * mag;
+      } else {
+        const float e2 = expf(2.f * mag * d1);
+        sin2ra = (0.5f * (e2 - 1.f / e2)) / (4.f * mag);
+        const float e1 = expf(mag * d1);
+        cosra = 0.5f * (e1 + 1.f / e1); rab1 = -(mag * mag);
+      }
+      const float cos2rm = 1.f / (cosra * cosra);
+      const float fac1 = (0.5f * d1 + sin2ra) * cos2rm;
+      const float fac3 = wvno * (0.5f * d1 - sin2ra) * cos2rm;
+      const float fac2 = wvno * fac3 / rab1;
+      w0 = rho1 * (fac1 + fac2); w1 = xl1 * fac2; w2 = xl1 * fac3;
+    }
+  }
+  // half-space (surfa.f:913-926), float32 like the reference
+  float ah, bh;
+  mv.ab(dr.jh, ah, bh);
+  const float rhoh = mv.rho(dr.jh);
+  const float cova = SD_DIV(c, ah), covb = SD_DIV(c, bh);
+  const float gam = SD_DIV(2.f, SD_MUL(covb, covb));
+  const float gamm1 = SD_SUB(gam, 1.f);
+  const float ra = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(cova, cova), 1.f))));
+  const float rb = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(covb, covb), 1.f))));
+  const float det = SD_SUB(wvnosq, SD_MUL(ra, rb));
+  const float h = SD_MUL(rhoh, omegsq);
+  const float brkt = SD_ADD(SD_MUL(-gamm1, wvno), SD_DIV(SD_MUL(SD_MUL(gam, ra), rb), wvno));
+  const double y0tz = (double)SD_DIV(SD_MUL(-h, brkt), det), y0tr = (double)SD_DIV(SD_MUL(-h, ra), det);
+  const double z0tz = (double)SD_DIV(SD_MUL(-h, rb), det), z0tr = y0tz;
+  if (rb == 0.f) return bh;  // surfa.f:1165
+
+  double xnorm = 0.0, bb = 1.0, alpha_sum = 0.0;
+  double zs_ur = 0.0, zs_uz = 1.0, zs_tz = z0tz, zs_tr = z0tr;  // start vector of solution 2
+  Quad9 Q;
+  const int jfirst = water ? 1 : 0;
+  const double dk = (double)wvno;
+  constexpr int kOrthEvery = 8;
+  constexpr double W7 = 7.0 / 32.0, W12 = 12.0 / 32.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    double yur = 1.0, yuz = 0.0, ytz = y0tz, ytr = y0tr;
+    double zur = zs_ur, zuz = zs_uz, ztz = zs_tz, ztr = zs_tr;
+    Q.i0yy = Q.i0yz = Q.i0zz = Q.i1yy = Q.i1yz = Q.i1zz = Q.i2yy = Q.i2yz = Q.i2zz = 0.0;
+    int since = 0;
+    alpha_sum = 0.0;
+    LayerF cur;
+    cur.ns = 0;
+    if (dr.jlast >= jfirst) cur = reigen_layer_setup(mv, dr.jlast, dr.nlast, wvno, wvnosq, omegsq);
+    for (int j = dr.jlast; j >= jfirst; --j) {
+      // float32 set-up of the next layer first: it does not depend on the FP64 work below
+      LayerF nxt;
+      nxt.ns = 0;
+      if (j > jfirst) nxt = reigen_layer_setup(mv, j - 1, mv.nsub(j - 1), wvno, wvnosq, omegsq);
+      if (cur.ns > 0) {
+        const StepMat2 sm = make_stepmat2(cur);
+        Raw12 R;
+        // first sub-layer peeled: its first knot initialises the sums, and the straight-line code lets the compiler
+        // interleave the next layer's float32 set-up with this FP64 stream (stacks of >= 21 layers have ns = 1)
+        boole_knot<true>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, W12, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        for (int s = 1; s < cur.ns; ++s) {
+          boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, W12, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        }
+        // closing: layer constants applied once (the yz sums of the squares enter doubled)
+        {
+          const double qw = (double)cur.qw, mu = (double)cur.mu, lam = (double)cur.lam, f12 = (double)cur.f12;
+          const double c0 = qw * (double)cur.rho;
+          const double c1b = qw * mu, c1a = fma(2.0, c1b, qw * lam);      // qw (lambda + 2 mu), qw mu
+          const double cA = c1b * (double)cur.f34, cB = -c1b * dk;
+          const double cC = -(qw * lam) * f12, cD = cC * (dk * lam);
+          const double R1 = R.r1 + R.r1, R4 = R.r4 + R.r4;
+          Q.i0yy = fma(c0, R.r3, fma(c0, R.r0, Q.i0yy)); Q.i0yz = fma(c0, R4, fma(c0, R1, Q.i0yz)); Q.i0zz = fma(c0, R.r5, fma(c0, R.r2, Q.i0zz));
+          Q.i1yy = fma(c1b, R.r3, fma(c1a, R.r0, Q.i1yy)); Q.i1yz = fma(c1b, R4, fma(c1a, R1, Q.i1yz)); Q.i1zz = fma(c1b, R.r5, fma(c1a, R.r2, Q.i1zz));
+          Q.i2yy = fma(cD, R.r0, fma(cC, R.q9, fma(cB, R.r3, fma(cA, R.q6, Q.i2yy))));
+          Q.i2yz = fma(cD, R1, fma(cC, R.q10, fma(cB, R4, fma(cA, R.q7, Q.i2yz))));
+          Q.i2zz = fma(cD, R.r2, fma(cC, R.q11, fma(cB, R.r5, fma(cA, R.q8, Q.i2zz))));
+        }
+        nsubsteps += (unsigned)cur.ns;
+        // Re-orthogonalisation: both solutions grow upwards and turn parallel (the P part dominates), and the
+        // eigenfunction is their small difference.  The reference notices that at the surface (xtest, surfa.f:1066)
+        // and integrates a second time from z + xnorm y -- 36 % of the evaluations of the benchmark set.  Here, every
+        // kOrthEvery layers the component of z along y is removed (z <- z - al y): the sums are bilinear forms in
+        // (y, z), so they are carried into the new basis exactly (Syz' = Syz - al Syy, Sz'z' = Szz - al (Syz + Syz')),
+        // the pair never becomes parallel and the first integration is already the accurate one.
+        if (++since >= kOrthEvery && j > jfirst) {
+          since = 0;
+          const double syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
+          const double syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
+          const double al = syz / syy;
+          zur = fma(-al, yur, zur); zuz = fma(-al, yuz, zuz); ztz = fma(-al, ytz, ztz); ztr = fma(-al, ytr, ztr);
+          alpha_sum += al;
+          // (the yz sums are stored doubled: S = 2 Syz)
+          { const double n = fma(-2.0 * al, Q.i0yy, Q.i0yz); Q.i0zz = fma(-0.5 * al, Q.i0yz + n, Q.i0zz); Q.i0yz = n; }
+          { const double n = fma(-2.0 * al, Q.i1yy, Q.i1yz); Q.i1zz = fma(-0.5 * al, Q.i1yz + n, Q.i1zz); Q.i1yz = n; }
+          { const double n = fma(-2.0 * al, Q.i2yy, Q.i2yz); Q.i2zz = fma(-0.5 * al, Q.i2yz + n, Q.i2zz); Q.i2yz = n; }
+        }
+      }
+      cur = nxt;
+    }
+    // combine with the surface ellipticity (surfa.f:1056-1065)
+    const double aa = zur - (double)ratio * zuz;
+    double b_ = (double)ratio * yuz - yur;
+    if (fabs(b_) < 1.e-10) b_ = copysign(1.e-10, b_);
+    xnorm = aa / b_;
+    bb = xnorm * yuz + zuz;
+    if (fabs(bb) < 1.e-10) bb = copysign(1.e-10, bb);
+    if (pass == 0) {
+      const float ampur = (float)((xnorm * yur + zur) / bb);
+      const float xtest = fabsf(ampur / ratio - 1.f);
+      // The reference forms the eigenfunction knot by knot (xnorm y + z, surfa.f:1076-1086) and squares it; the
+      // quadratic forms used here square the dynamic range of the cancellation instead: where y and z have grown
+      // nearly parallel (short periods, c above the crustal velocities: the P part grows by e^18 over the depth
+      // range) x^2 Qyy + x Qyz + Qzz loses every digit although the reference's first iteration is still fine.
+      // The conditioning of the two positive integrals is checked; below 1e-7 the second iteration is taken too
+      // (solution 2 restarted from the eigenfunction itself: no cancellation left in the sums).
+      const double a0 = xnorm * xnorm * Q.i0yy, b0 = xnorm * Q.i0yz, a1 = xnorm * xnorm * Q.i1yy, b1 = xnorm * Q.i1yz;
+      const bool lost = fabs(a0 + b0 + Q.i0zz) < 1.0e-7 * (fabs(a0) + fabs(b0) + fabs(Q.i0zz)) ||
+                        fabs(a1 + b1 + Q.i1zz) < 1.0e-7 * (fabs(a1) + fabs(b1) + fabs(Q.i1zz));
+      if (!(xtest >= 0.00001f) && !lost) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
+      // second iteration of the reference (surfa.f:986-998): solution 2 restarted from z + xnorm*y
+      SD_COUNT_SECOND_PASS();
+      // (in terms of this pass's start vector the eigenfunction is (xnorm - alpha_sum) y + z)
+      const double xo = xnorm - alpha_sum;
+      zs_ur = zs_ur + xo * 1.0; zs_uz = zs_uz + xo * 0.0; zs_tz = zs_tz + xo * y0tz; zs_tr = zs_tr + xo * y0tr;
+    }
+  }
+  const double ib2 = 1.0 / (bb * bb);
+  double s0 = (double)w0 + (xnorm * xnorm * Q.i0yy + xnorm * Q.i0yz + Q.i0zz) * ib2;
+  double s1 = (double)w1 + (xnorm * xnorm * Q.i1yy + xnorm * Q.i1yz + Q.i1zz) * ib2;
+  double s2 = (double)w2 + (xnorm * xnorm * Q.i2yy + xnorm * Q.i2yz + Q.i2zz) * ib2;
+  // half-space tail (surfa.f:1151-1178)
+  {
+    const double xo = xnorm - alpha_sum;   // coefficient of y relative to the start vectors of the last pass
+    double aur = (xo * 1.0 + zs_ur) / bb, auz = (xo * 0.0 + zs_uz) / bb;
+    if (water && dr.jh == 1) { aur = ratio; auz = 1.0; }
+    const double dra = ra, drb = rb, ddet = det, drho = rhoh;
+    const double xmu = (double)SD_MUL(SD_MUL(rhoh, bh), bh);
+    const double xlamb = (double)SD_MUL(rhoh, SD_SUB(SD_MUL(ah, ah), SD_MUL(SD_MUL(2.f, bh), bh)));
+    const double ap = -drho * (dk * aur + drb * auz) / ddet;
+    const double bp = -drho * (-dra * aur / dk - auz) / ddet;
+    const double a1 = -dk * ap / drho, a2 = -dk * drb * bp / drho, a3 = dra * ap / drho, a4 = (double)wvnosq * bp / drho;
+    const double dmmr = a1 * a1 / (2. * dra) + 2. * a1 * a2 / (dra + drb) + a2 * a2 / (2. * drb);
+    const double dmmz = a3 * a3 / (2. * dra) + 2. * a3 * a4 / (dra + drb) + a4 * a4 / (2. * drb);
+    const double drsz = -a1 * a3 / 2. - (a1 * a4 * drb + a2 * a3 * dra) / (dra + drb) - a2 * a4 / 2.;
+    const double dzsr = -a1 * a3 / 2. - (a1 * a4 * dra + a2 * a3 * drb) / (dra + drb) - a2 * a4 / 2.;
+    s0 += drho * (dmmr + dmmz);
+    s1 += (xlamb + 2. * xmu) * dmmr + xmu * dmmz;
+    s2 += xmu * dzsr - xlamb * drsz;
+  }
   return (float)(((double)wvno * s1 + s2) / ((double)omega * s0));  // surfa.f:1186
 }
 

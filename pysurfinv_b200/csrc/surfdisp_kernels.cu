@@ -974,7 +974,7 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
       const float T = p.tab.per[k];
       const float c = p.c_in[(size_t)model * K + k];
       float u;
-      if (KIND == 2) u = reigen_thread(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
+      if (KIND == 2) u = reigen_thread2(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
       else u = leigen_thread(mv, T, c, p.fact, nsub);
       urow[k] = u;
     }
@@ -1669,28 +1669,62 @@ int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_
   return 0;
 }
 
+// Per-thread context of the host entry points (surfdisp_host_batch, fast_surf_): the device block and the two streams
+// are kept between calls -- an unmodified models.py:27 loop calls fast_surf 50 000 times per point, and a
+// cudaMalloc + two cudaStreamCreate + cudaFree per call cost more than the solve.  One context per host thread and
+// device (the entry points stay re-entrant: no state is shared between threads); the block only grows.
+struct HostCtx {
+  int device = -1;
+  char* dev = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr, xs = nullptr;
+  ~HostCtx() { release(); }
+  void release() {
+    if (device < 0) return;
+    // (at thread exit the CUDA context may already be gone: errors are ignored)
+    if (dev) cudaFree(dev);
+    if (st) cudaStreamDestroy(st);
+    if (xs) cudaStreamDestroy(xs);
+    dev = nullptr; st = xs = nullptr; bytes = 0; device = -1;
+    cudaGetLastError();
+  }
+  int acquire(int dev_id, size_t need) {
+    if (device != dev_id) release();
+    CK(cudaSetDevice(dev_id));
+    if (device < 0) {
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
+      device = dev_id;
+    }
+    if (bytes < need) {
+      if (dev) { cudaFree(dev); dev = nullptr; bytes = 0; }
+      const size_t want = need < (size_t)(1 << 20) ? (size_t)(1 << 20) : need;
+      CK(cudaMalloc(&dev, want));
+      bytes = want;
+    }
+    return 0;
+  }
+};
+static thread_local HostCtx g_host_ctx;
+
 int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_models, int n_layers_max,
                         const int* n_layers, const float* layers, int n_periods, const float* periods,
                         float* c_out, float* u_out, int* nfound, int* flags) {
   if (n_models < 0 || n_layers_max < 2 || n_periods < 1 || n_periods > kMaxPer) return SURFDISP_EINVAL;
   if (n_models == 0) return 0;
   if (!n_layers || !layers || !c_out || !nfound || !periods) return SURFDISP_EINVAL;
-  CK(cudaSetDevice(device));
   const size_t total = surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods);
-  char* dev = nullptr;
-  CK(cudaMalloc(&dev, total));
-  cudaStream_t st = nullptr, xs = nullptr;
-  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { if (st) cudaStreamDestroy(st); cudaFree(dev); return cuda_fail(e, "cudaStreamCreate"); }
+  if (int rc = g_host_ctx.acquire(device, total)) return rc;
   const int chunks = n_models >= (1 << 16) ? 8 : 1;
   const int rc = surfdisp_host_batch_pipelined(opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out,
-                                               u_out, nfound, flags, dev, total, chunks, st, xs);
-  cudaStreamDestroy(st);
-  cudaStreamDestroy(xs);
-  cudaFree(dev);
+                                               u_out, nfound, flags, g_host_ctx.dev, g_host_ctx.bytes, chunks, g_host_ctx.st,
+                                               g_host_ctx.xs);
+  // a batch that needed more than 1 GiB does not keep it
+  if (g_host_ctx.bytes > ((size_t)1 << 30)) { cudaFree(g_host_ctx.dev); g_host_ctx.dev = nullptr; g_host_ctx.bytes = 0; }
   return rc;
 }
+
+void surfdisp_host_release(void) { g_host_ctx.release(); }
 
 void fast_surf_(const int* n_layer0, const int* kind0, const float* a_ref0, const float* b_ref0,
                 const float* rho_ref0, const float* d_ref0, const float* qs_ref0, const float* cvper,

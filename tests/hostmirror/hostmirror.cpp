@@ -418,7 +418,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     mv.ndiv = ndiv;
     mv.jj0 = (cst[C_BREF * ld + 0] <= 0.1e-10f) ? 1 : 0;
     unsigned long long ns = 0;
-    u_out[k] = (kind == 2) ? reigen_thread(mv, per[k], c_out[k], ratio_out[k], fact, ns)
+    static const bool plain_reigen = getenv("HM_PLAIN_REIGEN") != nullptr;   // (the untrimmed statement of the same integration)
+    u_out[k] = (kind == 2) ? (plain_reigen ? reigen_thread(mv, per[k], c_out[k], ratio_out[k], fact, ns) : reigen_thread2(mv, per[k], c_out[k], ratio_out[k], fact, ns))
                            : leigen_thread(mv, per[k], c_out[k], fact, ns);
   }
   if (sweeps) *sweeps += nsw;
