@@ -169,3 +169,57 @@ def priors(tmpl, p):
     if len(vm) >= 2 and (vm[-1] - vm[-2]) / (zm[-1] - zm[-2]) <= 0:
         bad |= S.P_BOTTOM
     return bad
+
+
+def _argrel(v, greater):
+    """scipy.signal.argrelmax / argrelmin (order 1, mode 'clip'): strict comparison with both neighbours, the
+    neighbours of the end points being the end points themselves -- so the ends are never extrema."""
+    v = np.asarray(v, dtype=np.float64)
+    if len(v) < 3:
+        return np.zeros(0, dtype=int)
+    l, r, c = v[:-2], v[2:], v[1:-1]
+    m = (c > l) & (c > r) if greater else (c < l) & (c < r)
+    return np.nonzero(m)[0] + 1
+
+
+def ricker(points, a):
+    """scipy.signal.ricker (SciPy <= 1.14, _wavelets.py; removed in 1.15)."""
+    A = 2 / (np.sqrt(3 * a) * (np.pi ** 0.25))
+    vec = np.arange(0, points) - (points - 1.0) / 2
+    return A * (1 - vec ** 2 / a ** 2) * np.exp(-vec ** 2 / (2 * a ** 2))
+
+
+def cwt_ricker(data, width):
+    """scipy.signal.cwt(data, ricker, [width])[0] (SciPy <= 1.14)."""
+    n = min(10 * width, len(data))
+    return np.convolve(data, ricker(n, width)[::-1], mode="same")
+
+
+def priors_ocean(tmpl, p):
+    """Bits of the violated rules of CascadiaOcean.isgood (reference models.py:571-677), as that code behaves:
+    `grp` is a Python LIST there, so `grp[1:] != grp[:-1]` is one bool (the jump rule only ever compares the first
+    two grid points, models.py:586-588) and `vs[grp == 'sediment']` is an empty selection (the monotonicity rules
+    of models.py:591-594 never fire)."""
+    z, vs, cls = grids_one(tmpl, np.asarray(p, dtype=np.float64))
+    bad = 0
+    vm, zm = vs[cls == S.C_MANTLE], z[cls == S.C_MANTLE]
+    if np.any(vs[cls == S.C_SEDIMENT] < 0.2):
+        bad |= S.P_SEDMIN
+    if len(vs) >= 2 and vs[1] < vs[0]:
+        bad |= S.P_FIRSTPAIR
+    if (vs[-1] - vs[-2]) / (z[-1] - z[-2]) <= 0:
+        bad |= S.P_BOTTOM
+    ext = np.sort(np.append(_argrel(vm, True), _argrel(vm, False)))
+    if len(ext) > 1 and np.any(np.abs(np.diff(vm[ext])) > 0.1 * vm.mean()):
+        bad |= S.P_OSCI
+    if len(_argrel(vm, True)) > 0:
+        bad |= S.P_LOCALMAX
+    slope = np.diff(vm) / np.diff(zm)
+    if slope.min() < slope[0] * 1.5:
+        bad |= S.P_SLOPE
+    width = 30 // (zm[1] - zm[0])
+    cw = cwt_ricker(vm - np.interp(zm, [zm[0], zm[-1]], [vm[0], vm[-1]]), width)
+    e2 = np.sort(np.append(_argrel(cw, True), _argrel(cw, False)))
+    if np.any(np.abs(np.diff(cw[e2])) > 0.3):
+        bad |= S.P_CWT
+    return bad

@@ -42,6 +42,29 @@ def misfit(c_obs, c_pred, uncer):
     return mis, chi, np.exp(-0.5 * chi)
 
 
+def misfit_cascadia(c_obs, c_pred, uncer, periods):
+    """Host mirror of ``PointCascadia.misfit`` (point.py:337-366): mean of the two period bands (T <= 40 s, T > 40 s)."""
+    if c_pred is None:
+        return 88888, 88888, 0
+    T = np.asarray(periods, dtype=np.float64)
+    c_obs = np.ma.masked_array(c_obs) if not np.ma.isMaskedArray(c_obs) else c_obs
+    n = c_obs.count()
+    bias = (c_obs - c_pred) / uncer
+    b1, b2 = bias[T <= 40], bias[T > 40]
+    e1, e2 = (b1.count() == 0), (b2.count() == 0)
+    if not e1 and not e2:
+        chi = ((b1 ** 2).mean() + (b2 ** 2).mean()) / 2 * n
+    elif e1 and not e2:
+        chi = (b2 ** 2).mean() * n
+    elif not e1 and e2:
+        chi = (b1 ** 2).mean() * n
+    else:
+        raise ValueError("All observations are masked???")
+    mis = np.sqrt(chi / n)
+    chi = chi if chi < 50 else np.sqrt(chi * 50.0)
+    return mis, chi, np.exp(-0.5 * chi)
+
+
 def accept(chi0, chi1, rnd):
     """Metropolis rule of point.py:34-37 with the uniform draw passed in."""
     if chi1 < chi0:

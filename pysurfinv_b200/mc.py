@@ -13,6 +13,53 @@ import os
 import numpy as np
 
 from . import api
+from .stack import Param, _is_spec
+
+# layer.prop['LayerName'] of the reference's layer classes (layers.py:142,161,194,209,224,242,270,292): the keys
+# Model1D.toYML (models.py:53-62) writes.  'LandSediment' / 'LandCrust' are not keys of the reference's own
+# layerClassDict (layers.py:552-568), so a file written with them cannot be read back by buildModel1D; for those
+# two the setting keeps the type key the user gave (documented deviation in favour of a readable file).
+_LAYER_NAME = {"Sediment": "Sediment", "Crust": "Crust", "Mantle": "OceanMantle", "OceanMantle": "OceanMantle",
+               "OceanWater": "OceanWater", "OceanSediment": "OceanSediment", "OceanCrust": "OceanCrust",
+               "OceanSedimentCascadia": "OceanSedimentCascadia", "ReferenceMantle": "ReferenceMantle",
+               "OceanMantleHybrid": "OceanMantleHybrid"}
+
+
+def setting_to_yml(setting):
+    """The dict Model1D.toYML() (reference models.py:53-62) returns for a model built from `setting`: every free
+    parameter as [v, vmin, vmax, step] (BrownianVar), fixed specs as plain numbers, 'Info' last."""
+    def conv(v):
+        if _is_spec(v):
+            if v[1] in ("fixed", "total"):
+                return v[0]
+            p = Param(v, "")
+            return [p.v0, p.vmin, p.vmax, p.step]
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        return v
+    out = {}
+    for name, parm in setting.items():
+        if name == "Info":
+            continue
+        d = {k: conv(v) for k, v in dict(parm).items()}
+        if name == "OceanWater":
+            d["Vs"] = 0          # layers.py:195
+        out[_LAYER_NAME.get(name, name)] = d
+    out["Info"] = dict(setting.get("Info", {}))
+    return out
+
+
+def write_point_npz(path, track, setting, obs, pid, chain_length):
+    """The per-point file Point.MCinvMP writes (reference point.py:112-123) and PostPoint / Model3D.loadInvDir read
+    (point.py:139-149, model3D.py:36-57): the sub-chains concatenated in order.
+    track: [n_subchains, steps, 3 + P] rows [misfit, L, accepted, parameters] (Model1D._dump, models.py:243-245)."""
+    tr = np.asarray(track, dtype=np.float64)
+    mc = tr.reshape(-1, tr.shape[-1])
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    np.savez_compressed(path, mcTrack=mc, setting=setting_to_yml(setting),
+                        obs={k: (v if np.ma.isMaskedArray(v) else np.asarray(v)) for k, v in obs.items()},
+                        invMeta={"pid": pid, "chainL": int(chain_length)})
+    return path
 
 
 class ChainEnsemble:
@@ -78,6 +125,12 @@ class ChainEnsemble:
     def mc_track(self):
         """[M, steps, 3 + P] numpy array."""
         return self.torch.stack(self.track, dim=1).cpu().numpy()
+
+    def save_point_npz(self, outdir, pid, setting, chain_length=None):
+        """<outdir>/<pid>.npz: all sub-chains of this point merged like Point.MCinvMP does (point.py:112-123)."""
+        tr = self.mc_track()
+        obs = {"T": self.periods, "c": self.obs, "uncer": self.sigma}
+        return write_point_npz(os.path.join(outdir, "%s.npz" % pid), tr, setting, obs, pid, chain_length or tr.shape[1])
 
     def save_npz(self, outdir, pid, setting, chain_length=None):
         """One file per chain, in the layout of Point.MCinv (point.py:78-85)."""

@@ -27,6 +27,15 @@ R_QUARTIC, R_OCEAN, R_MANTLE, R_CONST = 0, 1, 2, 3
 C_WATER, C_SEDIMENT, C_CRUST, C_MANTLE, C_OTHER = 0, 1, 2, 3, 4
 P_JUMP, P_VSMAX, P_MONO, P_BOTTOM = 1, 2, 4, 8
 P_ALL = 15
+# CascadiaOcean.isgood (models.py:571-677): sediment Vs >= 0.2, first grid pair not decreasing (what is left of the
+# jump rule there), oscillation limit, no local maximum in the mantle, no extreme decrease below the moho, wavelet rule
+P_SEDMIN, P_FIRSTPAIR, P_OSCI, P_LOCALMAX, P_SLOPE, P_CWT = 16, 32, 64, 128, 256, 512
+# the rule sets of the reference's model classes
+PRIOR_PRISM = P_JUMP | P_VSMAX | P_MONO | P_BOTTOM                    # CascadiaPrism.isgood      models.py:294-360
+PRIOR_CONTINENT = P_JUMP | P_VSMAX | P_MONO                           # CascadiaContinent.isgood  models.py:385-523
+PRIOR_OCEAN = P_SEDMIN | P_FIRSTPAIR | P_BOTTOM | P_OSCI | P_LOCALMAX | P_SLOPE | P_CWT   # CascadiaOcean.isgood :571-677
+PRIOR_OF_MODELTYPE = {"CascadiaPrism": PRIOR_PRISM, "CascadiaContinent": PRIOR_CONTINENT, "CascadiaOcean": PRIOR_OCEAN,
+                      "MCInv": 0, "General": 0}
 _CLASS = {'Sediment': C_SEDIMENT, 'Crust': C_CRUST, 'Mantle': C_MANTLE, 'OceanMantle': C_MANTLE, 'OceanWater': C_WATER,
           'OceanSediment': C_SEDIMENT, 'OceanSedimentCascadia': C_SEDIMENT, 'OceanCrust': C_CRUST}
 
