@@ -189,7 +189,21 @@ int surfdisp_measure_peaks(double out[3]);
 #define SURFDISP_P_JUMP 1        /* Vs jump between groups must not be negative (models.py:305-307) */
 #define SURFDISP_P_VSMAX 2       /* all Vs <= 4.9 km/s (models.py:312-313) */
 #define SURFDISP_P_MONO 4        /* Vs strictly increasing inside sediment and crust (models.py:318-321) */
-#define SURFDISP_P_BOTTOM 8      /* positive Vs gradient at the bottom of the mantle (models.py:355-356) */
+#define SURFDISP_P_BOTTOM 8      /* positive Vs gradient at the bottom of the mantle (models.py:355-356; for the ocean
+                                    rules: at the bottom of the whole grid, models.py:597-598) */
+/* CascadiaOcean.isgood (models.py:571-677), evaluated when prior_mask asks for any of the last five */
+#define SURFDISP_P_SEDMIN 16     /* Vs in the sediment >= 0.2 km/s (models.py:581-583) */
+#define SURFDISP_P_FIRSTPAIR 32  /* what is left of the jump rule there: `grp` is a Python list in that method, so only
+                                    the first two grid points are compared (models.py:586-588) */
+#define SURFDISP_P_OSCI 64       /* neighbouring local extrema of the mantle Vs differ by < 10 % of its mean (:603-611) */
+#define SURFDISP_P_LOCALMAX 128  /* no local maximum in the mantle (:616-619) */
+#define SURFDISP_P_SLOPE 256     /* no gradient below 1.5 x the gradient under the moho (:621-623) */
+#define SURFDISP_P_CWT 512       /* neighbouring extrema of the Mexican-hat transform (width 30 km) of the detrended
+                                    mantle profile differ by <= 0.3 (:626-635; scipy.signal.cwt / ricker of SciPy <= 1.14) */
+/* the rule sets of the reference's model classes */
+#define SURFDISP_PRIOR_PRISM (1 | 2 | 4 | 8)                        /* CascadiaPrism.isgood      models.py:294-360 */
+#define SURFDISP_PRIOR_CONTINENT (1 | 2 | 4)                        /* CascadiaContinent.isgood  models.py:385-523 */
+#define SURFDISP_PRIOR_OCEAN (16 | 32 | 8 | 64 | 128 | 256 | 512)   /* CascadiaOcean.isgood      models.py:571-677 */
 
 typedef struct SurfdispStackGroup {
   int kind, nfine_rule, nfine, h_mode;      /* h_mode 0: parameter is the thickness H, 1: BottomDepth */
@@ -212,8 +226,8 @@ typedef struct SurfdispStackTemplate {
 int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params,
                           int n_layers_max, float* layers, int* n_layers, void* stream);
 
-/* Prior checks only: priors device int[M] = SURFDISP_P_* bits violated (all four rules are evaluated,
- * whatever prior_mask says). */
+/* Prior checks only: priors device int[M] = SURFDISP_P_* bits violated (all rules are evaluated, whatever
+ * prior_mask says). */
 int surfdisp_check_priors(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int* priors,
                           void* stream);
 
@@ -239,6 +253,48 @@ int surfdisp_mc_propose(const SurfdispStackTemplate* tmpl, int n_chains, const f
 int surfdisp_mc_accept(int n_chains, int n_params, const float* chi1, const float* prop, float* chi0, float* cur,
                        const unsigned char* force_mask, unsigned char* accepted, unsigned long long seed,
                        unsigned int step_index, void* stream);
+
+/* ---- One whole Monte-Carlo step of an ensemble of chains, every stage on the device (Point.MCinv, point.py:40-76,
+ * for M chains at once; the chains of several points -- the grid nodes of model3D.py:50-57 -- run side by side):
+ *   proposal + model assembly (one kernel, warp per chain) -> surfdisp_batch stages (phase velocities) -> misfit +
+ *   Metropolis rule + state update + chain-track row (one kernel) -> step counter + 1.
+ * All launches go to `stream` and read the step index from a device counter, so a captured CUDA graph of one call
+ * can be replayed for the following steps.
+ *   step % chain_len == 0 starts a sub-chain (point.py:45-57): at step 0 the chains flagged in init_mask take their
+ *   current model as it is (perturbed first if it violates the priors); every other start is a uniform redraw over the
+ *   box; the first sample of a sub-chain is always kept. */
+typedef struct SurfdispMcState {
+  int n_chains, n_params, n_periods, n_layers_max;
+  int kind;                 /* SURFDISP_KIND_* of the observed curve */
+  int misfit_mode;          /* 0 Point.misfit (point.py:15-31), 1 PointCascadia.misfit (point.py:337-366) */
+  int chain_len;            /* sub-chain length (chainL of point.py:32); 0: no restarts */
+  int chains_per_point;     /* chain m belongs to point m / chains_per_point */
+  int track_steps;          /* rows of the track ring buffer (0: no track) */
+  int pad_;
+  unsigned long long seed;
+  /* device pointers */
+  float* cur;               /* [M][P] current models (in/out) */
+  float* prop;              /* [M][P] proposals of this step (out) */
+  float* chi0;              /* [M] chi-square of the current models (in/out) */
+  int* status;              /* [M] tries of the proposal, < 0: no admissible model found (the reference raises there;
+                               such a chain keeps its state and the row is written with accepted = 0) */
+  unsigned char* accepted;  /* [M] (out) */
+  const unsigned char* init_mask;   /* [M] or NULL */
+  float* misfit;            /* [M][3] (misfit, chiSqr, L) of the proposals (out) or NULL */
+  float* track;             /* [track_steps][M][3 + P] rows [misfit, L, accepted, parameters] (models.py:243-245) or NULL */
+  unsigned int* step;       /* [1] step counter (in/out) */
+  const float* bounds;      /* [n_points][3][64]: vmin, vmax, step of every free parameter (brownian.py:3-16) */
+  const float* obs;         /* [n_points][K] observed phase velocities */
+  const float* isig;        /* [n_points][K] 1 / uncertainty */
+  const unsigned char* use; /* [n_points][K] 0 = masked observation */
+  /* scratch owned by the caller */
+  float* layers; int* n_layers;          /* [5][M][n_layers_max], [M] */
+  float* c_pred; int* nfound; int* flags;   /* [M][K], [M], [M] */
+  void* workspace; size_t workspace_bytes;  /* surfdisp_workspace_bytes(M, n_layers_max, K) */
+} SurfdispMcState;
+
+int surfdisp_mc_step(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl, const SurfdispMcState* st,
+                     const float* periods /* HOST float[K] */, void* stream);
 
 const char* surfdisp_version(void);
 const char* surfdisp_last_cuda_error(void);

@@ -28,6 +28,18 @@ class SurfdispOpts(C.Structure):
                 ("flatten", C.c_int), ("stale_mmax", C.c_int), ("compute_group", C.c_int), ("exact_scan", C.c_int)]
 
 
+class SurfdispMcState(C.Structure):
+    """Mirror of ``SurfdispMcState`` in include/surfdisp_b200.h (one Monte-Carlo step of an ensemble of chains)."""
+    _fields_ = [("n_chains", C.c_int), ("n_params", C.c_int), ("n_periods", C.c_int), ("n_layers_max", C.c_int),
+                ("kind", C.c_int), ("misfit_mode", C.c_int), ("chain_len", C.c_int), ("chains_per_point", C.c_int),
+                ("track_steps", C.c_int), ("pad_", C.c_int), ("seed", C.c_ulonglong),
+                ("cur", C.c_void_p), ("prop", C.c_void_p), ("chi0", C.c_void_p), ("status", C.c_void_p),
+                ("accepted", C.c_void_p), ("init_mask", C.c_void_p), ("misfit", C.c_void_p), ("track", C.c_void_p),
+                ("step", C.c_void_p), ("bounds", C.c_void_p), ("obs", C.c_void_p), ("isig", C.c_void_p), ("use", C.c_void_p),
+                ("layers", C.c_void_p), ("n_layers", C.c_void_p), ("c_pred", C.c_void_p), ("nfound", C.c_void_p),
+                ("flags", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class SurfdispError(RuntimeError):
     pass
 
@@ -80,6 +92,10 @@ def load_library():
     L.surfdisp_mc_propose.restype = C.c_int
     L.surfdisp_mc_accept.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_ulonglong, C.c_uint, vp]
     L.surfdisp_mc_accept.restype = C.c_int
+    L.surfdisp_mc_step.argtypes = [C.POINTER(SurfdispOpts), C.POINTER(_stack.StackTemplateC), C.POINTER(SurfdispMcState), fp, vp]
+    L.surfdisp_mc_step.restype = C.c_int
+    L.surfdisp_host_release.argtypes = []
+    L.surfdisp_host_release.restype = None
     L.surfdisp_version.restype = C.c_char_p
     L.surfdisp_last_cuda_error.restype = C.c_char_p
     _lib = L
@@ -230,8 +246,8 @@ class DispersionSolver:
         return out
 
     def check_priors(self, template, params):
-        """SURFDISP P_* bits of the prior rules (CascadiaPrism.isgood, reference models.py:294-360) each model
-        violates; int32 device tensor [M]."""
+        """SURFDISP P_* bits of the prior rules each model violates (CascadiaPrism / CascadiaContinent / CascadiaOcean
+        .isgood, reference models.py:294-360, 385-523, 571-677; all rules are evaluated); int32 device tensor [M]."""
         torch = self.torch
         M = int(params.shape[0])
         out = torch.empty(M, dtype=torch.int32, device=self.device)

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "surfdisp_kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "surfdisp_core.cuh"), os.path.join(HERE, "csrc", "sd_libm.cuh"),
+DEPS = SRC + [os.path.join(HERE, "csrc", "surfdisp_core.cuh"), os.path.join(HERE, "csrc", "sd_libm.cuh"), os.path.join(HERE, "csrc", "surfdisp_mc.cuh"),
               os.path.join(os.path.dirname(HERE), "include", "surfdisp_b200.h")]
 OUT = os.path.join(HERE, "libsurfdisp_b200.so")
 

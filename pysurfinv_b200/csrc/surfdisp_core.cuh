@@ -694,14 +694,26 @@ SD_HD bool nevill_seq(F f, float c1, float c2, float del1, float del2, float& cc
 // On-the-fly view of the period-T model of calcul.f:325-337 (all n layers refreshed, flat1 with n).
 struct ModelView {
   const float* cst;
-  int ld, n, atten, ndiv, jj0;
+  int sc, sl;            // constant (component, layer) sits at cst[component * sc + layer * sl]: rows [8][ld] (sc = ld, sl = 1)
+                         // as the prep kernel writes them, or records [layer][8] (sc = 1, sl = 8) as phase 2 stages them
+  int n, atten, ndiv, jj0;
   float lt;
-  SD_HD void ab(int j, float& a, float& b) const { layer_ab(cst, ld, j, lt, atten, j == n - 1, a, b); }
-  SD_HD float rho(int j) const { return (j == n - 1) ? cst[C_RHOHS * ld + j] : cst[C_RHOFL * ld + j]; }
+  SD_HD float at(int comp, int j) const { return cst[comp * sc + j * sl]; }
+  SD_HD void ab(int j, float& a, float& b) const {
+    layer_ab_vals(at(C_AREF, j), at(C_BREF, j), at(C_QS, j), (j == n - 1) ? at(C_HSF, j) : at(C_DIF, j), lt, atten, a, b);
+  }
+  // b only (the layer-dropping walk needs nothing else): same roundings as ab()
+  SD_HD float b_only(int j) const {
+    const float br = at(C_BREF, j);
+    float b = br;
+    if (atten) b = SD_MUL(br, SD_ADD(1.0f, SD_FDIV(SD_MUL(at(C_QS, j), lt), SD_PI_ATT)));
+    return SD_MUL(b, (j == n - 1) ? at(C_HSF, j) : at(C_DIF, j));
+  }
+  SD_HD float rho(int j) const { return (j == n - 1) ? at(C_RHOHS, j) : at(C_RHOFL, j); }
   SD_HD int nsub(int j) const { return (ndiv > 1 && j >= jj0 && j < n - 1) ? ndiv : 1; }
   SD_HD float dsub(int j) const {
     if (j == n - 1) return 0.f;
-    const float d = cst[C_DFL * ld + j];
+    const float d = at(C_DFL, j);
     return (ndiv > 1 && j >= jj0) ? SD_DIV(d, (float)ndiv) : d;
   }
 };
@@ -717,8 +729,7 @@ SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, b
   const int n = mv.n;
   DropResult r; r.jh = n - 1; r.jlast = n - 2; r.nlast = mv.nsub(n - 2 < 0 ? 0 : n - 2);
   for (int j = 0; j < n; ++j) {
-    float a, b;
-    mv.ab(j, a, b);
+    const float b = mv.b_only(j);
     if (!(c - b < 0.f)) continue;
     const int ns = mv.nsub(j);
     const float ds = mv.dsub(j);
@@ -729,6 +740,8 @@ SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, b
     // next sub-layer has identical a,b (surfa.f:862-863 fall to 900), so the decision is taken here
     float a2, b2;
     mv.ab(j + 1, a2, b2);
+    float a = 0.f, b_chk;
+    if (use_a) mv.ab(j, a, b_chk);
     int dec;  // -1: half-space = this sub-layer, +1: next one, 0: keep going
     if (use_a) {
       const float da = a2 - a;
@@ -813,7 +826,7 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
   const float wvnosq = SD_MUL(wvno, wvno);
   const float omega = SD_DIV(SD_TWOPI, T);
   const float omegsq = SD_MUL(omega, omega);
-  const bool water = !(mv.cst[C_BREF * mv.ld + 0] > 0.f);
+  const bool water = !(mv.at(C_BREF, 0) > 0.f);
   // water layer integrals (surfa.f:879-910)
   float w0 = 0.f, w1 = 0.f, w2 = 0.f;
   if (water) {
@@ -996,7 +1009,7 @@ SD_HD LayerF reigen_layer_setup(const ModelView& mv, int j, int ns, float wvno, 
   const float b2 = b * b;
   const float xmu = rho * b2;
   const float xlamb = rho * (a * a - 2.f * b2);
-  const float ds = mv.cst[C_DFL * mv.ld + j] * ((mv.ndiv > 1 && j >= mv.jj0) ? sd_rcp((float)mv.ndiv) : 1.0f);   // surfa.f:800-815
+  const float ds = mv.at(C_DFL, j) * ((mv.ndiv > 1 && j >= mv.jj0) ? sd_rcp((float)mv.ndiv) : 1.0f);   // surfa.f:800-815
   const float h = -0.25f * ds;
   const float l2m = xlamb + 2.f * xmu;
   const float f12 = sd_rcp(l2m);
@@ -1067,7 +1080,7 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
   const float wvnosq = SD_MUL(wvno, wvno);
   const float omega = SD_DIV(SD_TWOPI, T);
   const float omegsq = SD_MUL(omega, omega);
-  const bool water = !(mv.cst[C_BREF * mv.ld + 0] > 0.f);
+  const bool water = !(mv.at(C_BREF, 0) > 0.f);
   // water layer integrals (surfa.f:879-910)
   float w0 = 0.f, w1 = 0.f, w2 = 0.f;
   if (water) {
@@ -1129,10 +1142,10 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
     cur.ns = 0;
     if (dr.jlast >= jfirst) cur = reigen_layer_setup(mv, dr.jlast, dr.nlast, wvno, wvnosq, omegsq);
     for (int j = dr.jlast; j >= jfirst; --j) {
-      // float32 set-up of the next layer first: it does not depend on the FP64 work below
-      LayerF nxt;
-      nxt.ns = 0;
-      if (j > jfirst) nxt = reigen_layer_setup(mv, j - 1, mv.nsub(j - 1), wvno, wvnosq, omegsq);
+      // float32 set-up of the next layer: it does not depend on the FP64 work of this one, and sits in the same
+      // basic block (computed unconditionally, for a clamped index), so that the compiler interleaves the two
+      const int jn = (j > jfirst) ? j - 1 : jfirst;
+      LayerF nxt = reigen_layer_setup(mv, jn, mv.nsub(jn), wvno, wvnosq, omegsq);
       if (cur.ns > 0) {
         const StepMat2 sm = make_stepmat2(cur);
         Raw12 R;

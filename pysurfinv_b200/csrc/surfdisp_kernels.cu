@@ -945,11 +945,17 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
   const int model0 = blockIdx.x * p.mpb;
   const int nmod = min(p.mpb, p.M - model0);
   const int per_model = NCONST * p.lpad;
-  // stage the constants of this block's models (coalesced float4 copies)
+  // stage the constants of this block's models: coalesced float4 reads of the rows [8][lpad], written as records
+  // [layer][8] -- a thread then reads all constants of a layer from one address (two 16-byte-aligned groups)
   {
     const float4* src = reinterpret_cast<const float4*>(p.consts + (size_t)model0 * per_model);
-    const int n4 = nmod * per_model / 4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) smem[i] = src[i];
+    const int n4 = nmod * per_model / 4, l4 = p.lpad / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = src[i];
+      const int ml = i / (NCONST * l4), r = i - ml * (NCONST * l4), comp = r / l4, lay = (r - comp * l4) * 4;
+      float* dst = sc + (size_t)ml * (per_model + NCONST) + (size_t)lay * NCONST + comp;   // (+ one record: the models' bank sets differ)
+      dst[0] = v.x; dst[NCONST] = v.y; dst[2 * NCONST] = v.z; dst[3 * NCONST] = v.w;
+    }
   }
   __syncthreads();
   unsigned long long nsub = 0;
@@ -964,13 +970,13 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
       urow[k] = 0.f;
     } else {
       ModelView mv;
-      mv.cst = sc + (size_t)ml * per_model;
-      mv.ld = p.lpad; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
+      mv.cst = sc + (size_t)ml * (per_model + NCONST);
+      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
       int ndiv = p.ndiv;
       const int ivre = p.ndiv_cap / (n - 1);
       if (ndiv > ivre) ndiv = ivre;
       mv.ndiv = ndiv;
-      mv.jj0 = (mv.cst[C_BREF * mv.ld + 0] <= 0.1e-10f) ? 1 : 0;
+      mv.jj0 = (mv.at(C_BREF, 0) <= 0.1e-10f) ? 1 : 0;
       const float T = p.tab.per[k];
       const float c = p.c_in[(size_t)model * K + k];
       float u;
@@ -1029,259 +1035,11 @@ __global__ void __launch_bounds__(256) misfit_kernel(const __grid_constant__ Mis
 
 
 
-// ------------------------------------------------------------------------------------ model builder
-// Thread per model.  All arithmetic in double like the reference's numpy code; results are rounded to float32
-// when stored (that is what f2py does to the arrays handed to fast_surf, fast_surf.pyf:6-19).
-__device__ double bspl_profile(const double* coef, int n, double z) {
-  // value at z in [0, 1] of sum_i coef_i B_i(z) with the basis of reference layers.py:4-45: degree 3 (n = 3) or
-  // 4 (n >= 4) de Boor recursion on the knot vector [-eps x (deg-1), 0, geometric interior knots, 1, 1+eps ...]
-  const double eps = 2.220446049250313e-16;
-  const int deg = 3 + (n >= 4);
-  double x[SURFDISP_MAX_COEF + 4];
-  for (int i = 0; i < deg - 1; ++i) x[i] = -eps;
-  x[deg - 1] = 0.0;
-  {
-    const int m = n - deg;            // number of interior knots
-    const double den = pow(2.0, (double)(m + 1)) - 1.0;
-    for (int kk = 0; kk < m; ++kk) x[deg + kk] = pow(2.0, (double)kk) * (2.0 - 1.0) / den;
-  }
-  x[n] = 1.0;
-  for (int i = n + 1; i < n + deg; ++i) x[i] = 1.0 + eps;
-  const int nc = n + deg - 1;
-  double b0[SURFDISP_MAX_COEF + 3], b1[SURFDISP_MAX_COEF + 3];
-  for (int i = 0; i < nc; ++i) { b0[i] = (z >= x[i] && z < x[i + 1]) ? 1.0 : 0.0; b1[i] = b0[i]; }
-  for (int r = 0; r < deg - 1; ++r) {
-    for (int i = 0; i < nc - r - 1; ++i) {
-      double col = 0.0;
-      const double d1 = x[i + r + 1] - x[i], d2 = x[i + r + 2] - x[i + 1];
-      if (d1 != 0.0) col += b0[i] * (z - x[i]) / d1;
-      if (d2 != 0.0) col += b0[i + 1] * (x[i + r + 2] - z) / d2;
-      b1[i] = col;
-    }
-    for (int i = 0; i < nc; ++i) b0[i] = b1[i];
-  }
-  double v = 0.0;
-  for (int i = 0; i < n; ++i) v += coef[i] * b1[i];
-  return v;
-}
-
-__device__ double stack_rho(int rule, double cst, double vs, double vp) {
-  if (rule == SURFDISP_R_QUARTIC) return 1.22679 + 1.53201 * vs - 0.83668 * vs * vs + 0.20673 * vs * vs * vs - 0.01656 * vs * vs * vs * vs;
-  if (rule == SURFDISP_R_OCEAN) return 0.541 + 0.3601 * vp;
-  if (rule == SURFDISP_R_MANTLE) return 3.4268 + (vs - 4.5) / 4.5;
-  return cst;
-}
-
-// Assembles one model from its parameter vector.  EMIT: write the layers; always returns the SURFDISP_P_* bits
-// of the violated prior rules (CascadiaPrism.isgood, models.py:294-360, evaluated on the fine grid without the
-// reference mantle like Model1D.seisPropGrids() does by default).
-template <bool EMIT>
-__device__ int assemble_stack(const SurfdispStackTemplate& t, const float* pm, int lmax, float* o_vp, float* o_vs,
-                              float* o_rho, float* o_h, float* o_qs, int* nl_out) {
-  int nl = 0, bad = 0;
-  bool overflow = false, any = false;
-  double z0 = -fmax(t.topo, 0.0);        // depth of the top of the next group (models.py:76-77)
-  double ztop_prev = 0.0;                 // bottom depth of the stack so far, for BottomDepth groups (0 if none)
-  double last_vs = 0.0, last_vp = 0.0, last_rho = 0.0, last_qs = 0.0;   // deepest grid values so far
-  int last_class = -1;
-  double bot_grad = 1.0;                  // Vs gradient at the bottom of the deepest mantle group
-  for (int gi = 0; gi < t.ngroups; ++gi) {
-    const SurfdispStackGroup& g = t.groups[gi];
-    const double hv = (g.h_param >= 0) ? (double)pm[g.h_param] : g.h_fixed;
-    double H = hv;
-    if (g.h_mode == 1 && any) H = hv - ztop_prev;
-    int N = g.nfine;
-    if (g.nfine_rule == SURFDISP_N_CRUST) N = (H >= 150.0) ? 60 : ((H > 60.0) ? 30 : ((H > 20.0) ? 15 : ((H > 10.0) ? 10 : 5)));
-    else if (g.nfine_rule == SURFDISP_N_OCRUST) N = min(max((int)rint(H / 2.0), 2), 10);
-    double coef[SURFDISP_MAX_COEF];
-    for (int i = 0; i < g.ncoef; ++i) coef[i] = (g.v_param[i] >= 0) ? (double)pm[g.v_param[i]] : g.v_fixed[i];
-    // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
-    if (H - 0.0 < 0.01) continue;
-    const bool is_ref = (g.kind == SURFDISP_G_REFMANTLE);
-    const double zstep = H / (double)N, ustep = 1.0 / (double)N;
-    double p_z = 0.0, p_vs = 0.0, p_vp = 0.0, p_rho = 0.0, p_qs = 0.0;   // previous grid point
-    const double vs0_ref = last_vs;
-    double vp_first = 0.0, rho_first = 0.0, qs_first = 0.0;
-    for (int j = 0; j <= N; ++j) {
-      const double zz = (j == N) ? H : (double)j * zstep;
-      const double u = (j == N) ? 1.0 : (double)j * ustep;
-      double vs;
-      if (g.kind == SURFDISP_G_WATER) vs = 0.0;
-      else if (g.kind == SURFDISP_G_CONST) vs = coef[0];
-      else if (g.kind == SURFDISP_G_LINEAR) vs = (j == N) ? coef[1] : coef[0] + (double)j * ((coef[1] - coef[0]) / (double)N);
-      else if (g.kind == SURFDISP_G_BSPLINE) {
-        if (g.ncoef == 1) vs = coef[0];
-        else if (g.ncoef == 2) vs = coef[0] * ((j == N) ? 0.0 : 1.0 + (double)j * ((0.0 - 1.0) / (double)N)) + coef[1] * u;
-        else vs = bspl_profile(coef, g.ncoef, u);
-      } else if (g.kind == SURFDISP_G_CASCADIA) vs = (0.02 * H * H + 1.27 * H + 0.29 * 0.1) / (H + 0.29);
-      else {  // reference mantle: linear continuation of the deepest Vs (layers.py:267-285)
-        const double vend = vs0_ref + H * g.slope;
-        vs = (j == N) ? vend : vs0_ref + (double)j * ((vend - vs0_ref) / (double)N);
-      }
-      double vp = g.vp_a * vs + g.vp_b;
-      double rho = stack_rho(g.rho_rule, g.rho_const, vs, vp);
-      double qs = g.qs;
-      if (is_ref) {
-        // Vp, rho, Qs continue from the deepest values above (layers.py:279-283)
-        if (j == 0) { vp_first = vp; rho_first = rho; qs_first = qs; }
-        vp = last_vp + (vp - vp_first); rho = last_rho + (rho - rho_first); qs = last_qs + (qs - qs_first);
-      }
-      if (!is_ref) {
-        // ---- prior rules on the grid (models.py:301-356)
-        if (vs > 4.9) bad |= SURFDISP_P_VSMAX;
-        if (j == 0 && any && g.gclass != last_class && vs < last_vs) bad |= SURFDISP_P_JUMP;
-        if (j > 0 && (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST) && !(vs - p_vs >= 2.220446049250313e-16))
-          bad |= SURFDISP_P_MONO;
-        if (j == 0 && any && g.gclass == last_class && (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST) &&
-            !(vs - last_vs >= 2.220446049250313e-16))
-          bad |= SURFDISP_P_MONO;   // two groups of the same class form one array in the reference's test
-        if (j == N && g.gclass == SURFDISP_C_MANTLE) bot_grad = (vs - p_vs) / (zz - p_z);
-      }
-      if (EMIT && j > 0) {
-        const double h = (zz + z0) - (p_z + z0);
-        if (h > 0.01) {   // models.py:102 (and models.py:20: h > 1e-3)
-          if (nl < lmax) {
-            o_vp[nl] = (float)(0.5 * (vp + p_vp)); o_vs[nl] = (float)(0.5 * (vs + p_vs));
-            o_rho[nl] = (float)(0.5 * (rho + p_rho)); o_h[nl] = (float)h;
-            o_qs[nl] = (float)(1.0 / (0.5 * (qs + p_qs)));
-            nl++;
-          } else overflow = true;
-        }
-      }
-      p_z = zz; p_vs = vs; p_vp = vp; p_rho = rho; p_qs = qs;
-    }
-    last_vs = p_vs; last_vp = p_vp; last_rho = p_rho; last_qs = p_qs;
-    if (!is_ref) last_class = g.gclass;
-    z0 = z0 + H;
-    ztop_prev = z0;
-    any = true;
-  }
-  if (!(bot_grad > 0.0)) bad |= SURFDISP_P_BOTTOM;
-  if (EMIT) *nl_out = overflow ? -1 : nl;
-  return bad;
-}
-
-__global__ void __launch_bounds__(128) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
-                                                           const float* __restrict__ params, int lmax,
-                                                           float* __restrict__ layers, int* __restrict__ nlay) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const float* pm = params + (size_t)m * t.nparams;
-  const size_t pl = (size_t)M * lmax;
-  float* o_vp = layers + 0 * pl + (size_t)m * lmax;
-  float* o_vs = layers + 1 * pl + (size_t)m * lmax;
-  float* o_rho = layers + 2 * pl + (size_t)m * lmax;
-  float* o_h = layers + 3 * pl + (size_t)m * lmax;
-  float* o_qs = layers + 4 * pl + (size_t)m * lmax;
-  int nl = 0;
-  assemble_stack<true>(t, pm, lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl);
-  const int nz = nl < 0 ? 0 : nl;
-  for (int j = nz; j < lmax; ++j) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
-  nlay[m] = nz;
-}
-
-__global__ void __launch_bounds__(128) check_priors_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
-                                                           const float* __restrict__ params, int* __restrict__ priors) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  priors[m] = assemble_stack<false>(t, params + (size_t)m * t.nparams, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-}
-
-// ------------------------------------------------------------------------------------ Monte-Carlo step
-// Philox4x32-10 (Salmon et al., SC'11): counter-based, so chain m at step s draws the same numbers whatever
-// the launch geometry.  counter = (chain, step, draw, stream id), key = seed.
-struct Philox {
-  unsigned int c0, c1, c2, c3, k0, k1;
-  unsigned int buf[4];
-  int have;
-  __device__ Philox(unsigned long long seed, unsigned int chain, unsigned int step, unsigned int stream_id)
-      : c0(chain), c1(step), c2(0u), c3(stream_id), k0((unsigned int)seed), k1((unsigned int)(seed >> 32)), have(0) {}
-  __device__ void block() {
-    unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const unsigned int h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
-      const unsigned int h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
-      const unsigned int y0 = h1 ^ x1 ^ a, y1 = l1, y2 = h0 ^ x3 ^ b, y3 = l0;
-      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-      a += 0x9E3779B9u; b += 0xBB67AE85u;
-    }
-    buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
-    c2++;
-    have = 4;
-  }
-  __device__ unsigned int next() { if (!have) block(); return buf[--have]; }
-  __device__ float uniform() { return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
-  __device__ float gauss() {   // Box-Muller
-    const float u1 = uniform(), u2 = uniform();
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-  }
-};
-
-struct McBounds { float lo[64], hi[64], step[64]; };
-constexpr int kMaxParams = 64;
-
-__global__ void __launch_bounds__(128) mc_propose_kernel(const __grid_constant__ SurfdispStackTemplate t,
-                                                         const __grid_constant__ McBounds bd, int M,
-                                                         const float* __restrict__ cur,
-                                                         const unsigned char* __restrict__ reset_mask,
-                                                         float* __restrict__ prop, int* __restrict__ status,
-                                                         unsigned long long seed, unsigned int step_index) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int P = t.nparams;
-  Philox rng(seed, (unsigned int)m, step_index, 1u);
-  const float* c = cur + (size_t)m * P;
-  float* q = prop + (size_t)m * P;
-  const bool restart = reset_mask && reset_mask[m];
-  int tries = 0, result = -1;
-  // MCinv.perturb (models.py:190-205): up to 1000 proposals, then MCinv.reset (models.py:206-219): up to 10000
-  for (int phase = restart ? 1 : 0; phase < 2 && result < 0; ++phase) {
-    const int limit = phase == 0 ? 1000 : 10000;
-    for (int a = 0; a < limit; ++a) {
-      ++tries;
-      for (int i = 0; i < P; ++i) {
-        const float lo = bd.lo[i], hi = bd.hi[i];
-        float v = 0.f;
-        bool ok = false;
-        if (phase == 0) {
-          // BrownianVar.move (brownian.py:20-27): Gaussian step, redrawn until strictly inside the bounds
-          for (int r = 0; r < 1000 && !ok; ++r) {
-            v = c[i] + bd.step[i] * rng.gauss();
-            ok = (v < hi && v > lo);
-          }
-        }
-        if (!ok) v = lo + (hi - lo) * rng.uniform();   // BrownianVar.reset (brownian.py:17-19)
-        q[i] = v;
-      }
-      const int bad = t.prior_mask ? (assemble_stack<false>(t, q, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) & t.prior_mask) : 0;
-      if (!bad) { result = tries; break; }
-    }
-  }
-  if (status) status[m] = result;
-}
-
-__global__ void __launch_bounds__(256) mc_accept_kernel(int M, int P, const float* __restrict__ chi1,
-                                                        const float* __restrict__ prop, float* __restrict__ chi0,
-                                                        float* __restrict__ cur, const unsigned char* __restrict__ force,
-                                                        unsigned char* __restrict__ accepted, unsigned long long seed,
-                                                        unsigned int step_index) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  Philox rng(seed, (unsigned int)m, step_index, 2u);
-  const float x0 = chi0[m], x1 = chi1[m];
-  bool acc = force && force[m];
-  if (!acc) {
-    // point.py:34-37: accept if chi1 < chi0, else if u > 1 - exp(-(chi1 - chi0) / 2)   (= (L0 - L1) / L0)
-    if (x1 < x0) acc = true;
-    else acc = (double)rng.uniform() > 1.0 - exp(-0.5 * ((double)x1 - (double)x0));
-  }
-  if (acc) {
-    chi0[m] = x1;
-    for (int i = 0; i < P; ++i) cur[(size_t)m * P + i] = prop[(size_t)m * P + i];
-  }
-  accepted[m] = acc ? 1 : 0;
-}
+// ------------------------------------------------------------------------------------ model builder, Monte-Carlo step
+}  // namespace
+#include "surfdisp_mc.cuh"
+namespace {
+using namespace mcdev;
 
 // ------------------------------------------------------------------------------------ pipe peaks
 // Register-resident FMA / MUFU chains: the denominators of the FP-pipe roofline (MEASURED_PEAKS.json
@@ -1494,7 +1252,7 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   p2.fact = pl.o.fact; p2.atten = pl.o.atten; p2.ndiv = pl.o.ndiv;
   p2.ndiv_cap = (pl.kind == 2) ? pl.o.ndiv_cap_rayleigh : pl.o.ndiv_cap_love;
   p2.tab = pl.tab;
-  const size_t per_model = (size_t)NCONST * pl.w.lpad * sizeof(float);
+  const size_t per_model = (size_t)NCONST * (pl.w.lpad + 1) * sizeof(float);   // shared-memory record stride of a model
   // models per block: the one whose (models x periods) work items fill whole warps best (40 periods: 4 models =
   // 160 threads, no idle lane; 3 models in 128 threads leave 8 of 128 lanes idle in every FP64 instruction)
   int mpb = 1;
@@ -1832,7 +1590,7 @@ int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const
   if (int rc = check_template(tmpl)) return rc;
   if (n_models == 0) return 0;
   if (!layers || !n_layers || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
-  build_stacks_kernel<<<(n_models + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
+  build_stacks_kernel<<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1842,7 +1600,7 @@ int surfdisp_check_priors(const SurfdispStackTemplate* tmpl, int n_models, const
   if (int rc = check_template(tmpl)) return rc;
   if (n_models == 0) return 0;
   if (!priors || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
-  check_priors_kernel<<<(n_models + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
+  check_priors_kernel<<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1862,8 +1620,8 @@ int surfdisp_mc_propose(const SurfdispStackTemplate* tmpl, int n_chains, const f
     if (!(hi[i] > lo[i]) || !(step[i] > 0.f)) return SURFDISP_EINVAL;
     bd.lo[i] = lo[i]; bd.hi[i] = hi[i]; bd.step[i] = step[i];
   }
-  mc_propose_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*tmpl, bd, n_chains, cur, reset_mask, prop,
-                                                                              status, seed, step_index);
+  mc_propose_kernel<<<(unsigned)(((size_t)n_chains * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(
+      *tmpl, bd, n_chains, cur, reset_mask, prop, status, seed, step_index);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1880,7 +1638,50 @@ int surfdisp_mc_accept(int n_chains, int n_params, const float* chi1, const floa
   return 0;
 }
 
-const char* surfdisp_version(void) { return "surfdisp_b200 0.1 (sm_100a)"; }
+int surfdisp_mc_step(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl, const SurfdispMcState* s,
+                     const float* periods, void* stream) {
+  if (!s || !periods) return SURFDISP_EINVAL;
+  if (int rc = check_template(tmpl)) return rc;
+  const int M = s->n_chains, P = s->n_params, K = s->n_periods;
+  if (M < 0 || P < 1 || P > kMaxParams || P != tmpl->nparams || K < 1 || K > kMaxPer || s->chains_per_point < 1 ||
+      (s->misfit_mode != 0 && s->misfit_mode != 1) || s->track_steps < 0)
+    return SURFDISP_EINVAL;
+  if (M == 0) return 0;
+  if (!s->cur || !s->prop || !s->chi0 || !s->status || !s->accepted || !s->step || !s->bounds || !s->obs || !s->isig ||
+      !s->use || !s->layers || !s->n_layers || !s->c_pred || !s->nfound || !s->workspace || (s->track_steps > 0 && !s->track))
+    return SURFDISP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- proposal + model assembly
+  McStepParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.M = M; mp.P = P; mp.lmax = s->n_layers_max; mp.chain_len = s->chain_len; mp.cur = s->cur; mp.prop = s->prop;
+  mp.status = s->status; mp.init_mask = s->init_mask; mp.layers = s->layers; mp.nlay = s->n_layers; mp.step_ptr = s->step;
+  mp.seed = s->seed; mp.bounds = reinterpret_cast<const McBounds*>(s->bounds); mp.chains_per_point = s->chains_per_point;
+  mc_propose_build_kernel<<<(unsigned)(((size_t)M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, st>>>(*tmpl, mp);
+  CK(cudaGetLastError());
+  // ---- phase velocities of the proposals
+  SurfdispOpts o;
+  if (opts) o = *opts; else surfdisp_default_opts(&o);
+  o.compute_group = 0;
+  int rc = surfdisp_batch(&o, s->kind, M, s->n_layers_max, s->n_layers, s->layers, K, periods, s->c_pred, nullptr, s->nfound,
+                          s->flags, s->workspace, s->workspace_bytes, stream);
+  if (rc) return rc;
+  // ---- misfit, Metropolis rule, state update, track row
+  McFinishParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.M = M; fp.P = P; fp.K = K; fp.mode = s->misfit_mode; fp.chain_len = s->chain_len; fp.chains_per_point = s->chains_per_point;
+  fp.track_steps = s->track_steps > 0 ? s->track_steps : 1; fp.c_pred = s->c_pred; fp.nfound = s->nfound; fp.status = s->status;
+  fp.obs = s->obs; fp.isig = s->isig; fp.use = s->use; fp.prop = s->prop; fp.cur = s->cur; fp.chi0 = s->chi0;
+  fp.accepted = s->accepted; fp.misfit_out = s->misfit; fp.track = s->track_steps > 0 ? s->track : nullptr; fp.step_ptr = s->step;
+  fp.seed = s->seed;
+  for (int k = 0; k < K; ++k) fp.per[k] = periods[k];
+  mc_finish_kernel<<<(M + 127) / 128, 128, 0, st>>>(fp);
+  mc_bump_kernel<<<1, 1, 0, st>>>(s->step);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+const char* surfdisp_version(void) { return "surfdisp_b200 0.2 (sm_100a)"; }
 const char* surfdisp_last_cuda_error(void) { return g_cuda_err; }
 
 }  // extern "C"

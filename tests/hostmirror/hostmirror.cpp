@@ -411,7 +411,7 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   // phase 2
   for (int k = 0; k < nfound; ++k) {
     ModelView mv;
-    mv.cst = cst.data(); mv.ld = ld; mv.n = n; mv.atten = atten; mv.lt = lt[k];
+    mv.cst = cst.data(); mv.sc = ld; mv.sl = 1; mv.n = n; mv.atten = atten; mv.lt = lt[k];
     int ndiv = ndiv0;
     const int ivre = ndiv_cap / (n - 1);
     if (ndiv > ivre) ndiv = ivre;

@@ -104,21 +104,114 @@ def test_chain_ensemble_recovers_a_model_and_writes_reference_layout(solver, tmp
     lay, nl = solver.build_stacks(t, truth)
     obs = solver.forward(lay, nl, per, kind=2)["c"][0].cpu().numpy()
     assert obs.min() > 1.0
-    ens = mc.ChainEnsemble(solver, t, per, obs, np.full(len(per), 0.01, np.float32), n_chains=256, seed=1)
+    ens = mc.ChainEnsemble(solver, t, per, obs, np.full(len(per), 0.01, np.float32), n_chains=256, seed=1, chain_length=150,
+                           track_steps=150)
     ens.run(150)
     tr = ens.mc_track()
     assert tr.shape == (256, 150, 3 + t.nparams)
     misfit = tr[:, :, 0]
     accepted = tr[:, :, 2]
     assert np.all(accepted[:, 0] == 1)
+    # chain 0 starts from the start model itself (point.py:47-50), the others from a uniform redraw (point.py:52)
+    assert np.array_equal(tr[0, 0, 3:], t.start_values()) and not np.array_equal(tr[1, 0, 3:], t.start_values())
     # the walk goes downhill: the misfit of the chains' current states (last accepted sample) at the end is
-    # well below the misfit of the start model
+    # well below the misfit of their first samples
     state = np.empty_like(misfit)
     for k in range(misfit.shape[1]):
         state[:, k] = np.where(accepted[:, k] == 1, misfit[:, k], state[:, k - 1] if k else misfit[:, 0])
     assert state[:, -1].mean() < 0.6 * state[:, 0].mean(), (state[:, 0].mean(), state[:, -1].mean())
     assert 0.02 < accepted[:, 1:].mean() < 0.98
+    # every recorded proposal is admissible and inside its box
+    lo, hi, _ = t.bounds()
+    flat = tr[:, :, 3:].reshape(-1, t.nparams).astype(np.float32)
+    assert np.all(flat >= lo[None, :]) and np.all(flat <= hi[None, :])
+    assert int((solver.check_priors(t, torch.from_numpy(flat[::37].copy()).cuda()) & t.prior_mask).abs().sum()) == 0
+    # the graph replay and the eager launches are the same chain: rerun without the graph
+    ens2 = mc.ChainEnsemble(solver, t, per, obs, np.full(len(per), 0.01, np.float32), n_chains=256, seed=1, chain_length=150,
+                            track_steps=150, use_graph=False)
+    ens2.run(40)
+    assert np.array_equal(ens2.mc_track(), tr[:, :40])
+    # the misfit of the step kernel is the misfit kernel's (and the reference's, tests/test_point_reference.py)
+    m3 = solver.misfit(ens.c_pred, ens.nfound, obs, np.full(len(per), 0.01, np.float32)).cpu().numpy()
+    np.testing.assert_allclose(ens.misfit3.cpu().numpy(), m3, rtol=1e-6)
     paths = ens.save_npz(str(tmp_path), "pt", SETTING, chain_length=150)
     z = np.load(paths[3], allow_pickle=True)
     assert z["mcTrack"].shape == (150, 3 + t.nparams) and z["invMeta"].item()["chainL"] == 150
     assert set(z["obs"].item().keys()) == {"T", "c", "uncer"} and "Crust" in z["setting"].item()
+    merged = np.load(ens.save_point_npz(str(tmp_path), "-120.0_45.0", SETTING, chain_length=150), allow_pickle=True)
+    assert merged["mcTrack"].shape == (256 * 150, 3 + t.nparams) and np.array_equal(merged["mcTrack"][150:300], z["mcTrack"] * 0 + tr[1])
+
+
+def test_restarts_and_points_side_by_side(solver):
+    """Sub-chain restarts every chain_length steps (point.py:45-57) and several points in one ensemble, each with its
+    own observed curve: a point's chains do not depend on which other points run beside them."""
+    import torch
+    from pysurfinv_b200 import mc
+    t = S.StackTemplate(SETTING, prior_mask=S.PRIOR_CONTINENT)
+    per = np.array([10, 14, 20, 28, 40, 60, 80], np.float32)
+    start = torch.from_numpy(t.start_values()[None, :]).cuda().contiguous()
+    obs = []
+    for sd in (5, 6, 7):
+        truth = solver.mc_propose(t, start, seed=sd, step_index=0, reset_mask=torch.ones(1, dtype=torch.uint8, device="cuda"))
+        lay, nl = solver.build_stacks(t, truth)
+        obs.append(solver.forward(lay, nl, per, kind=2)["c"][0].cpu().numpy())
+    obs = np.array(obs)
+    sig = np.full_like(obs, 0.01)
+    ens = mc.ChainEnsemble(solver, t, per, obs, sig, n_chains=16, seed=3, n_points=3, chain_length=10, track_steps=30).run(30)
+    tr = ens.mc_track().reshape(3, 16, 30, -1)
+    assert np.all(tr[:, :, [0, 10, 20], 2] == 1)                     # first sample of every sub-chain is kept
+    assert np.array_equal(tr[1, 0, 0, 3:], t.start_values())         # chain 0 of a point starts from the start model,
+    assert not np.array_equal(tr[1, 1, 0, 3:], t.start_values())     # the others from a uniform redraw (point.py:101, 47-52)
+    assert not np.array_equal(tr[1, 0, 10, 3:], t.start_values())    # later sub-chains: always a redraw (point.py:52)
+    assert ens.best_misfit().shape == (3,)
+    # a point's chains do not depend on the observations of the points beside it
+    ens_b = mc.ChainEnsemble(solver, t, per, obs[[0, 2, 1]], sig, n_chains=16, seed=3, n_points=3, chain_length=10, track_steps=30).run(30)
+    trb = ens_b.mc_track().reshape(3, 16, 30, -1)
+    assert np.array_equal(trb[0], tr[0]) and not np.array_equal(trb[1], tr[1])
+
+
+def test_prior_kernels_match_reference_verdicts(solver):
+    """check_priors against the verdicts of the reference's own CascadiaContinent.isgood / CascadiaOcean.isgood
+    (tests/golden/point_reference.json) and, bit by bit, against the numpy restatement on random ocean models."""
+    import torch
+    with open(os.path.join(os.path.dirname(__file__), "golden", "point_reference.json")) as f:
+        gold = json.load(f)
+    none = torch.zeros((1, 0), dtype=torch.float32, device="cuda")
+    for case in gold["priors"]["continent"]:
+        bad = int(solver.check_priors(S.StackTemplate(case["setting"]), none).cpu()[0])
+        assert ((bad & S.PRIOR_CONTINENT) == 0) == case["isgood"]
+    for case in gold["priors"]["ocean"]:
+        tt = S.StackTemplate(case["setting"])
+        bad = int(solver.check_priors(tt, none).cpu()[0])
+        assert ((bad & S.PRIOR_OCEAN) == 0) == case["isgood"]
+        assert (bad & S.PRIOR_OCEAN) == (MB.priors_ocean(tt, np.zeros(0)) & S.PRIOR_OCEAN)
+    ocean = dict(gold["ocean_setting"])
+    t = S.StackTemplate(ocean, prior_mask=S.PRIOR_OCEAN)
+    lo, hi, _ = t.bounds()
+    rng = np.random.default_rng(9)
+    params = (lo + (hi - lo) * rng.random((3000, t.nparams))).astype(np.float32)
+    got = solver.check_priors(t, torch.from_numpy(params).cuda()).cpu().numpy() & S.PRIOR_OCEAN
+    want = np.array([MB.priors_ocean(t, p.astype(np.float64)) for p in params]) & S.PRIOR_OCEAN
+    assert (got != want).mean() < 2e-3          # (threshold ties of the wavelet rule: summation order)
+    assert 0 < (got == 0).sum() < len(got)
+    # proposals under the ocean rules are admissible
+    cur = torch.from_numpy(np.tile(t.start_values(), (4096, 1))).cuda().contiguous()
+    status = torch.empty(4096, dtype=torch.int32, device="cuda")
+    prop = solver.mc_propose(t, cur, seed=2, step_index=1, status=status)
+    assert int((solver.check_priors(t, prop) & S.PRIOR_OCEAN != 0).sum()) == 0 and int((status < 1).sum()) == 0
+
+
+def test_misfit_kernel_matches_reference_fixtures(solver):
+    """surfdisp_misfit_batch against Point.misfit / PointCascadia.misfit of the reference itself (golden)."""
+    import torch
+    with open(os.path.join(os.path.dirname(__file__), "golden", "point_reference.json")) as f:
+        gold = json.load(f)
+    for c in gold["misfit"]:
+        K = len(c["T"])
+        pred = np.zeros((1, K), np.float32) if c["pred"] is None else np.array([c["pred"]], np.float32)
+        nf = torch.tensor([0 if c["pred"] is None else K], dtype=torch.int32, device="cuda")
+        mask = (~np.array(c["mask"])).astype(np.uint8)
+        for mode, key in ((0, "point"), (1, "cascadia")):
+            m = solver.misfit(torch.from_numpy(pred).cuda(), nf, c["obs"], c["uncer"], mask=mask, periods=c["T"], mode=mode).cpu().numpy()[0]
+            # float32 inputs (obs, prediction, 1/sigma) against the reference's float64: 1e-4 relative on chi-square
+            np.testing.assert_allclose(m, c[key], rtol=3e-4, atol=1e-30)
