@@ -1,4 +1,5 @@
-"""GPU box: Monte-Carlo ensemble throughput (chain steps per second, every stage on the device)."""
+"""GPU box: Monte-Carlo ensemble throughput (chain steps per second, every stage on the device, CUDA-graph replay).
+usage: python tools/mc_throughput.py [chains] [steps] [graph 0/1]"""
 import sys, time
 import numpy as np
 import torch
@@ -8,6 +9,7 @@ from tests.test_gpu_mc import SETTING
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+graph = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
 s = api.DispersionSolver("cuda:0")
 t = S.StackTemplate(SETTING, prior_mask=S.P_ALL)
 per = np.array([8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)
@@ -15,13 +17,12 @@ start = torch.from_numpy(t.start_values()[None, :]).cuda().contiguous()
 truth = s.mc_propose(t, start, seed=99, step_index=0, reset_mask=torch.ones(1, dtype=torch.uint8, device="cuda"))
 lay, nl = s.build_stacks(t, truth)
 obs = s.forward(lay, nl, per, kind=2)["c"][0].cpu().numpy()
-ens = mc.ChainEnsemble(s, t, per, obs, np.full(len(per), 0.01, np.float32), n_chains=M, seed=1)
-ens.step(first=True, record=False)
-for _ in range(3):
-    ens.step(record=False)
+ens = mc.ChainEnsemble(s, t, per, obs, np.full(len(per), 0.01, np.float32), n_chains=M, seed=1, chain_length=1 << 30, use_graph=graph)
+for _ in range(4):
+    ens.step()
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(steps):
-    ens.step(record=False)
+    ens.step()
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print("%d chains x %d steps x %d periods: %.1f ms/step, %.3g chain-steps/s, %.3g evals/s, accept rate %.2f"
-      % (M, steps, len(per), dt / steps * 1e3, M * steps / dt, M * steps * len(per) / dt, float(ens.accepted.float().mean())))
+print("%d chains x %d steps x %d periods (graph %d): %.3f ms/step, %.3g chain-steps/s, %.3g evals/s, accept rate %.2f"
+      % (M, steps, len(per), graph, dt / steps * 1e3, M * steps / dt, M * steps * len(per) / dt, float(ens.accepted.float().mean())))
