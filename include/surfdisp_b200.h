@@ -221,6 +221,17 @@ typedef struct SurfdispStackTemplate {
   SurfdispStackGroup groups[SURFDISP_MAX_GROUPS];
 } SurfdispStackTemplate;
 
+/* The host-buffer pipeline fed with PARAMETER vectors instead of layers (Model1D.forward for a batch: models.py:93-121
+ * = seisPropLayers + _calForward): params HOST float[M][nparams] (pinned for an asynchronous copy) are copied once,
+ * the stacks are assembled on the device (surfdisp_build_stacks), then the stages of surfdisp_host_batch_pipelined
+ * follow.  Host<->device traffic per model: 4 nparams bytes in, 8 K + 8 bytes out -- the layer arrays (20 Lmax bytes
+ * per model) never cross PCIe.  device_buffer: surfdisp_params_pipelined_bytes() bytes. */
+size_t surfdisp_params_pipelined_bytes(int n_models, int n_params, int n_layers_max, int n_periods);
+int surfdisp_host_params_pipelined(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl, int kind, int n_models,
+                                   int n_layers_max, const float* params, int n_periods, const float* periods,
+                                   float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                                   size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream);
+
 /* params: device float[M][nparams]; layers: device float[5][M][n_layers_max]; n_layers: device int[M]
  * (0 if a stack would need more than n_layers_max layers).  Asynchronous on `stream`. */
 int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params,

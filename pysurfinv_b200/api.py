@@ -92,6 +92,11 @@ def load_library():
     L.surfdisp_mc_propose.restype = C.c_int
     L.surfdisp_mc_accept.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_ulonglong, C.c_uint, vp]
     L.surfdisp_mc_accept.restype = C.c_int
+    L.surfdisp_params_pipelined_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.surfdisp_params_pipelined_bytes.restype = C.c_size_t
+    L.surfdisp_host_params_pipelined.argtypes = [C.POINTER(SurfdispOpts), C.POINTER(_stack.StackTemplateC), C.c_int, C.c_int, C.c_int,
+                                                 fp, C.c_int, fp, fp, fp, ip, ip, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    L.surfdisp_host_params_pipelined.restype = C.c_int
     L.surfdisp_mc_step.argtypes = [C.POINTER(SurfdispOpts), C.POINTER(_stack.StackTemplateC), C.POINTER(SurfdispMcState), fp, vp]
     L.surfdisp_mc_step.restype = C.c_int
     L.surfdisp_host_release.argtypes = []
@@ -367,6 +372,48 @@ class DispersionSolver:
                 st.copy_(hl[:, a:b])
                 run(st, hn[a:b], a, b)
         return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+
+
+def _forward_params_pinned(self, template, h_params, periods, kind=KIND_RAYLEIGH, group=True, chunks=None, lmax=None):
+    """Model1D.forward for a batch (reference models.py:93-121), host buffers in, host buffers out: h_params pinned
+    float32 [M][P] parameter vectors of `template`; one surfdisp_host_params_pipelined call copies them (4 P bytes
+    per model), assembles the stacks on the device, solves and copies c, U, nfound, flags back.  Returns views of
+    pinned result buffers the solver reuses (see forward_pinned)."""
+    torch = self.torch
+    M, P = int(h_params.shape[0]), template.nparams
+    if h_params.dtype != torch.float32 or h_params.dim() != 2 or int(h_params.shape[1]) != P or not h_params.is_contiguous():
+        raise ValueError("params must be a contiguous float32 tensor [M, %d]" % P)
+    per = np.ascontiguousarray(periods, dtype=np.float32)
+    K = int(per.size)
+    lmax = int(lmax) if lmax is not None else template.max_layers()
+    hc = self._pin("pc", (M, K), torch.float32)
+    hf = self._pin("pnf", (M,), torch.int32)
+    hg = self._pin("pfl", (M,), torch.int32)
+    hu = self._pin("pu", (M, K), torch.float32) if group else None
+    if M == 0:
+        return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+    compute = torch.cuda.current_stream(self.device)
+    if getattr(self, "_copy_stream", None) is None:
+        self._copy_stream = torch.cuda.Stream(self.device)
+    nch = chunks if chunks is not None else (8 if M >= (1 << 16) else 1)
+    need = int(self.lib.surfdisp_params_pipelined_bytes(M, P, lmax, K))
+    if getattr(self, "_pipe_buf", None) is None or self._pipe_buf.numel() < need:
+        self._pipe_buf = None
+        self._pipe_buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+    tc = template.to_c()
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    with torch.cuda.device(self.device):
+        rc = self.lib.surfdisp_host_params_pipelined(
+            C.byref(self.opts), C.byref(tc), int(kind), M, lmax, C.cast(C.c_void_p(h_params.data_ptr()), fp), K, _fptr(per),
+            C.cast(C.c_void_p(hc.data_ptr()), fp), C.cast(C.c_void_p(hu.data_ptr()), fp) if group else None,
+            C.cast(C.c_void_p(hf.data_ptr()), ip), C.cast(C.c_void_p(hg.data_ptr()), ip),
+            C.c_void_p(self._pipe_buf.data_ptr()), C.c_size_t(self._pipe_buf.numel()), max(1, min(int(nch), M)),
+            C.c_void_p(compute.cuda_stream), C.c_void_p(self._copy_stream.cuda_stream))
+    _check(rc, "surfdisp_host_params_pipelined")
+    return dict(c=hc.numpy(), u=None if hu is None else hu.numpy(), nfound=hf.numpy(), flags=hg.numpy())
+
+
+DispersionSolver.forward_params_pinned = _forward_params_pinned
 
 
 def host_batch(layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, opts=None, device=0):

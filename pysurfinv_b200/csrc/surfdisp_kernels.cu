@@ -1306,6 +1306,20 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   return 0;
 }
 
+static int check_template(const SurfdispStackTemplate* tmpl) {
+  if (!tmpl) return SURFDISP_EINVAL;
+  if (tmpl->ngroups < 1 || tmpl->ngroups > SURFDISP_MAX_GROUPS || tmpl->nparams < 0) return SURFDISP_EINVAL;
+  for (int g = 0; g < tmpl->ngroups; ++g) {
+    const SurfdispStackGroup& G = tmpl->groups[g];
+    if (G.ncoef < 0 || G.ncoef > SURFDISP_MAX_COEF || G.h_param >= tmpl->nparams) return SURFDISP_EINVAL;
+    if (G.kind < SURFDISP_G_WATER || G.kind > SURFDISP_G_REFMANTLE) return SURFDISP_EINVAL;
+    if (G.nfine_rule == SURFDISP_N_FIXED && G.nfine < 1) return SURFDISP_EINVAL;
+    if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
+    for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;
+  }
+  return 0;
+}
+
 size_t surfdisp_pipelined_bytes(int n_models, int n_layers_max, int n_periods) {
   if (n_models < 0 || n_layers_max < 2 || n_periods < 1) return 0;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -1313,27 +1327,41 @@ size_t surfdisp_pipelined_bytes(int n_models, int n_layers_max, int n_periods) {
   return al(nl) + 3 * al((size_t)n_models * sizeof(int)) + 2 * al(no) + surfdisp_workspace_bytes(n_models, n_layers_max, n_periods);
 }
 
-int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
-                                  const int* n_layers, const float* layers, int n_periods, const float* periods,
-                                  float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
-                                  size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream) {
+size_t surfdisp_params_pipelined_bytes(int n_models, int n_params, int n_layers_max, int n_periods) {
+  if (n_params < 0) return 0;
+  const size_t base = surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods);
+  return base ? base + ((size_t)n_models * n_params * sizeof(float) + 255) / 256 * 256 : 0;
+}
+
+// The host-buffer pipeline.  Source of the stacks: host layers (copied chunk by chunk under the first stages) or host
+// PARAMETER vectors (one small copy, the stacks are assembled on the device by build_stacks_kernel).
+static int host_pipeline(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                         const float* layers, const SurfdispStackTemplate* tmpl, const float* params, int n_periods,
+                         const float* periods, float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                         size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream) {
   if (n_models < 0 || n_layers_max < 2 || n_periods < 1 || n_periods > kMaxPer) return SURFDISP_EINVAL;
   if (n_models == 0) return 0;
-  if (!n_layers || !layers || !c_out || !nfound || !periods || !device_buffer) return SURFDISP_EINVAL;
-  if (device_bytes < surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods)) return SURFDISP_ENOMEM;
+  const bool from_params = (tmpl != nullptr);
+  if (!c_out || !nfound || !periods || !device_buffer) return SURFDISP_EINVAL;
+  if (from_params ? (!params && tmpl->nparams > 0) : (!n_layers || !layers)) return SURFDISP_EINVAL;
+  const int P = from_params ? tmpl->nparams : 0;
+  if (device_bytes < (from_params ? surfdisp_params_pipelined_bytes(n_models, P, n_layers_max, n_periods)
+                                  : surfdisp_pipelined_bytes(n_models, n_layers_max, n_periods)))
+    return SURFDISP_ENOMEM;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > 64) n_chunks = 64;
   if (n_chunks > n_models) n_chunks = n_models;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t M = (size_t)n_models, L = (size_t)n_layers_max, K = (size_t)n_periods;
-  const size_t nl = 5 * M * L * sizeof(float), no = M * K * sizeof(float), ni = M * sizeof(int);
+  const size_t nl = 5 * M * L * sizeof(float), no = M * K * sizeof(float), ni = M * sizeof(int), np_ = M * P * sizeof(float);
   char* dev = (char*)device_buffer;
   const size_t o_lay = 0, o_n = o_lay + al(nl), o_c = o_n + al(ni), o_u = o_c + al(no), o_nf = o_u + al(no),
-               o_fl = o_nf + al(ni), o_ws = o_fl + al(ni);
+               o_fl = o_nf + al(ni), o_par = o_fl + al(ni), o_ws = o_par + (from_params ? al(np_) : 0);
   float* d_lay = (float*)(dev + o_lay);
   int* d_n = (int*)(dev + o_n);
   float *d_c = (float*)(dev + o_c), *d_u = u_out ? (float*)(dev + o_u) : nullptr;
   int *d_nf = (int*)(dev + o_nf), *d_fl = (int*)(dev + o_fl);
+  float* d_par = (float*)(dev + o_par);
   Plan pl;
   int rc = make_plan(pl, opts, kind, n_models, n_layers_max, d_n, d_lay, n_periods, periods, d_c, d_u, d_nf, d_fl,
                      dev + o_ws, device_bytes - o_ws);
@@ -1351,21 +1379,30 @@ int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_mode
     PCK(cudaEventRecord(start, cs), "record");         // earlier work on the compute stream may still read the buffers
     PCK(cudaStreamWaitEvent(xs, start, 0), "wait");
     const int ks = k_split(pl);
-    // stage 1: host->device copy of chunk i under preparation + first-period root search of chunk i-1
-    for (int i = 0; i < n_chunks && rc == 0; ++i) {
-      const int a = (int)((long long)n_models * i / n_chunks), b = (int)((long long)n_models * (i + 1) / n_chunks);
-      const size_t cnt = (size_t)(b - a);
-      for (int comp = 0; comp < 5 && e == cudaSuccess; ++comp)
-        e = cudaMemcpyAsync(d_lay + comp * M * L + (size_t)a * L, layers + comp * M * L + (size_t)a * L, cnt * L * sizeof(float),
-                            cudaMemcpyHostToDevice, xs);
-      if (e != cudaSuccess) { rc = cuda_fail(e, "H2D layers"); break; }
-      PCK(cudaMemcpyAsync(d_n + a, n_layers + a, cnt * sizeof(int), cudaMemcpyHostToDevice, xs), "H2D nlay");
-      cudaEvent_t up;
-      PCK(new_event(up), "event");
-      PCK(cudaEventRecord(up, xs), "record");
-      PCK(cudaStreamWaitEvent(cs, up, 0), "wait");
-      if ((rc = stage_prep(pl, a, b, cs))) break;
-      if ((rc = stage_p1(pl, a, b, 0, ks, cs))) break;
+    if (from_params) {
+      // stage 1': one copy of the parameter vectors, model assembly on the device, preparation + first-period search
+      if (P > 0) PCK(cudaMemcpyAsync(d_par, params, np_, cudaMemcpyHostToDevice, cs), "H2D params");
+      build_stacks_kernel<<<(unsigned)((M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, cs>>>(*tmpl, n_models, d_par, n_layers_max, d_lay, d_n);
+      PCK(cudaGetLastError(), "build_stacks");
+      if ((rc = stage_prep(pl, 0, n_models, cs))) break;
+      if ((rc = stage_p1(pl, 0, n_models, 0, ks, cs))) break;
+    } else {
+      // stage 1: host->device copy of chunk i under preparation + first-period root search of chunk i-1
+      for (int i = 0; i < n_chunks && rc == 0; ++i) {
+        const int a = (int)((long long)n_models * i / n_chunks), b = (int)((long long)n_models * (i + 1) / n_chunks);
+        const size_t cnt = (size_t)(b - a);
+        for (int comp = 0; comp < 5 && e == cudaSuccess; ++comp)
+          e = cudaMemcpyAsync(d_lay + comp * M * L + (size_t)a * L, layers + comp * M * L + (size_t)a * L, cnt * L * sizeof(float),
+                              cudaMemcpyHostToDevice, xs);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D layers"); break; }
+        PCK(cudaMemcpyAsync(d_n + a, n_layers + a, cnt * sizeof(int), cudaMemcpyHostToDevice, xs), "H2D nlay");
+        cudaEvent_t up;
+        PCK(new_event(up), "event");
+        PCK(cudaEventRecord(up, xs), "record");
+        PCK(cudaStreamWaitEvent(cs, up, 0), "wait");
+        if ((rc = stage_prep(pl, a, b, cs))) break;
+        if ((rc = stage_p1(pl, a, b, 0, ks, cs))) break;
+      }
     }
     if (rc) break;
     // stage 2: the later periods on the whole batch (one persistent launch: its tail is paid once)
@@ -1398,6 +1435,23 @@ int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_mode
   if (rc == 0 && e1 != cudaSuccess) rc = cuda_fail(e1, "sync compute");
   if (rc == 0 && e2 != cudaSuccess) rc = cuda_fail(e2, "sync copy");
   return rc;
+}
+
+int surfdisp_host_batch_pipelined(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max,
+                                  const int* n_layers, const float* layers, int n_periods, const float* periods,
+                                  float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                                  size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream) {
+  return host_pipeline(opts, kind, n_models, n_layers_max, n_layers, layers, nullptr, nullptr, n_periods, periods, c_out, u_out,
+                       nfound, flags, device_buffer, device_bytes, n_chunks, compute_stream, copy_stream);
+}
+
+int surfdisp_host_params_pipelined(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl, int kind, int n_models,
+                                   int n_layers_max, const float* params, int n_periods, const float* periods,
+                                   float* c_out, float* u_out, int* nfound, int* flags, void* device_buffer,
+                                   size_t device_bytes, int n_chunks, void* compute_stream, void* copy_stream) {
+  if (int rc = check_template(tmpl)) return rc;
+  return host_pipeline(opts, kind, n_models, n_layers_max, nullptr, nullptr, tmpl, params, n_periods, periods, c_out, u_out,
+                       nfound, flags, device_buffer, device_bytes, n_chunks, compute_stream, copy_stream);
 }
 
 int surfdisp_misfit_batch(int mode, int n_models, int n_periods, const float* c_pred, const int* nfound,
@@ -1569,20 +1623,6 @@ int surfdisp_measure_peaks(double out[3]) {
   return 0;
 }
 
-
-static int check_template(const SurfdispStackTemplate* tmpl) {
-  if (!tmpl) return SURFDISP_EINVAL;
-  if (tmpl->ngroups < 1 || tmpl->ngroups > SURFDISP_MAX_GROUPS || tmpl->nparams < 0) return SURFDISP_EINVAL;
-  for (int g = 0; g < tmpl->ngroups; ++g) {
-    const SurfdispStackGroup& G = tmpl->groups[g];
-    if (G.ncoef < 0 || G.ncoef > SURFDISP_MAX_COEF || G.h_param >= tmpl->nparams) return SURFDISP_EINVAL;
-    if (G.kind < SURFDISP_G_WATER || G.kind > SURFDISP_G_REFMANTLE) return SURFDISP_EINVAL;
-    if (G.nfine_rule == SURFDISP_N_FIXED && G.nfine < 1) return SURFDISP_EINVAL;
-    if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
-    for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;
-  }
-  return 0;
-}
 
 int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const float* params, int n_layers_max,
                           float* layers, int* n_layers, void* stream) {

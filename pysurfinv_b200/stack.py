@@ -7,8 +7,8 @@ numeric entry written as a Brownian spec -- ``[v, 'abs'|'abs_pos'|'rel'|'rel_pos
 ``[v, vmin, vmax, step]`` (layers.py:583-598) -- becomes one free parameter; the parameter order is the order
 of ``MCinv._brownians`` (models.py:227-240), i.e. the column order of ``mcTrack`` rows (point.py:57,73).
 Supported layer types: Sediment, Crust, Mantle/OceanMantle, OceanWater, OceanSediment, OceanCrust,
-OceanSedimentCascadia, ReferenceMantle (``Info.refLayer``).  The thermal OceanMantleHybrid is out of scope
-(SURVEY 8 f-4).
+OceanSedimentCascadia, ReferenceMantle (also through ``Info.refLayer``).  Parameters of a layer the builder does
+not implement (Crust 'Gauss', OceanMantle 'deg', the thermal OceanMantleHybrid) raise instead of being ignored.
 """
 import ctypes as C
 
@@ -106,6 +106,20 @@ class StackTemplate:
         for name, parm in setting.items():
             if name == "Info":
                 continue
+            if name == "ReferenceMantle" or name == "HalfSpace":
+                # ReferenceMantle (layers.py:267-285): linear continuation of the deepest values, 20 fine layers.
+                # 'HalfSpace' (an extension, not a reference class): the same with ONE layer -- the explicit closing
+                # layer of the config-2 stacks (synth.crustal_models appends the same).
+                g = self._blank()
+                g.kind, g.nfine_rule, g.nfine, g.h_mode, g.h_param = G_REFMANTLE, N_FIXED, (20 if name == "ReferenceMantle" else 1), 0, -1
+                g.h_fixed = float(parm.get("H", 300.0 if name == "ReferenceMantle" else 10.0))
+                g.vp_a, g.vp_b, g.rho_rule, g.qs, g.slope = 1.76, 0.0, R_MANTLE, 150.0, float(parm.get("Slope", 0.0))
+                g.gclass = C_MANTLE
+                unknown = set(parm) - {"H", "Slope"}
+                if unknown:
+                    raise ValueError("%s: unsupported parameters %s" % (name, sorted(unknown)))
+                self.groups.append(g)
+                continue
             if name not in _TYPES:
                 raise ValueError("layer type %r is not supported by the device-side builder" % name)
             self.groups.append(self._group(name, dict(parm)))
@@ -152,6 +166,10 @@ class StackTemplate:
                 g.ncoef = len(vals)
                 for i, x in enumerate(vals):
                     g.v_param[i], g.v_fixed[i] = self._value(x, "%s.Vs[%d]" % (name, i))
+            else:
+                # (Crust 'Gauss', OceanMantle 'deg', ... change the Vs profile in the reference, layers.py:176-183, 256:
+                # dropping them silently would build a different model)
+                raise ValueError("%s: parameter %r is not supported by the device-side builder" % (name, key))
         if kind is None:   # Sediment / OceanCrust: constant or linear (layers.py:146-149, 228-231)
             kind = G_LINEAR if g.ncoef == 2 else G_CONST
             if g.ncoef not in (1, 2):
@@ -182,3 +200,27 @@ class StackTemplate:
         for g in self.groups:
             n += {N_FIXED: g.nfine, N_CRUST: 60, N_OCRUST: 10}[g.nfine_rule]
         return n
+
+
+def config2_template():
+    """BASELINE config 2 as a setting of the reference's own layer classes: sediment (1 layer), crust
+    (cubic B-spline, 4 coefficients, 15 fine layers for 20 < H <= 60 km), mantle to 200 km (5 coefficients, 60 fine
+    layers) and a closing half-space with the deepest grid values: n = 77.  Free parameters (12, in the order of
+    MCinv._brownians): sediment H and Vs, crust H and 4 coefficients, 5 mantle coefficients."""
+    setting = {"Sediment": {"H": [2.25, 0.5, 4.0, 0.1], "Vs": [1.75, 1.0, 2.5, 0.05]},
+               "Crust": {"H": [32.5, 20.0001, 45.0, 1.0], "Vs": [[3.3, 3.2, 4.0, 0.02], [3.5, 3.2, 4.0, 0.02],
+                                                                [3.7, 3.2, 4.0, 0.02], [3.9, 3.2, 4.0, 0.02]]},
+               "Mantle": {"BottomDepth": 200.0, "Vs": [[4.4, 4.1, 4.7, 0.02]] * 5},
+               "HalfSpace": {"H": 10.0}, "Info": {}}
+    return StackTemplate(setting), setting
+
+
+def config2_params(M, seed=20261018):
+    """M random parameter vectors of config 2, float32 [M, 12]: uniform in the boxes of SURVEY 8d, the crustal
+    coefficients sorted (monotone crust)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = np.empty((M, 12), np.float32)
+    p[:, 0] = rng.uniform(0.5, 4.0, M); p[:, 1] = rng.uniform(1.0, 2.5, M); p[:, 2] = rng.uniform(20.0001, 45.0, M)
+    p[:, 3:7] = np.sort(rng.uniform(3.2, 4.0, (M, 4)), axis=1)
+    p[:, 7:12] = rng.uniform(4.1, 4.7, (M, 5))
+    return p
