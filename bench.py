@@ -1,12 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- dispersion evaluations per second (BASELINE.json metric) on config 2:
-batched forward sweep, 1 Mi random sediment+crust+mantle models (n = 77 layers) x 40 periods (8-80 s),
-Rayleigh phase + group velocity, per GPU (weak scaling: every rank solves its own 1 Mi models).
+"""bench.py -- dispersion evaluations per second (BASELINE.json metric).
+
+Default workload = BASELINE config 2: batched forward sweep, 1 Mi random sediment + crust + mantle models (n = 77
+layers, described through the reference's own layer classes: pysurfinv_b200.stack.config2_template) x 40 periods
+(8-80 s), Rayleigh phase + group velocity, per GPU (weak scaling: every rank solves its own 1 Mi models).
 
     python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
     python bench.py --impl reference ...                      (CPU oracle port on the host cores)
+    python bench.py --workload mc   [--chains 256] [--love]   (configs 1 / 3: Monte-Carlo chains of one point)
+    python bench.py --workload grid [--points 2000 --chains 16]   (config 5: points sharded over the ranks,
+                                                               chain rows gathered inside the timed region)
 
-One JSON line on stdout (rank 0).  1 evaluation = one (model, period) producing c and U.
+One JSON line on stdout (rank 0).  1 evaluation = one (model, period) producing c (and U where the workload says so).
+  value      device-resident: the stacks are in HBM when the timed region starts
+  e2e        the call a user makes (Model1D.forward for a batch: parameter vectors on the host in, c / U / nfound /
+             flags on the host out), pinned host buffers, copies inside the timed region
+  e2e_layers the same through the fast_surf-level call (layer arrays on the host in)
 """
 import argparse
 import json
@@ -24,12 +33,20 @@ sys.path.insert(0, ROOT)
 METRIC = "dispersion evals/sec (models x periods, Rayleigh c+U)"
 UNIT = "evals/s"
 # FLOP-equivalents per unit of work, SURVEY.md 8(d): Rayleigh layer-step 150 FLOP + 4 transcendentals
-# (10 FLOP each), REIGEN sub-layer 1800 FLOP (fp64), flattening 12 FLOP + 3 transcendentals per layer.
-F_R, F_U, F_FLAT = 190.0, 1800.0, 42.0
-# FP64 FLOP the group-velocity kernel actually executes per sub-layer (per-layer step matrix + quadratic-form
-# accumulation instead of the reference's stage-by-stage RK4): 2 x DFMA + DMUL + DADD of the ncu capture
-# profiles/r1_ncu_prep_phase2_final.txt divided by the sub-layers counted on the device.
-F_U_EXEC = 520.0
+# (10 FLOP each), Love layer-step 20 FLOP + 2 transcendentals, REIGEN sub-layer 1800 FLOP (fp64).
+F_R, F_L, F_U = 190.0, 40.0, 1800.0
+# FP64 FLOP the group-velocity kernel executes per sub-layer: 2 x 203 DFMA + 82 DMUL + 4 DADD per thread and sub-layer
+# (ncu source counters, profiles/r2_ncu_phase2.txt), against ~1800 of the reference's stage-by-stage form
+F_U_EXEC = 492.0
+# DRAM bytes per model of the root-search launches and of the group-velocity launch (ncu dram__bytes_read + write at
+# 524288 models x 40 periods, profiles/r2_ncu_*.txt); algorithmic bytes per model: phase 1 reads the constants
+# 8 x lpad x 4 B at the first period and once more at the start of the later periods and writes c, ratio
+DRAM_P1_PER_MODEL, DRAM_P2_PER_MODEL = 5250.0, 3066.0
+WORKLOAD_SWEEP = "config2: batched forward sweep, %d random 77-layer sediment+crust+mantle models x %d periods 8-80 s per GPU, Rayleigh phase+group"
+
+
+def algo_p1_bytes(lpad, K):
+    return 2 * 8 * lpad * 4 + 2 * K * 4 + 16
 
 
 def parse():
@@ -38,8 +55,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--models", type=int, default=1 << 20, help="models per GPU per step")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "mc", "grid"],
+                    help="sweep: BASELINE config 2 (default, the headline); mc: one ensemble of Monte-Carlo chains on one "
+                         "point (configs 1 / 3); grid: points x chains sharded over the ranks with the result gather inside "
+                         "the timed region (config 5)")
+    ap.add_argument("--models", type=int, default=1 << 20, help="sweep: models per GPU per step")
     ap.add_argument("--periods", type=int, default=40)
+    ap.add_argument("--chains", type=int, default=256, help="mc: chains; grid: chains per point")
+    ap.add_argument("--points", type=int, default=2000, help="grid: points in total (sharded over the ranks)")
+    ap.add_argument("--mc-steps", type=int, default=50, help="mc / grid: Monte-Carlo steps per timed step")
+    ap.add_argument("--love", action="store_true", help="mc: joint Rayleigh + Love (config 3: a second ensemble of Love chains)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -93,18 +118,36 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_sample(per, seconds, nthreads, chunk=None, seed=99):
-    """Times the CPU oracle (float32-faithful port of fast_surf) on a bounded sample of the workload."""
+# ------------------------------------------------------------------------------------------------ workloads
+MC_SETTING = {"Sediment": {"H": [2.0, "abs_pos", 1.5, 0.1], "Vs": [[1.2, 0.8, 2.0, 0.05], [2.0, 1.2, 2.8, 0.05]]},
+              "Crust": {"H": [30.0, "abs", 12.0, 1.0], "Vs": [[3.3, "rel", 10, 0.02], [3.5, "rel", 10, 0.02],
+                                                            [3.7, "rel", 10, 0.02], [3.9, "rel", 10, 0.02]]},
+              "Mantle": {"BottomDepth": 200.0, "Vs": [[4.4, "abs", 0.3, 0.02], [4.3, "abs", 0.3, 0.02],
+                                                     [4.5, "abs", 0.3, 0.02], [4.4, "abs", 0.3, 0.02], [4.6, "abs", 0.3, 0.02]]},
+              "Info": {"refLayer": True, "modelType": "CascadiaPrism"}}
+MC_PERIODS = np.array([8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)   # point.py:400 + 8 s
+
+
+def cpu_sample(per, seconds, nthreads, kind=2, stacks=None, chunk=None, seed=99):
+    """Times the CPU oracle (float32-faithful port of fast_surf: the checker, here the reported CPU baseline) on a
+    bounded sample of the workload: config-2 stacks assembled by the numpy restatement of the reference's model
+    assembly, or the stacks given."""
     from oracle import oracle as O
-    from pysurfinv_b200 import synth
-    chunk = chunk or max(64, 16 * nthreads)
-    lay, nl = synth.crustal_models(chunk, seed=seed)
-    O.forward_batch(2, lay[:, :nthreads], nl[:nthreads], per, nthreads=nthreads)  # warm-up (page in, threads)
+    if stacks is None:
+        from oracle import model_builder as MB
+        from pysurfinv_b200 import stack as S
+        chunk = chunk or max(64, 16 * nthreads)
+        t, _ = S.config2_template()
+        lay, nl = MB.build_stacks(t, S.config2_params(chunk, seed=seed), 77)
+    else:
+        lay, nl = stacks
+        chunk = lay.shape[1]
+    O.forward_batch(kind, lay[:, :nthreads], nl[:nthreads], per, nthreads=nthreads)  # warm-up (page in, threads)
     done, t0 = 0, time.perf_counter()
     tot = {}
     while True:
         cnt = O.OracleCounters()
-        O.forward_batch(2, lay, nl, per, opts=O.make_opts(precision=0), nthreads=nthreads, counters=cnt)
+        O.forward_batch(kind, lay, nl, per, opts=O.make_opts(precision=0), nthreads=nthreads, counters=cnt)
         for k, v in cnt.as_dict().items():
             tot[k] = tot.get(k, 0) + v
         done += chunk
@@ -114,28 +157,66 @@ def cpu_sample(per, seconds, nthreads, chunk=None, seed=99):
     return done * len(per) / dt, done, dt, tot
 
 
+def mc_cpu_stacks(n, seed=5):
+    """Stacks of the Monte-Carlo workload for the CPU arm: admissible random models of MC_SETTING (numpy restatement of
+    the reference's model assembly and prior rules)."""
+    from oracle import model_builder as MB
+    from pysurfinv_b200 import stack as S
+    t = S.StackTemplate(MC_SETTING, prior_mask=S.PRIOR_PRISM)
+    lo, hi, _ = t.bounds()
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        p = (lo + (hi - lo) * rng.random(t.nparams)).astype(np.float32)
+        if MB.priors(t, p.astype(np.float64)) == 0:
+            out.append(p)
+    return MB.build_stacks(t, np.array(out), t.max_layers())
+
+
+def mc_workload_name(args, world):
+    if args.workload == "grid":
+        return ("config5: grid inversion, %d points x %d chains x %d Monte-Carlo steps per timed step, sharded by point over the "
+                "GPUs, chain rows all-gathered and best misfit all-reduced inside the timed region; 96-layer "
+                "sediment+crust+mantle B-spline models, %d periods 8-80 s, Rayleigh phase velocity"
+                % (args.points, args.chains, args.mc_steps, len(MC_PERIODS)))
+    return ("config%s: one-point Monte-Carlo inversion, %d chains x %d steps per timed step, 96-layer sediment+crust+mantle "
+            "B-spline model, %d periods 8-80 s, %s phase velocity" % ("3" if args.love else "1", args.chains, args.mc_steps,
+                                                                    len(MC_PERIODS), "Rayleigh + Love" if args.love else "Rayleigh"))
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port: no Fortran compiler in the image), all host
-    threads, bounded sample per step."""
+    """--impl reference: the reference's CPU path (oracle port: no Fortran compiler in the image or on the GPU box),
+    all host threads, bounded sample per step, on the same workload, metric and unit as the GPU arm."""
     if rank != 0:
         return
     from pysurfinv_b200 import synth
-    per = synth.log_periods(args.periods)
     nthreads = os.cpu_count() or 1
     sec = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    if args.workload == "sweep":
+        per, stacks, kinds = synth.log_periods(args.periods), None, (2,)
+        workload = WORKLOAD_SWEEP % (args.models, args.periods)
+        metric = METRIC
+    else:
+        per, stacks = MC_PERIODS, mc_cpu_stacks(max(64, 16 * nthreads))
+        kinds = (2, 1) if args.love else (2,)
+        workload = mc_workload_name(args, world)
+        metric = METRIC.replace("c+U", "c")
     for _ in range(args.warmup):
-        cpu_sample(per, 0.5, nthreads)
-    vals, tot_models, tot_t = [], 0, 0.0
+        cpu_sample(per, 0.5, nthreads, stacks=stacks)
+    tot_models, tot_t = 0, 0.0
     for _ in range(args.steps):
-        v, n, dt, _c = cpu_sample(per, sec, nthreads)
-        vals.append(v); tot_models += n; tot_t += dt
+        for kind in kinds:
+            v, n, dt, _c = cpu_sample(per, sec / len(kinds), nthreads, kind=kind, stacks=stacks)
+            tot_models += n; tot_t += dt
     value = tot_models * len(per) / tot_t
-    sample = "%d models x %d periods per step (%.1f s), config-2 generator" % (tot_models // max(1, args.steps), len(per), sec)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    sample = "%d models x %d periods per step (%.1f s) of the same generator" % (tot_models // max(1, args.steps), len(per), sec)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: 1Mi x 77-layer models x 40 periods, Rayleigh c+U (bounded CPU sample)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "config": {"workload": workload, "cpu_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of fast_surf (-O2, no FMA contraction, per-period std::vector set-up): a "
+                                     "conservative stand-in for gfortran -O3; context, not a target"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -162,6 +243,164 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def pin_to_gpu_numa(local):
+    """Binds this rank to the CPUs NVML reports as local to its GPU (its NUMA node): with N ranks on one host the pinned
+    staging buffers and the copy threads then sit next to the GPU's PCIe root instead of wherever the scheduler put
+    the process.  Returns what was done (for the JSON line)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "not pinned: %s" % type(e).__name__
+    return "not pinned"
+
+
+def run_mc(args, rank, world, local, dev, barrier):
+    """--workload mc / grid: ensembles of Metropolis chains, every stage on the device (pysurfinv_b200.mc)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from pysurfinv_b200 import api, mc, stack as S
+    from pysurfinv_b200.distributed import shard_range, gather_chain_rows
+    solver = api.DispersionSolver(dev)
+    t = S.StackTemplate(MC_SETTING, prior_mask=S.PRIOR_PRISM)
+    per = MC_PERIODS
+    K, P = len(per), t.nparams
+    grid = args.workload == "grid"
+    if grid:
+        lo, hi = shard_range(args.points, rank, world)
+        npts = hi - lo
+        npts_max = (args.points + world - 1) // world
+    else:
+        lo, npts, npts_max = 0, 1, 1
+    cpp = args.chains
+    # synthetic observations: the curve of an admissible random model per point (seeded by the global point index)
+    start = torch.from_numpy(np.tile(t.start_values(), (npts, 1))).to(dev).contiguous()
+    truth = torch.empty_like(start)
+    for i in range(npts):   # (one tiny launch per point, outside the timed region)
+        truth[i:i + 1] = solver.mc_propose(t, start[i:i + 1], seed=1000 + lo + i, step_index=0,
+                                           reset_mask=torch.ones(1, dtype=torch.uint8, device=dev))
+    lay, nl = solver.build_stacks(t, truth)
+    kinds = (2, 1) if (args.love and not grid) else (2,)
+    nsteps = args.mc_steps
+    ens = []
+    for kind in kinds:
+        obs = solver.forward(lay, nl, per, kind=kind, group=False)["c"].cpu().numpy()
+        ens.append(mc.ChainEnsemble(solver, t, per, obs, np.full_like(obs, 0.01), n_chains=cpp, seed=1 + rank, n_points=npts, kind=kind,
+                                    chain_length=1 << 30, track_steps=nsteps))
+    pinned = {}
+    pad_rows = None
+
+    def one_step(e2e):
+        rows = []
+        for e in ens:
+            for _ in range(nsteps):               # (the track is a ring of nsteps rows: a block fills it once)
+                e.step()
+            rows.append(e.track[:nsteps])
+        if grid:
+            # the only collective of the inversion loop (point.py:112-123 collects the sub-chain files; model3D.py:50-57
+            # reads one file per node): the rows of this block from every rank, and the best misfit of the block
+            r = rows[0].permute(1, 0, 2).contiguous()                       # [chains_local, steps, 3 + P]
+            if world > 1:
+                nonlocal pad_rows
+                if pad_rows is None:
+                    pad_rows = torch.zeros((npts_max * cpp,) + tuple(r.shape[1:]), dtype=r.dtype, device=dev)
+                pad_rows[: r.shape[0]] = r                                   # equal block per rank
+                full = gather_chain_rows(pad_rows)
+                best = r[:, :, 0].amin()
+                dist.all_reduce(best, op=dist.ReduceOp.MIN)
+                rows = [full]
+            else:
+                rows = [r]
+        if e2e:
+            for i, r in enumerate(rows):
+                if i not in pinned or pinned[i].shape != r.shape:
+                    pinned[i] = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+                pinned[i].copy_(r, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return rows
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step(False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_max = float(tm.item())
+    total_chains = (args.points if grid else 1) * cpp
+    evals = total_chains * nsteps * K * len(kinds) * args.steps
+    value = evals / (ms_max * 1e-3)
+    ctr = (C.c_ulonglong * 4)()
+    solver.lib.surfdisp_read_counters(ens[0].ws.data_ptr(), ctr, torch.cuda.current_stream(dev).cuda_stream)
+    coll_ms = None
+    if grid and world > 1:      # the collective alone (its share of the step)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(10):
+            gather_chain_rows(pad_rows)
+        barrier(); coll_ms = (time.perf_counter() - t0) / 10 * 1e3
+    e2e = None
+    if not args.no_e2e:         # end to end: the host receives the chain rows of every block (pinned D2H in the timed region)
+        one_step(True)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rows = one_step(True)
+        barrier(); dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": evals / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": int(sum(r.numel() for r in rows) * 4),
+               "note": "the chains live on the device; per timed step the host receives the [chains][steps][3+P] track rows"}
+    if rank == 0:
+        peaks = solver.measure_peaks()
+        ev_last = ens[0].M * K
+        cpu = None
+        if not args.no_cpu:
+            nth = os.cpu_count() or 1
+            v, n, dt, cc = cpu_sample(per, args.cpu_seconds, nth, stacks=mc_cpu_stacks(max(64, 16 * nth)))
+            cpu = {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
+                   "sample": "%d admissible 96-layer models x %d periods in %.1f s (forward solve only: the reference's Python "
+                             "model assembly and prior checks per sample are not in it)" % (n, K, dt)}
+        ach = ctr[0] / ev_last * F_R * value / world * 1e-12
+        line = {"metric": METRIC.replace("c+U", "c"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong" if grid else "weak", "vs_baseline": None,
+                "dtype": "f32 (root search), f64 (model assembly, misfit)", "data": "synthetic",
+                "config": {"workload": mc_workload_name(args, world), "chains_total": total_chains, "mc_steps_per_step": nsteps,
+                           "periods": K, "params": P, "ms_per_mc_step": ms_max / args.steps / nsteps / len(kinds),
+                           "chain_steps_per_s": total_chains * nsteps * args.steps * len(kinds) / (ms_max * 1e-3),
+                           "accept_rate": float(ens[0].accepted.float().mean()), "cuda_graph": True,
+                           "l2_policy": "compute / latency bound; every step rewrites %.1f MB of stacks and constants"
+                                        % (ens[0].M * 96 * 52 / 1e6),
+                           "collective_ms_per_step": coll_ms},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * nsteps * len(kinds) * args.steps,
+                "roofline": {"bound": "fp32", "kernel": "phase1_kernel<4> inside the Monte-Carlo step",
+                             "layer_steps_per_eval": ctr[0] / ev_last, "sweeps_per_eval": ctr[1] / ev_last,
+                             "achieved": ach, "peak": peaks[0], "unit": "TFLOP/s", "frac": ach / peaks[0] if peaks[0] else None,
+                             "note": "layer-steps of the last step x 190 FLOP-eq over the WHOLE step time (proposal, assembly, "
+                                     "search, misfit): per-kernel shares in profiles/r2_mc_launches.txt", "traffic": None},
+                "cpu_baseline": cpu}
+        emit(line)
+
+
 def main():
     args = parse()
     _claim_stdout()
@@ -173,10 +412,11 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pysurfinv_b200 import api, synth
+    from pysurfinv_b200 import api, synth, stack as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the solver has no CPU path)")
+    pinned_to = pin_to_gpu_numa(local) if world > 1 else "single rank: not pinned"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -188,15 +428,23 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
+    if args.workload != "sweep":
+        run_mc(args, rank, world, local, dev, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     M, K = args.models, args.periods
     per = synth.log_periods(K)
-    lay, nl = synth.crustal_models(M, seed=synth.DEFAULT_SEED + 1000 * rank)   # every rank its own models
     solver = api.DispersionSolver(dev)
-    h_lay = torch.from_numpy(lay).pin_memory()
-    h_nl = torch.from_numpy(nl).pin_memory()
-    d_lay = h_lay.to(dev); d_nl = h_nl.to(dev)
+    tmpl, _setting = S.config2_template()
+    lmax = 77
+    h_par = torch.from_numpy(S.config2_params(M, seed=synth.DEFAULT_SEED + 1000 * rank)).pin_memory()   # every rank its own models
+    d_par = h_par.to(dev)
+    d_lay, d_nl = solver.build_stacks(tmpl, d_par, lmax=lmax)     # the stacks resident in HBM (model assembly: SURVEY 8 f-1)
     out = solver.forward(d_lay, d_nl, per, kind=2)   # allocates outputs + workspace
     torch.cuda.synchronize(dev)
+    assert int(d_nl.min()) == 77 and int(d_nl.max()) == 77
 
     # ---- device-resident timing: K steps between CUDA events, max over ranks
     for _ in range(args.warmup):
@@ -221,6 +469,15 @@ def main():
     nfound_ok = int((out["nfound"] == K).sum().item())
     steps_ctr, sweeps_ctr, subu_ctr, models_ctr = solver.counters()
 
+    # ---- per-kernel durations (CUDA events inside the library, same workload) for the roofline
+    kms = []
+    for _ in range(max(1, args.steps)):
+        m3 = [0, 0, 0]
+        solver.forward(d_lay, d_nl, per, kind=2, out=out, kernel_ms=m3)
+        kms.append(m3)
+    kms = np.mean(np.array(kms), axis=0)
+    peaks = solver.measure_peaks()
+
     # ---- the same sweep for Love waves (kind = 1; the headline stays the Rayleigh configuration of BASELINE.json)
     out_l = solver.forward(d_lay, d_nl, per, kind=1)
     barrier()
@@ -233,56 +490,92 @@ def main():
     tl = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-    love = {"value": world * M * K * args.steps / (float(tl.item()) * 1e-3), "unit": UNIT,
-            "ms_per_step": float(tl.item()) / args.steps, "roots_found_frac": int((out_l["nfound"] == K).sum().item()) / M}
+    love_found = int(out_l["nfound"].sum().item())          # Love curves end where the root reaches the half-space velocity
+    love_full = int((out_l["nfound"] == K).sum().item())
+    l_steps, l_sweeps, l_sub, _ = solver.counters()
+    lk = [0, 0, 0]
+    solver.forward(d_lay, d_nl, per, kind=1, out=out_l, kernel_ms=lk)
+    l_ach = l_steps * F_L / (lk[1] * 1e-3) * 1e-12
+    love = {"value": world * love_found * args.steps / (float(tl.item()) * 1e-3), "unit": UNIT,
+            "note": "found evaluations only: %.1f %% of the Love curves end before the longest period (reference behaviour, "
+                    "identical root counts on both sides)" % (100.0 * (1.0 - love_full / M)),
+            "ms_per_step": float(tl.item()) / args.steps, "evals_found_frac": love_found / (M * K),
+            "roofline": {"bound": "fp32", "kernel": "phase1_kernel<4> (Love sweep)", "achieved": l_ach, "peak": peaks[0],
+                         "unit": "TFLOP/s", "frac": l_ach / peaks[0] if peaks[0] else None,
+                         "kernel_ms": {"prep": lk[0], "phase1": lk[1], "phase2": lk[2]},
+                         "layer_steps_per_eval": l_steps / max(1, love_found),
+                         "note": "a Love layer-step is 40 FLOP-equivalents (SURVEY 8d): the sweep is bound by the layer-record "
+                                 "loads, the reciprocal and the two series per step, not by FMA throughput"}}
     del out_l
 
-    # ---- per-kernel durations (CUDA events inside the library, same workload) for the roofline
-    kms = []
-    for _ in range(max(1, args.steps)):
-        m3 = [0, 0, 0]
-        solver.forward(d_lay, d_nl, per, kind=2, out=out, kernel_ms=m3)
-        kms.append(m3)
-    kms = np.mean(np.array(kms), axis=0)
-    peaks = solver.measure_peaks()
-
-    # ---- end to end: pinned host inputs -> H2D -> solve -> D2H of c, U, nfound, flags, every step
-    e2e = None
+    # ---- end to end
+    e2e = e2e_layers = None
     if not args.no_e2e:
-        for _ in range(min(args.warmup, 2)):
-            solver.forward_pinned(h_lay, h_nl, per, kind=2)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = solver.forward_pinned(h_lay, h_nl, per, kind=2)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * M * K * args.steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_lay.numel() * 4 + h_nl.numel() * 4),
-               "d2h_bytes_per_step": int(2 * M * K * 4 + 2 * M * 4)}
+        def timed(fn):
+            for _ in range(min(args.warmup, 2)):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = fn()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return world * M * K * args.steps / float(tt.item()), res
+        # (a) the user's call: parameter vectors on the host -> c, U, nfound, flags on the host
+        v, res = timed(lambda: solver.forward_params_pinned(tmpl, h_par, per, kind=2, lmax=lmax))
         assert int((torch.from_numpy(res["nfound"]) == K).sum()) == nfound_ok
+        d2h = int(2 * M * K * 4 + 2 * M * 4)
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(h_par.numel() * 4), "d2h_bytes_per_step": d2h,
+               "call": "DispersionSolver.forward_params_pinned -> surfdisp_host_params_pipelined: the batch form of "
+                       "Model1D.forward (models.py:93-121): parameter vectors in, stacks assembled on the device"}
+        # (b) the fast_surf-level call: layer arrays on the host in
+        h_lay = d_lay.cpu().pin_memory(); h_nl = d_nl.cpu().pin_memory()
+        v2, res2 = timed(lambda: solver.forward_pinned(h_lay, h_nl, per, kind=2))
+        assert int((torch.from_numpy(res2["nfound"]) == K).sum()) == nfound_ok
+        e2e_layers = {"value": v2, "unit": UNIT, "h2d_bytes_per_step": int(h_lay.numel() * 4 + h_nl.numel() * 4),
+                      "d2h_bytes_per_step": d2h, "call": "DispersionSolver.forward_pinned -> surfdisp_host_batch_pipelined "
+                                                          "(the batch form of fast_surf.fast_surf, models.py:27)"}
+        del h_lay
+
+    # ---- single-model latency of the drop-in entry (what an unmodified models.py:27 loop sees)
+    single = None
+    if rank == 0:
+        from pysurfinv_b200 import fast_surf as FS
+        lay1 = d_lay[:, 0].cpu().numpy().astype(np.float64)
+        per200 = np.zeros(200); per200[:18] = MC_PERIODS[1:]
+        FS.fast_surf(77, 2, lay1[0], lay1[1], lay1[2], lay1[3], lay1[4], per200, 18)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            FS.fast_surf(77, 2, lay1[0], lay1[1], lay1[2], lay1[3], lay1[4], per200, 18)
+        single = {"us_per_call": (time.perf_counter() - t0) / 50 * 1e6, "layers": 77, "periods": 18,
+                  "call": "fast_surf.fast_surf -> fast_surf_ (per-thread device context kept between calls)"}
 
     if rank == 0:
         flop_p1 = steps_ctr * F_R
+        lpad = 80
+        ach = flop_p1 / (kms[1] * 1e-3) * 1e-12
+        ex2 = subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12
         roof = {"bound": "fp32", "kernel": "phase1_kernel<4> (root search: 2 launches, first period / later periods)",
-                "achieved": flop_p1 / (kms[1] * 1e-3) * 1e-12, "peak": peaks[0], "unit": "TFLOP/s",
-                "frac": flop_p1 / (kms[1] * 1e-3) * 1e-12 / peaks[0] if peaks[0] else None,
+                "achieved": ach, "peak": peaks[0], "unit": "TFLOP/s", "frac": ach / peaks[0] if peaks[0] else None,
                 "peak_source": "surfdisp_measure_peaks(): register-resident FFMA chain, this run "
                                "(MEASURED_PEAKS.json has no FP32 figure; the path is FP-pipe bound, not HBM or tensor)",
                 "work_unit": "secular-function layer-step of one trial velocity = %.0f FLOP-equivalents (SURVEY 8d); "
                              "counted on the device" % F_R,
-                "traffic": None,
+                "traffic": DRAM_P1_PER_MODEL * M,
+                "traffic_note": "dram__bytes_read + write of the two root-search launches (ncu, profiles/r2_ncu_phase1.txt), scaled "
+                                "to this batch; algorithmic %.2e B (constants read by both launches + c, ratio written): HBM at "
+                                "<1 %% of its peak, the path is FP-pipe bound" % (algo_p1_bytes(lpad, K) * M),
                 "kernel_ms": {"prep": float(kms[0]), "phase1": float(kms[1]), "phase2": float(kms[2])},
                 "layer_steps_per_eval": steps_ctr / (M * K), "sweeps_per_eval": sweeps_ctr / (M * K),
                 "u_sublayers_per_eval": subu_ctr / (M * K),
-                "phase2": {"bound": "fp64", "achieved": subu_ctr * F_U / (kms[2] * 1e-3) * 1e-12, "peak": peaks[1],
-                           "unit": "TFLOP/s", "executed": subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12,
-                           "frac_executed": (subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12 / peaks[1]) if peaks[1] else None,
-                           "note": "achieved = reference-equivalent work (SURVEY 8d, %.0f FLOP per sub-layer); executed = "
-                                   "FP64 FLOP of this kernel's formulation (%.0f per sub-layer)" % (F_U, F_U_EXEC)},
+                "phase2": {"bound": "fp64", "executed": ex2, "peak": peaks[1], "unit": "TFLOP/s",
+                           "frac_executed": ex2 / peaks[1] if peaks[1] else None,
+                           "reference_equivalent_tflops": subu_ctr * F_U / (kms[2] * 1e-3) * 1e-12, "traffic": DRAM_P2_PER_MODEL * M,
+                           "note": "executed = FP64 FLOP of this kernel's formulation (%.0f per sub-layer, ncu instruction counts); "
+                                   "reference_equivalent = the same sub-layers at the reference's %.0f FLOP each -- a work-saving "
+                                   "factor, not a utilisation" % (F_U_EXEC, F_U)},
                 "mufu_peak_Tops": peaks[2]}
         cpu = None
         if not args.no_cpu:
@@ -290,21 +583,21 @@ def main():
             v, n, dt, cc = cpu_sample(per, args.cpu_seconds, nth)
             cpu = {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
                    "sample": "%d models x %d periods of the same generator in %.1f s; float32-faithful C++ oracle "
-                             "(no Fortran compiler in the image)" % (n, K, dt),
+                             "(no Fortran compiler in the image or on the GPU box)" % (n, K, dt),
+                   "note": "-O2, no FMA contraction, per-period std::vector set-up: a conservative stand-in for gfortran -O3",
                    "layer_steps_per_eval": cc["steps_R"] / (n * K), "sweeps_per_eval": cc["sweeps_R"] / (n * K)}
             roof["ref_equiv_tflops"] = value / world * (cc["steps_R"] / (n * K) * F_R + cc["sub_U"] / (n * K) * F_U) * 1e-12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (root search) + f64 (group-velocity ODE)",
                 "data": "synthetic",
-                "config": {"workload": "config2: batched forward sweep, %d random 77-layer sediment+crust+mantle models "
-                                       "x %d periods 8-80 s per GPU, Rayleigh phase+group" % (M, K),
-                           "models_per_gpu": M, "periods": K, "layers": int(lay.shape[2]),
+                "config": {"workload": WORKLOAD_SWEEP % (M, K),
+                           "models_per_gpu": M, "periods": K, "layers": lmax, "params_per_model": int(h_par.shape[1]),
                            "l2_policy": "inputs (%.2f GB layers + %.2f GB workspace per step) exceed the 126 MB L2"
-                                        % (lay.nbytes / 1e9, solver._ws.numel() / 1e9),
-                           "roots_found_frac": nfound_ok / M},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * args.steps, "roofline": roof, "cpu_baseline": cpu,
-                "love": love}
+                                        % (d_lay.numel() * 4 / 1e9, solver._ws.numel() / 1e9),
+                           "roots_found_frac": nfound_ok / M, "rank_cpu_affinity": pinned_to},
+                "clocks": clocks, "e2e": e2e, "e2e_layers": e2e_layers, "gpu_launches": 7 * args.steps, "roofline": roof,
+                "cpu_baseline": cpu, "love": love, "single_model_call": single}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

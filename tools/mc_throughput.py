@@ -24,5 +24,10 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(steps):
     ens.step()
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
+import ctypes as C
+arr = (C.c_ulonglong * 4)()
+s.lib.surfdisp_read_counters(ens.ws.data_ptr(), arr, torch.cuda.current_stream().cuda_stream)
+ev = M * len(per)
+print("last step: layer-steps/eval %.1f, sweeps/eval %.2f, full curves %.4f, mean layers %.1f" % (arr[0] / ev, arr[1] / ev, float((ens.nfound == len(per)).float().mean()), float(ens.stacks[1].float().mean())))
 print("%d chains x %d steps x %d periods (graph %d): %.3f ms/step, %.3g chain-steps/s, %.3g evals/s, accept rate %.2f"
       % (M, steps, len(per), graph, dt / steps * 1e3, M * steps / dt, M * steps * len(per) / dt, float(ens.accepted.float().mean())))
