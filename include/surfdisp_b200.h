@@ -88,6 +88,16 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
                    float* c_out, float* u_out, int* nfound, int* flags, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* surfdisp_batch with a NEIGHBOUR CURVE per model: c_hint device float[M][K] (or NULL) = phase velocities of a nearby
+ * model on the same periods -- in a Monte-Carlo walk the chain's current model, of which the proposal is a small
+ * perturbation.  From the second period on the root is searched around hint(k) + [c(k-1) - hint(k-1)] (the difference
+ * to the neighbour's curve, extrapolated) instead of around the extrapolation of the model's own earlier roots; the
+ * sign guards and the fall-back to the reference's scan are unchanged, so results do not depend on the hint (a wrong,
+ * zero or missing hint costs sweeps).  Rows with zeros are "no hint". */
+int surfdisp_batch_hinted(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                          const float* layers, int n_periods, const float* periods, const float* c_hint, float* c_out,
+                          float* u_out, int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Per-model misfit of predicted phase velocities against one observed curve.
  *   mode 0: Point.misfit (point.py:15-31); mode 1: PointCascadia.misfit (point.py:337-366)
  *   c_pred   device float[M][K], nfound device int[M] (models with nfound < K get the failure
@@ -301,6 +311,8 @@ typedef struct SurfdispMcState {
   /* scratch owned by the caller */
   float* layers; int* n_layers;          /* [5][M][n_layers_max], [M] */
   float* c_pred; int* nfound; int* flags;   /* [M][K], [M], [M] */
+  float* c_cur;                             /* [M][K] curve of every chain's current model (zero-initialised by the caller;
+                                               kept by the step: the neighbour curve of surfdisp_batch_hinted) or NULL */
   void* workspace; size_t workspace_bytes;  /* surfdisp_workspace_bytes(M, n_layers_max, K) */
 } SurfdispMcState;
 

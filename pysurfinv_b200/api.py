@@ -37,7 +37,7 @@ class SurfdispMcState(C.Structure):
                 ("accepted", C.c_void_p), ("init_mask", C.c_void_p), ("misfit", C.c_void_p), ("track", C.c_void_p),
                 ("step", C.c_void_p), ("bounds", C.c_void_p), ("obs", C.c_void_p), ("isig", C.c_void_p), ("use", C.c_void_p),
                 ("layers", C.c_void_p), ("n_layers", C.c_void_p), ("c_pred", C.c_void_p), ("nfound", C.c_void_p),
-                ("flags", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("flags", C.c_void_p), ("c_cur", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class SurfdispError(RuntimeError):
@@ -63,6 +63,9 @@ def load_library():
     L.surfdisp_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, fp,
                                  vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.surfdisp_batch.restype = C.c_int
+    L.surfdisp_batch_hinted.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, fp, vp,
+                                        vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.surfdisp_batch_hinted.restype = C.c_int
     L.surfdisp_misfit_batch.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, fp, fp, C.POINTER(C.c_ubyte), fp, vp, vp]
     L.surfdisp_misfit_batch.restype = C.c_int
     L.surfdisp_host_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, C.c_int, ip, fp,
@@ -162,10 +165,11 @@ class DispersionSolver:
             _check(self.lib.surfdisp_measure_peaks(arr), "surfdisp_measure_peaks")
         return tuple(float(x) for x in arr)
 
-    def forward(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, out=None, kernel_ms=None):
+    def forward(self, layers, nlay, periods, kind=KIND_RAYLEIGH, group=True, out=None, kernel_ms=None, hint=None):
         """layers: float32 device tensor [5, M, Lmax]; nlay: int32 device tensor [M]; periods: host
         sequence.  Returns dict of device tensors c[M,K], u[M,K], nfound[M], flags[M].  Asynchronous on
-        the current torch stream."""
+        the current torch stream.  hint: optional float32 device tensor [M, K], phase velocities of a nearby model
+        per model (surfdisp_batch_hinted): fewer sweeps, same results."""
         torch = self.torch
         if layers.dtype != torch.float32 or layers.dim() != 3 or layers.shape[0] != 5 or not layers.is_contiguous():
             raise ValueError("layers must be a contiguous float32 tensor [5, M, Lmax]")
@@ -191,7 +195,11 @@ class DispersionSolver:
                     K, _fptr(per), out["c"].data_ptr(),
                     out["u"].data_ptr() if (group and out.get("u") is not None) else None,
                     out["nfound"].data_ptr(), out["flags"].data_ptr(), ws.data_ptr(), ws.numel(), stream]
-            if kernel_ms is None:
+            if hint is not None:
+                if hint.dtype != torch.float32 or tuple(hint.shape) != (M, K) or not hint.is_contiguous() or hint.device != self.device:
+                    raise ValueError("hint must be a contiguous float32 device tensor [M, K]")
+                rc = self.lib.surfdisp_batch_hinted(*args[:8], hint.data_ptr(), *args[8:])
+            elif kernel_ms is None:
                 rc = self.lib.surfdisp_batch(*args)
             else:  # list that receives [prep_ms, phase1_ms, phase2_ms]; synchronises
                 ms = (C.c_float * 3)()

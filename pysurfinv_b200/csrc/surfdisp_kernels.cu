@@ -147,6 +147,7 @@ struct P1Params {
   int atten, stale, exact_scan;
   int k_begin, k_end;   // periods [k_begin, k_end) are done by this launch (the first period runs as a launch of its own)
   int* mm_state;        // layer-dropping depth carried from launch to launch
+  const float* hint;    // [M][K] neighbour curves (phase velocities of a nearby model on the same periods) or nullptr
   const int* order;     // order[i] - order_base = i-th model to hand out (nullptr: index order)
   int order_base;
   int mstride;  // float4 units between consecutive groups' shared-memory records
@@ -560,7 +561,27 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       // is taken by inverse polynomial interpolation; if the 4- and 6-point estimates disagree, P more points
       // are clustered around the estimate and the test is repeated.
       c_pred = c_prev;
-      if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
+      // Neighbour curve (optional, P1Params::hint): the dispersion curve of a nearby model on the same periods -- the
+      // chain's current model in a Monte-Carlo walk, whose proposal differs by one small step.  The DIFFERENCE to that
+      // curve varies slowly with the period, so it is extrapolated instead of the curve itself (linear in ln T from the
+      // third period on).  Only the centre of the cluster changes: the sign guards, the acceptance rules and the
+      // fall-back to the scan are the same, so a wrong or missing hint costs sweeps, never the root.
+      bool hinted = false;
+      if (p.hint && k >= 1) {
+        const float* hrow = p.hint + (size_t)model * K;
+        const float hk = hrow[k], hk1 = hrow[k - 1];
+        if (hk > 0.f && hk1 > 0.f) {
+          hinted = true;
+          const float d1 = c_prev - hk1;
+          c_pred = hk + d1;
+          if (k >= 2 && hrow[k - 2] > 0.f) {
+            const float d2 = c_prev2 - hrow[k - 2];
+            c_pred += (d1 - d2) * ((lt - p.tab.lt[k - 1]) / (p.tab.lt[k - 1] - p.tab.lt[k - 2]));
+          }
+        }
+      }
+      if (hinted) { /* c_pred is set */ }
+      else if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
       else if (k >= 2) {
         // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
         const float x0 = p.tab.lt[k - 1], x1 = p.tab.lt[k - 2], x = lt;
@@ -580,7 +601,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           fabsf(c_pred - c_prev) <= kMaxPredStep) {
         // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
         // around it; 2: window of P grid points moved up or down
-        fstage = (k >= 2 && j0 >= 4) ? 0 : 1;
+        fstage = ((k >= 2 || hinted) && j0 >= 4) ? 0 : 1;
         w0 = 2; dir = 0; wtry = 0; from_scan = false;
         stage = ST_FAST; need = NB_FAST;
       } else start_scan();
@@ -881,7 +902,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 
     if (period_done) {
       if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
-      if (k >= 2) {
+      if (k >= 2 || (k == 1 && p.hint)) {
         // A root more than 0.1 km/s off the extrapolation: mode hopping, or a branch that bends too fast to be
         // extrapolated (thick slow sediments at the short-period end).  Scan from c1 like the reference until
         // two periods in a row were predictable again.
@@ -1170,6 +1191,7 @@ struct Plan {
   int *nfound, *flags, *mm_state, *order, *buckets;
   unsigned long long* counters;
   unsigned int* queue;
+  const float* hint;
   PeriodTab tab;
 };
 
@@ -1194,6 +1216,7 @@ static int make_plan(Plan& pl, const SurfdispOpts* opts, int kind, int n_models,
   pl.mm_state = (int*)(ws + pl.w.mm_off);
   pl.order = (int*)(ws + pl.w.order_off);
   pl.buckets = (int*)(ws + pl.w.bucket_off);
+  pl.hint = nullptr;
   return fill_tab(pl.tab, n_periods, periods, pl.o.t_base);
 }
 
@@ -1231,6 +1254,7 @@ static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaSt
   p1.tab = pl.tab;
   p1.mm_state = pl.mm_state + a;
   p1.order = pl.order + a; p1.order_base = a;
+  p1.hint = pl.hint ? pl.hint + (size_t)a * pl.K : nullptr;
   p1.k_begin = k_begin; p1.k_end = k_end;
   CK(cudaMemsetAsync(pl.queue, 0, sizeof(unsigned int), st));
   return launch_phase1<P1_G>(p1, st);
@@ -1283,6 +1307,18 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   return 0;
 }
 
+static thread_local const float* g_batch_hint = nullptr;   // set by surfdisp_batch_hinted around its call of surfdisp_batch
+
+int surfdisp_batch_hinted(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
+                          const float* layers, int n_periods, const float* periods, const float* c_hint, float* c_out,
+                          float* u_out, int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+  g_batch_hint = c_hint;
+  const int rc = surfdisp_batch(opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out, u_out, nfound,
+                                flags, workspace, workspace_bytes, stream);
+  g_batch_hint = nullptr;
+  return rc;
+}
+
 int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layers_max, const int* n_layers,
                    const float* layers, int n_periods, const float* periods, float* c_out, float* u_out,
                    int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
@@ -1290,6 +1326,7 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   int rc = make_plan(pl, opts, kind, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out, u_out, nfound,
                      flags, workspace, workspace_bytes);
   if (rc || n_models == 0) return rc;
+  pl.hint = g_batch_hint;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(workspace, 0, kHdrBytes, st));
   if (g_prof_events) CK(cudaEventRecord(g_prof_events[0], st));
@@ -1703,8 +1740,8 @@ int surfdisp_mc_step(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl
   SurfdispOpts o;
   if (opts) o = *opts; else surfdisp_default_opts(&o);
   o.compute_group = 0;
-  int rc = surfdisp_batch(&o, s->kind, M, s->n_layers_max, s->n_layers, s->layers, K, periods, s->c_pred, nullptr, s->nfound,
-                          s->flags, s->workspace, s->workspace_bytes, stream);
+  int rc = surfdisp_batch_hinted(&o, s->kind, M, s->n_layers_max, s->n_layers, s->layers, K, periods, s->c_cur, s->c_pred, nullptr,
+                                 s->nfound, s->flags, s->workspace, s->workspace_bytes, stream);
   if (rc) return rc;
   // ---- misfit, Metropolis rule, state update, track row
   McFinishParams fp;
@@ -1712,7 +1749,7 @@ int surfdisp_mc_step(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl
   fp.M = M; fp.P = P; fp.K = K; fp.mode = s->misfit_mode; fp.chain_len = s->chain_len; fp.chains_per_point = s->chains_per_point;
   fp.track_steps = s->track_steps > 0 ? s->track_steps : 1; fp.c_pred = s->c_pred; fp.nfound = s->nfound; fp.status = s->status;
   fp.obs = s->obs; fp.isig = s->isig; fp.use = s->use; fp.prop = s->prop; fp.cur = s->cur; fp.chi0 = s->chi0;
-  fp.accepted = s->accepted; fp.misfit_out = s->misfit; fp.track = s->track_steps > 0 ? s->track : nullptr; fp.step_ptr = s->step;
+  fp.accepted = s->accepted; fp.misfit_out = s->misfit; fp.c_cur = s->c_cur; fp.track = s->track_steps > 0 ? s->track : nullptr; fp.step_ptr = s->step;
   fp.seed = s->seed;
   for (int k = 0; k < K; ++k) fp.per[k] = periods[k];
   mc_finish_kernel<<<(M + 127) / 128, 128, 0, st>>>(fp);

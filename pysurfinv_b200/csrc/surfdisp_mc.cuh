@@ -15,34 +15,66 @@ constexpr int kMaxMantleGrid = 128;      // grid points of the mantle-class grou
 constexpr double kEps = 2.220446049250313e-16;
 
 // value at z in [0, 1] of sum_i coef_i B_i(z) with the basis of reference layers.py:4-45: degree 3 (n = 3) or
-// 4 (n >= 4) de Boor recursion on the knot vector [-eps x (deg-1), 0, geometric interior knots, 1, 1+eps ...]
-__device__ double bspl_profile(const double* coef, int n, double z) {
-  const int deg = 3 + (n >= 4);
-  double x[SURFDISP_MAX_COEF + 4];
-  for (int i = 0; i < deg - 1; ++i) x[i] = -kEps;
-  x[deg - 1] = 0.0;
-  {
-    const int m = n - deg;            // number of interior knots: 2^kk / (2^(m+1) - 1)
-    const double den = (double)((1 << (m + 1)) - 1);
-    for (int kk = 0; kk < m; ++kk) x[deg + kk] = (double)(1 << kk) / den;
+// 4 (n >= 4) de Boor recursion on the knot vector [-eps x (deg-1), 0, geometric interior knots, 1, 1+eps ...].
+// The reference runs the recursion over all n + deg - 1 columns; only the deg columns around the knot interval of z
+// are non-zero, and a term whose lower-order factor is exactly zero adds nothing: the recursion below visits the
+// non-zero terms only, in the reference's order (same operations on them, bit-identical values, a quarter of the
+// divisions).  Knots are generated from their index (no array, no local memory).
+struct Knots {
+  int n, deg;
+  double q[SURFDISP_MAX_COEF];     // interior knots 2^k / (2^(m+1) - 1), k < m = n - deg
+  __device__ double at(int i) const {
+    if (i < deg - 1) return -kEps;
+    if (i == deg - 1) return 0.0;
+    if (i < n) return q[i - deg];
+    return (i == n) ? 1.0 : 1.0 + kEps;
   }
-  x[n] = 1.0;
-  for (int i = n + 1; i < n + deg; ++i) x[i] = 1.0 + kEps;
-  const int nc = n + deg - 1;
-  double b0[SURFDISP_MAX_COEF + 3], b1[SURFDISP_MAX_COEF + 3];
-  for (int i = 0; i < nc; ++i) { b0[i] = (z >= x[i] && z < x[i + 1]) ? 1.0 : 0.0; b1[i] = b0[i]; }
+};
+
+__device__ Knots make_knots(int n) {
+  Knots k;
+  k.n = n; k.deg = 3 + (n >= 4);
+  const int m = n - k.deg;
+  const double den = (double)((1 << (m + 1)) - 1);
+#pragma unroll
+  for (int kk = 0; kk < SURFDISP_MAX_COEF; ++kk) k.q[kk] = (kk < m) ? (double)(1 << kk) / den : 2.0;
+  return k;
+}
+
+__device__ double bspl_profile(const double* coef, const Knots& kn, double z) {
+  const int n = kn.n, deg = kn.deg, nc = n + deg - 1;
+  // knot interval of z: x[k] <= z < x[k+1]
+  int k = deg - 1;
+#pragma unroll
+  for (int kk = 0; kk < SURFDISP_MAX_COEF; ++kk) k += (kk < n - deg && z >= kn.q[kk]) ? 1 : 0;
+  if (z >= 1.0) k = n;
+  // w[j] = value of column k - r - 1 + j after round r (columns k-r-1 .. k can be non-zero)
+  double w[6] = {0.0, 1.0, 0.0, 0.0, 0.0, 0.0};   // before round 0: column k is 1 (w[1]); w[0] = column k-1 = 0
   for (int r = 0; r < deg - 1; ++r) {
-    for (int i = 0; i < nc - r - 1; ++i) {
+    double nw[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // new columns i = k-r-1 .. k; old column i sits at w[i - (k-r)] + 1 shift: old window starts at column k-r (w[1])
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (j > r + 1) continue;
+      const int i = k - r - 1 + j;
+      if (i < 0 || i > nc - r - 2) continue;
+      const double b_i = w[j], b_i1 = w[j + 1];      // old columns i and i+1
       double col = 0.0;
-      const double d1 = x[i + r + 1] - x[i], d2 = x[i + r + 2] - x[i + 1];
-      if (d1 != 0.0) col += b0[i] * (z - x[i]) / d1;
-      if (d2 != 0.0) col += b0[i + 1] * (x[i + r + 2] - z) / d2;
-      b1[i] = col;
+      if (b_i != 0.0) { const double xi = kn.at(i), d1 = kn.at(i + r + 1) - xi; if (d1 != 0.0) col += b_i * (z - xi) / d1; }
+      if (b_i1 != 0.0) { const double xe = kn.at(i + r + 2), d2 = xe - kn.at(i + 1); if (d2 != 0.0) col += b_i1 * (xe - z) / d2; }
+      nw[j + 1] = col;
     }
-    for (int i = 0; i < nc; ++i) b0[i] = b1[i];
+    // the window of the next round starts one column lower: new column k-r-1 (nw[1]) becomes w[1]
+#pragma unroll
+    for (int j = 0; j < 6; ++j) w[j] = nw[j];
   }
+  // columns k-deg+1 .. k sit in w[1 .. deg]
   double v = 0.0;
-  for (int i = 0; i < n; ++i) v += coef[i] * b1[i];
+#pragma unroll
+  for (int j = 1; j <= 5; ++j) {
+    const int i = k - (deg - 1) + (j - 1);
+    if (j <= deg && i >= 0 && i < n) v += coef[i] * w[j];
+  }
   return v;
 }
 
@@ -160,6 +192,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
     // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
     if (H - 0.0 < 0.01) continue;
     const bool is_ref = (g.kind == SURFDISP_G_REFMANTLE);
+    const Knots kn = make_knots((g.kind == SURFDISP_G_BSPLINE && g.ncoef >= 3) ? g.ncoef : 3);
     const bool mono_class = (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST);
     const double zstep = H / (double)N, ustep = 1.0 / (double)N;
     const double vs0_ref = last_vs;
@@ -180,7 +213,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
         else if (g.kind == SURFDISP_G_BSPLINE) {
           if (g.ncoef == 1) vs = coef[0];
           else if (g.ncoef == 2) vs = coef[0] * ((j == N) ? 0.0 : 1.0 + (double)j * ((0.0 - 1.0) / (double)N)) + coef[1] * u;
-          else vs = bspl_profile(coef, g.ncoef, u);
+          else vs = bspl_profile(coef, kn, u);
         } else if (g.kind == SURFDISP_G_CASCADIA) vs = (0.02 * H * H + 1.27 * H + 0.29 * 0.1) / (H + 0.29);
         else {  // reference mantle: linear continuation of the deepest Vs (layers.py:267-285)
           const double vend = vs0_ref + H * g.slope;
@@ -461,6 +494,7 @@ struct McFinishParams {
   float per[SURFDISP_MAX_PERIODS];
   const float* prop; float* cur; float* chi0;
   unsigned char* accepted; float* misfit_out;                       // [M][3] (misfit, chiSqr, L)
+  float* c_cur;                                                     // [M][K] curve of the chain's current model (hint of the next step) or nullptr
   float* track;                                                     // [track_steps][M][3 + P] or nullptr
   const unsigned int* step_ptr;
   unsigned long long seed;
@@ -512,6 +546,10 @@ __global__ void __launch_bounds__(128) mc_finish_kernel(const __grid_constant__ 
   if (acc) {
     p.chi0[m] = x1;
     for (int i = 0; i < p.P; ++i) p.cur[(size_t)m * p.P + i] = p.prop[(size_t)m * p.P + i];
+    if (p.c_cur) {   // the accepted model's curve guides the root search of the chain's next proposals (zeros: no hint)
+      const bool full = p.nfound[m] >= p.K;
+      for (int k = 0; k < p.K; ++k) p.c_cur[(size_t)m * p.K + k] = full ? p.c_pred[(size_t)m * p.K + k] : 0.f;
+    }
   }
   p.accepted[m] = acc ? 1 : 0;
   if (p.misfit_out) { float* o = p.misfit_out + (size_t)m * 3; o[0] = (float)misfit; o[1] = (float)chi; o[2] = (float)L; }

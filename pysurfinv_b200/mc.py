@@ -113,6 +113,7 @@ class ChainEnsemble:
         self.stacks = (torch.empty((5, self.M, self.lmax), dtype=torch.float32, device=dev),
                        torch.empty(self.M, dtype=torch.int32, device=dev))
         self.c_pred = torch.empty((self.M, K), dtype=torch.float32, device=dev)
+        self.c_cur = torch.zeros((self.M, K), dtype=torch.float32, device=dev)    # curves of the current models: search hints
         self.nfound = torch.empty(self.M, dtype=torch.int32, device=dev)
         self.flags = torch.empty(self.M, dtype=torch.int32, device=dev)
         self.ws = torch.empty(int(solver.lib.surfdisp_workspace_bytes(self.M, self.lmax, K)), dtype=torch.uint8, device=dev)
@@ -134,6 +135,7 @@ class ChainEnsemble:
         s.init_mask, s.misfit, s.track, s.step = p(self.init), p(self.misfit3), p(self.track), p(self.d_step)
         s.bounds, s.obs, s.isig, s.use = p(self.d_bounds), p(self.d_obs), p(self.d_isig), p(self.d_use)
         s.layers, s.n_layers, s.c_pred, s.nfound, s.flags = p(self.stacks[0]), p(self.stacks[1]), p(self.c_pred), p(self.nfound), p(self.flags)
+        s.c_cur = p(self.c_cur)
         s.workspace, s.workspace_bytes = p(self.ws), self.ws.numel()
         return s
 

@@ -364,3 +364,36 @@ def test_chunked_host_path_matches_device_path(solver):
         h = solver.forward_host(lay, nl, per, 2, chunks=chunks)
         assert np.array_equal(h["c"], d["c"].cpu().numpy()) and np.array_equal(h["u"], d["u"].cpu().numpy())
         assert np.array_equal(h["nfound"], d["nfound"].cpu().numpy()) and np.array_equal(h["flags"], d["flags"].cpu().numpy())
+
+
+def test_neighbour_curve_hints_change_sweeps_not_results(solver):
+    """surfdisp_batch_hinted: the curve of a nearby model (the chain's current model in a Monte-Carlo walk) centres the
+    trial velocities of the later periods.  Good hints save sweeps; good, wrong and missing hints all give the root
+    counts of the un-hinted search and the same roots to float32 noise -- and the oracle's."""
+    import torch
+    P18 = np.array([8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)
+    lay, nl = synth.ragged_models(6000, seed=91)
+    rng = np.random.default_rng(91)
+    lay2 = lay.copy()
+    lay2[1] *= (1.0 + rng.normal(0, 0.004, lay2[1].shape)).astype(np.float32)      # the neighbour: Vs moved by ~0.4 %
+    dl, dn = torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda()
+    for kind in (2, 1):
+        base = solver.forward(dl, dn, P18, kind=kind)
+        base = {k: v.clone() for k, v in base.items()}
+        sw0 = solver.counters()[1]
+        hint = solver.forward(torch.from_numpy(lay2).cuda(), dn, P18, kind=kind)["c"].clone()
+        good = solver.forward(dl, dn, P18, kind=kind, hint=hint)
+        sw1 = solver.counters()[1]
+        assert torch.equal(good["nfound"], base["nfound"])
+        assert float((good["c"] - base["c"]).abs().max()) < 3e-5
+        assert sw1 < 0.9 * sw0, (sw0, sw1)                       # the hint pays
+        junk = torch.from_numpy(rng.uniform(1.0, 5.0, tuple(hint.shape)).astype(np.float32)).cuda()
+        junk[::3] = 0.0                                           # every third model: no hint
+        bad = solver.forward(dl, dn, P18, kind=kind, hint=junk)
+        assert torch.equal(bad["nfound"], base["nfound"])
+        assert float((bad["c"] - base["c"]).abs().max()) < 3e-5
+        idx = np.arange(0, 6000, 12)
+        c0, u0, nf0, st0 = O.forward_batch(kind, lay[:, idx], nl[idx], P18, opts=O.make_opts(precision=0), nthreads=8)
+        ok = st0 != 3
+        assert np.array_equal(good["nfound"].cpu().numpy()[idx][ok], nf0[ok])
+        assert np.abs(good["c"].cpu().numpy()[idx] - c0)[ok].max() <= TOL
