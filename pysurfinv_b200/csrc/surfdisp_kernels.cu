@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   int mjx = 2, mjy = 2, round = 0, pit = 0, stride = 1;
   bool have_prev = false, own_mj = false;
   bool own_eval = false;    // this scan round evaluates every point on its own truncation (see build_scan)
+  bool own_half = false;    // ... and its lower points are done
   bool from_scan = false;   // the interpolation rounds refine a bracket found by the scan (fall-back: uniform-section polish)
   float bmin = 0.f;   // smallest b below the top layer (this period's records)
   // ---- result of the period
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     }
     if (__all_sync(0xffffffffu, stage == ST_DONE)) break;
     // ---- trial velocities of this iteration's sweep
-    own_eval = false;
+    if (need != NB_NONE) { own_eval = false; own_half = false; }
     if (need == NB_FAST) build_fast();
     else if (need == NB_REFINE) build_refine();
     else if (need == NB_SCAN) build_scan();
@@ -618,18 +619,17 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 
     // =========================================================== the sweep (the only call site)
     const bool active = (stage >= ST_FAST && stage <= ST_ELL);
+    bool process = active;
     if (active) {
-      // (one pass; two for a scan round on own truncations: first the lane's lower point, then the upper one)
-      for (int ps = 0; ps < (own_eval ? 2 : 1); ++ps) {
-        float2 cc = pc;
-        int me = meval;
-        if (own_eval) { cc = ps ? make_float2(pc.y, pc.y) : make_float2(pc.x, pc.x); me = ps ? mjy : mjx; }
-        const Sec2 sv = secular2(p.kind, cc, T, me, rec, ell_only);
-        my_steps += 2u * (unsigned)(me - 1); my_sweeps += 2;
-        if (!own_eval) { pd = sv.d; pe2 = sv.e2; pe3 = sv.e3; }
-        else if (ps == 0) { pd.x = sv.d.x; pe2.x = sv.e2.x; pe3.x = sv.e3.x; }
-        else { pd.y = sv.d.x; pe2.y = sv.e2.x; pe3.y = sv.e3.x; }
-      }
+      // (a scan round on own truncations takes two iterations: first every lane's lower point, then the upper one)
+      float2 cc = pc;
+      int me = meval;
+      if (own_eval) { cc = own_half ? make_float2(pc.y, pc.y) : make_float2(pc.x, pc.x); me = own_half ? mjy : mjx; }
+      const Sec2 sv = secular2(p.kind, cc, T, me, rec, ell_only);
+      my_steps += 2u * (unsigned)(me - 1); my_sweeps += 2;
+      if (!own_eval) { pd = sv.d; pe2 = sv.e2; pe3 = sv.e3; }
+      else if (!own_half) { pd.x = sv.d.x; pe2.x = sv.e2.x; pe3.x = sv.e3.x; own_half = true; process = false; }
+      else { pd.y = sv.d.x; pe2.y = sv.e2.x; pe3.y = sv.e3.x; own_half = false; }
     }
 
 #ifdef P1_DEBUG
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 #endif
     // =========================================================== what the results mean, per stage
     bool do_interp = false, period_done = false, model_done = false;
-    if (active) {
+    if (process) {
       __syncwarp(gmask);
       slots[1 + 2 * gl] = make_float4(pc.x, pd.x, pe2.x, pe3.x);
       slots[2 + 2 * gl] = make_float4(pc.y, pd.y, pe2.y, pe3.y);
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       if (ev) { jb = __ffs(ev); it++; do_interp = true; }                                   // point i is list entry i + 1
       else if (signbit(dlast) != signbit(E1.d)) { jb = P + 1; it++; do_interp = true; }
       else interp_failed();
-    } else if (stage == ST_SCAN) {
+    } else if (stage == ST_SCAN && process) {
       // ---- scan for the first sign change on the grid c1 + i dc (calcul.f:155-167).  The reference examines
       // every grid point.  Here only the first round does; after it every 4th grid point is evaluated (stride 4)
       // and the skipped ones are examined only where they can matter: around a sign change between two coarse
