@@ -179,6 +179,11 @@ int surfdisp_measure_peaks(double out[3]);
 #define SURFDISP_G_BSPLINE 3    /* B-spline, ncoef coefficients                  Crust / Mantle  :158, :239  */
 #define SURFDISP_G_CASCADIA 4   /* (0.02 H^2 + 1.27 H + 0.029) / (H + 0.29)      OceanSedimentCascadia :289  */
 #define SURFDISP_G_REFMANTLE 5  /* linear continuation below the model           ReferenceMantle :267        */
+#define SURFDISP_G_HYBRID 6     /* thermal mantle: half-space-cooling temperature (ThermSeis.HSCM, ThermSeis.py:56-101)
+                                   -> Vs by the mineral-physics relations of OceanSeisRitz (ThermSeis.py:103-176), B-spline
+                                   perturbation (coefficients [0, v_1 .. v_ncoef]) below the depth where melting starts,
+                                   joined by a not-a-knot cubic spline; Qs from OceanSeisRuan (ThermSeis.py:320-448)
+                                                                                    OceanMantleHybrid layers.py:297-363 */
 /* number of fine layers of a group */
 #define SURFDISP_N_FIXED 0
 #define SURFDISP_N_CRUST 1      /* 5/10/15/30/60 by thickness, layers.py:161-173 */
@@ -222,6 +227,10 @@ typedef struct SurfdispStackGroup {
   int v_param[SURFDISP_MAX_COEF];           /* per Vs coefficient: free-parameter index or -1 (v_fixed) */
   double v_fixed[SURFDISP_MAX_COEF];
   double h_fixed, vp_a, vp_b, rho_const, qs, slope;   /* Vp = vp_a Vs + vp_b; slope: km/s per km (REFMANTLE) */
+  /* SURFDISP_G_HYBRID only */
+  int age_param, pad_;                      /* ThermAge: free-parameter index or -1 (age_fixed), Myr */
+  double age_fixed, tp, period, q_age;      /* potential temperature (deg C, 1325); period of the Q model (Info.period, 1 s);
+                                               age of the Q model (Info.lithoAge when Info.lithoAgeQ), < 0: the ThermAge */
 } SurfdispStackGroup;
 
 typedef struct SurfdispStackTemplate {

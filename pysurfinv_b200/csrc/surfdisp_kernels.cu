@@ -279,7 +279,10 @@ enum { ST_FETCH = 0, ST_PERIOD, ST_FAST, ST_REFINE, ST_SCAN, ST_POLISH, ST_ELL, 
 // Which trial velocities the next sweep of a group needs (built in ONE place, right before the sweep)
 enum { NB_NONE = 0, NB_FAST, NB_REFINE, NB_SCAN, NB_POLISH, NB_ELL };
 
-template <int G>
+// FIRST: the launch that does one period per model from scratch (k_begin = 0, k_end = 1): every model scans, the
+// cluster / window path of the later periods is compiled out -- a smaller loop body for the launch whose short
+// sweeps make it the most sensitive to instruction fetch.
+template <int G, bool FIRST>
 __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
   static_assert(G == 4 || G == 8, "4 or 8 lanes x 2 trial velocities per model");
   constexpr int P = 2 * G;   // trial velocities per round; point i lives in lane i/2, component i%2
@@ -568,7 +571,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       // third period on).  Only the centre of the cluster changes: the sign guards, the acceptance rules and the
       // fall-back to the scan are the same, so a wrong or missing hint costs sweeps, never the root.
       bool hinted = false;
-      if (p.hint && k >= 1) {
+      if (!FIRST && p.hint && k >= 1) {
         const float* hrow = p.hint + (size_t)model * K;
         const float hk = hrow[k], hk1 = hrow[k - 1];
         if (hk > 0.f && hk1 > 0.f) {
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           }
         }
       }
-      if (hinted) { /* c_pred is set */ }
+      if (FIRST || hinted) { /* no prediction needed / c_pred is set */ }
       else if (k == 1) c_pred = c_prev + 0.02f;   // phase velocity grows with period: bias the first window upwards
       else if (k >= 2) {
         // extrapolation of the previous roots in ln T: linear, quadratic from the fourth period on
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       // (an extrapolation that moves the root by more than 0.15 km/s is not trusted: where the branch is that steep --
       // thick slow sediments, coarse period lists -- the cluster can land on a higher mode with an even number of roots
       // between c1 and it, which the sign guard cannot see; scan from c1 like the reference)
-      if (!p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000 &&
+      if (!FIRST && !p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000 &&
           fabsf(c_pred - c_prev) <= kMaxPredStep) {
         // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
         // around it; 2: window of P grid points moved up or down
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     if (__all_sync(0xffffffffu, stage == ST_DONE)) break;
     // ---- trial velocities of this iteration's sweep
     if (need != NB_NONE) { own_eval = false; own_half = false; }
-    if (need == NB_FAST) build_fast();
+    if (!FIRST && need == NB_FAST) build_fast();
     else if (need == NB_REFINE) build_refine();
     else if (need == NB_SCAN) build_scan();
     else if (need == NB_POLISH) build_polish();
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       SamplePt sp; sp.c = v.x; sp.d = v.y; sp.e2 = v.z; sp.e3 = v.w;
       return sp;
     };
-    if (stage == ST_FAST) {
+    if (!FIRST && stage == ST_FAST) {
       const float d0 = gshfl<G>(gmask, pd.x, 0);
       const unsigned evc = change_mask(pd, d0) & ~((2u << w0) - 1u);     // changes between cluster / window points
       const unsigned evw = pair_mask(signbit(pd.x) != signbit(d0), signbit(pd.y) != signbit(d0));
@@ -1102,8 +1105,8 @@ int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
   return 0;
 }
 
-template <int G>
-int launch_phase1(const P1Params& p, cudaStream_t st) {
+template <int G, bool FIRST>
+int launch_phase1_t(const P1Params& p, cudaStream_t st) {
   P1Params q = p;
   q.mstride = p.lpad + 1;  // +1 float4: consecutive groups start 16 B apart mod 128 B (bank spread)
   // 128-thread CTAs (128/G models) for ordinary stacks; deep stacks (up to 1000 layers, 16 KB of layer records
@@ -1113,19 +1116,26 @@ int launch_phase1(const P1Params& p, cudaStream_t st) {
   const int groups = threads / G;
   size_t smem = (size_t)groups * (q.mstride + 2 * G + 2) * sizeof(float4);   // layer records + sample slots
   if (smem > 220 * 1024) return SURFDISP_EINVAL;
-  CK(cudaFuncSetAttribute(phase1_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(phase1_kernel<G, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148, occ = 1;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<G>, threads, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<G, FIRST>, threads, smem));
   if (occ < 1) occ = 1;
   long long need = ((long long)p.M + groups - 1) / groups;
   long long grid = (long long)sms * occ;  // persistent: one resident wave, models pulled from a queue
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  phase1_kernel<G><<<(unsigned)grid, threads, smem, st>>>(q);
+  phase1_kernel<G, FIRST><<<(unsigned)grid, threads, smem, st>>>(q);
   CK(cudaGetLastError());
   return 0;
+}
+
+template <int G>
+int launch_phase1(const P1Params& p, cudaStream_t st) {
+  // (exact_scan launches cover all periods at once and scan everywhere: the general instantiation)
+  if (p.k_begin == 0 && p.k_end == 1 && !p.exact_scan) return launch_phase1_t<G, true>(p, st);
+  return launch_phase1_t<G, false>(p, st);
 }
 
 }  // namespace
@@ -1349,7 +1359,8 @@ static int check_template(const SurfdispStackTemplate* tmpl) {
   for (int g = 0; g < tmpl->ngroups; ++g) {
     const SurfdispStackGroup& G = tmpl->groups[g];
     if (G.ncoef < 0 || G.ncoef > SURFDISP_MAX_COEF || G.h_param >= tmpl->nparams) return SURFDISP_EINVAL;
-    if (G.kind < SURFDISP_G_WATER || G.kind > SURFDISP_G_REFMANTLE) return SURFDISP_EINVAL;
+    if (G.kind < SURFDISP_G_WATER || G.kind > SURFDISP_G_HYBRID) return SURFDISP_EINVAL;
+    if (G.kind == SURFDISP_G_HYBRID && (G.ncoef < 1 || G.ncoef + 1 > SURFDISP_MAX_COEF || G.age_param >= tmpl->nparams)) return SURFDISP_EINVAL;
     if (G.nfine_rule == SURFDISP_N_FIXED && G.nfine < 1) return SURFDISP_EINVAL;
     if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
     for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;

@@ -88,10 +88,198 @@ __device__ __forceinline__ double stack_rho(int rule, double cst, double vs, dou
 struct WarpScratch {
   double vm[kMaxMantleGrid];    // Vs and depth of the mantle-class grid points
   double zm[kMaxMantleGrid];
-  double cw[kMaxMantleGrid];    // detrended profile, then its wavelet transform
-  double dt[kMaxMantleGrid];
+  double cw[kMaxMantleGrid];    // detrended profile, then its wavelet transform (thermal group: spline abscissae)
+  double dt[kMaxMantleGrid];    //                                                (thermal group: spline ordinates)
+  double hv[kMaxMantleGrid];    // thermal group: Vs, Qs and spline slopes on its grid
+  double hq[kMaxMantleGrid];
+  double hs[kMaxMantleGrid];
   float q[64];                  // the proposal being tested
 };
+
+// ------------------------------------------------------------------------------------ thermal mantle (OceanMantleHybrid)
+// ThermSeis.HSCM (ThermSeis.py:56-101): half-space cooling with an adiabat below the depth where the conductive
+// gradient falls to 0.4 K/km; the mantle temperature Tm follows from a bisection on that depth (the reference's
+// finite-difference derivative and its 0.01 km stopping rule included).
+struct Hscm { double den, Tm, z_ad, Tp; };
+
+__device__ Hscm hscm_setup(double age, double Tp) {
+  Hscm h;
+  h.Tp = Tp;
+  h.den = 2.0 * sqrt(age * 365.0 * 24.0 * 3600.0 * 1.0 * (1e-6 / 1e-6));
+  const double T0 = 0.0, Da = 0.4;
+  double z0 = 0.0, z1 = 400.0;
+  while (z1 - z0 > 0.01) {
+    const double z2 = (z1 + z0) / 2.0;
+    const double fz = erf(z2 * 1e3 / h.den), dfz = (erf((z2 + 0.001) * 1e3 / h.den) - fz) / 0.001 + 1e-10;
+    if (fz / dfz - z2 - (Tp - T0) / Da < 0.0) z0 = z2; else z1 = z2;
+  }
+  h.Tm = (Da * z1 + Tp - T0) / erf(z1 * 1e3 / h.den) + T0;
+  h.z_ad = z0;
+  return h;
+}
+// temperature [K] at depth z [km]; zfirst = first grid depth (a grid that starts below z_ad is all adiabat)
+__device__ __forceinline__ double hscm_T(const Hscm& h, double z) {
+  const double T = (z > h.z_ad) ? h.Tp + z * 0.4 : h.Tm * erf(z * 1e3 / h.den);
+  return T + 273.15;
+}
+__device__ __forceinline__ double hscm_P(double z) { return 3.4e3 * 9.8 * z * 1000.0; }
+
+// OceanSeisRitz._pt2vs, RhoType 'raw' (ThermSeis.py:132-176): Voigt-Reuss-Hill shear modulus of five minerals
+__constant__ double kRitz[5][14] = {
+    {3.222e3, 1.182e3, 129, -16e-3, 4.2, 0, 82, -14e-3, 1.4, -30, 0.2010e-4, 0.1390e-7, 0.1627e-2, -0.3380},
+    {3.198e3, 0.804e3, 111, -12e-3, 6.0, -10, 81, -11e-3, 2.0, -29, 0.3871e-4, 0.0446e-7, 0.0343e-2, -1.7278},
+    {3.280e3, 0.377e3, 105, -13e-3, 6.2, 13, 67, -10e-3, 1.7, -6, 0.3206e-4, 0.0811e-7, 0.1347e-2, -1.8167},
+    {3.578e3, 0.702e3, 198, -28e-3, 5.7, 12, 108, -12e-3, 0.8, -24, 0.6969e-4, -0.0108e-7, -3.0799e-2, 5.0395},
+    {3.565e3, 0.758e3, 173, -21e-3, 4.9, 7, 92, -10e-3, 1.4, -7, 0.0991e-4, 0.1165e-7, 1.0624e-2, -2.5000}};
+__constant__ double kRitzW[5] = {0.75, 0.21, 0.035, 0.0, 0.005};
+
+__device__ double ritz_vs(double T, double P_pa) {
+  const double P = P_pa / 1e9, T0 = 273.15, P0 = 101.325e-6, X = 0.1;
+  double srho = 0.0, smu = 0.0, simu = 0.0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double* d = kRitz[i];
+    const double alpha = d[10] + d[11] * T + d[12] / T + d[13] / (T * T);
+    const double rho0X = d[0] * d[1] / 1e3;
+    const double mu = d[6] + (T - T0) * d[7] + (P - P0) * d[8] + X * d[9];
+    const double K = d[2] + (T - T0) * d[3] + (P - P0) * d[4] + X * d[5];
+    const double rho = rho0X * (1.0 - alpha * (T - T0) + (P - P0) / K);
+    srho += kRitzW[i] * rho; smu += kRitzW[i] * mu; simu += kRitzW[i] / mu;
+  }
+  const double mu = 0.5 * (smu + 1.0 / simu);
+  return sqrt(mu * 1e9 / srho) / 1000.0;
+}
+
+// OceanSeisRuan: Qs = J1 / J2 of OceanSeisYaTa._anel with the Ruan2018 solidus (ThermSeis.py:320-448)
+__device__ double ruan_qs(double T, double P, double period) {
+  const double Pg = P / 1e9;
+  const double Tn = T / (-5.1 * Pg * Pg + 92.5 * Pg + 1120.6 + 273.15);
+  const double Aeta = (Tn < 0.94) ? 1.0 : ((Tn < 1.0) ? exp(-(Tn - 0.94) / (Tn - Tn * 0.94) * log(5.0)) : 1.0 / 5.0);
+  const double mu_U = (72.45 - 0.01094 * (T - 273.15) + 1.75 * P * 1e-9) * 1e9;
+  const double eta = 6.22e21 * exp(4.625e5 / 8.314 * (1.0 / T - 1.0 / (1200.0 + 273.15))) *
+                     exp(7.913e-6 / 8.314 * (P / T - 1.5e9 / (1200.0 + 273.15))) * Aeta;
+  const double tau_ns = period / (2.0 * 3.141592653589793 * (eta / mu_U));
+  const double A_P = (Tn < 0.91) ? 0.01 : ((Tn < 0.96) ? 0.01 + 0.4 * (Tn - 0.91) : 0.03);
+  const double sig = (Tn < 0.92) ? 4.0 : ((Tn < 1.0) ? 4.0 + 37.5 * (Tn - 0.92) : 7.0);
+  const double A_B = 0.664, tau_np = 6e-5, alpha = 0.38;
+  const double ta = pow(tau_ns, alpha), lg = log(tau_np / tau_ns) / (sqrt(2.0) * sig);
+  const double J1 = 1.0 + A_B * ta / alpha + sqrt(2.0 * 3.141592653589793) / 2.0 * A_P * sig * (1.0 - erf(lg));
+  const double J2 = 3.141592653589793 / 2.0 * A_B * ta + 3.141592653589793 / 2.0 * (A_P * exp(-(lg * lg))) + tau_ns;
+  return J1 / J2;
+}
+
+// OceanMantleHybrid._calVs / _calOthers (layers.py:302-363) for the N + 1 <= 64 grid points of the group, by one warp:
+// ws.hv = Vs, ws.hq = Qs.  coef = the len(Vs) perturbation coefficients (the basis has one more, its first coefficient 0).
+__device__ void hybrid_profile(const SurfdispStackGroup& g, const double* coef, double therm_age, double H, int N,
+                               double crust_h, double z_top, WarpScratch& ws) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const double age = fmax(1e-3, therm_age);
+  const Hscm hv = hscm_setup(age, g.tp);
+  const Hscm hm = (g.tp == 1325.0) ? hv : hscm_setup(age, 1325.0);     // meltStart: HSCM(age) with the default Tp (layers.py:313)
+  // depth where melting starts: first of linspace(0, 200, 200) with T > 0.92 x (damp solidus)
+  int first = 200;
+  for (int i = lane; i < 200; i += 32) {
+    const double z = (i == 199) ? 200.0 : (double)i * (200.0 / 199.0);
+    const double Pg = hscm_P(z) / 1e9;
+    if (hscm_T(hm, z) > 0.92 * (-5.1 * Pg * Pg + 92.5 * Pg + 1120.6 + 273.15)) { first = i; break; }
+  }
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(full, first, o));
+  const double z_melt = ((first >= 199) ? 200.0 : (double)first * (200.0 / 199.0)) - crust_h;
+  const double xL = z_melt, xH = (z_melt + crust_h) * 1.7 - crust_h;
+  const double zstep = H / (double)N, ustep = 1.0 / (double)N;
+  double pc[SURFDISP_MAX_COEF];
+  pc[0] = 0.0;
+  for (int i = 0; i < g.ncoef; ++i) pc[i + 1] = coef[i];
+  const Knots kn = make_knots(g.ncoef + 1);
+  // thermal Vs and perturbed Vs of this lane's grid points (two chunks), compaction of the spline's knots
+  double zj[2], vt[2];
+  int npts = 0;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int j = 32 * c + lane;
+    const bool act = j <= N;
+    zj[c] = (j == N) ? H : (double)j * zstep;
+    double y2 = 0.0;
+    vt[c] = 0.0;
+    if (act) {
+      const double zz = crust_h + zj[c];
+      vt[c] = ritz_vs(hscm_T(hv, zz), hscm_P(zz));
+      y2 = bspl_profile(pc, kn, (j == N) ? 1.0 : (double)j * ustep) + vt[c];
+    }
+    const bool k1 = act && zj[c] < xL, k2 = act && zj[c] > xH;
+    const unsigned km = __ballot_sync(full, k1 || k2);
+    if (k1 || k2) { const int idx = npts + __popc(km & ((1u << lane) - 1u)); ws.cw[idx] = zj[c]; ws.dt[idx] = k1 ? vt[c] : y2; }
+    npts += __popc(km);
+  }
+  __syncwarp();
+  // knot slopes of scipy's CubicSpline (not-a-knot): tridiagonal system, eliminated by one lane
+  const double* xs = ws.cw; const double* ys = ws.dt;
+  if (lane == 0 && npts >= 2) {
+    double* sl = ws.hs; double* bd = ws.hv; double* rh = ws.hq;      // slopes, eliminated diagonal, eliminated right-hand side
+    if (npts == 2) { sl[0] = sl[1] = (ys[1] - ys[0]) / (xs[1] - xs[0]); }
+    else if (npts == 3) {
+      // parabola through three points: s0 + s1 = 2 m0, dx1 s0 + 2 (dx0 + dx1) s1 + dx0 s2 = 3 (dx0 m1 + dx1 m0), s1 + s2 = 2 m1
+      const double d0 = xs[1] - xs[0], d1 = xs[2] - xs[1], m0 = (ys[1] - ys[0]) / d0, m1 = (ys[2] - ys[1]) / d1;
+      const double s1 = (3.0 * (d0 * m1 + d1 * m0) - 2.0 * d1 * m0 - 2.0 * d0 * m1) / (d0 + d1);
+      sl[0] = 2.0 * m0 - s1; sl[1] = s1; sl[2] = 2.0 * m1 - s1;
+    } else {
+      const int n = npts;
+      auto dxf = [&](int i) { return xs[i + 1] - xs[i]; };
+      auto mf = [&](int i) { return (ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]); };
+      // row 0: [dx1, x2 - x0]
+      double d = xs[2] - xs[0];
+      bd[0] = dxf(1);
+      double cprev = d;
+      rh[0] = ((dxf(0) + 2.0 * d) * dxf(1) * mf(0) + dxf(0) * dxf(0) * mf(1)) / d;
+      for (int i = 1; i < n - 1; ++i) {
+        const double a = dxf(i), b = 2.0 * (dxf(i - 1) + dxf(i)), c = dxf(i - 1);
+        const double r = 3.0 * (dxf(i) * mf(i - 1) + dxf(i - 1) * mf(i));
+        const double w = a / bd[i - 1];
+        bd[i] = b - w * cprev; rh[i] = r - w * rh[i - 1];
+        cprev = c;
+      }
+      d = xs[n - 1] - xs[n - 3];
+      {
+        const double a = d, b = dxf(n - 2);
+        const double r = (dxf(n - 2) * dxf(n - 2) * mf(n - 3) + (2.0 * d + dxf(n - 2)) * dxf(n - 3) * mf(n - 2)) / d;
+        const double w = a / bd[n - 2];
+        bd[n - 1] = b - w * cprev; rh[n - 1] = r - w * rh[n - 2];
+      }
+      sl[n - 1] = rh[n - 1] / bd[n - 1];
+      for (int i = n - 2; i >= 0; --i) {
+        const double c = (i == 0) ? (xs[2] - xs[0]) : dxf(i - 1);
+        sl[i] = (rh[i] - c * sl[i + 1]) / bd[i];
+      }
+    }
+  }
+  __syncwarp();
+  // evaluation on the grid (extrapolation with the end pieces), Qs of the anelastic model
+  const double age_q = fmax(1e-3, (g.q_age < 0.0) ? therm_age : g.q_age);
+  const Hscm hqm = (age_q == age) ? hm : hscm_setup(age_q, 1325.0);
+  double vs_out[2], qs_out[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int j = 32 * c + lane;
+    vs_out[c] = vt[c]; qs_out[c] = 0.0;
+    if (j <= N) {
+      if (npts >= 2) {
+        int i = 0;
+        while (i < npts - 2 && xs[i + 1] <= zj[c]) ++i;
+        const double dx = xs[i + 1] - xs[i], m = (ys[i + 1] - ys[i]) / dx, t = (ws.hs[i] + ws.hs[i + 1] - 2.0 * m) / dx;
+        const double h = zj[c] - xs[i];
+        vs_out[c] = ((t / dx * h + ((m - ws.hs[i]) / dx - t)) * h + ws.hs[i]) * h + ys[i];
+      }
+      const double zq = z_top + zj[c];
+      qs_out[c] = fmin(ruan_qs(hscm_T(hqm, zq), hscm_P(zq), g.period), 5000.0);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) { const int j = 32 * c + lane; if (j <= N) { ws.hv[j] = vs_out[c]; ws.hq[j] = qs_out[c]; } }
+  __syncwarp();
+}
 
 // Rules of CascadiaOcean.isgood that look at the mantle profile (reference models.py:603-635), on the nm grid points
 // in ws.vm / ws.zm.  scipy.signal.argrelmax / argrelmin: strict comparison with both neighbours, end points never
@@ -177,6 +365,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
   double last_vs = 0.0, last_vp = 0.0, last_rho = 0.0, last_qs = 0.0;   // deepest grid values so far
   double end_vs1 = 0.0, end_vs2 = 0.0, end_z1 = 0.0, end_z2 = 0.0;       // last two grid points of the model proper
   double first_vs0 = 0.0, first_vs1 = 0.0;
+  double crust_h = 0.0;                   // thickness of the crust-class groups above (thermal mantle)
   int last_class = -1;
   double bot_grad = 1.0;                  // Vs gradient at the bottom of the deepest mantle group
   for (int gi = 0; gi < t.ngroups; ++gi) {
@@ -192,6 +381,11 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
     // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
     if (H - 0.0 < 0.01) continue;
     const bool is_ref = (g.kind == SURFDISP_G_REFMANTLE);
+    const bool is_hyb = (g.kind == SURFDISP_G_HYBRID);
+    if (is_hyb) {
+      if (N > 63) N = 63;
+      hybrid_profile(g, coef, (g.age_param >= 0) ? (double)pm[g.age_param] : g.age_fixed, H, N, crust_h, z0, ws);
+    }
     const Knots kn = make_knots((g.kind == SURFDISP_G_BSPLINE && g.ncoef >= 3) ? g.ncoef : 3);
     const bool mono_class = (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST);
     const double zstep = H / (double)N, ustep = 1.0 / (double)N;
@@ -215,6 +409,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
           else if (g.ncoef == 2) vs = coef[0] * ((j == N) ? 0.0 : 1.0 + (double)j * ((0.0 - 1.0) / (double)N)) + coef[1] * u;
           else vs = bspl_profile(coef, kn, u);
         } else if (g.kind == SURFDISP_G_CASCADIA) vs = (0.02 * H * H + 1.27 * H + 0.29 * 0.1) / (H + 0.29);
+        else if (is_hyb) vs = ws.hv[j];
         else {  // reference mantle: linear continuation of the deepest Vs (layers.py:267-285)
           const double vend = vs0_ref + H * g.slope;
           vs = (j == N) ? vend : vs0_ref + (double)j * ((vend - vs0_ref) / (double)N);
@@ -222,7 +417,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
       }
       double vp = g.vp_a * vs + g.vp_b;
       double rho = stack_rho(g.rho_rule, g.rho_const, vs, vp);
-      double qs = g.qs;
+      double qs = (is_hyb && act) ? ws.hq[j] : g.qs;
       if (is_ref) { vp = last_vp + (vp - vp_first); rho = last_rho + (rho - rho_first); qs = last_qs + (qs - g.qs); }
       // the grid point before this lane's
       double p_z = __shfl_up_sync(full, zz, 1), p_vs = __shfl_up_sync(full, vs, 1), p_vp = __shfl_up_sync(full, vp, 1);
@@ -269,6 +464,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
       }
       if (base == 0 && !is_ref && ngrid == 0) { first_vs0 = __shfl_sync(full, vs, 0); first_vs1 = __shfl_sync(full, vs, 1); }
     }
+    if (g.gclass == SURFDISP_C_CRUST && H / (double)N > 0.01) crust_h += H;    // OceanMantleHybrid.getCrustH (layers.py:304-311)
     if (!is_ref) {
       last_class = g.gclass;
       ngrid += N + 1;
@@ -299,7 +495,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
 // ------------------------------------------------------------------------------------ kernels: builder, priors
 constexpr int kMcThreads = 128;     // 4 warps = 4 models / chains per block
 
-__global__ void __launch_bounds__(kMcThreads) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
+__global__ void __launch_bounds__(kMcThreads, 4) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
                                                                   const float* __restrict__ params, int lmax,
                                                                   float* __restrict__ layers, int* __restrict__ nlay) {
   __shared__ WarpScratch scratch[kMcThreads / 32];
@@ -319,7 +515,7 @@ __global__ void __launch_bounds__(kMcThreads) build_stacks_kernel(const __grid_c
   if (lane == 0) nlay[m] = nz;
 }
 
-__global__ void __launch_bounds__(kMcThreads) check_priors_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
+__global__ void __launch_bounds__(kMcThreads, 4) check_priors_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
                                                                   const float* __restrict__ params, int* __restrict__ priors) {
   __shared__ WarpScratch scratch[kMcThreads / 32];
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -402,7 +598,7 @@ __device__ int propose_warp(const SurfdispStackTemplate& t, const McBounds& bd, 
   return -1;
 }
 
-__global__ void __launch_bounds__(kMcThreads) mc_propose_kernel(const __grid_constant__ SurfdispStackTemplate t,
+__global__ void __launch_bounds__(kMcThreads, 4) mc_propose_kernel(const __grid_constant__ SurfdispStackTemplate t,
                                                                 const __grid_constant__ McBounds bd, int M,
                                                                 const float* __restrict__ cur,
                                                                 const unsigned char* __restrict__ reset_mask,
@@ -434,7 +630,7 @@ struct McStepParams {
   int chains_per_point;
 };
 
-__global__ void __launch_bounds__(kMcThreads) mc_propose_build_kernel(const __grid_constant__ SurfdispStackTemplate t,
+__global__ void __launch_bounds__(kMcThreads, 4) mc_propose_build_kernel(const __grid_constant__ SurfdispStackTemplate t,
                                                                       const __grid_constant__ McStepParams p) {
   __shared__ WarpScratch scratch[kMcThreads / 32];
   __shared__ McBounds sbd[kMcThreads / 32];

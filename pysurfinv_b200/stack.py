@@ -18,7 +18,7 @@ MAX_GROUPS = 8
 MAX_COEF = 8
 
 # group kinds (Vs profile)                       reference class
-G_WATER, G_CONST, G_LINEAR, G_BSPLINE, G_CASCADIA, G_REFMANTLE = 0, 1, 2, 3, 4, 5
+G_WATER, G_CONST, G_LINEAR, G_BSPLINE, G_CASCADIA, G_REFMANTLE, G_HYBRID = 0, 1, 2, 3, 4, 5, 6
 # fine-layer rules
 N_FIXED, N_CRUST, N_OCRUST = 0, 1, 2
 # density rules
@@ -36,7 +36,7 @@ PRIOR_CONTINENT = P_JUMP | P_VSMAX | P_MONO                           # Cascadia
 PRIOR_OCEAN = P_SEDMIN | P_FIRSTPAIR | P_BOTTOM | P_OSCI | P_LOCALMAX | P_SLOPE | P_CWT   # CascadiaOcean.isgood :571-677
 PRIOR_OF_MODELTYPE = {"CascadiaPrism": PRIOR_PRISM, "CascadiaContinent": PRIOR_CONTINENT, "CascadiaOcean": PRIOR_OCEAN,
                       "MCInv": 0, "General": 0}
-_CLASS = {'Sediment': C_SEDIMENT, 'Crust': C_CRUST, 'Mantle': C_MANTLE, 'OceanMantle': C_MANTLE, 'OceanWater': C_WATER,
+_CLASS = {'Sediment': C_SEDIMENT, 'Crust': C_CRUST, 'Mantle': C_MANTLE, 'OceanMantle': C_MANTLE, 'OceanMantleHybrid': C_MANTLE, 'OceanWater': C_WATER,
           'OceanSediment': C_SEDIMENT, 'OceanSedimentCascadia': C_SEDIMENT, 'OceanCrust': C_CRUST}
 
 
@@ -45,7 +45,9 @@ class Group(C.Structure):
                 ("h_param", C.c_int), ("ncoef", C.c_int), ("rho_rule", C.c_int), ("gclass", C.c_int),
                 ("v_param", C.c_int * MAX_COEF), ("v_fixed", C.c_double * MAX_COEF),
                 ("h_fixed", C.c_double), ("vp_a", C.c_double), ("vp_b", C.c_double), ("rho_const", C.c_double),
-                ("qs", C.c_double), ("slope", C.c_double)]
+                ("qs", C.c_double), ("slope", C.c_double),
+                ("age_param", C.c_int), ("pad_", C.c_int), ("age_fixed", C.c_double), ("tp", C.c_double),
+                ("period", C.c_double), ("q_age", C.c_double)]
 
 
 class StackTemplateC(C.Structure):
@@ -59,6 +61,7 @@ _TYPES = {
     "Crust": (G_BSPLINE, N_CRUST, 0, 1.80, 0.0, R_QUARTIC, 0.0, 600.0),                # layers.py:158-189
     "Mantle": (G_BSPLINE, N_CRUST, 0, 1.76, 0.0, R_MANTLE, 0.0, 150.0),                # layers.py:239-265
     "OceanMantle": (G_BSPLINE, N_CRUST, 0, 1.76, 0.0, R_MANTLE, 0.0, 150.0),
+    "OceanMantleHybrid": (G_HYBRID, N_CRUST, 0, 1.76, 0.0, R_MANTLE, 0.0, 150.0),    # layers.py:297-363 (Qs from the thermal model)
     "OceanWater": (G_WATER, N_FIXED, 1, 0.0, 1.475, R_CONST, 1.027, 10000.0),          # layers.py:191-204
     "OceanSediment": (G_CONST, N_FIXED, 1, 1.23, 1.28, R_OCEAN, 0.0, 80.0),            # layers.py:206-219
     "OceanSedimentCascadia": (G_CASCADIA, N_FIXED, 1, 1.23, 1.28, R_OCEAN, 0.0, 80.0), # layers.py:289-295
@@ -103,6 +106,7 @@ class StackTemplate:
         self.groups = []
         info = dict(setting.get("Info", {}))
         self.topo = float(info.get("topo", 0.0))
+        self._info = info
         for name, parm in setting.items():
             if name == "Info":
                 continue
@@ -138,6 +142,7 @@ class StackTemplate:
         for i in range(MAX_COEF):
             g.v_param[i] = -1
         g.h_param = -1
+        g.age_param, g.tp, g.period, g.q_age = -1, 1325.0, 1.0, -1.0
         return g
 
     def _value(self, v, where):
@@ -166,10 +171,28 @@ class StackTemplate:
                 g.ncoef = len(vals)
                 for i, x in enumerate(vals):
                     g.v_param[i], g.v_fixed[i] = self._value(x, "%s.Vs[%d]" % (name, i))
+            elif name == "OceanMantleHybrid" and key in ("ThermAge", "Tp", "Conversion"):
+                if key == "ThermAge":
+                    g.age_param, g.age_fixed = self._value(val, "%s.ThermAge" % name)
+                elif key == "Tp":
+                    if _is_spec(val) and val[1] not in ("fixed", "total"):
+                        raise ValueError("OceanMantleHybrid: Tp must be fixed")
+                    g.tp = float(val[0] if _is_spec(val) else val)
+                elif val != "Ritzwoller":
+                    raise ValueError("OceanMantleHybrid: only the 'Ritzwoller' conversion is built on the device")
             else:
                 # (Crust 'Gauss', OceanMantle 'deg', ... change the Vs profile in the reference, layers.py:176-183, 256:
                 # dropping them silently would build a different model)
                 raise ValueError("%s: parameter %r is not supported by the device-side builder" % (name, key))
+        if kind == G_HYBRID:
+            # (the perturbation has len(Vs) + 1 B-spline coefficients, the first one 0: layers.py:323, 340)
+            if g.ncoef + 1 > MAX_COEF or g.ncoef < 2:
+                raise ValueError("OceanMantleHybrid: 2 .. %d Vs coefficients" % (MAX_COEF - 1))
+            info = self._info
+            g.period = float(info.get("period", 1))
+            g.q_age = float(info["lithoAge"]) if (info.get("lithoAgeQ", False) and info.get("lithoAge") is not None) else -1.0
+            if "ThermAge" not in parm:
+                raise ValueError("OceanMantleHybrid needs ThermAge")
         if kind is None:   # Sediment / OceanCrust: constant or linear (layers.py:146-149, 228-231)
             kind = G_LINEAR if g.ncoef == 2 else G_CONST
             if g.ncoef not in (1, 2):

@@ -109,3 +109,46 @@ def test_parameters_to_dispersion_chain(solver):
     ok = st0 != 3
     assert np.array_equal(g["nfound"].cpu().numpy()[ok], nf0[ok])
     assert np.abs(g["c"].cpu().numpy() - c0)[ok].max() <= 1e-4
+
+
+THERMAL = {"OceanWater": {"H": 2.5}, "OceanSedimentCascadia": {"H": [1, "rel_pos", 100, 0.1]}, "OceanCrust": {"H": 7, "Vs": [3.25, 3.94]},
+           "OceanMantleHybrid": {"BottomDepth": 200, "Conversion": "Ritzwoller", "ThermAge": [4, "rel_pos", 200, 0.4],
+                                 "Vs": [[0, "abs", 0.4, 0.01], [0, "abs", 0.4, 0.01], [0, "abs", 0.4, 0.01], [0, "abs", 0.2, 0.01]]},
+           "Info": {"modelType": "CascadiaOcean", "period": 10, "refLayer": True, "lithoAgeQ": True, "lithoAge": 0.6, "topo": -2.5}}
+
+
+def test_thermal_mantle_group_matches_reference_classes(solver):
+    """the thermal parameterisation (OceanMantleHybrid, layers.py:297-363: half-space cooling -> Vs by
+    OceanSeisRitz, B-spline perturbation below the melting depth joined by a not-a-knot spline, Qs by OceanSeisRuan)
+    assembled on the device: against stacks produced by the reference's own classes (thermal_reference.json), against
+    the numpy restatement on random parameter vectors of the config-1 setting of point.py:374-391, and the
+    CascadiaOcean prior verdicts on those thermal profiles."""
+    import torch
+    with open(os.path.join(os.path.dirname(__file__), "golden", "thermal_reference.json")) as f:
+        gold = json.load(f)
+    none = torch.zeros((1, 0), dtype=torch.float32, device="cuda")
+    for c in gold["stacks"]:
+        t = S.StackTemplate(c["setting"])
+        lay, nl = solver.build_stacks(t, none, lmax=t.max_layers())
+        n = int(nl[0])
+        assert n == len(c["h"])
+        got = lay[:, 0, :n].cpu().numpy()
+        for row, key in ((0, "vp"), (1, "vs"), (2, "rho"), (3, "h")):
+            np.testing.assert_allclose(got[row], np.array(c[key]), rtol=3e-7, atol=1e-7)
+        np.testing.assert_allclose(1.0 / got[4], np.array(c["qs"]), rtol=1e-6)
+        bad = int(solver.check_priors(t, none).cpu()[0]) & S.PRIOR_OCEAN
+        assert (bad == 0) == c["isgood"]
+    t = S.StackTemplate(THERMAL, prior_mask=S.PRIOR_OCEAN)
+    assert t.nparams == 6 and t.max_layers() == 92
+    params = _random_params(t, 400, 17)
+    _compare(solver, t, params, t.max_layers())
+    got = solver.check_priors(t, torch.from_numpy(params).cuda()).cpu().numpy() & S.PRIOR_OCEAN
+    want = np.array([MB.priors_ocean(t, p.astype(np.float64)) for p in params]) & S.PRIOR_OCEAN
+    assert (got != want).mean() < 0.01 and 0 < (got == 0).sum() < len(got)
+    # the whole chain on the real config-1 parameterisation: parameters -> stacks -> dispersion, against the oracle
+    per = np.array([10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)
+    good = params[got == 0][:64]
+    lay, nl = solver.build_stacks(t, torch.from_numpy(good).cuda())
+    g = solver.forward(lay, nl, per, kind=2)
+    c0, u0, nf0, st0 = O.forward_batch(2, lay.cpu().numpy(), nl.cpu().numpy(), per, opts=O.make_opts(precision=0), nthreads=8)
+    assert np.array_equal(g["nfound"].cpu().numpy(), nf0) and np.abs(g["c"].cpu().numpy() - c0).max() <= 1e-4

@@ -115,3 +115,17 @@ def test_reference_postpoint_loads_our_file(gold, tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("THRES")][0].split()
     assert abs(float(line[1]) - gold["postpoint"]["thres"]) < 1e-9 and int(line[2]) == gold["postpoint"]["acc_final"]
+
+
+def test_thermal_mantle_restatement_matches_reference_classes():
+    """oracle.model_builder.hybrid_mantle (HSCM + OceanSeisRitz + OceanSeisRuan + not-a-knot spline) against stacks the
+    reference's own OceanMantleHybrid produced (tests/golden/make_golden_thermal.py), and the ocean prior verdicts."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "thermal_reference.json")) as f:
+        gold = json.load(f)
+    for c in gold["stacks"]:
+        t = S.StackTemplate(c["setting"])
+        h, vs, vp, rho, qs = MB.build_one(t, np.zeros(0))
+        assert len(h) == len(c["h"])
+        for mine, key in ((h, "h"), (vs, "vs"), (vp, "vp"), (rho, "rho"), (qs, "qs")):
+            np.testing.assert_allclose(mine, np.array(c[key]), rtol=1e-12, atol=1e-12)
+        assert ((MB.priors_ocean(t, np.zeros(0)) & S.PRIOR_OCEAN) == 0) == c["isgood"]
