@@ -1353,6 +1353,11 @@ int surfdisp_batch(const SurfdispOpts* opts, int kind, int n_models, int n_layer
   return 0;
 }
 
+static bool has_hybrid(const SurfdispStackTemplate* tmpl) {
+  for (int g = 0; g < tmpl->ngroups; ++g) if (tmpl->groups[g].kind == SURFDISP_G_HYBRID) return true;
+  return false;
+}
+
 static int check_template(const SurfdispStackTemplate* tmpl) {
   if (!tmpl) return SURFDISP_EINVAL;
   if (tmpl->ngroups < 1 || tmpl->ngroups > SURFDISP_MAX_GROUPS || tmpl->nparams < 0) return SURFDISP_EINVAL;
@@ -1430,7 +1435,8 @@ static int host_pipeline(const SurfdispOpts* opts, int kind, int n_models, int n
     if (from_params) {
       // stage 1': one copy of the parameter vectors, model assembly on the device, preparation + first-period search
       if (P > 0) PCK(cudaMemcpyAsync(d_par, params, np_, cudaMemcpyHostToDevice, cs), "H2D params");
-      build_stacks_kernel<<<(unsigned)((M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, cs>>>(*tmpl, n_models, d_par, n_layers_max, d_lay, d_n);
+      if (has_hybrid(tmpl)) build_stacks_kernel<true><<<(unsigned)((M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, cs>>>(*tmpl, n_models, d_par, n_layers_max, d_lay, d_n);
+      else build_stacks_kernel<false><<<(unsigned)((M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, cs>>>(*tmpl, n_models, d_par, n_layers_max, d_lay, d_n);
       PCK(cudaGetLastError(), "build_stacks");
       if ((rc = stage_prep(pl, 0, n_models, cs))) break;
       if ((rc = stage_p1(pl, 0, n_models, 0, ks, cs))) break;
@@ -1678,7 +1684,8 @@ int surfdisp_build_stacks(const SurfdispStackTemplate* tmpl, int n_models, const
   if (int rc = check_template(tmpl)) return rc;
   if (n_models == 0) return 0;
   if (!layers || !n_layers || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
-  build_stacks_kernel<<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
+  if (has_hybrid(tmpl)) build_stacks_kernel<true><<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
+  else build_stacks_kernel<false><<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, n_layers_max, layers, n_layers);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1688,7 +1695,8 @@ int surfdisp_check_priors(const SurfdispStackTemplate* tmpl, int n_models, const
   if (int rc = check_template(tmpl)) return rc;
   if (n_models == 0) return 0;
   if (!priors || (tmpl->nparams > 0 && !params)) return SURFDISP_EINVAL;
-  check_priors_kernel<<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
+  if (has_hybrid(tmpl)) check_priors_kernel<true><<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
+  else check_priors_kernel<false><<<(unsigned)(((size_t)n_models * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(*tmpl, n_models, params, priors);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1708,8 +1716,12 @@ int surfdisp_mc_propose(const SurfdispStackTemplate* tmpl, int n_chains, const f
     if (!(hi[i] > lo[i]) || !(step[i] > 0.f)) return SURFDISP_EINVAL;
     bd.lo[i] = lo[i]; bd.hi[i] = hi[i]; bd.step[i] = step[i];
   }
-  mc_propose_kernel<<<(unsigned)(((size_t)n_chains * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(
-      *tmpl, bd, n_chains, cur, reset_mask, prop, status, seed, step_index);
+  if (has_hybrid(tmpl))
+    mc_propose_kernel<true><<<(unsigned)(((size_t)n_chains * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(
+        *tmpl, bd, n_chains, cur, reset_mask, prop, status, seed, step_index);
+  else
+    mc_propose_kernel<false><<<(unsigned)(((size_t)n_chains * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, (cudaStream_t)stream>>>(
+        *tmpl, bd, n_chains, cur, reset_mask, prop, status, seed, step_index);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1745,7 +1757,8 @@ int surfdisp_mc_step(const SurfdispOpts* opts, const SurfdispStackTemplate* tmpl
   mp.M = M; mp.P = P; mp.lmax = s->n_layers_max; mp.chain_len = s->chain_len; mp.cur = s->cur; mp.prop = s->prop;
   mp.status = s->status; mp.init_mask = s->init_mask; mp.layers = s->layers; mp.nlay = s->n_layers; mp.step_ptr = s->step;
   mp.seed = s->seed; mp.bounds = reinterpret_cast<const McBounds*>(s->bounds); mp.chains_per_point = s->chains_per_point;
-  mc_propose_build_kernel<<<(unsigned)(((size_t)M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, st>>>(*tmpl, mp);
+  if (has_hybrid(tmpl)) mc_propose_build_kernel<true><<<(unsigned)(((size_t)M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, st>>>(*tmpl, mp);
+  else mc_propose_build_kernel<false><<<(unsigned)(((size_t)M * 32 + kMcThreads - 1) / kMcThreads), kMcThreads, 0, st>>>(*tmpl, mp);
   CK(cudaGetLastError());
   // ---- phase velocities of the proposals
   SurfdispOpts o;

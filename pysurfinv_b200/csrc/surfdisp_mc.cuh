@@ -353,7 +353,8 @@ __device__ int ocean_mantle_rules(WarpScratch& ws, int nm) {
 // every lane) the SURFDISP_P_* bits of the violated prior rules -- CascadiaPrism / CascadiaContinent.isgood
 // (models.py:294-360, 385-523) and, where `rules` asks for them, CascadiaOcean.isgood (models.py:571-677) --
 // evaluated on the fine grid without the reference mantle like Model1D.seisPropGrids() does by default.
-template <bool EMIT>
+// HYB: the template has a thermal mantle group (compiled out otherwise: its erf / spline code costs registers)
+template <bool EMIT, bool HYB>
 __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* pm, int rules, int lmax, float* o_vp,
                                    float* o_vs, float* o_rho, float* o_h, float* o_qs, int* nl_out, WarpScratch& ws) {
   const unsigned full = 0xffffffffu;
@@ -381,7 +382,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
     // z = linspace(0, H, N+1); a group thinner than 0.01 km is skipped altogether (models.py:82)
     if (H - 0.0 < 0.01) continue;
     const bool is_ref = (g.kind == SURFDISP_G_REFMANTLE);
-    const bool is_hyb = (g.kind == SURFDISP_G_HYBRID);
+    const bool is_hyb = HYB && (g.kind == SURFDISP_G_HYBRID);
     if (is_hyb) {
       if (N > 63) N = 63;
       hybrid_profile(g, coef, (g.age_param >= 0) ? (double)pm[g.age_param] : g.age_fixed, H, N, crust_h, z0, ws);
@@ -495,6 +496,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
 // ------------------------------------------------------------------------------------ kernels: builder, priors
 constexpr int kMcThreads = 128;     // 4 warps = 4 models / chains per block
 
+template <bool HYB>
 __global__ void __launch_bounds__(kMcThreads, 4) build_stacks_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
                                                                   const float* __restrict__ params, int lmax,
                                                                   float* __restrict__ layers, int* __restrict__ nlay) {
@@ -509,18 +511,19 @@ __global__ void __launch_bounds__(kMcThreads, 4) build_stacks_kernel(const __gri
   float* o_h = layers + 3 * pl + (size_t)m * lmax;
   float* o_qs = layers + 4 * pl + (size_t)m * lmax;
   int nl = 0;
-  assemble_stack_warp<true>(t, pm, 0, lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl, scratch[threadIdx.x >> 5]);
+  assemble_stack_warp<true, HYB>(t, pm, 0, lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl, scratch[threadIdx.x >> 5]);
   const int nz = nl < 0 ? 0 : nl;
   for (int j = nz + lane; j < lmax; j += 32) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
   if (lane == 0) nlay[m] = nz;
 }
 
+template <bool HYB>
 __global__ void __launch_bounds__(kMcThreads, 4) check_priors_kernel(const __grid_constant__ SurfdispStackTemplate t, int M,
                                                                   const float* __restrict__ params, int* __restrict__ priors) {
   __shared__ WarpScratch scratch[kMcThreads / 32];
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
-  const int bad = assemble_stack_warp<false>(t, params + (size_t)m * t.nparams, 0x7fffffff, 0, nullptr, nullptr, nullptr, nullptr,
+  const int bad = assemble_stack_warp<false, HYB>(t, params + (size_t)m * t.nparams, 0x7fffffff, 0, nullptr, nullptr, nullptr, nullptr,
                                              nullptr, nullptr, scratch[threadIdx.x >> 5]);
   if ((threadIdx.x & 31) == 0) priors[m] = bad;
 }
@@ -563,6 +566,7 @@ constexpr int kMaxParams = 64;
 // One admissible proposal for the chain of this warp, into ws.q (lanes over parameters; the prior rules by the whole
 // warp).  MCinv.perturb (models.py:190-205): up to 1000 proposals, then MCinv.reset (models.py:206-219): up to 10000.
 // Returns the number of tries, -1 if no admissible model was found (the reference raises there).
+template <bool HYB>
 __device__ int propose_warp(const SurfdispStackTemplate& t, const McBounds& bd, const float* cur, bool restart,
                             unsigned long long seed, unsigned int chain, unsigned int step_index, WarpScratch& ws) {
   const int lane = threadIdx.x & 31;
@@ -589,7 +593,7 @@ __device__ int propose_warp(const SurfdispStackTemplate& t, const McBounds& bd, 
         ws.q[i] = v;
       }
       __syncwarp();
-      const int bad = t.prior_mask ? (assemble_stack_warp<false>(t, ws.q, t.prior_mask, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+      const int bad = t.prior_mask ? (assemble_stack_warp<false, HYB>(t, ws.q, t.prior_mask, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                   nullptr, ws) & t.prior_mask) : 0;
       __syncwarp();
       if (!bad) return tries;
@@ -598,6 +602,7 @@ __device__ int propose_warp(const SurfdispStackTemplate& t, const McBounds& bd, 
   return -1;
 }
 
+template <bool HYB>
 __global__ void __launch_bounds__(kMcThreads, 4) mc_propose_kernel(const __grid_constant__ SurfdispStackTemplate t,
                                                                 const __grid_constant__ McBounds bd, int M,
                                                                 const float* __restrict__ cur,
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(kMcThreads, 4) mc_propose_kernel(const __grid_
   WarpScratch& ws = scratch[threadIdx.x >> 5];
   const int P = t.nparams;
   const bool restart = reset_mask && reset_mask[m];
-  const int result = propose_warp(t, bd, cur + (size_t)m * P, restart, seed, (unsigned)m, step_index, ws);
+  const int result = propose_warp<HYB>(t, bd, cur + (size_t)m * P, restart, seed, (unsigned)m, step_index, ws);
   for (int i = lane; i < P; i += 32) prop[(size_t)m * P + i] = ws.q[i];
   if (status && lane == 0) status[m] = result;
 }
@@ -630,6 +635,7 @@ struct McStepParams {
   int chains_per_point;
 };
 
+template <bool HYB>
 __global__ void __launch_bounds__(kMcThreads, 4) mc_propose_build_kernel(const __grid_constant__ SurfdispStackTemplate t,
                                                                       const __grid_constant__ McStepParams p) {
   __shared__ WarpScratch scratch[kMcThreads / 32];
@@ -652,13 +658,13 @@ __global__ void __launch_bounds__(kMcThreads, 4) mc_propose_build_kernel(const _
   if (init) {
     for (int i = lane; i < P; i += 32) ws.q[i] = cur[i];
     __syncwarp();
-    const int bad = t.prior_mask ? (assemble_stack_warp<false>(t, ws.q, t.prior_mask, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+    const int bad = t.prior_mask ? (assemble_stack_warp<false, HYB>(t, ws.q, t.prior_mask, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 nullptr, ws) & t.prior_mask) : 0;
     __syncwarp();
     take_cur = !bad;
   }
   if (!take_cur) {
-    result = propose_warp(t, sbd[w], cur, start && !init, p.seed, (unsigned)m, step, ws);
+    result = propose_warp<HYB>(t, sbd[w], cur, start && !init, p.seed, (unsigned)m, step, ws);
     if (result < 0) {   // no admissible model: the chain keeps its state, the row is flagged (status < 0)
       for (int i = lane; i < P; i += 32) ws.q[i] = cur[i];
       __syncwarp();
@@ -674,7 +680,7 @@ __global__ void __launch_bounds__(kMcThreads, 4) mc_propose_build_kernel(const _
   float* o_h = p.layers + 3 * pl + (size_t)m * p.lmax;
   float* o_qs = p.layers + 4 * pl + (size_t)m * p.lmax;
   int nl = 0;
-  assemble_stack_warp<true>(t, ws.q, 0, p.lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl, ws);
+  assemble_stack_warp<true, HYB>(t, ws.q, 0, p.lmax, o_vp, o_vs, o_rho, o_h, o_qs, &nl, ws);
   const int nz = nl < 0 ? 0 : nl;
   for (int j = nz + lane; j < p.lmax; j += 32) { o_vp[j] = 0.f; o_vs[j] = 0.f; o_rho[j] = 0.f; o_h[j] = 0.f; o_qs[j] = 0.f; }
   if (lane == 0) p.nlay[m] = nz;
