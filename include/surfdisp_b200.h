@@ -98,6 +98,17 @@ int surfdisp_batch_hinted(const SurfdispOpts* opts, int kind, int n_models, int 
                           const float* layers, int n_periods, const float* periods, const float* c_hint, float* c_out,
                           float* u_out, int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Rayleigh phase velocities AND their partial derivatives with respect to Vp, Vs and density of every layer of each
+ * period's (attenuation-corrected, flattened) model: REIGEN's dcda, dcdb, dcdr (surfa.f:1130-1135, 1179-1185,
+ * 1202-1208) -- computed by the reference along with the group velocity and kept in COMMON /derivd/; here they are an
+ * output.  They replace the 2 n + 1 forward solves per model of the finite-difference SensKernelPert
+ * (senskernel.py:130-158).  dcda / dcdb / dcdr: device float[M][K][n_layers_max] (zero below the layer-dropping depth,
+ * in liquid layers, beyond nfound).  The other arguments as surfdisp_batch. */
+int surfdisp_partials_batch(const SurfdispOpts* opts, int n_models, int n_layers_max, const int* n_layers,
+                            const float* layers, int n_periods, const float* periods, float* c_out, float* dcda,
+                            float* dcdb, float* dcdr, int* nfound, int* flags, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* Per-model misfit of predicted phase velocities against one observed curve.
  *   mode 0: Point.misfit (point.py:15-31); mode 1: PointCascadia.misfit (point.py:337-366)
  *   c_pred   device float[M][K], nfound device int[M] (models with nfound < K get the failure

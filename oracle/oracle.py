@@ -55,6 +55,8 @@ def lib():
         L.surfdisp_oracle_batch.argtypes = [C.POINTER(OracleOpts), C.c_int, C.c_int, C.c_int, ip, dp,
                                             C.c_int, dp, dp, dp, ip, ip, C.POINTER(OracleCounters), C.c_int]
         L.surfdisp_oracle_batch.restype = C.c_int
+        L.surfdisp_oracle_partials.argtypes = [C.POINTER(OracleOpts), C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, dp]
+        L.surfdisp_oracle_partials.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -118,3 +120,19 @@ def forward_batch(kind, layers, nlay, periods, opts=None, nthreads=1, counters=N
     if rc != 0:
         raise ValueError("oracle batch: bad arguments")
     return c, u, nf, st
+
+
+def partials(vp, vs, rho, h, qsinv, periods, opts=None):
+    """Rayleigh fundamental-mode partial derivatives of REIGEN (surfa.f:1130-1135, 1179-1185, 1202-1208):
+    dict(c [K], dcda, dcdb, dcdr [K, n]) with respect to Vp, Vs, density of the layers of each period's
+    attenuation-corrected, flattened model."""
+    o = opts if opts is not None else make_opts()
+    a = np.ascontiguousarray(vp, dtype=np.float64); b = np.ascontiguousarray(vs, dtype=np.float64)
+    r = np.ascontiguousarray(rho, dtype=np.float64); d = np.ascontiguousarray(h, dtype=np.float64)
+    q = np.ascontiguousarray(qsinv, dtype=np.float64); per = np.ascontiguousarray(periods, dtype=np.float64)
+    n, K = len(b), len(per)
+    c = np.zeros(K); da = np.zeros((K, n)); db = np.zeros((K, n)); dr = np.zeros((K, n))
+    st = lib().surfdisp_oracle_partials(C.byref(o), n, _dp(a), _dp(b), _dp(r), _dp(d), _dp(q), K, _dp(per), _dp(c), _dp(da), _dp(db), _dp(dr))
+    if st < 0:
+        raise ValueError("oracle: bad arguments")
+    return dict(c=c, dcda=da, dcdb=db, dcdr=dr, status=st)

@@ -99,6 +99,12 @@ struct Solver {
   RM t_base;
   // results (1-based k, 1-based iq)
   std::vector<std::vector<R>> c, ratio, ugr, cvar;
+  // partial derivatives of the phase velocity of the last REIGEN call, per ORIGINAL layer of the period's model (the
+  // reference keeps them per sub-layer in COMMON /derivd/, surfa.f:1130-1135, 1182-1185, 1202-1208; a layer's
+  // derivative is the sum over its sub-layers); filled only when want_partials is set
+  bool want_partials = false;
+  std::vector<double> p_dcda, p_dcdb, p_dcdr;
+  std::vector<std::vector<double>> all_dcda, all_dcdb, all_dcdr;   // [period][layer], fundamental mode
   std::vector<int> imax;
 
   void setup_consts() {
@@ -602,20 +608,25 @@ struct Solver {
     int ivre = o.ndiv_cap_r / mm1;
     if (ndiv > ivre) ndiv = ivre;
     R div = R((float)ndiv);
+    std::vector<int> orig(lm + 2);          // original layer of every (sub-)layer
+    for (int j = 0; j <= lm + 1; ++j) orig[j] = j;
+    const int lm_orig = lm;
     if (ndiv > 1) {  // surfa.f:787-820
       int jj = 1;
       if (lb[1] <= R(0.1e-10f)) jj = 2;
       int newm = (mm1 - jj + 1) * ndiv + jj;
       std::vector<R> nd(newm + 2), na(newm + 2), nb(newm + 2), nr(newm + 2);
-      for (int j = 1; j < jj; ++j) { nd[j] = ld[j]; na[j] = la[j]; nb[j] = lb[j]; nr[j] = lrho[j]; }
+      std::vector<int> no(newm + 2, 0);
+      for (int j = 1; j < jj; ++j) { nd[j] = ld[j]; na[j] = la[j]; nb[j] = lb[j]; nr[j] = lrho[j]; no[j] = j; }
       for (int j = jj; j <= mm1; ++j) {
         int ldiv = (j - jj) * ndiv;
         for (int i = 1; i <= ndiv; ++i) {
           int q = jj + ldiv + i - 1;
-          nd[q] = ld[j] / div; na[q] = la[j]; nb[q] = lb[j]; nr[q] = lrho[j];
+          nd[q] = ld[j] / div; na[q] = la[j]; nb[q] = lb[j]; nr[q] = lrho[j]; no[q] = j;
         }
       }
-      nd[newm] = 0; na[newm] = la[lm]; nb[newm] = lb[lm]; nr[newm] = lrho[lm];
+      nd[newm] = 0; na[newm] = la[lm]; nb[newm] = lb[lm]; nr[newm] = lrho[lm]; no[newm] = lm;
+      orig.swap(no);
       ld.swap(nd); la.swap(na); lb.swap(nb); lrho.swap(nr);
       lm = newm;
     }
@@ -785,6 +796,7 @@ struct Solver {
     R aur = 0, auz = 0, atz = 0, atr = 0;
     int m;
     bool early = false;
+    std::vector<double> sub_dcda(ntot + 2, 0.0), sub_dcdb(ntot + 2, 0.0), sub_dcdr(ntot + 2, 0.0);
     for (m = 1; m <= lm; ++m) {
       if (lb[m] <= R(0)) continue;
       if (m >= lm) break;
@@ -815,6 +827,14 @@ struct Solver {
       sumi1 = R((xlamb[m] + R(2) * xmu[m]) * dmmr + xmu[m] * dmmz + sumi1);
       sumi2 = R(xmu[m] * dzsr - xlamb[m] * drsz + sumi2);
       sumi3 = R((xlamb[m] + R(2) * xmu[m]) * smmz + xmu[m] * smmr + sumi3);
+      if (want_partials) {  // surfa.f:1130-1135
+        D dldl = -wvnosq * dmmr + R(2) * wvno * drsz - smmz;
+        D dldm = -wvnosq * (R(2) * dmmr + dmmz) - R(2) * wvno * dzsr - (R(2) * smmz + smmr);
+        D dldr = omegsq * (dmmr + dmmz);
+        sub_dcdb[m] = R(2) * lrho[m] * lb[m] * c_ * (dldm - R(2) * dldl) / wvno;
+        sub_dcda[m] = R(2) * lrho[m] * la[m] * c_ * dldl / wvno;
+        sub_dcdr[m] = (c_ / wvno) * (dldr + xlamb[m] * dldl / lrho[m] + xmu[m] * dldm / lrho[m]);
+      }
       if (m_abs(auz) + m_abs(aur) - R(1.0e-15f) <= R(0)) { early = true; break; }  // -> 7002
     }
     if (m > lm) m = lm;
@@ -845,6 +865,20 @@ struct Solver {
       sumi1 = R((xlamb[m] + R(2) * xmu[m]) * dmmr + xmu[m] * dmmz + sumi1);
       sumi2 = R(xmu[m] * dzsr - xlamb[m] * drsz + sumi2);
       sumi3 = R((xlamb[m] + R(2) * xmu[m]) * smmz + xmu[m] * smmr + sumi3);
+      if (want_partials) {  // surfa.f:1179-1185 (half-space), 1202-1208 (normalisation by dL/dk)
+        D dldr = omegsq * (dmmr + dmmz);
+        D dldm = -wvnosq * (R(2) * dmmr + dmmz) - R(2) * wvno * dzsr - (R(2) * smmz + smmr);
+        D dldl = -wvnosq * dmmr + R(2) * wvno * drsz - smmz;
+        sub_dcda[m] = R(2) * lrho[m] * la[m] * c_ * dldl / wvno;
+        sub_dcdb[m] = R(2) * lrho[m] * lb[m] * c_ * (dldm - R(2) * dldl) / wvno;
+        sub_dcdr[m] = (c_ / wvno) * (dldr + xlamb[m] * dldl / lrho[m] + xmu[m] * dldm / lrho[m]);
+        const D dldk = -R(2) * (wvno * sumi1 + sumi2);
+        p_dcda.assign(lm_orig + 1, 0.0); p_dcdb.assign(lm_orig + 1, 0.0); p_dcdr.assign(lm_orig + 1, 0.0);
+        const int first = (lb[1] <= R(0)) ? 2 : 1;
+        for (int q = first; q <= m; ++q) {
+          p_dcda[orig[q]] += sub_dcda[q] / dldk; p_dcdb[orig[q]] += sub_dcdb[q] / dldk; p_dcdr[orig[q]] += sub_dcdr[q] / dldk;
+        }
+      }
     }
     ugr_out = (wvno * sumi1 + sumi2) / (omega * sumi0);  // surfa.f:1186
     R wvar = (-sumi2 + m_sqrt(m_abs(sumi2 * sumi2 - sumi1 * (sumi3 - omegsq * sumi0)))) / sumi1;
@@ -963,6 +997,10 @@ struct Solver {
         else reigen(R(t[lip]), c[iq][lip], ratio[iq][lip], u, cv);
         ugr[iq][lip] = u;
         cvar[iq][lip] = cv;
+        if (want_partials && ifunc == 2 && iq == 1) {
+          if ((int)all_dcda.size() < kmax + 1) { all_dcda.resize(kmax + 1); all_dcdb.resize(kmax + 1); all_dcdr.resize(kmax + 1); }
+          all_dcda[lip] = p_dcda; all_dcdb[lip] = p_dcdb; all_dcdr[lip] = p_dcdr;
+        }
       }
     }
     return status;
@@ -1007,6 +1045,29 @@ int dispatch(const OracleOpts& o, int kind, int n, const double* a, const double
 }
 
 }  // namespace
+
+// Rayleigh phase-velocity partial derivatives of the fundamental mode (REIGEN, surfa.f:1130-1135, 1179-1185, 1202-1208):
+// dcda, dcdb, dcdr [nper][n] with respect to Vp, Vs, density of every layer of the period's (attenuation-corrected,
+// flattened) model; rows of periods without a root are zero.  Returns the oracle status.
+template <typename RM, typename R>
+static int partials_one(const OracleOpts& o, int n, const double* a, const double* b, const double* rho, const double* d,
+                        const double* qs, int nper, const double* per, double* c_out, double* dcda, double* dcdb, double* dcdr) {
+  Solver<RM, R> s;
+  s.o = o;
+  s.want_partials = true;
+  const int st = s.run(2, n, a, b, rho, d, qs, nper, per);
+  for (int k = 1; k <= nper; ++k) {
+    const bool ok = k <= s.imax[1];
+    if (c_out) c_out[k - 1] = ok ? (double)s.c[1][k] : 0.0;
+    for (int i = 1; i <= n; ++i) {
+      const bool have = ok && k < (int)s.all_dcda.size() && i < (int)s.all_dcda[k].size();
+      dcda[(size_t)(k - 1) * n + i - 1] = have ? s.all_dcda[k][i] : 0.0;
+      dcdb[(size_t)(k - 1) * n + i - 1] = have ? s.all_dcdb[k][i] : 0.0;
+      dcdr[(size_t)(k - 1) * n + i - 1] = have ? s.all_dcdr[k][i] : 0.0;
+    }
+  }
+  return st;
+}
 
 extern "C" {
 
@@ -1064,6 +1125,16 @@ int surfdisp_oracle_batch(const OracleOpts* o, int kind, int M, int lmax, const 
     }
   }
   return 0;
+}
+
+
+int surfdisp_oracle_partials(const OracleOpts* o, int n, const double* a, const double* b, const double* rho, const double* d,
+                             const double* qs, int nper, const double* per, double* c_out, double* dcda, double* dcdb,
+                             double* dcdr) {
+  if (!o || n < 2 || nper < 1 || !dcda || !dcdb || !dcdr) return -1;
+  if (o->precision == 0) return partials_one<float, float>(*o, n, a, b, rho, d, qs, nper, per, c_out, dcda, dcdb, dcdr);
+  if (o->precision == 1) return partials_one<float, double>(*o, n, a, b, rho, d, qs, nper, per, c_out, dcda, dcdb, dcdr);
+  return partials_one<double, double>(*o, n, a, b, rho, d, qs, nper, per, c_out, dcda, dcdb, dcdr);
 }
 
 }  // extern "C"

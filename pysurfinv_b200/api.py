@@ -66,6 +66,9 @@ def load_library():
     L.surfdisp_batch_hinted.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, fp, vp,
                                         vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.surfdisp_batch_hinted.restype = C.c_int
+    L.surfdisp_partials_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, vp, vp, C.c_int, fp, vp, vp, vp, vp, vp, vp,
+                                          vp, C.c_size_t, vp]
+    L.surfdisp_partials_batch.restype = C.c_int
     L.surfdisp_misfit_batch.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, fp, fp, C.POINTER(C.c_ubyte), fp, vp, vp]
     L.surfdisp_misfit_batch.restype = C.c_int
     L.surfdisp_host_batch.argtypes = [C.POINTER(SurfdispOpts), C.c_int, C.c_int, C.c_int, C.c_int, ip, fp,
@@ -206,6 +209,28 @@ class DispersionSolver:
                 rc = self.lib.surfdisp_batch_profiled(*args, ms)
                 kernel_ms[:] = [float(x) for x in ms]
         _check(rc, "surfdisp_batch")
+        return out
+
+    def partials(self, layers, nlay, periods):
+        """Rayleigh phase velocities and REIGEN's partial derivatives (surfa.f:1130-1135, 1179-1185, 1202-1208): dict of
+        device tensors c [M, K], dcda / dcdb / dcdr [M, K, Lmax] (with respect to Vp, Vs, density of the layers of each
+        period's attenuation-corrected, flattened model), nfound, flags."""
+        torch = self.torch
+        per = np.ascontiguousarray(periods, dtype=np.float32)
+        M, lmax, K = int(layers.shape[1]), int(layers.shape[2]), int(per.size)
+        out = dict(c=torch.empty((M, K), dtype=torch.float32, device=self.device),
+                   nfound=torch.empty(M, dtype=torch.int32, device=self.device), flags=torch.empty(M, dtype=torch.int32, device=self.device))
+        for k in ("dcda", "dcdb", "dcdr"):
+            out[k] = torch.empty((M, K, lmax), dtype=torch.float32, device=self.device)
+        if M == 0:
+            return out
+        ws = self.workspace(M, lmax, K)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.surfdisp_partials_batch(C.byref(self.opts), M, lmax, nlay.data_ptr(), layers.data_ptr(), K, _fptr(per),
+                                                  out["c"].data_ptr(), out["dcda"].data_ptr(), out["dcdb"].data_ptr(), out["dcdr"].data_ptr(),
+                                                  out["nfound"].data_ptr(), out["flags"].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _check(rc, "surfdisp_partials_batch")
         return out
 
     def counters(self):

@@ -1260,6 +1260,164 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
   return (float)(((double)wvno * s1 + s2) / ((double)omega * s0));  // surfa.f:1186
 }
 
+// ----------------------------------------------------------------------------------------------
+// Partial derivatives of the Rayleigh phase velocity with respect to Vp, Vs and density of every layer of the
+// period's model (REIGEN's dcda, dcdb, dcdr: surfa.f:1130-1135 per (sub-)layer, 1179-1185 for the half-space,
+// 1202-1208 normalisation by dL/dk) -- what the reference computes along with the group velocity and never hands
+// out; they replace the 2n + 1 forward solves of the finite-difference SensKernelPert (senskernel.py:130-158).
+// Two integrations with the re-orthogonalisation schedule of reigen_thread2: the first one yields the surface
+// combination (xnorm, bb) and the total of the re-orthogonalisation coefficients; in the second one the
+// eigenfunction is known in every segment, (x_seg y + z) / bb with x_seg = xnorm - (alpha_total - alpha_so_far), so
+// the Boole integrals of the layer are formed from the eigenfunction itself.
+// out_da / out_db / out_dr: [n] entries with stride `os` (zero where the layer is below the truncation or liquid).
+// Returns false when the half-space is degenerate (rb = 0, surfa.f:1165).
+SD_HD bool reigen_partials_thread(const ModelView& mv, float T, float c, float ratio, float fact, float* out_da,
+                                  float* out_db, float* out_dr, int os) {
+  const int n = mv.n;
+  for (int j = 0; j < n; ++j) { out_da[j * os] = 0.f; out_db[j * os] = 0.f; out_dr[j * os] = 0.f; }
+  const DropResult dr = eigen_drop(mv, c, T, fact, true);
+  const float wvno = SD_DIV(SD_TWOPI, SD_MUL(c, T));
+  const float wvnosq = SD_MUL(wvno, wvno);
+  const float omega = SD_DIV(SD_TWOPI, T);
+  const float omegsq = SD_MUL(omega, omega);
+  const bool water = !(mv.at(C_BREF, 0) > 0.f);
+  double w1 = 0.0, w2 = 0.0;     // water-layer parts of I1, I2 (surfa.f:879-910)
+  if (water) {
+    float a1, b1;
+    mv.ab(0, a1, b1);
+    const float rho1 = mv.rho(0), d1 = mv.dsub(0);
+    const float xl1 = rho1 * (a1 * a1 - 2.f * b1 * b1);
+    const float ra = c / a1, x = ra * ra - 1.f, mag = wvno * sqrtf(fabsf(x));
+    if (mag > 1.0e-35f) {
+      float sin2ra, cosra, rab1;
+      if (x >= 0.f) { sin2ra = sinf(2.f * mag * d1) / (4.f * mag); cosra = cosf(mag * d1); rab1 = mag * mag; }
+      else {
+        const float e2 = expf(2.f * mag * d1), e1 = expf(mag * d1);
+        sin2ra = (0.5f * (e2 - 1.f / e2)) / (4.f * mag); cosra = 0.5f * (e1 + 1.f / e1); rab1 = -(mag * mag);
+      }
+      const float cos2rm = 1.f / (cosra * cosra);
+      const float fac3 = wvno * (0.5f * d1 - sin2ra) * cos2rm, fac2 = wvno * fac3 / rab1;
+      w1 = xl1 * fac2; w2 = xl1 * fac3;
+    }
+  }
+  float ah, bh;
+  mv.ab(dr.jh, ah, bh);
+  const float rhoh = mv.rho(dr.jh);
+  const float cova = SD_DIV(c, ah), covb = SD_DIV(c, bh);
+  const float gam = SD_DIV(2.f, SD_MUL(covb, covb)), gamm1 = SD_SUB(gam, 1.f);
+  const float ra = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(cova, cova), 1.f))));
+  const float rb = SD_MUL(wvno, sqrtf(fabsf(SD_SUB(SD_MUL(covb, covb), 1.f))));
+  const float det = SD_SUB(wvnosq, SD_MUL(ra, rb));
+  const float hh = SD_MUL(rhoh, omegsq);
+  const float brkt = SD_ADD(SD_MUL(-gamm1, wvno), SD_DIV(SD_MUL(SD_MUL(gam, ra), rb), wvno));
+  const double y0tz = (double)SD_DIV(SD_MUL(-hh, brkt), det), y0tr = (double)SD_DIV(SD_MUL(-hh, ra), det);
+  const double z0tz = (double)SD_DIV(SD_MUL(-hh, rb), det), z0tr = y0tz;
+  if (rb == 0.f) return false;
+  const int jfirst = water ? 1 : 0;
+  const double dk = (double)wvno, dk2 = (double)wvnosq, dom2 = (double)omegsq;
+  constexpr int kOrthEvery = 8;
+  constexpr double W7 = 7.0 / 32.0, W12 = 12.0 / 32.0;
+  double xnorm = 0.0, bb = 1.0, alpha_total = 0.0, sumi1 = w1, sumi2 = w2;
+  for (int pass = 0; pass < 2; ++pass) {
+    double yur = 1.0, yuz = 0.0, ytz = y0tz, ytr = y0tr;
+    double zur = 0.0, zuz = 1.0, ztz = z0tz, ztr = z0tr;
+    double alpha_sofar = 0.0;
+    int since = 0;
+    for (int j = dr.jlast; j >= jfirst; --j) {
+      const int ns = (j == dr.jlast) ? dr.nlast : mv.nsub(j);
+      const LayerF L = reigen_layer_setup(mv, j, ns, wvno, wvnosq, omegsq);
+      if (L.ns <= 0) continue;
+      const StepMat2 sm = make_stepmat2(L);
+      const double xs = xnorm - (alpha_total - alpha_sofar), ib = 1.0 / bb;
+      double Err = 0, Ezz = 0, Eztr = 0, Ertz = 0, Etrtr = 0, Etztz = 0;   // Boole sums (weights / 32) of the eigenfunction products
+      for (int sub = 0; sub < L.ns; ++sub) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int kk = 0; kk < 5; ++kk) {
+          if (pass == 1) {
+            const double w = (kk == 0 || kk == 4) ? W7 : ((kk == 2) ? W12 : 1.0);
+            const double eur = (xs * yur + zur) * ib, euz = (xs * yuz + zuz) * ib, etz = (xs * ytz + ztz) * ib, etr = (xs * ytr + ztr) * ib;
+            Err += w * eur * eur; Ezz += w * euz * euz; Eztr += w * euz * etr; Ertz += w * eur * etz;
+            Etrtr += w * etr * etr; Etztz += w * etz * etz;
+          }
+          if (kk < 4) { rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr); }
+        }
+      }
+      if (pass == 1) {
+        // integrals of the layer (surfa.f:1100-1129) from the raw sums; ur' = tr / mu - k uz, uz' = (tz + k lambda ur) / (lambda + 2 mu)
+        const double qw = (double)L.qw, mu = (double)L.mu, lam = (double)L.lam, f12 = (double)L.f12, f34 = (double)L.f34;
+        const double dmmr = qw * Err, dmmz = qw * Ezz;
+        const double smmr = qw * (f34 * f34 * Etrtr - 2.0 * f34 * dk * Eztr + dk2 * Ezz);
+        const double smmz = qw * f12 * f12 * (Etztz + 2.0 * dk * lam * Ertz + dk2 * lam * lam * Err);
+        const double drsz = qw * f12 * (Ertz + dk * lam * Err);
+        const double dzsr = qw * (f34 * Eztr - dk * Ezz);
+        sumi1 += (lam + 2.0 * mu) * dmmr + mu * dmmz;
+        sumi2 += mu * dzsr - lam * drsz;
+        const double dldl = -dk2 * dmmr + 2.0 * dk * drsz - smmz;
+        const double dldm = -dk2 * (2.0 * dmmr + dmmz) - 2.0 * dk * dzsr - (2.0 * smmz + smmr);
+        const double dldr = dom2 * (dmmr + dmmz);
+        float a, b;
+        mv.ab(j, a, b);
+        const double rho = (double)L.rho;
+        out_db[j * os] = (float)(2.0 * rho * (double)b * (double)c * (dldm - 2.0 * dldl) / dk);      // surfa.f:1133-1135 (un-normalised)
+        out_da[j * os] = (float)(2.0 * rho * (double)a * (double)c * dldl / dk);
+        out_dr[j * os] = (float)(((double)c / dk) * (dldr + lam * dldl / rho + mu * dldm / rho));
+      }
+      if (++since >= kOrthEvery && j > jfirst) {
+        since = 0;
+        const double syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
+        const double syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
+        const double al = syz / syy;
+        zur = fma(-al, yur, zur); zuz = fma(-al, yuz, zuz); ztz = fma(-al, ytz, ztz); ztr = fma(-al, ytr, ztr);
+        alpha_sofar += al;
+      }
+    }
+    if (pass == 0) {
+      alpha_total = alpha_sofar;
+      const double aa = zur - (double)ratio * zuz;
+      double b_ = (double)ratio * yuz - yur;
+      if (fabs(b_) < 1.e-10) b_ = copysign(1.e-10, b_);
+      xnorm = aa / b_;
+      bb = xnorm * yuz + zuz;
+      if (fabs(bb) < 1.e-10) bb = copysign(1.e-10, bb);
+    }
+  }
+  // half-space (surfa.f:1145-1185): amplitudes at its top from the start vectors
+  {
+    const double xo = xnorm - alpha_total;
+    double aur = (xo * 1.0 + 0.0) / bb, auz = (xo * 0.0 + 1.0) / bb;
+    if (water && dr.jh == 1) { aur = ratio; auz = 1.0; }
+    const double dra = ra, drb = rb, ddet = det, drho = rhoh;
+    const double xmu = (double)SD_MUL(SD_MUL(rhoh, bh), bh);
+    const double xlamb = (double)SD_MUL(rhoh, SD_SUB(SD_MUL(ah, ah), SD_MUL(SD_MUL(2.f, bh), bh)));
+    const double ap = -drho * (dk * aur + drb * auz) / ddet;
+    const double bp = -drho * (-dra * aur / dk - auz) / ddet;
+    const double a1 = -dk * ap / drho, a2 = -dk * drb * bp / drho, a3 = dra * ap / drho, a4 = dk2 * bp / drho;
+    const double dmmr = a1 * a1 / (2. * dra) + 2. * a1 * a2 / (dra + drb) + a2 * a2 / (2. * drb);
+    const double dmmz = a3 * a3 / (2. * dra) + 2. * a3 * a4 / (dra + drb) + a4 * a4 / (2. * drb);
+    const double smmz = dra * a3 * a3 / 2. + 2. * dra * drb * a3 * a4 / (dra + drb) + drb * a4 * a4 / 2.;
+    const double smmr = dra * a1 * a1 / 2. + 2. * dra * drb * a1 * a2 / (dra + drb) + drb * a2 * a2 / 2.;
+    const double drsz = -a1 * a3 / 2. - (a1 * a4 * drb + a2 * a3 * dra) / (dra + drb) - a2 * a4 / 2.;
+    const double dzsr = -a1 * a3 / 2. - (a1 * a4 * dra + a2 * a3 * drb) / (dra + drb) - a2 * a4 / 2.;
+    sumi1 += (xlamb + 2. * xmu) * dmmr + xmu * dmmz;
+    sumi2 += xmu * dzsr - xlamb * drsz;
+    const double dldr = dom2 * (dmmr + dmmz);
+    const double dldm = -dk2 * (2. * dmmr + dmmz) - 2. * dk * dzsr - (2. * smmz + smmr);
+    const double dldl = -dk2 * dmmr + 2. * dk * drsz - smmz;
+    out_da[dr.jh * os] = (float)(2. * drho * (double)ah * (double)c * dldl / dk);
+    out_db[dr.jh * os] = (float)(2. * drho * (double)bh * (double)c * (dldm - 2. * dldl) / dk);
+    out_dr[dr.jh * os] = (float)(((double)c / dk) * (dldr + xlamb * dldl / drho + xmu * dldm / drho));
+  }
+  const double idldk = 1.0 / (-2.0 * (dk * sumi1 + sumi2));      // surfa.f:1203
+  for (int j = jfirst; j <= dr.jh; ++j) {
+    out_da[j * os] = (float)((double)out_da[j * os] * idldk);
+    out_db[j * os] = (float)((double)out_db[j * os] * idldk);
+    out_dr[j * os] = (float)((double)out_dr[j * os] * idldk);
+  }
+  return true;
+}
+
 // Love group velocity (LEIGEN, surfa.f:374-606), float32 like the reference.
 SD_HD float leigen_thread(const ModelView& mv, float T, float c, float fact, unsigned long long& nsubsteps) {
   const DropResult dr = eigen_drop(mv, c, T, (fact <= 0.f) ? 7.0f : fact, false);

@@ -1014,6 +1014,62 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
   if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(&p.counters[2], nsub);
 }
 
+// ------------------------------------------------------------------------------------ partial derivatives
+// Thread per (model, period) like phase 2: REIGEN's dcda / dcdb / dcdr (surfa.f:1130-1135, 1179-1185, 1202-1208).
+struct PdParams {
+  int M, lpad, K, mpb, lmax;
+  const int* nlay;
+  const float* consts;
+  const float* c_in;
+  const float* ratio_in;
+  const int* nfound;
+  float *dcda, *dcdb, *dcdr;     // [M][K][lmax]
+  float fact;
+  int atten, ndiv, ndiv_cap;
+  PeriodTab tab;
+};
+
+__global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) partials_kernel(const __grid_constant__ PdParams p) {
+  extern __shared__ float4 smem[];
+  float* sc = reinterpret_cast<float*>(smem);
+  const int K = p.K;
+  const int model0 = blockIdx.x * p.mpb;
+  const int nmod = min(p.mpb, p.M - model0);
+  const int per_model = NCONST * p.lpad;
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.consts + (size_t)model0 * per_model);
+    const int n4 = nmod * per_model / 4, l4 = p.lpad / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = src[i];
+      const int ml = i / (NCONST * l4), r = i - ml * (NCONST * l4), comp = r / l4, lay = (r - comp * l4) * 4;
+      float* dst = sc + (size_t)ml * (per_model + NCONST) + (size_t)lay * NCONST + comp;
+      dst[0] = v.x; dst[NCONST] = v.y; dst[2 * NCONST] = v.z; dst[3 * NCONST] = v.w;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nmod * K; t += blockDim.x) {
+    const int k = t / nmod, ml = t - k * nmod;
+    const int model = model0 + ml;
+    const size_t o = ((size_t)model * K + k) * p.lmax;
+    const int n = p.nlay[model];
+    bool done = false;
+    if (k < p.nfound[model] && n >= 2 && n <= p.lmax) {
+      ModelView mv;
+      mv.cst = sc + (size_t)ml * (per_model + NCONST);
+      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
+      int ndiv = p.ndiv;
+      const int ivre = p.ndiv_cap / (n - 1);
+      if (ndiv > ivre) ndiv = ivre;
+      mv.ndiv = ndiv;
+      mv.jj0 = (mv.at(C_BREF, 0) <= 0.1e-10f) ? 1 : 0;
+      done = reigen_partials_thread(mv, p.tab.per[k], p.c_in[(size_t)model * K + k], p.ratio_in[(size_t)model * K + k], p.fact,
+                                    p.dcda + o, p.dcdb + o, p.dcdr + o, 1);
+      for (int j = n; j < p.lmax; ++j) { p.dcda[o + j] = 0.f; p.dcdb[o + j] = 0.f; p.dcdr[o + j] = 0.f; }
+    }
+    if (!done) for (int j = 0; j < p.lmax; ++j) { p.dcda[o + j] = 0.f; p.dcdb[o + j] = 0.f; p.dcdr[o + j] = 0.f; }
+  }
+}
+
 // ------------------------------------------------------------------------------------ misfit
 struct MisfitParams {
   int mode, M, K, ncount;
@@ -1370,6 +1426,40 @@ static int check_template(const SurfdispStackTemplate* tmpl) {
     if ((G.kind == SURFDISP_G_LINEAR && G.ncoef < 2) || ((G.kind == SURFDISP_G_CONST || G.kind == SURFDISP_G_BSPLINE) && G.ncoef < 1)) return SURFDISP_EINVAL;
     for (int i = 0; i < G.ncoef; ++i) if (G.v_param[i] >= tmpl->nparams) return SURFDISP_EINVAL;
   }
+  return 0;
+}
+
+int surfdisp_partials_batch(const SurfdispOpts* opts, int n_models, int n_layers_max, const int* n_layers, const float* layers,
+                            int n_periods, const float* periods, float* c_out, float* dcda, float* dcdb, float* dcdr,
+                            int* nfound, int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dcda || !dcdb || !dcdr) return SURFDISP_EINVAL;
+  Plan pl;
+  int rc = make_plan(pl, opts, SURFDISP_KIND_RAYLEIGH, n_models, n_layers_max, n_layers, layers, n_periods, periods, c_out, nullptr,
+                     nfound, flags, workspace, workspace_bytes);
+  if (rc || n_models == 0) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(workspace, 0, kHdrBytes, st));
+  if ((rc = stage_prep(pl, 0, n_models, st))) return rc;
+  const int ks = k_split(pl);
+  if ((rc = stage_p1(pl, 0, n_models, 0, ks, st))) return rc;
+  if ((rc = stage_p1(pl, 0, n_models, ks, n_periods, st))) return rc;
+  PdParams pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.M = n_models; pd.lpad = pl.w.lpad; pd.K = pl.K; pd.lmax = pl.lmax; pd.nlay = pl.nlay; pd.consts = pl.consts; pd.c_in = pl.c_out;
+  pd.ratio_in = pl.ratio; pd.nfound = pl.nfound; pd.dcda = dcda; pd.dcdb = dcdb; pd.dcdr = dcdr; pd.fact = pl.o.fact;
+  pd.atten = pl.o.atten; pd.ndiv = pl.o.ndiv; pd.ndiv_cap = pl.o.ndiv_cap_rayleigh; pd.tab = pl.tab;
+  const size_t per_model = (size_t)NCONST * (pl.w.lpad + 1) * sizeof(float);
+  if (per_model > 200 * 1024) return SURFDISP_EINVAL;
+  int mpb = (int)((96 * 1024) / per_model);
+  if (mpb < 1) mpb = 1;
+  if (mpb * pl.K > P2_THREADS) mpb = P2_THREADS / pl.K < 1 ? 1 : P2_THREADS / pl.K;
+  pd.mpb = mpb;
+  int threads = round_up(mpb * pl.K, 32);
+  if (threads > P2_THREADS) threads = P2_THREADS;
+  const size_t smem = mpb * per_model;
+  CK(cudaFuncSetAttribute(partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  partials_kernel<<<(n_models + mpb - 1) / mpb, threads, smem, st>>>(pd);
+  CK(cudaGetLastError());
   return 0;
 }
 

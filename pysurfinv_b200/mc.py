@@ -82,7 +82,7 @@ class ChainEnsemble:
         self.misfit_mode, self.kind, self.chain_length = int(misfit_mode), int(kind), int(chain_length)
         self.lmax = int(lmax) if lmax is not None else template.max_layers()
         dev = solver.device
-        bc = lambda x, dt: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), (self.n_points, K)))
+        bc = lambda x, dt: np.array(np.broadcast_to(np.asarray(x, dtype=dt), (self.n_points, K)))   # (writable copies)
         self.obs, self.sigma = bc(obs, np.float32), bc(sigma, np.float32)
         self.mask = None if mask is None else bc(mask, np.uint8)
         use = np.ones((self.n_points, K), np.uint8) if mask is None else (self.mask != 0).astype(np.uint8)

@@ -427,6 +427,26 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   return nfound;
 }
 
+// Partial derivatives of REIGEN for one model (the device function compiled for the host): dcda / dcdb / dcdr [K][n]
+// given the phase velocities and ellipticities of hm_forward.
+void hm_partials(int n, const float* a, const float* b, const float* rho, const float* d, const float* qs, int K,
+                 const float* per, const float* c, const float* ratio, float t_base, int atten, int flatten, int ndiv0,
+                 int ndiv_cap, float fact, float* dcda, float* dcdb, float* dcdr) {
+  std::vector<float> cst((size_t)NCONST * n);
+  prep_model(n, 2, flatten, a, b, rho, d, qs, cst.data(), n);
+  for (int k = 0; k < K; ++k) {
+    ModelView mv;
+    mv.cst = cst.data(); mv.sc = n; mv.sl = 1; mv.n = n; mv.atten = atten; mv.lt = logf(t_base / per[k]);
+    int ndiv = ndiv0;
+    const int ivre = ndiv_cap / (n - 1);
+    if (ndiv > ivre) ndiv = ivre;
+    mv.ndiv = ndiv;
+    mv.jj0 = (cst[C_BREF * n + 0] <= 0.1e-10f) ? 1 : 0;
+    if (c[k] > 0.f) reigen_partials_thread(mv, per[k], c[k], ratio[k], fact, dcda + (size_t)k * n, dcdb + (size_t)k * n, dcdr + (size_t)k * n, 1);
+    else for (int j = 0; j < n; ++j) { dcda[(size_t)k * n + j] = 0; dcdb[(size_t)k * n + j] = 0; dcdr[(size_t)k * n + j] = 0; }
+  }
+}
+
 // Bit-for-bit comparison of the glibc logf / powf restatement (sd_libm.cuh) with the host libm over every
 // float in [lo, hi).  out = {count, logf mismatches, powf(x, 2.275) mismatches, powf(x, 5) mismatches}.
 void hm_libm_check(float lo, float hi, long long* out) {

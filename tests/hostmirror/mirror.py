@@ -23,8 +23,22 @@ def lib():
                                  C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp,
                                  C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong)]
         L.hm_forward.restype = C.c_int
+        L.hm_partials.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_int, fp, fp, fp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_float, fp, fp, fp]
+        L.hm_partials.restype = None
         _LIB = L
     return _LIB
+
+
+def partials(vp, vs, rho, h, qsinv, periods, c, ratio, ndiv=5, ndiv_cap=99):
+    """REIGEN partial derivatives of the kernels' per-lane code (host build): dcda, dcdb, dcdr [K, n]."""
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
+    a, b, r, d, q, per, cc, rt = f(vp), f(vs), f(rho), f(h), f(qsinv), f(periods), f(c), f(ratio)
+    K, n = len(per), len(b)
+    out = [np.zeros((K, n), np.float32) for _ in range(3)]
+    p = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    lib().hm_partials(n, p(a), p(b), p(r), p(d), p(q), K, p(per), p(cc), p(rt), 1.0, 1, 1, ndiv, ndiv_cap, 4.0, p(out[0]), p(out[1]), p(out[2]))
+    return dict(dcda=out[0], dcdb=out[1], dcdr=out[2])
 
 
 def forward(kind, vp, vs, rho, h, qsinv, periods, G=4, stale=1, ndiv=5, ndiv_cap=None, exact_scan=0):
