@@ -41,7 +41,7 @@ F_U_EXEC = 492.0
 # DRAM bytes per model of the root-search launches and of the group-velocity launch (ncu dram__bytes_read + write at
 # 524288 models x 40 periods, profiles/r2_ncu_*.txt); algorithmic bytes per model: phase 1 reads the constants
 # 8 x lpad x 4 B at the first period and once more at the start of the later periods and writes c, ratio
-DRAM_P1_PER_MODEL, DRAM_P2_PER_MODEL = 5250.0, 3066.0
+DRAM_P1_PER_MODEL, DRAM_P2_PER_MODEL = 5965.0, 3063.0
 WORKLOAD_SWEEP = "config2: batched forward sweep, %d random 77-layer sediment+crust+mantle models x %d periods 8-80 s per GPU, Rayleigh phase+group"
 
 
@@ -551,6 +551,14 @@ def main():
             FS.fast_surf(77, 2, lay1[0], lay1[1], lay1[2], lay1[3], lay1[4], per200, 18)
         single = {"us_per_call": (time.perf_counter() - t0) / 50 * 1e6, "layers": 77, "periods": 18,
                   "call": "fast_surf.fast_surf -> fast_surf_ (per-thread device context kept between calls)"}
+        if not args.no_cpu:     # the same single-model call on one host core (oracle port; cpu_baseline leg)
+            from oracle import oracle as O
+            f32 = lambda x: x.astype(np.float32).astype(np.float64)
+            O.forward(2, f32(lay1[0]), f32(lay1[1]), f32(lay1[2]), f32(lay1[3]), f32(lay1[4]), MC_PERIODS[1:], opts=O.make_opts(precision=0))
+            t0 = time.perf_counter()
+            for _ in range(10):
+                O.forward(2, f32(lay1[0]), f32(lay1[1]), f32(lay1[2]), f32(lay1[3]), f32(lay1[4]), MC_PERIODS[1:], opts=O.make_opts(precision=0))
+            single["cpu_port_us_per_call"] = (time.perf_counter() - t0) / 10 * 1e6
 
     if rank == 0:
         flop_p1 = steps_ctr * F_R
