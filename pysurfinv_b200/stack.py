@@ -7,8 +7,9 @@ numeric entry written as a Brownian spec -- ``[v, 'abs'|'abs_pos'|'rel'|'rel_pos
 ``[v, vmin, vmax, step]`` (layers.py:583-598) -- becomes one free parameter; the parameter order is the order
 of ``MCinv._brownians`` (models.py:227-240), i.e. the column order of ``mcTrack`` rows (point.py:57,73).
 Supported layer types: Sediment, Crust, Mantle/OceanMantle, OceanWater, OceanSediment, OceanCrust,
-OceanSedimentCascadia, ReferenceMantle (also through ``Info.refLayer``).  Parameters of a layer the builder does
-not implement (Crust 'Gauss', OceanMantle 'deg', the thermal OceanMantleHybrid) raise instead of being ignored.
+OceanSedimentCascadia, OceanMantleHybrid (the thermal mantle, 'Ritzwoller' conversion), ReferenceMantle (also
+through ``Info.refLayer``).  Parameters of a layer the builder does not implement (Crust 'Gauss', OceanMantle
+'deg', other thermal conversions) raise instead of being ignored.
 """
 import ctypes as C
 
@@ -218,10 +219,27 @@ class StackTemplate:
         return (np.array([p.vmin for p in self.params], np.float32), np.array([p.vmax for p in self.params], np.float32),
                 np.array([p.step for p in self.params], np.float32))
 
-    def max_layers(self):
-        n = 0
+    def max_layers(self, lo=None, hi=None):
+        """Upper bound of the layer count over the parameter box [lo, hi] (default: the template's own bounds).
+        The fine-layer rules grow with the group thickness, so the bound follows from the largest thickness each
+        group can take: the array stride of the stacks and the shared-memory record of the root search are sized
+        by it (a loose bound halves the resident CTAs of phase 1).  A stack that still overflows it is flagged by
+        the builder (status < 0), never truncated."""
+        tlo, thi, _ = self.bounds() if self.params else (np.zeros(0), np.zeros(0), None)
+        lo = tlo if lo is None else np.asarray(lo, np.float64).reshape(-1, self.nparams).min(axis=0)
+        hi = thi if hi is None else np.asarray(hi, np.float64).reshape(-1, self.nparams).max(axis=0)
+        n, zlo, zhi, have = 0, -max(self.topo, 0.0), -max(self.topo, 0.0), False   # (models.py:76-77)
         for g in self.groups:
-            n += {N_FIXED: g.nfine, N_CRUST: 60, N_OCRUST: 10}[g.nfine_rule]
+            h_lo, h_hi = (float(lo[g.h_param]), float(hi[g.h_param])) if g.h_param >= 0 else (g.h_fixed, g.h_fixed)
+            if g.h_mode == 1 and have:     # BottomDepth: what is left under the groups above
+                h_lo, h_hi = max(h_lo - zhi, 0.0), max(h_hi - zlo, 0.0)
+            if g.nfine_rule == N_CRUST:
+                n += 60 if h_hi >= 150.0 else 30 if h_hi > 60.0 else 15 if h_hi > 20.0 else 10 if h_hi > 10.0 else 5
+            elif g.nfine_rule == N_OCRUST:
+                n += min(max(int(np.rint(h_hi / 2.0)), 2), 10)
+            else:
+                n += g.nfine
+            zlo, zhi, have = zlo + max(h_lo, 0.0), zhi + max(h_hi, 0.0), True
         return n
 
 

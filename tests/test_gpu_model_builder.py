@@ -139,7 +139,7 @@ def test_thermal_mantle_group_matches_reference_classes(solver):
         bad = int(solver.check_priors(t, none).cpu()[0]) & S.PRIOR_OCEAN
         assert (bad == 0) == c["isgood"]
     t = S.StackTemplate(THERMAL, prior_mask=S.PRIOR_OCEAN)
-    assert t.nparams == 6 and t.max_layers() == 92
+    assert t.nparams == 6 and t.max_layers() == 86
     params = _random_params(t, 400, 17)
     _compare(solver, t, params, t.max_layers())
     got = solver.check_priors(t, torch.from_numpy(params).cuda()).cpu().numpy() & S.PRIOR_OCEAN

@@ -47,7 +47,7 @@ def test_template_parameter_order_and_bounds():
     lo, hi, step = t.bounds()
     assert np.allclose(lo[:3], [0.5, 0.8, 20.0]) and np.allclose(hi[:3], [3.5, 2.6, 40.0])
     assert np.isclose(lo[3], 3.3 * 0.9) and np.isclose(step[7], 0.3)      # step clamped to half the range (brownian.py:8)
-    assert len(t.groups) == 4 and t.groups[3].kind == S.G_REFMANTLE and t.max_layers() == 1 + 60 + 60 + 20
+    assert len(t.groups) == 4 and t.groups[3].kind == S.G_REFMANTLE and t.max_layers() == 1 + 15 + 60 + 20 and t.max_layers(hi=t.bounds()[1] + 30) == 1 + 30 + 60 + 20
     c = t.to_c()
     assert c.ngroups == 4 and c.nparams == 8 and c.groups[1].v_param[1] == -1 and abs(c.groups[1].v_fixed[3] - 3.9) < 1e-12
     lay, nl = MB.build_stacks(t, t.start_values()[None, :], 96)
