@@ -110,6 +110,19 @@ SD_HD void prep_model(int n, int kind, int flatten, const float* a, const float*
   }
 }
 
+// Upper bound of every running thickness sum the layer-dropping walks can form (surfa.f:92-106, 854-866: float32
+// additions, in layer order, of the flattened thicknesses of a subset of the layers above the half-space; every
+// addition rounds by at most 2^-24 and sub-layer thicknesses RN(d / ndiv) add up to d (1 + 2^-24) at most, so the
+// real sum with a margin of 1e-4 covers 1600 additions).  A walk whose limit fact*c*T is not below the bound drops
+// nothing; both phases skip it then.  -1 = unknown.  (prep_kernel forms the same sum with a warp reduction.)
+SD_HD float stack_depth_bound(const float* cst, int ld, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n - 1; ++i) { const float d = cst[C_DFL * ld + i]; s += (double)(d > 0.f ? d : 0.f); }
+  if (!(s == s)) return -1.f;
+  float f = (float)(s * 1.0001);
+  return ((double)f < s * 1.00005) ? -1.f : f;   // (never: the conversion rounds by 6e-8)
+}
+
 // Attenuation-corrected, flattened (a, b) of layer i for the period whose log term is lt = ln(t_base/T)
 // (calcul.f:121-127 then flat1 scaling).  as_half selects the half-space flattening factor.
 SD_HD void layer_ab_vals(float ar, float br, float qs, float f, float lt, int atten, float& a, float& b) {
@@ -698,6 +711,7 @@ struct ModelView {
                          // as the prep kernel writes them, or records [layer][8] (sc = 1, sl = 8) as phase 2 stages them
   int n, atten, ndiv, jj0;
   float lt;
+  float dtot = -1.f;     // upper bound of the thickness sums of eigen_drop() (prep_kernel), -1 = unknown
   SD_HD float at(int comp, int j) const { return cst[comp * sc + j * sl]; }
   SD_HD void ab(int j, float& a, float& b) const {
     layer_ab_vals(at(C_AREF, j), at(C_BREF, j), at(C_QS, j), (j == n - 1) ? at(C_HSF, j) : at(C_DIF, j), lt, atten, a, b);
@@ -728,6 +742,8 @@ SD_HD DropResult eigen_drop(const ModelView& mv, float c, float T, float fact, b
   float sum = 0.f;
   const int n = mv.n;
   DropResult r; r.jh = n - 1; r.jlast = n - 2; r.nlast = mv.nsub(n - 2 < 0 ? 0 : n - 2);
+  // the whole stack is thinner than the limit: the walk below would run to the end without a decision
+  if (mv.dtot >= 0.f && mv.dtot <= dmax) return r;
   for (int j = 0; j < n; ++j) {
     const float b = mv.b_only(j);
     if (!(c - b < 0.f)) continue;

@@ -34,7 +34,7 @@ struct PeriodTab {
 };
 
 struct WsLayout {
-  size_t consts_off, ratio_off, mm_off, order_off, bucket_off, total;
+  size_t consts_off, ratio_off, mm_off, order_off, dtot_off, bucket_off, total;
   int lpad;
 };
 constexpr int kOrderBuckets = 1024;   // models are handed out in the order of their top shear velocity (bucket sort)
@@ -50,7 +50,8 @@ WsLayout ws_layout(int M, int lmax, int K) {
   size_t ratio = (size_t)M * K * sizeof(float);
   w.mm_off = w.ratio_off + ((ratio + 255) / 256) * 256;
   w.order_off = w.mm_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
-  w.bucket_off = w.order_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.dtot_off = w.order_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.bucket_off = w.dtot_off + (((size_t)M * sizeof(float) + 255) / 256) * 256;
   w.total = w.bucket_off + 2 * kOrderBuckets * sizeof(int);
   return w;
 }
@@ -72,12 +73,13 @@ int cuda_fail(cudaError_t e, const char* where) {
 __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, int kind, int flatten,
                                                    const int* __restrict__ nlay,
                                                    const float* __restrict__ layers, size_t comp_stride,
-                                                   float* __restrict__ consts) {
+                                                   float* __restrict__ consts, float* __restrict__ dtot) {
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
   const int n = nlay[m];
-  if (n < 2 || n > lmax) return;
+  if (n < 2 || n > lmax) { if (lane == 0) dtot[m] = -1.f; return; }
+  double dsum = 0.0;    // thickness of the flattened stack above the half-space (see below)
   const size_t pl = comp_stride;   // distance between the five input rows (the whole batch, not the launched range)
   const float* a = layers + 0 * pl + (size_t)m * lmax;
   const float* b = layers + 1 * pl + (size_t)m * lmax;
@@ -128,8 +130,15 @@ __global__ void __launch_bounds__(128) prep_kernel(int M, int lmax, int lpad, in
       out[C_AREF * ld + i] = ai; out[C_BREF * ld + i] = bi; out[C_QS * ld + i] = qi;
       out[C_DIF * ld + i] = o_dif; out[C_RHOFL * ld + i] = o_rhofl; out[C_DFL * ld + i] = o_dfl;
       out[C_HSF * ld + i] = o_hsf; out[C_RHOHS * ld + i] = o_rhohs;
+      if (i < n - 1) dsum += (double)fmaxf(o_dfl, 0.f);
     }
   }
+  // Upper bound of every running thickness sum the layer-dropping walks can form (surfa.f:92-106, 854-866: float32
+  // additions of a subset of these thicknesses in layer order; each addition rounds by at most 2^-24, and sub-layer
+  // thicknesses RN(d / ndiv) add up to d (1 + 2^-24) at most).  A walk whose limit fact*c*T is not below it drops
+  // nothing: both phases skip the walk then.  -1 = unknown (NaN thickness).
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if (lane == 0) dtot[m] = (dsum == dsum) ? __double2float_ru(dsum * 1.0001) : -1.f;
 }
 
 // ------------------------------------------------------------------------------------ phase 1
@@ -147,6 +156,7 @@ struct P1Params {
   int atten, stale, exact_scan;
   int k_begin, k_end;   // periods [k_begin, k_end) are done by this launch (the first period runs as a launch of its own)
   int* mm_state;        // layer-dropping depth carried from launch to launch
+  const float* dtot;    // per model: upper bound of the thickness sums of the layer-dropping walk (prep_kernel), -1 = unknown
   const float* hint;    // [M][K] neighbour curves (phase velocities of a nearby model on the same periods) or nullptr
   const int* order;     // order[i] - order_base = i-th model to hand out (nullptr: index order)
   int order_base;
@@ -349,6 +359,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
 
   const float cspan = (float)(1 << ((P - 2) / 2 - 1)) - 0.5f;   // outermost cluster offset in units of the spacing
 
+  // layer dropping for one trial velocity by the lanes of the group; nothing is dropped -- and the walk skipped --
+  // when even the whole stack is thinner than the limit fact*c*T (most periods beyond the first few)
+  auto drop_coop = [&](float c) -> int {
+    const float dt = rec[ld].x;
+    if (dt >= 0.f && dt <= SD_MUL(SD_MUL(p.fact, c), T)) return n;
+    return layer_drop_coop<G>(c, T, p.fact, n, rec, gmask, gl);
+  };
+
   // ---- request builders
   auto build_fast = [&]() {
     // stages 0/1: point 0 = c1 itself, point 1 = half way to the window, points 2..P-1 = cluster / window; an odd
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       }
     }
     pc = make_float2(cc[0], cc[1]);
-    mw = layer_drop_coop<G>(gshfl<G>(gmask, pc.y, G - 1), T, p.fact, n, rec, gmask, gl);
+    mw = drop_coop(gshfl<G>(gmask, pc.y, G - 1));
     meval = mw; ell_only = 0;
   };
   auto build_scan = [&]() {
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     for (int t = 0; t < stride; ++t) cy = SD_ADD(cy, p.dc);
     pc = make_float2(cx, cy);
     const float ctop = gshfl<G>(gmask, pc.y, G - 1);
-    meval = layer_drop_coop<G>(ctop, T, p.fact, n, rec, gmask, gl);
+    meval = drop_coop(ctop);
     own_mj = !(ctop < bmin + 0.3f);
     const bool above_hs = !(ctop < rec[meval - 1].y) || p.exact_scan;
     if (own_mj || above_hs) {
@@ -501,6 +519,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         } else {
           my_models += (gl == 0 && p.k_begin == 0);
           cst = p.consts + (size_t)model * NCONST * p.lpad;
+          // (kept in the padding record of the group's layer records: see drop_coop)
+          if (gl == 0) rec[ld] = make_float4(p.dtot[model], 0.f, 0.f, 0.f);
           // first start velocity, fast_surf.f:157-171
           {
             const float b0 = cst[C_BREF * ld + 0];
@@ -742,7 +762,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           const bool found = gshfl<G>(gmask, (int)(jy ? chy : chx), sl) != 0;
           lo = gshfl<G>(gmask, jy ? pc.x : cpx, sl); hi = gshfl<G>(gmask, jy ? pc.y : pc.x, sl);
           dlo = gshfl<G>(gmask, jy ? pd.x : dpx, sl); dhi = gshfl<G>(gmask, jy ? pd.y : pd.x, sl);
-          mm = layer_drop_coop<G>(hi, T, p.fact, n, rec, gmask, gl);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
+          mm = drop_coop(hi);   // the last DLTAR with idrop=0 leaves COMMON mmax (surfa.f:94-105)
           if (found) {
             // ---- polish inside [lo,hi] (replaces NEVILL, surfa.f:2-83).  The round's points sample one smooth
             // function around the bracket (same truncation depth), so the interpolation rounds of the fast path
@@ -882,7 +902,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         // the reference's bracket is the grid interval around the root; its upper end fixes mmax
         float hg = c1 + (floorf((croot - c1) / p.dc) + 1.f) * p.dc;
         if (!(hg > croot)) hg += p.dc;
-        const int mnew = layer_drop_coop<G>(hg, T, p.fact, n, rec, gmask, gl);
+        const int mnew = drop_coop(hg);
         const float bh1 = rec[mnew - 1].y;
         if (croot > bh1 || (bh1 > croot - 0.021f && bh1 < croot + 0.021f)) interp_failed();   // calcul.f:191 / kink: point-by-point path
         else {
@@ -945,6 +965,7 @@ struct P2Params {
   const float* c_in;
   const float* ratio_in;
   const int* nfound;
+  const float* dtot;
   float* u_out;
   unsigned long long* counters;
   float fact;
@@ -995,7 +1016,7 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
     } else {
       ModelView mv;
       mv.cst = sc + (size_t)ml * (per_model + NCONST);
-      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
+      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k]; mv.dtot = p.dtot[model];
       int ndiv = p.ndiv;
       const int ivre = p.ndiv_cap / (n - 1);
       if (ndiv > ivre) ndiv = ivre;
@@ -1023,6 +1044,7 @@ struct PdParams {
   const float* c_in;
   const float* ratio_in;
   const int* nfound;
+  const float* dtot;
   float *dcda, *dcdb, *dcdr;     // [M][K][lmax]
   float fact;
   int atten, ndiv, ndiv_cap;
@@ -1056,7 +1078,7 @@ __global__ void __launch_bounds__(P2_THREADS, P2_MINBLK) partials_kernel(const _
     if (k < p.nfound[model] && n >= 2 && n <= p.lmax) {
       ModelView mv;
       mv.cst = sc + (size_t)ml * (per_model + NCONST);
-      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k];
+      mv.sc = 1; mv.sl = NCONST; mv.n = n; mv.atten = p.atten; mv.lt = p.tab.lt[k]; mv.dtot = p.dtot[model];
       int ndiv = p.ndiv;
       const int ivre = p.ndiv_cap / (n - 1);
       if (ndiv > ivre) ndiv = ivre;
@@ -1255,6 +1277,7 @@ struct Plan {
   const int* nlay; const float* layers;
   float *c_out, *u_out, *consts, *ratio;
   int *nfound, *flags, *mm_state, *order, *buckets;
+  float* dtot;     // per model: upper bound of the layer-dropping thickness sums (prep_kernel)
   unsigned long long* counters;
   unsigned int* queue;
   const float* hint;
@@ -1281,6 +1304,7 @@ static int make_plan(Plan& pl, const SurfdispOpts* opts, int kind, int n_models,
   pl.ratio = (float*)(ws + pl.w.ratio_off);
   pl.mm_state = (int*)(ws + pl.w.mm_off);
   pl.order = (int*)(ws + pl.w.order_off);
+  pl.dtot = (float*)(ws + pl.w.dtot_off);
   pl.buckets = (int*)(ws + pl.w.bucket_off);
   pl.hint = nullptr;
   return fill_tab(pl.tab, n_periods, periods, pl.o.t_base);
@@ -1294,7 +1318,7 @@ static int stage_prep(const Plan& pl, int a, int b, cudaStream_t st) {
   if (m <= 0) return 0;
   prep_kernel<<<(unsigned)(((size_t)m * 32 + 127) / 128), 128, 0, st>>>(
       m, pl.lmax, pl.w.lpad, pl.kind, pl.o.flatten, pl.nlay + a, pl.layers + (size_t)a * pl.lmax, (size_t)pl.M * pl.lmax,
-      pl.consts + (size_t)a * NCONST * pl.w.lpad);
+      pl.consts + (size_t)a * NCONST * pl.w.lpad, pl.dtot + a);
   CK(cudaGetLastError());
   // hand-out order of this range: order[a .. b) = the models a .. b-1 sorted by bucket
   CK(cudaMemsetAsync(pl.buckets, 0, 2 * kOrderBuckets * sizeof(int), st));
@@ -1318,7 +1342,7 @@ static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaSt
   p1.flags = pl.flags ? pl.flags + a : nullptr; p1.counters = pl.counters; p1.queue = pl.queue;
   p1.dc = pl.o.dc; p1.fact = pl.o.fact; p1.atten = pl.o.atten; p1.stale = pl.o.stale_mmax; p1.exact_scan = pl.o.exact_scan;
   p1.tab = pl.tab;
-  p1.mm_state = pl.mm_state + a;
+  p1.mm_state = pl.mm_state + a; p1.dtot = pl.dtot + a;
   p1.order = pl.order + a; p1.order_base = a;
   p1.hint = pl.hint ? pl.hint + (size_t)a * pl.K : nullptr;
   p1.k_begin = k_begin; p1.k_end = k_end;
@@ -1338,7 +1362,7 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   p2.kind = pl.kind; p2.M = m; p2.lpad = pl.w.lpad; p2.lmax = pl.lmax; p2.K = pl.K; p2.nlay = pl.nlay + a;
   p2.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
   p2.c_in = pl.c_out + (size_t)a * pl.K; p2.ratio_in = pl.ratio + (size_t)a * pl.K; p2.nfound = pl.nfound + a;
-  p2.u_out = pl.u_out + (size_t)a * pl.K; p2.counters = pl.counters;
+  p2.u_out = pl.u_out + (size_t)a * pl.K; p2.counters = pl.counters; p2.dtot = pl.dtot + a;
   p2.fact = pl.o.fact; p2.atten = pl.o.atten; p2.ndiv = pl.o.ndiv;
   p2.ndiv_cap = (pl.kind == 2) ? pl.o.ndiv_cap_rayleigh : pl.o.ndiv_cap_love;
   p2.tab = pl.tab;
@@ -1446,7 +1470,7 @@ int surfdisp_partials_batch(const SurfdispOpts* opts, int n_models, int n_layers
   PdParams pd;
   memset(&pd, 0, sizeof(pd));
   pd.M = n_models; pd.lpad = pl.w.lpad; pd.K = pl.K; pd.lmax = pl.lmax; pd.nlay = pl.nlay; pd.consts = pl.consts; pd.c_in = pl.c_out;
-  pd.ratio_in = pl.ratio; pd.nfound = pl.nfound; pd.dcda = dcda; pd.dcdb = dcdb; pd.dcdr = dcdr; pd.fact = pl.o.fact;
+  pd.ratio_in = pl.ratio; pd.nfound = pl.nfound; pd.dtot = pl.dtot; pd.dcda = dcda; pd.dcdb = dcdb; pd.dcdr = dcdr; pd.fact = pl.o.fact;
   pd.atten = pl.o.atten; pd.ndiv = pl.o.ndiv; pd.ndiv_cap = pl.o.ndiv_cap_rayleigh; pd.tab = pl.tab;
   const size_t per_model = (size_t)NCONST * (pl.w.lpad + 1) * sizeof(float);
   if (per_model > 200 * 1024) return SURFDISP_EINVAL;

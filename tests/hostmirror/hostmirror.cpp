@@ -412,6 +412,8 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
   for (int k = 0; k < nfound; ++k) {
     ModelView mv;
     mv.cst = cst.data(); mv.sc = ld; mv.sl = 1; mv.n = n; mv.atten = atten; mv.lt = lt[k];
+    static const bool no_bound = getenv("HM_NO_DTOT") != nullptr;    // (always walk, like round 1)
+    if (!no_bound) mv.dtot = stack_depth_bound(cst.data(), ld, n);
     int ndiv = ndiv0;
     const int ivre = ndiv_cap / (n - 1);
     if (ndiv > ivre) ndiv = ivre;
