@@ -8,6 +8,7 @@ layers, described through the reference's own layer classes: pysurfinv_b200.stac
     python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
     python bench.py --impl reference ...                      (CPU oracle port on the host cores)
     python bench.py --workload mc   [--chains 256] [--love]   (configs 1 / 3: Monte-Carlo chains of one point)
+    python bench.py --workload mc --thermal [--chains 4096]   (config 4: the ocean model with the thermal mantle, 10-150 s)
     python bench.py --workload grid [--points 2000 --chains 16]   (config 5: points sharded over the ranks,
                                                                chain rows gathered inside the timed region)
 
@@ -65,6 +66,7 @@ def parse():
     ap.add_argument("--points", type=int, default=2000, help="grid: points in total (sharded over the ranks)")
     ap.add_argument("--mc-steps", type=int, default=50, help="mc / grid: Monte-Carlo steps per timed step")
     ap.add_argument("--love", action="store_true", help="mc: joint Rayleigh + Love (config 3: a second ensemble of Love chains)")
+    ap.add_argument("--thermal", action="store_true", help="mc / grid: the ocean model with the thermal mantle, periods 10-150 s (config 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -126,6 +128,23 @@ MC_SETTING = {"Sediment": {"H": [2.0, "abs_pos", 1.5, 0.1], "Vs": [[1.2, 0.8, 2.
                                                      [4.5, "abs", 0.3, 0.02], [4.4, "abs", 0.3, 0.02], [4.6, "abs", 0.3, 0.02]]},
               "Info": {"refLayer": True, "modelType": "CascadiaPrism"}}
 MC_PERIODS = np.array([8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80], np.float32)   # point.py:400 + 8 s
+# config 4: the ocean model of point.py:374-391 with the thermal mantle (OceanMantleHybrid: half-space cooling + OceanSeisRitz +
+# OceanSeisRuan, layers.py:297-363), CascadiaOcean prior rules, Rayleigh 10-150 s.  The reference's classes give this setting
+# 86 layers (water, sediment, 4 crustal layers, 60 mantle layers, 20 reference-mantle layers).
+THERMAL_SETTING = {"OceanWater": {"H": 2.5}, "OceanSedimentCascadia": {"H": [1, "rel_pos", 100, 0.1]},
+                   "OceanCrust": {"H": 7, "Vs": [3.25, 3.94]},
+                   "OceanMantleHybrid": {"BottomDepth": 200, "Conversion": "Ritzwoller", "ThermAge": [4, "rel_pos", 200, 0.4],
+                                         "Vs": [[0, "abs", 0.4, 0.01], [0, "abs", 0.4, 0.01], [0, "abs", 0.4, 0.01], [0, "abs", 0.2, 0.01]]},
+                   "Info": {"modelType": "CascadiaOcean", "period": 10, "refLayer": True, "lithoAgeQ": True, "lithoAge": 4.0, "topo": -2.5}}
+THERMAL_PERIODS = np.array([10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80, 100, 125, 150], np.float32)
+
+
+def mc_case(args):
+    """(setting, prior rule set, periods, layer count, label) of the Monte-Carlo workloads."""
+    from pysurfinv_b200 import stack as S
+    if getattr(args, "thermal", False):
+        return THERMAL_SETTING, S.PRIOR_OCEAN, THERMAL_PERIODS, 86, "86-layer ocean model with the thermal mantle (OceanMantleHybrid)", "10-150 s"
+    return MC_SETTING, S.PRIOR_PRISM, MC_PERIODS, 96, "96-layer sediment+crust+mantle B-spline model", "8-80 s"
 
 
 def cpu_sample(per, seconds, nthreads, kind=2, stacks=None, chunk=None, seed=99):
@@ -157,31 +176,33 @@ def cpu_sample(per, seconds, nthreads, kind=2, stacks=None, chunk=None, seed=99)
     return done * len(per) / dt, done, dt, tot
 
 
-def mc_cpu_stacks(n, seed=5):
-    """Stacks of the Monte-Carlo workload for the CPU arm: admissible random models of MC_SETTING (numpy restatement of
+def mc_cpu_stacks(args, n, seed=5):
+    """Stacks of the Monte-Carlo workload for the CPU arm: admissible random models of its setting (numpy restatement of
     the reference's model assembly and prior rules)."""
     from oracle import model_builder as MB
     from pysurfinv_b200 import stack as S
-    t = S.StackTemplate(MC_SETTING, prior_mask=S.PRIOR_PRISM)
+    setting, prior, _per, _nl, _label, _rng = mc_case(args)
+    t = S.StackTemplate(setting, prior_mask=prior)
+    check = MB.priors_ocean if prior == S.PRIOR_OCEAN else MB.priors
     lo, hi, _ = t.bounds()
     rng = np.random.default_rng(seed)
     out = []
     while len(out) < n:
         p = (lo + (hi - lo) * rng.random(t.nparams)).astype(np.float32)
-        if MB.priors(t, p.astype(np.float64)) == 0:
+        if check(t, p.astype(np.float64)) & prior == 0:
             out.append(p)
     return MB.build_stacks(t, np.array(out), t.max_layers())
 
 
 def mc_workload_name(args, world):
+    _s, _p, per, _nl, label, prange = mc_case(args)
     if args.workload == "grid":
         return ("config5: grid inversion, %d points x %d chains x %d Monte-Carlo steps per timed step, sharded by point over the "
-                "GPUs, chain rows all-gathered and best misfit all-reduced inside the timed region; 96-layer "
-                "sediment+crust+mantle B-spline models, %d periods 8-80 s, Rayleigh phase velocity"
-                % (args.points, args.chains, args.mc_steps, len(MC_PERIODS)))
-    return ("config%s: one-point Monte-Carlo inversion, %d chains x %d steps per timed step, 96-layer sediment+crust+mantle "
-            "B-spline model, %d periods 8-80 s, %s phase velocity" % ("3" if args.love else "1", args.chains, args.mc_steps,
-                                                                    len(MC_PERIODS), "Rayleigh + Love" if args.love else "Rayleigh"))
+                "GPUs, chain rows all-gathered and best misfit all-reduced inside the timed region; %s, "
+                "%d periods %s, Rayleigh phase velocity" % (args.points, args.chains, args.mc_steps, label, len(per), prange))
+    cfg = "4" if getattr(args, "thermal", False) else ("3" if args.love else "1")
+    return ("config%s: one-point Monte-Carlo inversion, %d chains x %d steps per timed step, %s, %d periods %s, %s phase velocity"
+            % (cfg, args.chains, args.mc_steps, label, len(per), prange, "Rayleigh + Love" if args.love else "Rayleigh"))
 
 
 def run_reference(args, rank, world):
@@ -197,7 +218,7 @@ def run_reference(args, rank, world):
         workload = WORKLOAD_SWEEP % (args.models, args.periods)
         metric = METRIC
     else:
-        per, stacks = MC_PERIODS, mc_cpu_stacks(max(64, 16 * nthreads))
+        per, stacks = mc_case(args)[2], mc_cpu_stacks(args, max(64, 16 * nthreads))
         kinds = (2, 1) if args.love else (2,)
         workload = mc_workload_name(args, world)
         metric = METRIC.replace("c+U", "c")
@@ -270,8 +291,8 @@ def run_mc(args, rank, world, local, dev, barrier):
     from pysurfinv_b200 import api, mc, stack as S
     from pysurfinv_b200.distributed import shard_range, gather_chain_rows
     solver = api.DispersionSolver(dev)
-    t = S.StackTemplate(MC_SETTING, prior_mask=S.PRIOR_PRISM)
-    per = MC_PERIODS
+    setting, prior, per, nl_case, _label, _prange = mc_case(args)
+    t = S.StackTemplate(setting, prior_mask=prior)
     K, P = len(per), t.nparams
     grid = args.workload == "grid"
     if grid:
@@ -375,10 +396,10 @@ def run_mc(args, rank, world, local, dev, barrier):
         cpu = None
         if not args.no_cpu:
             nth = os.cpu_count() or 1
-            v, n, dt, cc = cpu_sample(per, args.cpu_seconds, nth, stacks=mc_cpu_stacks(max(64, 16 * nth)))
+            v, n, dt, cc = cpu_sample(per, args.cpu_seconds, nth, stacks=mc_cpu_stacks(args, max(64, 16 * nth)))
             cpu = {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
-                   "sample": "%d admissible 96-layer models x %d periods in %.1f s (forward solve only: the reference's Python "
-                             "model assembly and prior checks per sample are not in it)" % (n, K, dt)}
+                   "sample": "%d admissible %d-layer models x %d periods in %.1f s (forward solve only: the reference's Python "
+                             "model assembly and prior checks per sample are not in it)" % (n, nl_case, K, dt)}
         ach = ctr[0] / ev_last * F_R * value / world * 1e-12
         line = {"metric": METRIC.replace("c+U", "c"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -389,7 +410,7 @@ def run_mc(args, rank, world, local, dev, barrier):
                            "chain_steps_per_s": total_chains * nsteps * args.steps * len(kinds) / (ms_max * 1e-3),
                            "accept_rate": float(ens[0].accepted.float().mean()), "cuda_graph": True,
                            "l2_policy": "compute / latency bound; every step rewrites %.1f MB of stacks and constants"
-                                        % (ens[0].M * 96 * 52 / 1e6),
+                                        % (ens[0].M * ens[0].lmax * 52 / 1e6),
                            "collective_ms_per_step": coll_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * nsteps * len(kinds) * args.steps,
                 "roofline": {"bound": "fp32", "kernel": "phase1_kernel<4> inside the Monte-Carlo step",

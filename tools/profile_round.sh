@@ -4,7 +4,7 @@
 #   stage launches : ncu launch list of the short command (after it exited 0 without ncu)
 #   stage phase1   : ncu --set full of the two root-search launches
 #   stage other    : ncu --set full of prep + phase 2
-#   stage mcbench  : bench lines of the Monte-Carlo / grid workloads (configs 1, 3, 5)
+#   stage mcbench  : bench lines of the Monte-Carlo / grid workloads (configs 1, 3, 4, 5)
 # Nothing printed under ncu is a bench value.
 TAG=${1:-r2}; STAGE=${2:-bench}
 mkdir -p gpurun_out
@@ -28,7 +28,7 @@ other)
   tail -2 gpurun_out/ncu_$TAG.log ;;
 mcbench)
   rm -f gpurun_out/mc_bench_$TAG.jsonl
-  for w in "--workload mc --chains 256" "--workload mc --chains 256 --love" "--workload mc --chains 131072 --mc-steps 10" "--workload grid --points 2000 --chains 16 --mc-steps 20"; do
+  for w in "--workload mc --chains 256" "--workload mc --chains 256 --love" "--workload mc --chains 131072 --mc-steps 10" "--workload grid --points 2000 --chains 16 --mc-steps 20" "--workload mc --thermal --chains 256" "--workload mc --thermal --chains 32768 --mc-steps 10"; do
     python bench.py $w --cpu-seconds 4 >> gpurun_out/mc_bench_$TAG.jsonl 2>> gpurun_out/mc_bench_$TAG.err
   done
   python - <<PY
