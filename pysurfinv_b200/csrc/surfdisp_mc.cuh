@@ -102,16 +102,34 @@ struct WarpScratch {
 // finite-difference derivative and its 0.01 km stopping rule included).
 struct Hscm { double den, Tm, z_ad, Tp; };
 
+// Called by all lanes of a warp.  The reference bisects [0, 400] km until the interval is <= 0.01 km: always 16
+// halvings, every midpoint a multiple of 400 / 2^16 (exact in binary).  Here five halvings at a time: the lanes
+// evaluate the 31 interior points of a 32-section, then every lane walks the bisection's own path through those
+// signs (so the result is the reference's even where the signs are not monotone); the 16th halving on its own.
 __device__ Hscm hscm_setup(double age, double Tp) {
   Hscm h;
   h.Tp = Tp;
   h.den = 2.0 * sqrt(age * 365.0 * 24.0 * 3600.0 * 1.0 * (1e-6 / 1e-6));
   const double T0 = 0.0, Da = 0.4;
-  double z0 = 0.0, z1 = 400.0;
-  while (z1 - z0 > 0.01) {
-    const double z2 = (z1 + z0) / 2.0;
+  const int lane = threadIdx.x & 31;
+  auto below = [&](double z2) -> bool {
     const double fz = erf(z2 * 1e3 / h.den), dfz = (erf((z2 + 0.001) * 1e3 / h.den) - fz) / 0.001 + 1e-10;
-    if (fz / dfz - z2 - (Tp - T0) / Da < 0.0) z0 = z2; else z1 = z2;
+    return fz / dfz - z2 - (Tp - T0) / Da < 0.0;
+  };
+  double z0 = 0.0, w = 400.0;
+  for (int r = 0; r < 3; ++r) {
+    const double sw = w / 32.0;
+    const unsigned neg = __ballot_sync(0xffffffffu, lane > 0 && below(z0 + (double)lane * sw));
+    int lo = 0, hi = 32;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { const int mid = (lo + hi) >> 1; if ((neg >> mid) & 1u) lo = mid; else hi = mid; }
+    z0 = z0 + (double)lo * sw;
+    w = sw;
+  }
+  double z1 = z0 + w;
+  {
+    const double z2 = (z1 + z0) / 2.0;
+    if (below(z2)) z0 = z2; else z1 = z2;
   }
   h.Tm = (Da * z1 + Tp - T0) / erf(z1 * 1e3 / h.den) + T0;
   h.z_ad = z0;
@@ -170,6 +188,8 @@ __device__ double ruan_qs(double T, double P, double period) {
 
 // OceanMantleHybrid._calVs / _calOthers (layers.py:302-363) for the N + 1 <= 64 grid points of the group, by one warp:
 // ws.hv = Vs, ws.hq = Qs.  coef = the len(Vs) perturbation coefficients (the basis has one more, its first coefficient 0).
+// WANT_QS = false (prior checks): ws.hq is not filled.
+template <bool WANT_QS>
 __device__ void hybrid_profile(const SurfdispStackGroup& g, const double* coef, double therm_age, double H, int N,
                                double crust_h, double z_top, WarpScratch& ws) {
   const unsigned full = 0xffffffffu;
@@ -214,8 +234,20 @@ __device__ void hybrid_profile(const SurfdispStackGroup& g, const double* coef, 
     npts += __popc(km);
   }
   __syncwarp();
-  // knot slopes of scipy's CubicSpline (not-a-knot): tridiagonal system, eliminated by one lane
+  // knot slopes of scipy's CubicSpline (not-a-knot): tridiagonal system.  Interval widths, secant slopes, diagonal and
+  // right-hand side of the interior rows by the lanes (kept in the free upper halves of the arrays: npts <= 64), the
+  // two-term elimination by one lane
   const double* xs = ws.cw; const double* ys = ws.dt;
+  double* sdx = ws.cw + 64; double* sm = ws.dt + 64;
+  if (npts >= 4) {
+    for (int i = lane; i < npts - 1; i += 32) { sdx[i] = xs[i + 1] - xs[i]; sm[i] = (ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]); }
+    __syncwarp();
+    for (int i = 1 + lane; i < npts - 1; i += 32) {
+      ws.hv[i] = 2.0 * (sdx[i - 1] + sdx[i]);
+      ws.hq[i] = 3.0 * (sdx[i] * sm[i - 1] + sdx[i - 1] * sm[i]);
+    }
+    __syncwarp();
+  }
   if (lane == 0 && npts >= 2) {
     double* sl = ws.hs; double* bd = ws.hv; double* rh = ws.hq;      // slopes, eliminated diagonal, eliminated right-hand side
     if (npts == 2) { sl[0] = sl[1] = (ys[1] - ys[0]) / (xs[1] - xs[0]); }
@@ -226,38 +258,39 @@ __device__ void hybrid_profile(const SurfdispStackGroup& g, const double* coef, 
       sl[0] = 2.0 * m0 - s1; sl[1] = s1; sl[2] = 2.0 * m1 - s1;
     } else {
       const int n = npts;
-      auto dxf = [&](int i) { return xs[i + 1] - xs[i]; };
-      auto mf = [&](int i) { return (ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]); };
       // row 0: [dx1, x2 - x0]
       double d = xs[2] - xs[0];
-      bd[0] = dxf(1);
+      bd[0] = sdx[1];
       double cprev = d;
-      rh[0] = ((dxf(0) + 2.0 * d) * dxf(1) * mf(0) + dxf(0) * dxf(0) * mf(1)) / d;
-      for (int i = 1; i < n - 1; ++i) {
-        const double a = dxf(i), b = 2.0 * (dxf(i - 1) + dxf(i)), c = dxf(i - 1);
-        const double r = 3.0 * (dxf(i) * mf(i - 1) + dxf(i - 1) * mf(i));
-        const double w = a / bd[i - 1];
-        bd[i] = b - w * cprev; rh[i] = r - w * rh[i - 1];
-        cprev = c;
+      rh[0] = ((sdx[0] + 2.0 * d) * sdx[1] * sm[0] + sdx[0] * sdx[0] * sm[1]) / d;
+      double bprev = bd[0], rprev = rh[0];
+      for (int i = 1; i < n - 1; ++i) {       // bd[i], rh[i] hold the row's diagonal and right-hand side
+        const double w = sdx[i] / bprev;
+        bprev = bd[i] - w * cprev; rprev = rh[i] - w * rprev;
+        bd[i] = bprev; rh[i] = rprev;
+        cprev = sdx[i - 1];
       }
       d = xs[n - 1] - xs[n - 3];
       {
-        const double a = d, b = dxf(n - 2);
-        const double r = (dxf(n - 2) * dxf(n - 2) * mf(n - 3) + (2.0 * d + dxf(n - 2)) * dxf(n - 3) * mf(n - 2)) / d;
-        const double w = a / bd[n - 2];
-        bd[n - 1] = b - w * cprev; rh[n - 1] = r - w * rh[n - 2];
+        const double a = d, b = sdx[n - 2];
+        const double r = (sdx[n - 2] * sdx[n - 2] * sm[n - 3] + (2.0 * d + sdx[n - 2]) * sdx[n - 3] * sm[n - 2]) / d;
+        const double w = a / bprev;
+        bd[n - 1] = b - w * cprev; rh[n - 1] = r - w * rprev;
       }
-      sl[n - 1] = rh[n - 1] / bd[n - 1];
+      double snext = rh[n - 1] / bd[n - 1];
+      sl[n - 1] = snext;
       for (int i = n - 2; i >= 0; --i) {
-        const double c = (i == 0) ? (xs[2] - xs[0]) : dxf(i - 1);
-        sl[i] = (rh[i] - c * sl[i + 1]) / bd[i];
+        const double c = (i == 0) ? (xs[2] - xs[0]) : sdx[i - 1];
+        snext = (rh[i] - c * snext) / bd[i];
+        sl[i] = snext;
       }
     }
   }
   __syncwarp();
   // evaluation on the grid (extrapolation with the end pieces), Qs of the anelastic model
   const double age_q = fmax(1e-3, (g.q_age < 0.0) ? therm_age : g.q_age);
-  const Hscm hqm = (age_q == age) ? hm : hscm_setup(age_q, 1325.0);
+  Hscm hqm = hm;
+  if (WANT_QS && age_q != age) hqm = hscm_setup(age_q, 1325.0);
   double vs_out[2], qs_out[2];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -271,8 +304,10 @@ __device__ void hybrid_profile(const SurfdispStackGroup& g, const double* coef, 
         const double h = zj[c] - xs[i];
         vs_out[c] = ((t / dx * h + ((m - ws.hs[i]) / dx - t)) * h + ws.hs[i]) * h + ys[i];
       }
-      const double zq = z_top + zj[c];
-      qs_out[c] = fmin(ruan_qs(hscm_T(hqm, zq), hscm_P(zq), g.period), 5000.0);
+      if (WANT_QS) {
+        const double zq = z_top + zj[c];
+        qs_out[c] = fmin(ruan_qs(hscm_T(hqm, zq), hscm_P(zq), g.period), 5000.0);
+      }
     }
   }
   __syncwarp();
@@ -299,13 +334,21 @@ __device__ int ocean_mantle_rules(WarpScratch& ws, int nm) {
   if (smin < slope0 * 1.5) bad |= SURFDISP_P_SLOPE;
   // extrema of the profile: local maxima (models.py:616-619), oscillation limit (models.py:603-611)
   {
+    // the lanes flag the extrema of their grid points; the (few) flagged ones are then visited in order
     bool anymax = false;
     double prev = 0.0; int have = 0, next = 0; bool osc = false;
-    for (int i = 1; i < nm - 1; ++i) {      // (sequential and uniform: at most 126 steps on shared memory)
-      const double v = ws.vm[i], l = ws.vm[i - 1], r = ws.vm[i + 1];
-      const bool mx = (v > l && v > r), mn = (v < l && v < r);
-      anymax |= mx;
-      if (mx || mn) { if (have && fabs(v - prev) > 0.1 * mean) osc = true; prev = v; have = 1; ++next; }
+    for (int base = 0; base < nm; base += 32) {
+      const int i = base + lane;
+      bool mx = false, mn = false;
+      if (i >= 1 && i < nm - 1) { const double v = ws.vm[i], l = ws.vm[i - 1], r = ws.vm[i + 1]; mx = (v > l && v > r); mn = (v < l && v < r); }
+      anymax |= __any_sync(0xffffffffu, mx);
+      unsigned ext = __ballot_sync(0xffffffffu, mx || mn);
+      while (ext) {
+        const double v = ws.vm[base + __ffs(ext) - 1];
+        ext &= ext - 1u;
+        if (have && fabs(v - prev) > 0.1 * mean) osc = true;
+        prev = v; have = 1; ++next;
+      }
     }
     if (anymax) bad |= SURFDISP_P_LOCALMAX;
     if (next > 1 && osc) bad |= SURFDISP_P_OSCI;
@@ -338,9 +381,17 @@ __device__ int ocean_mantle_rules(WarpScratch& ws, int nm) {
       for (int r = 0, i = lane; i < nm; i += 32, ++r) ws.cw[i] = out[r];
       __syncwarp();
       double prev = 0.0; int have = 0; bool big = false;
-      for (int i = 1; i < nm - 1; ++i) {
-        const double v = ws.cw[i], l = ws.cw[i - 1], r = ws.cw[i + 1];
-        if ((v > l && v > r) || (v < l && v < r)) { if (have && fabs(v - prev) > 0.3) big = true; prev = v; have = 1; }
+      for (int base = 0; base < nm; base += 32) {
+        const int i = base + lane;
+        bool ex = false;
+        if (i >= 1 && i < nm - 1) { const double v = ws.cw[i], l = ws.cw[i - 1], r = ws.cw[i + 1]; ex = (v > l && v > r) || (v < l && v < r); }
+        unsigned ext = __ballot_sync(0xffffffffu, ex);
+        while (ext) {
+          const double v = ws.cw[base + __ffs(ext) - 1];
+          ext &= ext - 1u;
+          if (have && fabs(v - prev) > 0.3) big = true;
+          prev = v; have = 1;
+        }
       }
       if (big) bad |= SURFDISP_P_CWT;
       __syncwarp();
@@ -385,7 +436,7 @@ __device__ int assemble_stack_warp(const SurfdispStackTemplate& t, const float* 
     const bool is_hyb = HYB && (g.kind == SURFDISP_G_HYBRID);
     if (is_hyb) {
       if (N > 63) N = 63;
-      hybrid_profile(g, coef, (g.age_param >= 0) ? (double)pm[g.age_param] : g.age_fixed, H, N, crust_h, z0, ws);
+      hybrid_profile<EMIT>(g, coef, (g.age_param >= 0) ? (double)pm[g.age_param] : g.age_fixed, H, N, crust_h, z0, ws);
     }
     const Knots kn = make_knots((g.kind == SURFDISP_G_BSPLINE && g.ncoef >= 3) ? g.ncoef : 3);
     const bool mono_class = (g.gclass == SURFDISP_C_SEDIMENT || g.gclass == SURFDISP_C_CRUST);
