@@ -133,6 +133,12 @@ int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_mo
                         float* c_out, float* u_out, int* nfound, int* flags);
 void surfdisp_host_release(void);
 
+/* Tuning: from how many models on the later periods of the root search run as two launches -- a fast-path launch
+ * without scan code that hands the models whose period needs the point-by-point scan (calcul.f:155-167) over to the
+ * general launch, which resumes them at that period (default 98304; n_models <= 0 restores it).  Results do not
+ * depend on it (tests/test_gpu_parity.py: bit-identical).  Process-wide. */
+void surfdisp_set_split_min_models(int n_models);
+
 /* The same with caller-owned device memory and streams, as a pipeline: the batch is cut into n_chunks chunks;
  * chunk i is copied host->device on copy_stream while chunk i-1 is prepared and its first period searched on
  * compute_stream; the later periods run as one launch over the whole batch; the group velocities are computed

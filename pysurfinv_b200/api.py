@@ -107,6 +107,8 @@ def load_library():
     L.surfdisp_mc_step.restype = C.c_int
     L.surfdisp_host_release.argtypes = []
     L.surfdisp_host_release.restype = None
+    L.surfdisp_set_split_min_models.argtypes = [C.c_int]
+    L.surfdisp_set_split_min_models.restype = None
     L.surfdisp_version.restype = C.c_char_p
     L.surfdisp_last_cuda_error.restype = C.c_char_p
     _lib = L

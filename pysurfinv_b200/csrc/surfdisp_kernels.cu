@@ -34,7 +34,7 @@ struct PeriodTab {
 };
 
 struct WsLayout {
-  size_t consts_off, ratio_off, mm_off, order_off, dtot_off, bucket_off, total;
+  size_t consts_off, ratio_off, mm_off, order_off, dtot_off, mmh_off, defer_off, dstate_off, bucket_off, total;
   int lpad;
 };
 constexpr int kOrderBuckets = 1024;   // models are handed out in the order of their top shear velocity (bucket sort)
@@ -51,7 +51,10 @@ WsLayout ws_layout(int M, int lmax, int K) {
   w.mm_off = w.ratio_off + ((ratio + 255) / 256) * 256;
   w.order_off = w.mm_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
   w.dtot_off = w.order_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
-  w.bucket_off = w.dtot_off + (((size_t)M * sizeof(float) + 255) / 256) * 256;
+  w.mmh_off = w.dtot_off + (((size_t)M * sizeof(float) + 255) / 256) * 256;
+  w.defer_off = w.mmh_off + (((size_t)M * K * sizeof(short) + 255) / 256) * 256;
+  w.dstate_off = w.defer_off + (((size_t)M * sizeof(int) + 255) / 256) * 256;
+  w.bucket_off = w.dstate_off + (((size_t)M * sizeof(float2) + 255) / 256) * 256;
   w.total = w.bucket_off + 2 * kOrderBuckets * sizeof(int);
   return w;
 }
@@ -157,6 +160,12 @@ struct P1Params {
   int k_begin, k_end;   // periods [k_begin, k_end) are done by this launch (the first period runs as a launch of its own)
   int* mm_state;        // layer-dropping depth carried from launch to launch
   const float* dtot;    // per model: upper bound of the thickness sums of the layer-dropping walk (prep_kernel), -1 = unknown
+  // ---- hand-over from the fast-path instantiation to the general one (see phase1_kernel)
+  short* mmh;           // [M][K] dropping depth left by every finished period: what a resumed model replays its refreshes with
+  int* defer_list;      // models the fast-path launch handed over; their count
+  unsigned int* ndefer;
+  float2* dstate;       // per handed-over model: (last prediction error, periods of good predictions still required)
+  int resume;           // 1: this launch continues the models of `order` (ndefer of them) at the period they stopped at
   const float* hint;    // [M][K] neighbour curves (phase velocities of a nearby model on the same periods) or nullptr
   const int* order;     // order[i] - order_base = i-th model to hand out (nullptr: index order)
   int order_base;
@@ -285,17 +294,20 @@ __device__ __noinline__ bool nevill_out_of_line(const SecFn& f, float c1, float 
 // advance through their periods and models independently, and the expensive code (the sweep) is always
 // executed by all of them together (a structured loop nest would make groups that need an extra round, or
 // that sit in the scan of their first period, serialise the others).
-enum { ST_FETCH = 0, ST_PERIOD, ST_FAST, ST_REFINE, ST_SCAN, ST_POLISH, ST_ELL, ST_DONE };
+enum { ST_FETCH = 0, ST_PERIOD, ST_FAST, ST_REFINE, ST_SCAN, ST_POLISH, ST_ELL, ST_DONE, ST_DEFER };
+enum { P1_GENERAL = 0, P1_FIRST = 1, P1_FAST = 2 };
 // Which trial velocities the next sweep of a group needs (built in ONE place, right before the sweep)
 enum { NB_NONE = 0, NB_FAST, NB_REFINE, NB_SCAN, NB_POLISH, NB_ELL };
 
 // FIRST: the launch that does one period per model from scratch (k_begin = 0, k_end = 1): every model scans, the
 // cluster / window path of the later periods is compiled out -- a smaller loop body for the launch whose short
 // sweeps make it the most sensitive to instruction fetch.
-template <int G, bool FIRST>
+template <int G, int MODE>
 __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __grid_constant__ P1Params p) {
   static_assert(G == 4 || G == 8, "4 or 8 lanes x 2 trial velocities per model");
   constexpr int P = 2 * G;   // trial velocities per round; point i lives in lane i/2, component i%2
+  constexpr bool FIRST = (MODE == P1_FIRST);
+  constexpr bool NOSCAN = (MODE == P1_FAST);
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -334,6 +346,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
   float* rrow = p.ratio_out;
   float c1 = 1.f, c_prev = 0.f, c_prev2 = 0.f, c_prev3 = 0.f, pred_err = 1.0e-3f, c_pred = 0.f, b_top = 0.f, T = 1.f;
   int hopped = 0;            // > 0: the root left the extrapolation of its branch; periods of good predictions still required
+  int kfirst = 0;            // the first period of the current model in this launch
+  bool force_scan = false;   // resumed model: its first period here goes to the scan at once
   bool mid_liquid = false;
   // ---- the sweep request of the current iteration (per lane) and its result
   float2 pc = make_float2(1.f, 1.f), pd = make_float2(0.f, 0.f), pe2 = pd, pe3 = pd;
@@ -418,12 +432,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     ell_only = 0;
   };
   auto start_scan = [&]() {
+    if constexpr (NOSCAN) { stage = ST_DEFER; need = NB_NONE; return; }
     cbase = c1; cP = 0.f; dP = 0.f; have_prev = false; round = 0; stride = 1;
     stage = ST_SCAN; need = NB_SCAN;
   };
   // the interpolation rounds gave up: the cluster / window rounds restart as a scan; a bracket that came from
   // the scan is polished by uniform section instead (mmax is pinned already)
   auto interp_failed = [&]() {
+    if constexpr (NOSCAN) { stage = ST_DEFER; need = NB_NONE; return; }
     if (from_scan) { from_scan = false; lo0 = lo; hi0 = hi; dlo0 = dlo; dhi0 = dhi; pit = 0; stage = ST_POLISH; need = NB_POLISH; }
     else start_scan();
   };
@@ -504,7 +520,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
     if (stage == ST_FETCH && warp_fetch) {
       if (gl == 0) {
         model = (int)atomicAdd(p.queue, 1u);
-        if (model < p.M && p.order) model = p.order[model] - p.order_base;
+        const int mtot = p.resume ? min((int)*p.ndefer, p.M) : p.M;
+        if (model >= mtot) model = p.M;
+        else if (p.order) model = p.order[model] - p.order_base;
       }
       model = gshfl<G>(gmask, model, 0);
       if (model >= p.M) stage = ST_DONE;
@@ -533,16 +551,24 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
             if (b0 < 0.1f) c1 = 0.5f;
           }
           mm = n;  // reference COMMON mmax carried from period to period
-          nfound = 0; flag = 0; k = p.k_begin; hopped = 0;
+          nfound = 0; flag = 0; k = p.resume ? p.nfound[model] : p.k_begin; hopped = 0;
+          kfirst = k; force_scan = false;
           c_prev = c_prev2 = c_prev3 = 0.f; pred_err = 1.0e-3f;
           stage = ST_PERIOD;
           if (k > 0) {
             // continuing a model whose earlier periods were done by a previous launch
             nfound = p.nfound[model];
-            if (nfound < k) { stage = ST_FETCH; n = 2; }   // it ended there: nothing to do
+            if (nfound < k || k >= p.k_end) { stage = ST_FETCH; n = 2; }   // it ended there: nothing to do
             else {
-              // the layers below the dropping depth keep the values the first period gave them
+              // the layers below the dropping depth keep the values of the last period that refreshed them (SURVEY
+              // Q1): all of them the first period's, then every later period its own dropping depth
               bmin = refresh(n, p.tab.lt[0]) - 0.05f;
+              if (p.stale) for (int kk = 1; kk < k; ++kk) refresh((int)p.mmh[(size_t)model * K + kk - 1], p.tab.lt[kk]);
+              if (p.resume) {
+                // handed over by the fast-path launch at the point where it would have started the scan of period k
+                const float2 ds = p.dstate[model];
+                pred_err = ds.x; hopped = (int)ds.y; force_scan = true;
+              }
               mm = p.mm_state[model];
               flag = p.flags ? p.flags[model] : 0;
               c_prev = crow[k - 1];
@@ -557,7 +583,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       T = p.tab.per[k];
       const float lt = p.tab.lt[k];
       const float bm = refresh(p.stale ? mm : n, lt);
-      if (k == p.k_begin) {
+      if (k == kfirst) {
         // liquid layers below the top one: the in-sweep ellipticity is not valid for such stacks (all n records
         // are in shared memory at a model's first period here)
         bool l = false;
@@ -621,7 +647,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       // (an extrapolation that moves the root by more than 0.15 km/s is not trusted: where the branch is that steep --
       // thick slow sediments, coarse period lists -- the cluster can land on a higher mode with an even number of roots
       // between c1 and it, which the sign guard cannot see; scan from c1 like the reference)
-      if (!FIRST && !p.exact_scan && k >= 1 && !hopped && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000 &&
+      if (!FIRST && !p.exact_scan && k >= 1 && !hopped && !force_scan && !(SD_ADD(c1, p.dc) < 0.8f * b_top) && j0 < 1000 &&
           fabsf(c_pred - c_prev) <= kMaxPredStep) {
         // fstage 0 (from the third period on): cluster around the predicted root; 1: window of P-2 grid points
         // around it; 2: window of P grid points moved up or down
@@ -629,14 +655,15 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
         w0 = 2; dir = 0; wtry = 0; from_scan = false;
         stage = ST_FAST; need = NB_FAST;
       } else start_scan();
+      force_scan = false;
     }
     if (__all_sync(0xffffffffu, stage == ST_DONE)) break;
     // ---- trial velocities of this iteration's sweep
     if (need != NB_NONE) { own_eval = false; own_half = false; }
     if (!FIRST && need == NB_FAST) build_fast();
     else if (need == NB_REFINE) build_refine();
-    else if (need == NB_SCAN) build_scan();
-    else if (need == NB_POLISH) build_polish();
+    else if (!NOSCAN && need == NB_SCAN) build_scan();
+    else if (!NOSCAN && need == NB_POLISH) build_polish();
     else if (need == NB_ELL) build_ell();
     need = NB_NONE;
 
@@ -711,7 +738,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       if (ev) { jb = __ffs(ev); it++; do_interp = true; }                                   // point i is list entry i + 1
       else if (signbit(dlast) != signbit(E1.d)) { jb = P + 1; it++; do_interp = true; }
       else interp_failed();
-    } else if (stage == ST_SCAN && process) {
+    } else if (!NOSCAN && stage == ST_SCAN && process) {
       // ---- scan for the first sign change on the grid c1 + i dc (calcul.f:155-167).  The reference examines
       // every grid point.  Here only the first round does; after it every 4th grid point is evaluated (stride 4)
       // and the skipped ones are examined only where they can matter: around a sign change between two coarse
@@ -819,7 +846,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
           else need = NB_SCAN;
         }
       }
-    } else if (stage == ST_POLISH) {
+    } else if (!NOSCAN && stage == ST_POLISH) {
       const unsigned ev = change_mask(pd, dlo);
       const float dlast = gshfl<G>(gmask, pd.y, G - 1);
       bool have_root = false, lstop = false;
@@ -923,8 +950,18 @@ __global__ void __launch_bounds__(P1_THREADS, P1_MINBLK) phase1_kernel(const __g
       }
     }
 
+    if (NOSCAN && stage == ST_DEFER) {
+      // this period needs the point-by-point path, which this instantiation does not contain: the model is handed
+      // over, with what the general instantiation needs to go on exactly where the scan would have started
+      if (gl == 0) {
+        p.nfound[model] = nfound; p.mm_state[model] = mm; if (p.flags) p.flags[model] = flag;
+        p.dstate[model] = make_float2(pred_err, (float)hopped);
+        p.defer_list[atomicAdd(p.ndefer, 1u)] = model;
+      }
+      stage = ST_FETCH;
+    }
     if (period_done) {
-      if (gl == 0) { crow[k] = croot; rrow[k] = ratio; }
+      if (gl == 0) { crow[k] = croot; rrow[k] = ratio; p.mmh[(size_t)model * K + k] = (short)mm; }
       if (k >= 2 || (k == 1 && p.hint)) {
         // A root more than 0.1 km/s off the extrapolation: mode hopping, or a branch that bends too fast to be
         // extrapolated (thick slow sediments at the short-period end).  Scan from c1 like the reference until
@@ -987,9 +1024,10 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
   extern __shared__ float4 smem[];
   float* sc = reinterpret_cast<float*>(smem);
   const int K = p.K;
+  const int per_model = NCONST * p.lpad;
   const int model0 = blockIdx.x * p.mpb;
   const int nmod = min(p.mpb, p.M - model0);
-  const int per_model = NCONST * p.lpad;
+  unsigned long long nsub = 0;
   // stage the constants of this block's models: coalesced float4 reads of the rows [8][lpad], written as records
   // [layer][8] -- a thread then reads all constants of a layer from one address (two 16-byte-aligned groups)
   {
@@ -1003,7 +1041,6 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
     }
   }
   __syncthreads();
-  unsigned long long nsub = 0;
   for (int t = threadIdx.x; t < nmod * K; t += blockDim.x) {
     // period-major inside the block: the 32 work items of a warp are neighbouring periods of the block's models,
     // i.e. integrations of similar depth (the depth grows with the period)
@@ -1183,7 +1220,7 @@ int fill_tab(PeriodTab& tab, int K, const float* periods, float t_base) {
   return 0;
 }
 
-template <int G, bool FIRST>
+template <int G, int MODE>
 int launch_phase1_t(const P1Params& p, cudaStream_t st) {
   P1Params q = p;
   q.mstride = p.lpad + 1;  // +1 float4: consecutive groups start 16 B apart mod 128 B (bank spread)
@@ -1194,26 +1231,51 @@ int launch_phase1_t(const P1Params& p, cudaStream_t st) {
   const int groups = threads / G;
   size_t smem = (size_t)groups * (q.mstride + 2 * G + 2) * sizeof(float4);   // layer records + sample slots
   if (smem > 220 * 1024) return SURFDISP_EINVAL;
-  CK(cudaFuncSetAttribute(phase1_kernel<G, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(phase1_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148, occ = 1;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<G, FIRST>, threads, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<G, MODE>, threads, smem));
   if (occ < 1) occ = 1;
   long long need = ((long long)p.M + groups - 1) / groups;
   long long grid = (long long)sms * occ;  // persistent: one resident wave, models pulled from a queue
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  phase1_kernel<G, FIRST><<<(unsigned)grid, threads, smem, st>>>(q);
+  phase1_kernel<G, MODE><<<(unsigned)grid, threads, smem, st>>>(q);
   CK(cudaGetLastError());
   return 0;
 }
 
+#ifndef P1_SPLIT
+#define P1_SPLIT 1      // later periods: fast-path instantiation + hand-over to the general one (0: the general one alone)
+#endif
+// Three instantiations of the root search:
+//   P1_FIRST    one period per model from scratch: every model scans, no cluster / window / refinement code
+//   P1_FAST     later periods, interpolation rounds only: no scan / polish code and none of its state in registers;
+//               a model whose period needs the point-by-point path (1 % of the config-2 models) is handed over
+//   P1_GENERAL  everything; runs the handed-over models from the period they stopped at (and exact_scan launches)
+// The hand-over pays for large batches only: the handed-over models -- among them the few that scan at every period,
+// a serial chain of a few milliseconds -- start when the fast-path launch has ended.  Small batches (Monte-Carlo
+// ensembles of a few thousand chains) keep the single general launch.  Measured: Rayleigh sweep of
+// 2^20 models unchanged, Love sweep 229 -> 203 ms (a third of the Love models scan somewhere: in one launch their
+// scans sit in warps beside models on the fast path), 131072-chain Monte-Carlo step 21.8 -> 21.2 ms, 256 chains
+// 1.35 -> 1.96 ms (hence the threshold).
+constexpr int kSplitMinDefault = 98304;
+int g_split_min_models = kSplitMinDefault;   // (surfdisp_set_split_min_models: tests force the hand-over on small batches)
+static bool p1_split(const P1Params& p) { return P1_SPLIT && p.k_begin >= 1 && !p.exact_scan && p.M >= g_split_min_models; }
+
 template <int G>
 int launch_phase1(const P1Params& p, cudaStream_t st) {
-  // (exact_scan launches cover all periods at once and scan everywhere: the general instantiation)
-  if (p.k_begin == 0 && p.k_end == 1 && !p.exact_scan) return launch_phase1_t<G, true>(p, st);
-  return launch_phase1_t<G, false>(p, st);
+  if (p.k_begin == 0 && p.k_end == 1 && !p.exact_scan) return launch_phase1_t<G, P1_FIRST>(p, st);
+  if (!p1_split(p)) return launch_phase1_t<G, P1_GENERAL>(p, st);
+  CK(cudaMemsetAsync(p.ndefer, 0, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned int), st));
+  const int rc = launch_phase1_t<G, P1_FAST>(p, st);
+  if (rc) return rc;
+  P1Params r = p;
+  r.resume = 1; r.order = p.defer_list; r.order_base = 0;
+  CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned int), st));
+  return launch_phase1_t<G, P1_GENERAL>(r, st);
 }
 
 }  // namespace
@@ -1278,6 +1340,7 @@ struct Plan {
   float *c_out, *u_out, *consts, *ratio;
   int *nfound, *flags, *mm_state, *order, *buckets;
   float* dtot;     // per model: upper bound of the layer-dropping thickness sums (prep_kernel)
+  short* mmh; int* defer_list; float2* dstate; unsigned int* ndefer;   // hand-over between the root-search launches
   unsigned long long* counters;
   unsigned int* queue;
   const float* hint;
@@ -1305,6 +1368,8 @@ static int make_plan(Plan& pl, const SurfdispOpts* opts, int kind, int n_models,
   pl.mm_state = (int*)(ws + pl.w.mm_off);
   pl.order = (int*)(ws + pl.w.order_off);
   pl.dtot = (float*)(ws + pl.w.dtot_off);
+  pl.mmh = (short*)(ws + pl.w.mmh_off); pl.defer_list = (int*)(ws + pl.w.defer_off); pl.dstate = (float2*)(ws + pl.w.dstate_off);
+  pl.ndefer = (unsigned int*)(ws + 128);
   pl.buckets = (int*)(ws + pl.w.bucket_off);
   pl.hint = nullptr;
   return fill_tab(pl.tab, n_periods, periods, pl.o.t_base);
@@ -1332,9 +1397,15 @@ static int stage_prep(const Plan& pl, int a, int b, cudaStream_t st) {
 }
 
 // root search of the periods [k_begin, k_end) for the models [a, b)
+static void fill_p1(const Plan& pl, int a, int b, int k_begin, int k_end, P1Params& p1);
 static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaStream_t st) {
   if (b <= a || k_end <= k_begin) return 0;
   P1Params p1;
+  fill_p1(pl, a, b, k_begin, k_end, p1);
+  if (!p1_split(p1)) CK(cudaMemsetAsync(pl.queue, 0, sizeof(unsigned int), st));   // (the split launches reset it themselves)
+  return launch_phase1<P1_G>(p1, st);
+}
+static void fill_p1(const Plan& pl, int a, int b, int k_begin, int k_end, P1Params& p1) {
   memset(&p1, 0, sizeof(p1));
   p1.kind = pl.kind; p1.M = b - a; p1.lpad = pl.w.lpad; p1.lmax = pl.lmax; p1.K = pl.K; p1.nlay = pl.nlay + a;
   p1.consts = pl.consts + (size_t)a * NCONST * pl.w.lpad;
@@ -1343,13 +1414,11 @@ static int stage_p1(const Plan& pl, int a, int b, int k_begin, int k_end, cudaSt
   p1.dc = pl.o.dc; p1.fact = pl.o.fact; p1.atten = pl.o.atten; p1.stale = pl.o.stale_mmax; p1.exact_scan = pl.o.exact_scan;
   p1.tab = pl.tab;
   p1.mm_state = pl.mm_state + a; p1.dtot = pl.dtot + a;
+  p1.mmh = pl.mmh + (size_t)a * pl.K; p1.defer_list = pl.defer_list + a; p1.dstate = pl.dstate + a; p1.ndefer = pl.ndefer; p1.resume = 0;
   p1.order = pl.order + a; p1.order_base = a;
   p1.hint = pl.hint ? pl.hint + (size_t)a * pl.K : nullptr;
   p1.k_begin = k_begin; p1.k_end = k_end;
-  CK(cudaMemsetAsync(pl.queue, 0, sizeof(unsigned int), st));
-  return launch_phase1<P1_G>(p1, st);
 }
-
 static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   const int m = b - a;
   if (m <= 0 || !pl.u_out) return 0;
@@ -1705,6 +1774,8 @@ int surfdisp_host_batch(const SurfdispOpts* opts, int device, int kind, int n_mo
 }
 
 void surfdisp_host_release(void) { g_host_ctx.release(); }
+
+void surfdisp_set_split_min_models(int n_models) { g_split_min_models = (n_models > 0) ? n_models : kSplitMinDefault; }
 
 void fast_surf_(const int* n_layer0, const int* kind0, const float* a_ref0, const float* b_ref0,
                 const float* rho_ref0, const float* d_ref0, const float* qs_ref0, const float* cvper,

@@ -310,6 +310,28 @@ def test_config4_deep_stacks_ndiv_zero(solver):
     _check(g, lay, nl, per, 2)
 
 
+def test_config4_thermal_ocean_models(solver):
+    """BASELINE config 4 on its real parameterisation: the ocean model of point.py:374-391 (water, sediment, crust,
+    OceanMantleHybrid thermal mantle, reference mantle: 86 layers) with random admissible parameters, Rayleigh
+    10-150 s.  The stacks are assembled by the numpy restatement of the reference's classes; the water layer makes
+    the search start at 0.5 km/s (fast_surf.f:170) and the sweep pass a liquid layer."""
+    import bench
+    from oracle import model_builder as MB
+    from pysurfinv_b200 import stack as S
+    t = S.StackTemplate(bench.THERMAL_SETTING, prior_mask=S.PRIOR_OCEAN)
+    lo, hi, _ = t.bounds()
+    rng = np.random.default_rng(404)
+    params = []
+    while len(params) < 300:
+        p = (lo + (hi - lo) * rng.random(t.nparams)).astype(np.float32)
+        if MB.priors_ocean(t, p.astype(np.float64)) & S.PRIOR_OCEAN == 0:
+            params.append(p)
+    lay, nl = MB.build_stacks(t, np.array(params), t.max_layers())
+    assert int(nl.max()) == 86 and float(lay[1, :, 0].max()) == 0.0
+    g = _gpu(solver, lay, nl, bench.THERMAL_PERIODS, 2)
+    _check(g, lay, nl, bench.THERMAL_PERIODS, 2)
+
+
 def test_config4_love_steep_branch_coarse_periods(solver):
     """Config-4 stacks, Love, 10 s period steps: the curve jumps by 1.7 km/s between the first two periods; the third
     period must not be extrapolated onto a higher mode (tests/test_hostmirror.py, same models)."""
@@ -397,3 +419,53 @@ def test_neighbour_curve_hints_change_sweeps_not_results(solver):
         ok = st0 != 3
         assert np.array_equal(good["nfound"].cpu().numpy()[idx][ok], nf0[ok])
         assert np.abs(good["c"].cpu().numpy()[idx] - c0)[ok].max() <= TOL
+
+
+def test_hand_over_between_root_search_launches_changes_nothing(solver):
+    """Large batches run the later periods as two launches: a fast-path instantiation that contains no scan code and
+    hands the models whose period needs the point-by-point scan (calcul.f:155-167) over to the general one, which
+    resumes them where the scan would have started (stale layer records rebuilt from the recorded dropping depths)
+    on a side stream beside the first group-velocity pass.  Forced here on small batches of the families that scan
+    most (velocity inversions, water layers, 100-period lists, Love): bit-identical c, U, root counts and flags, on
+    the device path, with hints, and through both host-buffer pipelines."""
+    import torch
+    from pysurfinv_b200 import stack as S
+    lib = solver.lib
+    P100 = synth.log_periods(100, 5.0, 120.0)
+    cases = [(synth.crustal_models(3000, seed=501, lvz=True), P100, 2), (synth.crustal_models(3000, seed=502, lvz=True), P100, 1),
+             (synth.ragged_models(3000, seed=503), synth.log_periods(24), 2), (synth.crustal_models(4000, seed=504), synth.log_periods(), 2),
+             (synth.crustal_models(1500, seed=505, n_crust=15, n_mantle=130, zmax=400.0), np.arange(10.0, 151.0, 10.0, dtype=np.float32), 1)]
+    handed = 0
+    try:
+        for (lay, nl), per, kind in cases:
+            dl, dn = torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda()
+            lib.surfdisp_set_split_min_models(0)
+            ref = {k: v.cpu().numpy() for k, v in solver.forward(dl, dn, per, kind=kind).items()}
+            hint = torch.from_numpy(ref["c"] * np.float32(1.002)).cuda().contiguous()
+            ref_h = {k: v.cpu().numpy() for k, v in solver.forward(dl, dn, per, kind=kind, hint=hint).items()}
+            lib.surfdisp_set_split_min_models(1)
+            got = {k: v.cpu().numpy() for k, v in solver.forward(dl, dn, per, kind=kind).items()}
+            got_h = {k: v.cpu().numpy() for k, v in solver.forward(dl, dn, per, kind=kind, hint=hint).items()}
+            host = solver.forward_host(lay, nl, per, kind, chunks=3)
+            for a, b in ((ref, got), (ref_h, got_h), (ref, host)):
+                for key in ("c", "u", "nfound", "flags"):
+                    assert np.array_equal(a[key], b[key]), key
+            cnt = torch.zeros(64, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            # (the number of handed-over models of the last call sits in the workspace header)
+            cnt.copy_(solver._ws[:256].view(torch.int32))
+            handed += int(cnt[32])
+        # parameters-fed pipeline (config-2 setting)
+        t, _ = S.config2_template()
+        params = S.config2_params(5000, seed=506)
+        per = synth.log_periods()
+        lib.surfdisp_set_split_min_models(0)
+        a = solver.forward_params_pinned(t, torch.from_numpy(params).pin_memory(), per)
+        a = {k: np.array(v) for k, v in a.items()}
+        lib.surfdisp_set_split_min_models(1)
+        b = solver.forward_params_pinned(t, torch.from_numpy(params).pin_memory(), per)
+        for key in ("c", "u", "nfound", "flags"):
+            assert np.array_equal(a[key], b[key]), key
+    finally:
+        lib.surfdisp_set_split_min_models(0)
+    assert handed > 100      # the path was taken
