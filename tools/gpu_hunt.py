@@ -112,7 +112,9 @@ def main():
     out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "parity_report.json")
     only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     solver = api.DispersionSolver("cuda:0")
-    rep = {"curves_per_family_and_wave_type": curves, "host_threads": os.cpu_count(), "results": {}}
+    # the chunks of 16384 curves take the three-launch root search of large batches (fast-path launch + hand-over)
+    solver.lib.surfdisp_set_split_min_models(8192)
+    rep = {"curves_per_family_and_wave_type": curves, "host_threads": os.cpu_count(), "split_min_models": 8192, "results": {}}
     t0 = time.time()
     for fam in FAMILIES:
         for kind in (2, 1):

@@ -2,7 +2,7 @@
 # GPU box: the round's evidence.  usage: bash tools/profile_round.sh <tag> <stage>
 #   stage bench    : plain bench (the numbers) + reference arm
 #   stage launches : ncu launch list of the short command (after it exited 0 without ncu)
-#   stage phase1   : ncu --set full of the two root-search launches
+#   stage phase1   : ncu --set full of the three root-search launches
 #   stage other    : ncu --set full of prep + phase 2
 #   stage mcbench  : bench lines of the Monte-Carlo / grid workloads (configs 1, 3, 4, 5)
 # Nothing printed under ncu is a bench value.
@@ -20,7 +20,7 @@ launches)
   tail -9 gpurun_out/launches_$TAG.csv | cut -c 1-200 ;;
 phase1)
   $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 2
-  ncu --set full --clock-control none --import-source on -k regex:phase1 -s 6 -c 2 -o gpurun_out/prof_phase1_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:phase1 -s 9 -c 3 -o gpurun_out/prof_phase1_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_$TAG.log ;;
 other)
   $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 2
