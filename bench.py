@@ -139,6 +139,12 @@ THERMAL_SETTING = {"OceanWater": {"H": 2.5}, "OceanSedimentCascadia": {"H": [1, 
 THERMAL_PERIODS = np.array([10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 50, 60, 70, 80, 100, 125, 150], np.float32)
 
 
+def p1_launches(n_models):
+    """Launches of the root search per batch: first period + later periods, the later periods as a fast-path launch and a
+    hand-over launch from 98304 models on (kSplitMinDefault in csrc/surfdisp_kernels.cu)."""
+    return 3 if n_models >= 98304 else 2
+
+
 def mc_case(args):
     """(setting, prior rule set, periods, layer count, label) of the Monte-Carlo workloads."""
     from pysurfinv_b200 import stack as S
@@ -412,7 +418,7 @@ def run_mc(args, rank, world, local, dev, barrier):
                            "l2_policy": "compute / latency bound; every step rewrites %.1f MB of stacks and constants"
                                         % (ens[0].M * ens[0].lmax * 52 / 1e6),
                            "collective_ms_per_step": coll_ms},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * nsteps * len(kinds) * args.steps,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (7 + p1_launches(ens[0].M)) * nsteps * len(kinds) * args.steps,
                 "roofline": {"bound": "fp32", "kernel": "phase1_kernel<4> inside the Monte-Carlo step",
                              "layer_steps_per_eval": ctr[0] / ev_last, "sweeps_per_eval": ctr[1] / ev_last,
                              "achieved": ach, "peak": peaks[0], "unit": "TFLOP/s", "frac": ach / peaks[0] if peaks[0] else None,
@@ -625,7 +631,7 @@ def main():
                            "l2_policy": "inputs (%.2f GB layers + %.2f GB workspace per step) exceed the 126 MB L2"
                                         % (d_lay.numel() * 4 / 1e9, solver._ws.numel() / 1e9),
                            "roots_found_frac": nfound_ok / M, "rank_cpu_affinity": pinned_to},
-                "clocks": clocks, "e2e": e2e, "e2e_layers": e2e_layers, "gpu_launches": 7 * args.steps, "roofline": roof,
+                "clocks": clocks, "e2e": e2e, "e2e_layers": e2e_layers, "gpu_launches": (5 + p1_launches(M)) * args.steps, "roofline": roof,
                 "cpu_baseline": cpu, "love": love, "single_model_call": single}
         emit(line)
     if world > 1:
