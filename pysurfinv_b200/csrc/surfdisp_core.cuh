@@ -277,7 +277,15 @@ void half_terms(float arg, float kd, float kd2, float& rsin, float& sinr, float&
 #if defined(__CUDA_ARCH__) && !defined(SD_REC_GENERIC)
 struct RecLoader {
   unsigned base;
-  __device__ __forceinline__ explicit RecLoader(const float4* rec) : base((unsigned)__cvta_generic_to_shared(rec)) {}
+  __device__ __forceinline__ explicit RecLoader(const float4* rec) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(rec);
+    // Passed through an identity shuffle: where the sweep has a single call site in a kernel, ptxas specialises it for
+    // that kernel and re-derives the address from the thread index and the kernel parameters in EVERY layer step (17
+    // instructions of 200: cheaper than a register in its cost model).  A shuffle result cannot be recomputed.
+    unsigned lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    base = __shfl_sync(__activemask(), b, lane);
+  }
   __device__ __forceinline__ float4 operator()(int m) const {
     float4 r;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(base + 16u * (unsigned)m));
