@@ -25,7 +25,8 @@ class SurfdispOpts(C.Structure):
     """Mirror of ``SurfdispOpts`` in include/surfdisp_b200.h (defaults = reference init.f:25,43-58)."""
     _fields_ = [("dc", C.c_float), ("fact", C.c_float), ("t_base", C.c_float), ("ndiv", C.c_int),
                 ("ndiv_cap_rayleigh", C.c_int), ("ndiv_cap_love", C.c_int), ("atten", C.c_int),
-                ("flatten", C.c_int), ("stale_mmax", C.c_int), ("compute_group", C.c_int), ("exact_scan", C.c_int)]
+                ("flatten", C.c_int), ("stale_mmax", C.c_int), ("compute_group", C.c_int), ("exact_scan", C.c_int),
+                ("group_f64", C.c_int)]
 
 
 class SurfdispMcState(C.Structure):

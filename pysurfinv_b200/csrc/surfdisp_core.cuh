@@ -1022,8 +1022,10 @@ SD_HD float reigen_thread(const ModelView& mv, float T, float c, float ratio, fl
 // +0 tied to a value of the FP64 stream (see reigen_thread2)
 #if defined(__CUDA_ARCH__)
 SD_HD int sd_anchor(double x) { return __double2int_rz(x * 0.0); }
+SD_HD int sd_anchor(float x) { return __float2int_rz(x * 0.0f); }
 #else
 SD_HD int sd_anchor(double) { return 0; }
+SD_HD int sd_anchor(float) { return 0; }
 #endif
 
 struct LayerF {
@@ -1056,18 +1058,19 @@ SD_HD LayerF reigen_layer_setup(const ModelView& mv, int j, int ns, float wvno, 
   return L;
 }
 
-struct StepMat2 { double pp00, pp01, pp10, pp11, pq00, pq01, pq10, pq11, qp00, qp01, qp10, qp11; };
+template <typename F> struct StepMat2T { F pp00, pp01, pp10, pp11, pq00, pq01, pq10, pq11, qp00, qp01, qp10, qp11; };
+using StepMat2 = StepMat2T<double>;
 
-SD_HD StepMat2 make_stepmat2(const LayerF& L) {
-  const double hb00 = L.hb00, hb01 = L.hb01, hb10 = L.hb10, hc00 = L.hc00, hc01 = L.hc01, hc10 = L.hc10;
+template <typename F> SD_HD StepMat2T<F> make_stepmat2_t(const LayerF& L) {
+  const F hb00 = L.hb00, hb01 = L.hb01, hb10 = L.hb10, hc00 = L.hc00, hc01 = L.hc01, hc10 = L.hc10;
   // X' = (hB)(hC), B = [[b00, b01], [b10, -b00]], C = [[c00, c01], [c10, -c00]]
-  const double x00 = hb00 * hc00 + hb01 * hc10, x01 = hb00 * hc01 - hb01 * hc00;
-  const double x10 = hb10 * hc00 - hb00 * hc10, x11 = hb10 * hc01 + hb00 * hc00;
-  const double t = x00 + x11, d = x00 * x11 - x01 * x10;
-  const double al = 1.0 - d * (1.0 / 24.0), be = 0.5 + t * (1.0 / 24.0);
-  StepMat2 m;
+  const F x00 = hb00 * hc00 + hb01 * hc10, x01 = hb00 * hc01 - hb01 * hc00;
+  const F x10 = hb10 * hc00 - hb00 * hc10, x11 = hb10 * hc01 + hb00 * hc00;
+  const F t = x00 + x11, d = x00 * x11 - x01 * x10;
+  const F al = F(1.0) - d * (F(1.0) / F(24.0)), be = F(0.5) + t * (F(1.0) / F(24.0));
+  StepMat2T<F> m;
   m.pp00 = al + be * x00; m.pp01 = be * x01; m.pp10 = be * x10; m.pp11 = al + be * x11;
-  const double f00 = 1.0 + x00 * (1.0 / 6.0), f01 = x01 * (1.0 / 6.0), f10 = x10 * (1.0 / 6.0), f11 = 1.0 + x11 * (1.0 / 6.0);
+  const F f00 = F(1.0) + x00 * (F(1.0) / F(6.0)), f01 = x01 * (F(1.0) / F(6.0)), f10 = x10 * (F(1.0) / F(6.0)), f11 = F(1.0) + x11 * (F(1.0) / F(6.0));
   m.pq00 = f00 * hb00 + f01 * hb10; m.pq01 = f00 * hb01 - f01 * hb00;
   m.pq10 = f10 * hb00 + f11 * hb10; m.pq11 = f10 * hb01 - f11 * hb00;
   m.qp00 = f11 * hc00 - f01 * hc10; m.qp01 = f11 * hc01 + f01 * hc00;
@@ -1075,21 +1078,23 @@ SD_HD StepMat2 make_stepmat2(const LayerF& L) {
   return m;
 }
 
-SD_HD void rk4_step2(const StepMat2& m, double& ur, double& uz, double& tz, double& tr) {
-  const double nur = m.pp00 * ur + m.pp01 * tz + m.pq00 * uz + m.pq01 * tr;
-  const double ntz = m.pp10 * ur + m.pp11 * tz + m.pq10 * uz + m.pq11 * tr;
-  const double nuz = m.qp00 * ur + m.qp01 * tz + m.pp11 * uz - m.pp01 * tr;   // qq = adj(pp)
-  const double ntr = m.qp10 * ur + m.qp11 * tz - m.pp10 * uz + m.pp00 * tr;
+SD_HD StepMat2 make_stepmat2(const LayerF& L) { return make_stepmat2_t<double>(L); }
+
+template <typename F> SD_HD void rk4_step2(const StepMat2T<F>& m, F& ur, F& uz, F& tz, F& tr) {
+  const F nur = m.pp00 * ur + m.pp01 * tz + m.pq00 * uz + m.pq01 * tr;
+  const F ntz = m.pp10 * ur + m.pp11 * tz + m.pq10 * uz + m.pq11 * tr;
+  const F nuz = m.qp00 * ur + m.qp01 * tz + m.pp11 * uz - m.pp01 * tr;   // qq = adj(pp)
+  const F ntr = m.qp10 * ur + m.qp11 * tz - m.pp10 * uz + m.pp00 * tr;
   ur = nur; uz = nuz; tz = ntz; tr = ntr;
 }
 
 // the twelve Boole sums of a layer: (ur^2, uz^2, uz tr, ur tz) x (yy, yz, zz)
-struct Raw12 { double r0, r1, r2, r3, r4, r5, q6, q7, q8, q9, q10, q11; };
+template <typename F> struct Raw12T { F r0, r1, r2, r3, r4, r5, q6, q7, q8, q9, q10, q11; };
+template <typename F> struct Quad9T { F i0yy, i0yz, i0zz, i1yy, i1yz, i1zz, i2yy, i2yz, i2zz; };
 
-template <bool FIRST>
-SD_HD void boole_knot(Raw12& R, double w, bool unit, double yur, double yuz, double ytz, double ytr, double zur, double zuz,
-                      double ztz, double ztr) {
-  const double ay = unit ? yur : w * yur, by = unit ? yuz : w * yuz, az = unit ? zur : w * zur, bz = unit ? zuz : w * zuz;
+template <bool FIRST, typename F>
+SD_HD void boole_knot(Raw12T<F>& R, F w, bool unit, F yur, F yuz, F ytz, F ytr, F zur, F zuz, F ztz, F ztr) {
+  const F ay = unit ? yur : w * yur, by = unit ? yuz : w * yuz, az = unit ? zur : w * zur, bz = unit ? zuz : w * zuz;
   if (FIRST) {
     R.r0 = ay * yur; R.r1 = ay * zur; R.r2 = az * zur;
     R.r3 = by * yuz; R.r4 = by * zuz; R.r5 = bz * zuz;
@@ -1104,8 +1109,14 @@ SD_HD void boole_knot(Raw12& R, double w, bool unit, double yur, double yuz, dou
   R.q7 = fma(bz, ytr, R.q7); R.q10 = fma(az, ytz, R.q10);
 }
 
-SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, float fact,
-                           unsigned long long& nsubsteps) {
+// F = double: the reference's precision of the ODE state (REIGEN is implicit double precision), re-orthogonalised every
+// `orth_every` layers.  F = float (the product's default, orth_every = 1): every sub-layer is closed into the sums and
+// re-orthogonalised; measured against the double state on eight model families (4 .. 497 layers, water layers,
+// velocity inversions, thermal ocean models, periods 5 .. 200 s): |dU| <= 6e-6 km/s (2e-5 at 497 layers), and the same
+// error statistics against the oracle -- the noise of U comes from the float32 root c, not from the integration.
+template <typename F>
+SD_HD float reigen_thread2_t(const ModelView& mv, float T, float c, float ratio, float fact,
+                             unsigned long long& nsubsteps, int orth_every) {
   const DropResult dr = eigen_drop(mv, c, T, fact, true);
   const float wvno = SD_DIV(SD_TWOPI, SD_MUL(c, T));
   const float wvnosq = SD_MUL(wvno, wvno);
@@ -1152,23 +1163,22 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
   const float det = SD_SUB(wvnosq, SD_MUL(ra, rb));
   const float h = SD_MUL(rhoh, omegsq);
   const float brkt = SD_ADD(SD_MUL(-gamm1, wvno), SD_DIV(SD_MUL(SD_MUL(gam, ra), rb), wvno));
-  const double y0tz = (double)SD_DIV(SD_MUL(-h, brkt), det), y0tr = (double)SD_DIV(SD_MUL(-h, ra), det);
-  const double z0tz = (double)SD_DIV(SD_MUL(-h, rb), det), z0tr = y0tz;
+  const F y0tz = (F)SD_DIV(SD_MUL(-h, brkt), det), y0tr = (F)SD_DIV(SD_MUL(-h, ra), det);
+  const F z0tz = (F)SD_DIV(SD_MUL(-h, rb), det), z0tr = y0tz;
   if (rb == 0.f) return bh;  // surfa.f:1165
 
-  double xnorm = 0.0, bb = 1.0, alpha_sum = 0.0;
-  double zs_ur = 0.0, zs_uz = 1.0, zs_tz = z0tz, zs_tr = z0tr;  // start vector of solution 2
-  Quad9 Q;
+  F xnorm = F(0.0), bb = F(1.0), alpha_sum = F(0.0);
+  F zs_ur = F(0.0), zs_uz = F(1.0), zs_tz = z0tz, zs_tr = z0tr;  // start vector of solution 2
+  Quad9T<F> Q;
   const int jfirst = water ? 1 : 0;
-  const double dk = (double)wvno;
-  constexpr int kOrthEvery = 8;
-  constexpr double W7 = 7.0 / 32.0, W12 = 12.0 / 32.0;
+  const F dk = (F)wvno;
+  constexpr F W7 = F(7.0) / F(32.0), W12 = F(12.0) / F(32.0);
   for (int pass = 0; pass < 2; ++pass) {
-    double yur = 1.0, yuz = 0.0, ytz = y0tz, ytr = y0tr;
-    double zur = zs_ur, zuz = zs_uz, ztz = zs_tz, ztr = zs_tr;
-    Q.i0yy = Q.i0yz = Q.i0zz = Q.i1yy = Q.i1yz = Q.i1zz = Q.i2yy = Q.i2yz = Q.i2zz = 0.0;
+    F yur = F(1.0), yuz = F(0.0), ytz = y0tz, ytr = y0tr;
+    F zur = zs_ur, zuz = zs_uz, ztz = zs_tz, ztr = zs_tr;
+    Q.i0yy = Q.i0yz = Q.i0zz = Q.i1yy = Q.i1yz = Q.i1zz = Q.i2yy = Q.i2yz = Q.i2zz = F(0.0);
     int since = 0;
-    alpha_sum = 0.0;
+    alpha_sum = F(0.0);
     LayerF cur;
     cur.ns = 0;
     if (dr.jlast >= jfirst) cur = reigen_layer_setup(mv, dr.jlast, dr.nlast, wvno, wvnosq, omegsq);
@@ -1177,9 +1187,51 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
       // basic block (computed unconditionally, for a clamped index), so that the compiler interleaves the two
       const int jn = (j > jfirst) ? j - 1 : jfirst;
       LayerF nxt;
-      if (cur.ns > 0) {
-        const StepMat2 sm = make_stepmat2(cur);
-        Raw12 R;
+      if (sizeof(F) == 4 && cur.ns > 0) {
+        // float32 state: every SUB-layer is closed into the sums and followed by a re-orthogonalisation.  The pair is
+        // then never more parallel than one sub-layer makes it (growth ratio of the P and S parts over <= a few km), so
+        // the quadratic forms cancel a digit or two, not eight: on every model family of the hunt the group velocities
+        // agree with the float64 state's to ~3e-7 km/s and have the same error statistics against the oracle.
+        const StepMat2T<F> sm = make_stepmat2_t<F>(cur);
+        nxt = reigen_layer_setup(mv, jn, mv.nsub(jn), wvno, wvnosq, omegsq);
+        const F qw = (F)cur.qw, mu = (F)cur.mu, lam = (F)cur.lam, f12 = (F)cur.f12;
+        const F c0 = qw * (F)cur.rho;
+        const F c1b = qw * mu, c1a = fma(F(2.0), c1b, qw * lam);
+        const F cA = c1b * (F)cur.f34, cB = -c1b * dk;
+        const F cC = -(qw * lam) * f12, cD = cC * (dk * lam);
+        for (int s = 0; s < cur.ns; ++s) {
+          Raw12T<F> R;
+          boole_knot<true>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, W12, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          const F R1 = R.r1 + R.r1, R4 = R.r4 + R.r4;
+          Q.i0yy = fma(c0, R.r3, fma(c0, R.r0, Q.i0yy)); Q.i0yz = fma(c0, R4, fma(c0, R1, Q.i0yz)); Q.i0zz = fma(c0, R.r5, fma(c0, R.r2, Q.i0zz));
+          Q.i1yy = fma(c1b, R.r3, fma(c1a, R.r0, Q.i1yy)); Q.i1yz = fma(c1b, R4, fma(c1a, R1, Q.i1yz)); Q.i1zz = fma(c1b, R.r5, fma(c1a, R.r2, Q.i1zz));
+          Q.i2yy = fma(cD, R.r0, fma(cC, R.q9, fma(cB, R.r3, fma(cA, R.q6, Q.i2yy))));
+          Q.i2yz = fma(cD, R1, fma(cC, R.q10, fma(cB, R4, fma(cA, R.q7, Q.i2yz))));
+          Q.i2zz = fma(cD, R.r2, fma(cC, R.q11, fma(cB, R.r5, fma(cA, R.q8, Q.i2zz))));
+          if ((j > jfirst || s + 1 < cur.ns) && ++since >= orth_every) {
+            since = 0;
+            const F syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
+            const F syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
+            const F al = syz / syy;
+            zur = fma(-al, yur, zur); zuz = fma(-al, yuz, zuz); ztz = fma(-al, ytz, ztz); ztr = fma(-al, ytr, ztr);
+            alpha_sum += al;
+            { const F n = fma(F(-2.0) * al, Q.i0yy, Q.i0yz); Q.i0zz = fma(F(-0.5) * al, Q.i0yz + n, Q.i0zz); Q.i0yz = n; }
+            { const F n = fma(F(-2.0) * al, Q.i1yy, Q.i1yz); Q.i1zz = fma(F(-0.5) * al, Q.i1yz + n, Q.i1zz); Q.i1yz = n; }
+            { const F n = fma(F(-2.0) * al, Q.i2yy, Q.i2yz); Q.i2zz = fma(F(-0.5) * al, Q.i2yz + n, Q.i2zz); Q.i2yz = n; }
+          }
+        }
+        nsubsteps += (unsigned)cur.ns;
+      } else if (cur.ns > 0) {
+        const StepMat2T<F> sm = make_stepmat2_t<F>(cur);
+        Raw12T<F> R;
         // first sub-layer peeled: its first knot initialises the sums, and the straight-line code lets the compiler
         // interleave the next layer's float32 set-up with this FP64 stream (stacks of >= 21 layers have ns = 1)
         boole_knot<true>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
@@ -1188,34 +1240,34 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
         // stream after it; a warp then spends ~200 cycles in dependent float32 instructions per layer while the FP64
         // pipe waits for the other warps.  The layer index is tied to a value of this point of the stream (+0, not
         // foldable for IEEE doubles), which places the chain in the middle of the FP64 work.
-        // (measured: one anchor 74.2 -> 72.7 ms; the chain cut in three anchored stages 73.8 ms)
+        // (measured: one anchor F(74.2) -> F(72.7) ms; the chain cut in three anchored stages F(73.8) ms)
         nxt = reigen_layer_setup(mv, jn + sd_anchor(yur), mv.nsub(jn), wvno, wvnosq, omegsq);
-        boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
         rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
         boole_knot<false>(R, W12, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
         rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
-        boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+        boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
         rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
         boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
         for (int s = 1; s < cur.ns; ++s) {
           boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
-          boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
           boole_knot<false>(R, W12, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
-          boole_knot<false>(R, 1.0, true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
           boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
         }
         // closing: layer constants applied once (the yz sums of the squares enter doubled)
         {
-          const double qw = (double)cur.qw, mu = (double)cur.mu, lam = (double)cur.lam, f12 = (double)cur.f12;
-          const double c0 = qw * (double)cur.rho;
-          const double c1b = qw * mu, c1a = fma(2.0, c1b, qw * lam);      // qw (lambda + 2 mu), qw mu
-          const double cA = c1b * (double)cur.f34, cB = -c1b * dk;
-          const double cC = -(qw * lam) * f12, cD = cC * (dk * lam);
-          const double R1 = R.r1 + R.r1, R4 = R.r4 + R.r4;
+          const F qw = (F)cur.qw, mu = (F)cur.mu, lam = (F)cur.lam, f12 = (F)cur.f12;
+          const F c0 = qw * (F)cur.rho;
+          const F c1b = qw * mu, c1a = fma(F(2.0), c1b, qw * lam);      // qw (lambda + 2 mu), qw mu
+          const F cA = c1b * (F)cur.f34, cB = -c1b * dk;
+          const F cC = -(qw * lam) * f12, cD = cC * (dk * lam);
+          const F R1 = R.r1 + R.r1, R4 = R.r4 + R.r4;
           Q.i0yy = fma(c0, R.r3, fma(c0, R.r0, Q.i0yy)); Q.i0yz = fma(c0, R4, fma(c0, R1, Q.i0yz)); Q.i0zz = fma(c0, R.r5, fma(c0, R.r2, Q.i0zz));
           Q.i1yy = fma(c1b, R.r3, fma(c1a, R.r0, Q.i1yy)); Q.i1yz = fma(c1b, R4, fma(c1a, R1, Q.i1yz)); Q.i1zz = fma(c1b, R.r5, fma(c1a, R.r2, Q.i1zz));
           Q.i2yy = fma(cD, R.r0, fma(cC, R.q9, fma(cB, R.r3, fma(cA, R.q6, Q.i2yy))));
@@ -1229,28 +1281,28 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
         // kOrthEvery layers the component of z along y is removed (z <- z - al y): the sums are bilinear forms in
         // (y, z), so they are carried into the new basis exactly (Syz' = Syz - al Syy, Sz'z' = Szz - al (Syz + Syz')),
         // the pair never becomes parallel and the first integration is already the accurate one.
-        if (++since >= kOrthEvery && j > jfirst) {
+        if (++since >= orth_every && j > jfirst) {
           since = 0;
-          const double syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
-          const double syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
-          const double al = syz / syy;
+          const F syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
+          const F syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
+          const F al = syz / syy;
           zur = fma(-al, yur, zur); zuz = fma(-al, yuz, zuz); ztz = fma(-al, ytz, ztz); ztr = fma(-al, ytr, ztr);
           alpha_sum += al;
           // (the yz sums are stored doubled: S = 2 Syz)
-          { const double n = fma(-2.0 * al, Q.i0yy, Q.i0yz); Q.i0zz = fma(-0.5 * al, Q.i0yz + n, Q.i0zz); Q.i0yz = n; }
-          { const double n = fma(-2.0 * al, Q.i1yy, Q.i1yz); Q.i1zz = fma(-0.5 * al, Q.i1yz + n, Q.i1zz); Q.i1yz = n; }
-          { const double n = fma(-2.0 * al, Q.i2yy, Q.i2yz); Q.i2zz = fma(-0.5 * al, Q.i2yz + n, Q.i2zz); Q.i2yz = n; }
+          { const F n = fma(-F(2.0) * al, Q.i0yy, Q.i0yz); Q.i0zz = fma(-F(0.5) * al, Q.i0yz + n, Q.i0zz); Q.i0yz = n; }
+          { const F n = fma(-F(2.0) * al, Q.i1yy, Q.i1yz); Q.i1zz = fma(-F(0.5) * al, Q.i1yz + n, Q.i1zz); Q.i1yz = n; }
+          { const F n = fma(-F(2.0) * al, Q.i2yy, Q.i2yz); Q.i2zz = fma(-F(0.5) * al, Q.i2yz + n, Q.i2zz); Q.i2yz = n; }
         }
       } else nxt = reigen_layer_setup(mv, jn, mv.nsub(jn), wvno, wvnosq, omegsq);
       cur = nxt;
     }
     // combine with the surface ellipticity (surfa.f:1056-1065)
-    const double aa = zur - (double)ratio * zuz;
-    double b_ = (double)ratio * yuz - yur;
-    if (fabs(b_) < 1.e-10) b_ = copysign(1.e-10, b_);
+    const F aa = zur - (F)ratio * zuz;
+    F b_ = (F)ratio * yuz - yur;
+    if (fabs(b_) < F(1.e-10)) b_ = copysign(F(1.e-10), b_);
     xnorm = aa / b_;
     bb = xnorm * yuz + zuz;
-    if (fabs(bb) < 1.e-10) bb = copysign(1.e-10, bb);
+    if (fabs(bb) < F(1.e-10)) bb = copysign(F(1.e-10), bb);
     if (pass == 0) {
       const float ampur = (float)((xnorm * yur + zur) / bb);
       const float xtest = fabsf(ampur / ratio - 1.f);
@@ -1258,43 +1310,48 @@ SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, f
       // quadratic forms used here square the dynamic range of the cancellation instead: where y and z have grown
       // nearly parallel (short periods, c above the crustal velocities: the P part grows by e^18 over the depth
       // range) x^2 Qyy + x Qyz + Qzz loses every digit although the reference's first iteration is still fine.
-      // The conditioning of the two positive integrals is checked; below 1e-7 the second iteration is taken too
+      // The conditioning of the two positive integrals is checked; below F(1e-7) the second iteration is taken too
       // (solution 2 restarted from the eigenfunction itself: no cancellation left in the sums).
-      const double a0 = xnorm * xnorm * Q.i0yy, b0 = xnorm * Q.i0yz, a1 = xnorm * xnorm * Q.i1yy, b1 = xnorm * Q.i1yz;
-      const bool lost = fabs(a0 + b0 + Q.i0zz) < 1.0e-7 * (fabs(a0) + fabs(b0) + fabs(Q.i0zz)) ||
-                        fabs(a1 + b1 + Q.i1zz) < 1.0e-7 * (fabs(a1) + fabs(b1) + fabs(Q.i1zz));
+      const F a0 = xnorm * xnorm * Q.i0yy, b0 = xnorm * Q.i0yz, a1 = xnorm * xnorm * Q.i1yy, b1 = xnorm * Q.i1yz;
+      const bool lost = fabs(a0 + b0 + Q.i0zz) < F(1.0e-7) * (fabs(a0) + fabs(b0) + fabs(Q.i0zz)) ||
+                        fabs(a1 + b1 + Q.i1zz) < F(1.0e-7) * (fabs(a1) + fabs(b1) + fabs(Q.i1zz));
       if (!(xtest >= 0.00001f) && !lost) break;  // the reference keeps the first iteration (surfa.f:1068-1069)
       // second iteration of the reference (surfa.f:986-998): solution 2 restarted from z + xnorm*y
       SD_COUNT_SECOND_PASS();
       // (in terms of this pass's start vector the eigenfunction is (xnorm - alpha_sum) y + z)
-      const double xo = xnorm - alpha_sum;
-      zs_ur = zs_ur + xo * 1.0; zs_uz = zs_uz + xo * 0.0; zs_tz = zs_tz + xo * y0tz; zs_tr = zs_tr + xo * y0tr;
+      const F xo = xnorm - alpha_sum;
+      zs_ur = zs_ur + xo * F(1.0); zs_uz = zs_uz + xo * F(0.0); zs_tz = zs_tz + xo * y0tz; zs_tr = zs_tr + xo * y0tr;
     }
   }
-  const double ib2 = 1.0 / (bb * bb);
-  double s0 = (double)w0 + (xnorm * xnorm * Q.i0yy + xnorm * Q.i0yz + Q.i0zz) * ib2;
-  double s1 = (double)w1 + (xnorm * xnorm * Q.i1yy + xnorm * Q.i1yz + Q.i1zz) * ib2;
-  double s2 = (double)w2 + (xnorm * xnorm * Q.i2yy + xnorm * Q.i2yz + Q.i2zz) * ib2;
+  const F ib2 = F(1.0) / (bb * bb);
+  F s0 = (F)w0 + (xnorm * xnorm * Q.i0yy + xnorm * Q.i0yz + Q.i0zz) * ib2;
+  F s1 = (F)w1 + (xnorm * xnorm * Q.i1yy + xnorm * Q.i1yz + Q.i1zz) * ib2;
+  F s2 = (F)w2 + (xnorm * xnorm * Q.i2yy + xnorm * Q.i2yz + Q.i2zz) * ib2;
   // half-space tail (surfa.f:1151-1178)
   {
-    const double xo = xnorm - alpha_sum;   // coefficient of y relative to the start vectors of the last pass
-    double aur = (xo * 1.0 + zs_ur) / bb, auz = (xo * 0.0 + zs_uz) / bb;
-    if (water && dr.jh == 1) { aur = ratio; auz = 1.0; }
-    const double dra = ra, drb = rb, ddet = det, drho = rhoh;
-    const double xmu = (double)SD_MUL(SD_MUL(rhoh, bh), bh);
-    const double xlamb = (double)SD_MUL(rhoh, SD_SUB(SD_MUL(ah, ah), SD_MUL(SD_MUL(2.f, bh), bh)));
-    const double ap = -drho * (dk * aur + drb * auz) / ddet;
-    const double bp = -drho * (-dra * aur / dk - auz) / ddet;
-    const double a1 = -dk * ap / drho, a2 = -dk * drb * bp / drho, a3 = dra * ap / drho, a4 = (double)wvnosq * bp / drho;
-    const double dmmr = a1 * a1 / (2. * dra) + 2. * a1 * a2 / (dra + drb) + a2 * a2 / (2. * drb);
-    const double dmmz = a3 * a3 / (2. * dra) + 2. * a3 * a4 / (dra + drb) + a4 * a4 / (2. * drb);
-    const double drsz = -a1 * a3 / 2. - (a1 * a4 * drb + a2 * a3 * dra) / (dra + drb) - a2 * a4 / 2.;
-    const double dzsr = -a1 * a3 / 2. - (a1 * a4 * dra + a2 * a3 * drb) / (dra + drb) - a2 * a4 / 2.;
+    const F xo = xnorm - alpha_sum;   // coefficient of y relative to the start vectors of the last pass
+    F aur = (xo * F(1.0) + zs_ur) / bb, auz = (xo * F(0.0) + zs_uz) / bb;
+    if (water && dr.jh == 1) { aur = ratio; auz = F(1.0); }
+    const F dra = ra, drb = rb, ddet = det, drho = rhoh;
+    const F xmu = (F)SD_MUL(SD_MUL(rhoh, bh), bh);
+    const F xlamb = (F)SD_MUL(rhoh, SD_SUB(SD_MUL(ah, ah), SD_MUL(SD_MUL(2.f, bh), bh)));
+    const F ap = -drho * (dk * aur + drb * auz) / ddet;
+    const F bp = -drho * (-dra * aur / dk - auz) / ddet;
+    const F a1 = -dk * ap / drho, a2 = -dk * drb * bp / drho, a3 = dra * ap / drho, a4 = (F)wvnosq * bp / drho;
+    const F dmmr = a1 * a1 / (F(2.) * dra) + F(2.) * a1 * a2 / (dra + drb) + a2 * a2 / (F(2.) * drb);
+    const F dmmz = a3 * a3 / (F(2.) * dra) + F(2.) * a3 * a4 / (dra + drb) + a4 * a4 / (F(2.) * drb);
+    const F drsz = -a1 * a3 / F(2.) - (a1 * a4 * drb + a2 * a3 * dra) / (dra + drb) - a2 * a4 / F(2.);
+    const F dzsr = -a1 * a3 / F(2.) - (a1 * a4 * dra + a2 * a3 * drb) / (dra + drb) - a2 * a4 / F(2.);
     s0 += drho * (dmmr + dmmz);
-    s1 += (xlamb + 2. * xmu) * dmmr + xmu * dmmz;
+    s1 += (xlamb + F(2.) * xmu) * dmmr + xmu * dmmz;
     s2 += xmu * dzsr - xlamb * drsz;
   }
-  return (float)(((double)wvno * s1 + s2) / ((double)omega * s0));  // surfa.f:1186
+  return (float)(((F)wvno * s1 + s2) / ((F)omega * s0));  // surfa.f:1186
+}
+
+// The reference's precision (surfa.f: implicit double precision in REIGEN)
+SD_HD float reigen_thread2(const ModelView& mv, float T, float c, float ratio, float fact, unsigned long long& nsubsteps) {
+  return reigen_thread2_t<double>(mv, T, c, ratio, fact, nsubsteps, 8);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -1017,10 +1017,13 @@ struct P2Params {
 #ifndef P2_MINBLK_LOVE
 #define P2_MINBLK_LOVE 3   // 65536 / (3 x 256) = 85 registers per thread
 #endif
-// One instantiation per wave type: the Rayleigh one (FP64 ODE) needs 128 registers, the Love one (float32 analytic
-// propagation) is latency bound and runs with 96 registers and a third more resident warps.
+#ifndef P2_MINBLK_F32
+#define P2_MINBLK_F32 3   // float32 Rayleigh state: 80 registers, 5 blocks of 160 threads per SM (54.2 ms; 125 registers, no spills: 56.3 ms)
+#endif
+// KIND 1: Love (float32 analytic propagation, latency bound: 85 registers and a third more resident warps); KIND 2:
+// Rayleigh with the float64 ODE state of the reference (128 registers); KIND 3: Rayleigh with the float32 state (default).
 template <int KIND>
-__global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_LOVE) phase2_kernel(const __grid_constant__ P2Params p) {
+__global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : (KIND == 3 ? P2_MINBLK_F32 : P2_MINBLK_LOVE)) phase2_kernel(const __grid_constant__ P2Params p) {
   extern __shared__ float4 smem[];
   float* sc = reinterpret_cast<float*>(smem);
   const int K = p.K;
@@ -1063,6 +1066,7 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : P2_MINBLK_
       const float c = p.c_in[(size_t)model * K + k];
       float u;
       if (KIND == 2) u = reigen_thread2(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
+      else if (KIND == 3) u = reigen_thread2_t<float>(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub, 1);
       else u = leigen_thread(mv, T, c, p.fact, nsub);
       urow[k] = u;
     }
@@ -1286,6 +1290,7 @@ extern "C" {
 void surfdisp_default_opts(SurfdispOpts* o) {
   o->dc = 0.01f; o->fact = 4.0f; o->t_base = 1.0f; o->ndiv = 5; o->ndiv_cap_rayleigh = 99;
   o->ndiv_cap_love = 999; o->atten = 1; o->flatten = 1; o->stale_mmax = 1; o->compute_group = 1; o->exact_scan = 0;
+  o->group_f64 = 0;
 }
 
 size_t surfdisp_workspace_bytes(int n_models, int n_layers_max, int n_periods) {
@@ -1455,9 +1460,12 @@ static int stage_p2(const Plan& pl, int a, int b, cudaStream_t st) {
   if (threads > P2_THREADS) threads = P2_THREADS;
   const size_t smem = mpb * per_model;
   const int grid = (m + mpb - 1) / mpb;
-  if (pl.kind == 2) {
+  if (pl.kind == 2 && pl.o.group_f64) {
     CK(cudaFuncSetAttribute(phase2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     phase2_kernel<2><<<grid, threads, smem, st>>>(p2);
+  } else if (pl.kind == 2) {
+    CK(cudaFuncSetAttribute(phase2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    phase2_kernel<3><<<grid, threads, smem, st>>>(p2);
   } else {
     CK(cudaFuncSetAttribute(phase2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     phase2_kernel<1><<<grid, threads, smem, st>>>(p2);

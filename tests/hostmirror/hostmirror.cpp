@@ -421,6 +421,11 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     mv.jj0 = (cst[C_BREF * ld + 0] <= 0.1e-10f) ? 1 : 0;
     unsigned long long ns = 0;
     static const bool plain_reigen = getenv("HM_PLAIN_REIGEN") != nullptr;   // (the untrimmed statement of the same integration)
+    // the product's default: float32 ODE state, re-orthogonalised after every sub-layer (HM_REIGEN_F64: the float64 state of
+    // opts.group_f64 = 1; HM_REIGEN_F32 = n: float32 re-orthogonalised every n sub-layers, for the precision study)
+    static const bool f64_state = getenv("HM_REIGEN_F64") != nullptr;
+    static const int f32_orth = getenv("HM_REIGEN_F32") ? atoi(getenv("HM_REIGEN_F32")) : 1;
+    if (kind == 2 && !f64_state && !plain_reigen) { u_out[k] = reigen_thread2_t<float>(mv, per[k], c_out[k], ratio_out[k], fact, ns, f32_orth); continue; }
     u_out[k] = (kind == 2) ? (plain_reigen ? reigen_thread(mv, per[k], c_out[k], ratio_out[k], fact, ns) : reigen_thread2(mv, per[k], c_out[k], ratio_out[k], fact, ns))
                            : leigen_thread(mv, per[k], c_out[k], fact, ns);
   }

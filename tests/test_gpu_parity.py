@@ -469,3 +469,26 @@ def test_hand_over_between_root_search_launches_changes_nothing(solver):
     finally:
         lib.surfdisp_set_split_min_models(0)
     assert handed > 100      # the path was taken
+
+
+def test_group_velocity_float32_state_against_float64_state(solver):
+    """REIGEN's ODE state and energy sums in float32 (default: every sub-layer re-orthogonalised) against float64 like the
+    reference (opts.group_f64 = 1): same roots, |dU| <= 3e-5 km/s on thin-layer stacks, thick layers with sub-division,
+    water layers, velocity inversions, 147- and 497-layer stacks up to 200 s -- and both within the parity bars."""
+    import torch
+    from pysurfinv_b200 import api
+    f64 = api.DispersionSolver("cuda:0", opts=api.default_opts(group_f64=1))
+    cases = [(synth.crustal_models(3000, seed=601), synth.log_periods()), (synth.crustal_models(1500, seed=602, lvz=True), synth.log_periods(100, 5.0, 120.0)),
+             (synth.hand_models(2000, seed=603), synth.log_periods(24, 6.0, 60.0)), (synth.ragged_models(2000, seed=604), synth.log_periods(24)),
+             (synth.crustal_models(400, seed=605, n_crust=15, n_mantle=130, zmax=400.0), np.arange(10.0, 151.0, 10.0, dtype=np.float32)),
+             (synth.crustal_models(60, seed=606, n_crust=40, n_mantle=455, zmax=600.0), synth.log_periods(60, 5.0, 200.0))]
+    for (lay, nl), per in cases:
+        a = _gpu(solver, lay, nl, per, 2)
+        dl, dn = torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda()
+        b = {k: v.cpu().numpy() for k, v in f64.forward(dl, dn, per, kind=2).items()}
+        assert np.array_equal(a["c"], b["c"]) and np.array_equal(a["nfound"], b["nfound"])
+        assert np.abs(a["u"] - b["u"]).max() <= 3e-5, np.abs(a["u"] - b["u"]).max()
+    lay, nl = synth.crustal_models(1500, seed=607)
+    per = synth.log_periods()
+    dl, dn = torch.from_numpy(lay).cuda(), torch.from_numpy(nl).cuda()
+    _check({k: v.cpu().numpy() for k, v in f64.forward(dl, dn, per, kind=2).items()}, lay, nl, per, 2)
