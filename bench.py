@@ -36,9 +36,10 @@ UNIT = "evals/s"
 # FLOP-equivalents per unit of work, SURVEY.md 8(d): Rayleigh layer-step 150 FLOP + 4 transcendentals
 # (10 FLOP each), Love layer-step 20 FLOP + 2 transcendentals, REIGEN sub-layer 1800 FLOP (fp64).
 F_R, F_L, F_U = 190.0, 40.0, 1800.0
-# FP64 FLOP the group-velocity kernel executes per sub-layer: 2 x 203 DFMA + 82 DMUL + 4 DADD per thread and sub-layer
-# (ncu source counters, profiles/r2_ncu_phase2.txt), against ~1800 of the reference's stage-by-stage form
-F_U_EXEC = 492.0
+# FLOP the group-velocity kernel executes per sub-layer (float32 state, packed pairs; ncu instruction counters,
+# profiles/r2_ncu_phase2.txt: FFMA, FMUL, FADD per thread and sub-layer), against ~1800 of the reference's stage-by-stage
+# form in float64
+F_U_EXEC = 560.0
 # DRAM bytes per model of the root-search launches and of the group-velocity launch (ncu dram__bytes_read + write at
 # 524288 models x 40 periods, profiles/r2_ncu_*.txt); algorithmic bytes per model: phase 1 reads the constants
 # 8 x lpad x 4 B at the first period and once more at the start of the later periods and writes c, ratio
@@ -592,7 +593,7 @@ def main():
         lpad = 80
         ach = flop_p1 / (kms[1] * 1e-3) * 1e-12
         ex2 = subu_ctr * F_U_EXEC / (kms[2] * 1e-3) * 1e-12
-        roof = {"bound": "fp32", "kernel": "phase1_kernel<4> (root search: 2 launches, first period / later periods)",
+        roof = {"bound": "fp32", "kernel": "phase1_kernel<4> (root search: 3 launches -- first period, fast path, handed-over models)",
                 "achieved": ach, "peak": peaks[0], "unit": "TFLOP/s", "frac": ach / peaks[0] if peaks[0] else None,
                 "peak_source": "surfdisp_measure_peaks(): register-resident FFMA chain, this run "
                                "(MEASURED_PEAKS.json has no FP32 figure; the path is FP-pipe bound, not HBM or tensor)",
@@ -605,12 +606,13 @@ def main():
                 "kernel_ms": {"prep": float(kms[0]), "phase1": float(kms[1]), "phase2": float(kms[2])},
                 "layer_steps_per_eval": steps_ctr / (M * K), "sweeps_per_eval": sweeps_ctr / (M * K),
                 "u_sublayers_per_eval": subu_ctr / (M * K),
-                "phase2": {"bound": "fp64", "executed": ex2, "peak": peaks[1], "unit": "TFLOP/s",
-                           "frac_executed": ex2 / peaks[1] if peaks[1] else None,
+                "phase2": {"bound": "fp32", "executed": ex2, "peak": peaks[0], "unit": "TFLOP/s",
+                           "frac_executed": ex2 / peaks[0] if peaks[0] else None,
                            "reference_equivalent_tflops": subu_ctr * F_U / (kms[2] * 1e-3) * 1e-12, "traffic": DRAM_P2_PER_MODEL * M,
-                           "note": "executed = FP64 FLOP of this kernel's formulation (%.0f per sub-layer, ncu instruction counts); "
-                                   "reference_equivalent = the same sub-layers at the reference's %.0f FLOP each -- a work-saving "
-                                   "factor, not a utilisation" % (F_U_EXEC, F_U)},
+                           "note": "executed = float32 FLOP of this kernel's formulation (%.0f per sub-layer, ncu instruction counts; "
+                                   "float32 ODE state re-orthogonalised after every sub-layer, the float64 state of the reference is "
+                                   "opts.group_f64 = 1); reference_equivalent = the same sub-layers at the reference's %.0f FLOP each "
+                                   "-- a work-saving factor, not a utilisation" % (F_U_EXEC, F_U)},
                 "mufu_peak_Tops": peaks[2]}
         cpu = None
         if not args.no_cpu:
@@ -624,7 +626,7 @@ def main():
             roof["ref_equiv_tflops"] = value / world * (cc["steps_R"] / (n * K) * F_R + cc["sub_U"] / (n * K) * F_U) * 1e-12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (root search) + f64 (group-velocity ODE)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (root search and group-velocity ODE state; the reference's float64 state: opts.group_f64)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD_SWEEP % (M, K),
                            "models_per_gpu": M, "periods": K, "layers": lmax, "params_per_model": int(h_par.shape[1]),

@@ -1114,9 +1114,13 @@ SD_HD void boole_knot(Raw12T<F>& R, F w, bool unit, F yur, F yuz, F ytz, F ytr, 
 // re-orthogonalised; measured against the double state on eight model families (4 .. 497 layers, water layers,
 // velocity inversions, thermal ocean models, periods 5 .. 200 s): |dU| <= 6e-6 km/s (2e-5 at 497 layers), and the same
 // error statistics against the oracle -- the noise of U comes from the float32 root c, not from the integration.
-template <typename F>
+// PK (float state only): the two solutions travel as packed pairs (y, z) per component -- the RK4 step applies ONE
+// matrix to both, and of the twelve Boole sums the (yy, zz) halves of every triple are a packed operation: 16 instead of
+// 32 instructions per step, 12 instead of 18 per knot.
+template <typename F, bool PK = false>
 SD_HD float reigen_thread2_t(const ModelView& mv, float T, float c, float ratio, float fact,
                              unsigned long long& nsubsteps, int orth_every) {
+  static_assert(!PK || sizeof(F) == 4, "packed pairs are float32");
   const DropResult dr = eigen_drop(mv, c, T, fact, true);
   const float wvno = SD_DIV(SD_TWOPI, SD_MUL(c, T));
   const float wvnosq = SD_MUL(wvno, wvno);
@@ -1199,8 +1203,48 @@ SD_HD float reigen_thread2_t(const ModelView& mv, float T, float c, float ratio,
         const F c1b = qw * mu, c1a = fma(F(2.0), c1b, qw * lam);
         const F cA = c1b * (F)cur.f34, cB = -c1b * dk;
         const F cC = -(qw * lam) * f12, cD = cC * (dk * lam);
+        // (PK: the step matrix broadcast into pairs once per layer; qq = adj(pp) needs two entries negated)
+        V2 Ppp00, Ppp01, Ppp10, Ppp11, Ppq00, Ppq01, Ppq10, Ppq11, Pqp00, Pqp01, Pqp10, Pqp11, Pnpp01, Pnpp10;
+        if (PK) {
+          Ppp00 = vs((float)sm.pp00); Ppp01 = vs((float)sm.pp01); Ppp10 = vs((float)sm.pp10); Ppp11 = vs((float)sm.pp11);
+          Ppq00 = vs((float)sm.pq00); Ppq01 = vs((float)sm.pq01); Ppq10 = vs((float)sm.pq10); Ppq11 = vs((float)sm.pq11);
+          Pqp00 = vs((float)sm.qp00); Pqp01 = vs((float)sm.qp01); Pqp10 = vs((float)sm.qp10); Pqp11 = vs((float)sm.qp11);
+          Pnpp01 = vs(-(float)sm.pp01); Pnpp10 = vs(-(float)sm.pp10);
+        }
         for (int s = 0; s < cur.ns; ++s) {
           Raw12T<F> R;
+          if (PK) {
+            V2 pur = v2((float)yur, (float)zur), puz = v2((float)yuz, (float)zuz), ptz = v2((float)ytz, (float)ztz), ptr = v2((float)ytr, (float)ztr);
+            V2 R02, R35, Q68, Q911;
+            float r1, r4, q7, q10;
+            const V2 w7 = vs(7.0f / 32.0f), w12 = vs(12.0f / 32.0f);
+            // knot 0 (weight 7/32) initialises the sums
+            {
+              const V2 A = vmul(w7, pur), B = vmul(w7, puz);
+              R02 = vmul(A, pur); r1 = vx(A) * vy(pur); R35 = vmul(B, puz); r4 = vx(B) * vy(puz);
+              Q68 = vmul(B, ptr); q7 = vx(B) * vy(ptr); Q911 = vmul(A, ptz); q10 = vx(A) * vy(ptz);
+              q7 = fmaf(vy(B), vx(ptr), q7); q10 = fmaf(vy(A), vx(ptz), q10);
+            }
+#pragma unroll
+            for (int kn = 1; kn <= 4; ++kn) {
+              {
+                const V2 nur = vfma(Ppp00, pur, vfma(Ppp01, ptz, vfma(Ppq00, puz, vmul(Ppq01, ptr))));
+                const V2 ntz = vfma(Ppp10, pur, vfma(Ppp11, ptz, vfma(Ppq10, puz, vmul(Ppq11, ptr))));
+                const V2 nuz = vfma(Pqp00, pur, vfma(Pqp01, ptz, vfma(Ppp11, puz, vmul(Pnpp01, ptr))));
+                const V2 ntr = vfma(Pqp10, pur, vfma(Pqp11, ptz, vfma(Pnpp10, puz, vmul(Ppp00, ptr))));
+                pur = nur; puz = nuz; ptz = ntz; ptr = ntr;
+              }
+              // weights 32/32 (knots 1, 3), 12/32 (knot 2), 7/32 (knot 4)
+              const V2 A = (kn == 2) ? vmul(w12, pur) : ((kn == 4) ? vmul(w7, pur) : pur);
+              const V2 B = (kn == 2) ? vmul(w12, puz) : ((kn == 4) ? vmul(w7, puz) : puz);
+              R02 = vfma(A, pur, R02); r1 = fmaf(vx(A), vy(pur), r1); R35 = vfma(B, puz, R35); r4 = fmaf(vx(B), vy(puz), r4);
+              Q68 = vfma(B, ptr, Q68); q7 = fmaf(vx(B), vy(ptr), q7); Q911 = vfma(A, ptz, Q911); q10 = fmaf(vx(A), vy(ptz), q10);
+              q7 = fmaf(vy(B), vx(ptr), q7); q10 = fmaf(vy(A), vx(ptz), q10);
+            }
+            yur = vx(pur); zur = vy(pur); yuz = vx(puz); zuz = vy(puz); ytz = vx(ptz); ztz = vy(ptz); ytr = vx(ptr); ztr = vy(ptr);
+            R.r0 = vx(R02); R.r2 = vy(R02); R.r1 = r1; R.r3 = vx(R35); R.r5 = vy(R35); R.r4 = r4;
+            R.q6 = vx(Q68); R.q8 = vy(Q68); R.q7 = q7; R.q9 = vx(Q911); R.q11 = vy(Q911); R.q10 = q10;
+          } else {
           boole_knot<true>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
           boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
@@ -1210,6 +1254,7 @@ SD_HD float reigen_thread2_t(const ModelView& mv, float T, float c, float ratio,
           boole_knot<false>(R, F(1.0), true, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
           rk4_step2(sm, yur, yuz, ytz, ytr); rk4_step2(sm, zur, zuz, ztz, ztr);
           boole_knot<false>(R, W7, false, yur, yuz, ytz, ytr, zur, zuz, ztz, ztr);
+          }
           const F R1 = R.r1 + R.r1, R4 = R.r4 + R.r4;
           Q.i0yy = fma(c0, R.r3, fma(c0, R.r0, Q.i0yy)); Q.i0yz = fma(c0, R4, fma(c0, R1, Q.i0yz)); Q.i0zz = fma(c0, R.r5, fma(c0, R.r2, Q.i0zz));
           Q.i1yy = fma(c1b, R.r3, fma(c1a, R.r0, Q.i1yy)); Q.i1yz = fma(c1b, R4, fma(c1a, R1, Q.i1yz)); Q.i1zz = fma(c1b, R.r5, fma(c1a, R.r2, Q.i1zz));

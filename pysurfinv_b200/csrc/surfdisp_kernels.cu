@@ -1018,7 +1018,7 @@ struct P2Params {
 #define P2_MINBLK_LOVE 3   // 65536 / (3 x 256) = 85 registers per thread
 #endif
 #ifndef P2_MINBLK_F32
-#define P2_MINBLK_F32 3   // float32 Rayleigh state: 80 registers, 5 blocks of 160 threads per SM (54.2 ms; 125 registers, no spills: 56.3 ms)
+#define P2_MINBLK_F32 2   // float32 Rayleigh state, packed pairs: 119 registers, no spills, 46.4 ms (80 registers with 250 B of spills: 46.7; 64: 49.2)
 #endif
 // KIND 1: Love (float32 analytic propagation, latency bound: 85 registers and a third more resident warps); KIND 2:
 // Rayleigh with the float64 ODE state of the reference (128 registers); KIND 3: Rayleigh with the float32 state (default).
@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(P2_THREADS, KIND == 2 ? P2_MINBLK : (KIND == 3
       const float c = p.c_in[(size_t)model * K + k];
       float u;
       if (KIND == 2) u = reigen_thread2(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub);
-      else if (KIND == 3) u = reigen_thread2_t<float>(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub, 1);
+      else if (KIND == 3) u = reigen_thread2_t<float, true>(mv, T, c, p.ratio_in[(size_t)model * K + k], p.fact, nsub, 1);
       else u = leigen_thread(mv, T, c, p.fact, nsub);
       urow[k] = u;
     }

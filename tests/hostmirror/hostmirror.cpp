@@ -425,7 +425,12 @@ int hm_forward(int G, int kind, int n, const float* a, const float* b, const flo
     // opts.group_f64 = 1; HM_REIGEN_F32 = n: float32 re-orthogonalised every n sub-layers, for the precision study)
     static const bool f64_state = getenv("HM_REIGEN_F64") != nullptr;
     static const int f32_orth = getenv("HM_REIGEN_F32") ? atoi(getenv("HM_REIGEN_F32")) : 1;
-    if (kind == 2 && !f64_state && !plain_reigen) { u_out[k] = reigen_thread2_t<float>(mv, per[k], c_out[k], ratio_out[k], fact, ns, f32_orth); continue; }
+    static const bool scalar_f32 = getenv("HM_REIGEN_SCALAR") != nullptr;    // (the float32 state without packed pairs)
+    if (kind == 2 && !f64_state && !plain_reigen) {
+      u_out[k] = scalar_f32 ? reigen_thread2_t<float, false>(mv, per[k], c_out[k], ratio_out[k], fact, ns, f32_orth)
+                            : reigen_thread2_t<float, true>(mv, per[k], c_out[k], ratio_out[k], fact, ns, f32_orth);
+      continue;
+    }
     u_out[k] = (kind == 2) ? (plain_reigen ? reigen_thread(mv, per[k], c_out[k], ratio_out[k], fact, ns) : reigen_thread2(mv, per[k], c_out[k], ratio_out[k], fact, ns))
                            : leigen_thread(mv, per[k], c_out[k], fact, ns);
   }
