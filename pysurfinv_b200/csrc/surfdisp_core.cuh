@@ -1265,7 +1265,7 @@ SD_HD float reigen_thread2_t(const ModelView& mv, float T, float c, float ratio,
             since = 0;
             const F syy = yur * yur + yuz * yuz + ytz * ytz + ytr * ytr;
             const F syz = yur * zur + yuz * zuz + ytz * ztz + ytr * ztr;
-            const F al = syz / syy;
+            const F al = (F)SD_FDIV((float)syz, (float)syy);      // (any coefficient is carried through the sums exactly: no IEEE division needed)
             zur = fma(-al, yur, zur); zuz = fma(-al, yuz, zuz); ztz = fma(-al, ytz, ztz); ztr = fma(-al, ytr, ztr);
             alpha_sum += al;
             { const F n = fma(F(-2.0) * al, Q.i0yy, Q.i0yz); Q.i0zz = fma(F(-0.5) * al, Q.i0yz + n, Q.i0zz); Q.i0yz = n; }
