@@ -36,10 +36,11 @@ UNIT = "evals/s"
 # FLOP-equivalents per unit of work, SURVEY.md 8(d): Rayleigh layer-step 150 FLOP + 4 transcendentals
 # (10 FLOP each), Love layer-step 20 FLOP + 2 transcendentals, REIGEN sub-layer 1800 FLOP (fp64).
 F_R, F_L, F_U = 190.0, 40.0, 1800.0
-# FLOP the group-velocity kernel executes per sub-layer (float32 state, packed pairs; ncu instruction counters,
-# profiles/r2_ncu_phase2.txt: FFMA, FMUL, FADD per thread and sub-layer), against ~1800 of the reference's stage-by-stage
-# form in float64
-F_U_EXEC = 560.0
+# FLOP the group-velocity kernel executes per sub-layer (float32 state, packed pairs, one sub-layer per layer as in
+# config 2): 71 FFMA + 64 FFMA2 + 26 FMUL2 + 8 FMUL + 6 FADD in the sub-layer body, 26 FFMA + 87 FMUL + 13 FADD of set-up
+# per layer (SASS of the loop; the ncu counters of profiles/r2_ncu_phase2.txt give the same FFMA : FMUL : FADD mix with a
+# packed instruction counted once), against ~1800 of the reference's stage-by-stage form in float64
+F_U_EXEC = 616.0
 # DRAM bytes per model of the root-search launches and of the group-velocity launch (ncu dram__bytes_read + write at
 # 524288 models x 40 periods, profiles/r2_ncu_*.txt); algorithmic bytes per model: phase 1 reads the constants
 # 8 x lpad x 4 B at the first period and once more at the start of the later periods and writes c, ratio
