@@ -4,13 +4,17 @@
 //   prep_kernel    warp per model, lanes over layers   layers[5][M][Lmax] -> consts[M][8][lpad]  (flat1.f, once per model)
 //   phase1_kernel  4 lanes x 2 packed trial velocities per model, 8 models per warp; every group is a state
 //                  machine and one loop iteration = one sweep of the secular function for every group.
-//                  Launch 1: first period (the reference's scan, calcul.f:155-167).  Launch 2: later periods
+//                  Launch 1 (P1_FIRST): first period (the reference's scan, calcul.f:155-167).  Later periods
 //                  (cluster of trial velocities around the extrapolated root, inverse interpolation, scan as
-//                  fall-back)                           -> c[M][K], ratio[M][K], nfound[M], flags[M]
+//                  fall-back): one general launch (P1_GENERAL), or -- large batches -- a fast-path launch without
+//                  scan code (P1_FAST) that hands the models needing a scan over to the general one
+//                                                       -> c[M][K], ratio[M][K], nfound[M], flags[M]
 //   phase2_kernel  thread per (model, period)          energy integrals -> U[M][K]  (calcul.f:224-404,
-//                                       REIGEN surfa.f:714-1190 in FP64 / LEIGEN surfa.f:374-606 in FP32)
-//   build_stacks / check_priors / mc_propose / mc_accept / misfit kernels: the callers on either side of the
-//   solver (model assembly, Monte-Carlo step), thread or warp per model.
+//                  REIGEN surfa.f:714-1190 with a float32 state as packed pairs (default) or the reference's float64
+//                  state (opts.group_f64) / LEIGEN surfa.f:374-606 in float32)
+//   partials_kernel, misfit_kernel and, in surfdisp_mc.cuh, build_stacks / check_priors / mc_propose[_build] /
+//   mc_finish / mc_accept kernels: the callers on either side of the solver (model assembly, Monte-Carlo step),
+//   warp per model.
 // No tensor cores: the work is a serial chain of tiny structured propagator products with
 // data-dependent branches.
 #include <cuda_runtime.h>
