@@ -2,6 +2,7 @@
 lane against the oracle.  This checks the kernel math and the round logic (cluster / window / interpolation
 rounds, coarse scan with its kink guard, uniform-section and sequential polish)
 without a GPU; the CUDA build itself is checked in test_gpu_parity.py."""
+import os
 import numpy as np
 import pytest
 
@@ -77,3 +78,35 @@ def test_steep_branch_on_a_coarse_period_list_is_not_extrapolated():
         lay, nl = synth.crustal_models(100, seed=seed, n_crust=15, n_mantle=130, zmax=400.0)
         dc, du = _run(lay, nl, per, 1)
         assert dc.max() < 1e-4
+
+
+def test_float32_group_velocity_state_against_float64_state(tmp_path):
+    """REIGEN's ODE state in float32 as packed pairs with every sub-layer re-orthogonalised (the product's default) against
+    the reference's float64 state (opts.group_f64 = 1), through the host build of the same per-lane code: thin-layer
+    stacks, thick layers with ndiv = 5 sub-layers (the case that needs the re-orthogonalisation per SUB-layer), water
+    layers.  The mirror reads its switches once per process, hence the two child processes."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        "from pysurfinv_b200 import synth\n"
+        "from tests.hostmirror import mirror as HM\n"
+        "out = []\n"
+        "for (lay, nl), per in ((synth.crustal_models(40, seed=811), synth.log_periods(20)), (synth.hand_models(60, seed=812), synth.log_periods(16, 6.0, 60.0)),\n"
+        "                       (synth.ragged_models(40, seed=813), synth.log_periods(12))):\n"
+        "    for m in range(lay.shape[1]):\n"
+        "        n = nl[m]\n"
+        "        r = HM.forward(2, lay[0, m, :n], lay[1, m, :n], lay[2, m, :n], lay[3, m, :n], lay[4, m, :n], per)\n"
+        "        u = np.zeros(len(per), np.float32); u[:len(r['u'])] = r['u']; out.append(u)\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n")
+    res = {}
+    for mode, env in (("f32", {}), ("f64", {"HM_REIGEN_F64": "1"})):
+        e = dict(os.environ); e.update(env)
+        e["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__))) + os.pathsep + e.get("PYTHONPATH", "")
+        f = str(tmp_path / ("u_%s.npy" % mode))
+        subprocess.check_call([sys.executable, "-c", script, f], env=e)
+        res[mode] = np.load(f)
+    d = np.abs(res["f32"] - res["f64"])
+    assert res["f64"].max() > 2.0 and np.count_nonzero(res["f64"]) > 2000
+    assert d.max() <= 1.5e-5, d.max()
+    assert np.median(d) <= 1.0e-6
