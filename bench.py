@@ -52,6 +52,21 @@ def algo_p1_bytes(lpad, K):
     return 2 * 8 * lpad * 4 + 2 * K * 4 + 16
 
 
+def hbm_roofline(algo_bytes, traffic_bytes, ms):
+    """The memory side of the roofline for a kernel: algorithmic bytes per launch over its duration against the copy
+    bandwidth the driver measured on this pool (MEASURED_PEAKS.json; the profiling recipe's fallback if absent).  For this
+    path it documents that HBM is not the bound."""
+    peak, src = 6650.0, "fallback of B200_PROFILING.md"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        pass
+    ach = algo_bytes / (ms * 1e-3) * 1e-9
+    return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
+            "traffic": traffic_bytes, "algorithmic_bytes": algo_bytes}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -614,6 +629,7 @@ def main():
                                    "float32 ODE state re-orthogonalised after every sub-layer, the float64 state of the reference is "
                                    "opts.group_f64 = 1); reference_equivalent = the same sub-layers at the reference's %.0f FLOP each "
                                    "-- a work-saving factor, not a utilisation" % (F_U_EXEC, F_U)},
+                "hbm": hbm_roofline(algo_p1_bytes(lpad, K) * M, DRAM_P1_PER_MODEL * M, float(kms[1])),
                 "mufu_peak_Tops": peaks[2]}
         cpu = None
         if not args.no_cpu:
