@@ -80,7 +80,6 @@ class ChainEnsemble:
         self.n_points, self.cpp = int(n_points), int(n_chains)
         self.M, self.P, self.seed, self.K = self.n_points * self.cpp, template.nparams, int(seed), K
         self.misfit_mode, self.kind, self.chain_length = int(misfit_mode), int(kind), int(chain_length)
-        self.lmax = int(lmax) if lmax is not None else template.max_layers()
         dev = solver.device
         bc = lambda x, dt: np.array(np.broadcast_to(np.asarray(x, dtype=dt), (self.n_points, K)))   # (writable copies)
         self.obs, self.sigma = bc(obs, np.float32), bc(sigma, np.float32)
@@ -89,6 +88,8 @@ class ChainEnsemble:
         if np.any(use.sum(axis=1) == 0):
             raise ValueError("All observations are masked???")          # point.py:356
         lo, hi, st = template.bounds() if bounds is None else bounds
+        # (array stride of the stacks: the most layers any model inside the boxes can have)
+        self.lmax = int(lmax) if lmax is not None else template.max_layers(lo, hi)
         bnd = np.zeros((self.n_points, 3, 64), np.float32)
         for i, b in enumerate((lo, hi, st)):
             bnd[:, i, :self.P] = np.broadcast_to(np.asarray(b, np.float32), (self.n_points, self.P))

@@ -64,3 +64,24 @@ def test_priors_match_reference_isgood(gold):
         assert (bad == 0) == case["isgood"], (case["setting"], bad)
         n_good += case["isgood"]
     assert 0 < n_good < len(gold["priors"])
+
+
+def test_layer_bound_follows_the_parameter_boxes():
+    """StackTemplate.max_layers(lo, hi): the fine-layer rules grow with the group thickness, so the bound is taken at the
+    largest thickness inside the boxes -- per-point boxes ([n_points, P]) count with their union -- and every model
+    drawn from the boxes stays within it."""
+    setting = {"Sediment": {"H": [2.0, "abs_pos", 1.5, 0.1], "Vs": [1.5, 0.8, 2.6, 0.05]},
+               "Crust": {"H": [30.0, "abs", 10.0, 1.0], "Vs": [[3.3, "rel", 10, 0.02], [3.5, "rel", 10, 0.02], [3.7, "rel", 10, 0.02]]},
+               "Mantle": {"BottomDepth": 200.0, "Vs": [[4.4, "abs", 0.3, 0.02], [4.3, "abs", 0.3, 0.02], [4.5, "abs", 0.3, 0.02]]},
+               "Info": {}}
+    t = S.StackTemplate(setting)
+    lo, hi, _ = t.bounds()
+    assert t.max_layers() == t.max_layers(lo, hi) == 1 + 15 + 60
+    wide = np.tile(hi, (3, 1)); wide[1, 2] = 70.0            # one point lets the crust grow beyond 60 km: 30 fine layers
+    assert t.max_layers(np.tile(lo, (3, 1)), wide) == 1 + 30 + 60
+    thin = hi.copy(); thin[2] = 19.0                         # crust never above 20 km: 10 fine layers
+    assert t.max_layers(lo, thin) == 1 + 10 + 60
+    rng = np.random.default_rng(5)
+    params = (lo + (hi - lo) * rng.random((200, t.nparams))).astype(np.float32)
+    lay, nl = MB.build_stacks(t, params, t.max_layers())
+    assert nl.max() <= t.max_layers() and nl.min() >= 1 + 10 + 60
